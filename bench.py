@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""Headline benchmark: valid mel frames / second of the CompTransTTS forward path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): transformer_fs2 + supervised-duration model (learn_alignment False),
+LJSpeech shape, batch 16, src_lens 100..70, free-running inference with the duration predictor pinned to
+8 frames / phoneme -> M = 800, 10 880 valid frames per step.  A "step" is one
+`model(...)` call.  For N > 1 (torchrun, one rank per GPU) every rank runs its own batch of 16 utterances
+(independent shards, no collective on the data path) -> weak scaling; value = all ranks' frames / max time.
+
+`--impl reference` times the reference's CPU implementation of the same forward (the oracle port:
+oracle/ctts_oracle.py, PyTorch fp32 on all host threads) on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "comprehensive-transformer-tts_b200"), os.path.join(ROOT, "tests", "golden")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+FRAMES_PER_PHONEME = 8
+BATCH = 16
+METRIC = "mel-frames/sec (batch-16 LJSpeech shape)"
+UNIT = "mel-frames/s"
+FFN_FLOP_PER_FRAME = 2 * 256 * 9 * 1024  # the dominant kernel: Conv1d(256->1024, k=9) of one decoder FFN
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops_sustained"], src="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(hbm=6650.0, tensor=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+def build_workload(seed):
+    from ctts_b200 import configs, spec, synth
+    p, m, t = configs.builtin_configs("LJSpeech", block_type="transformer_fs2", learn_alignment=False)
+    sd = synth.synthetic_state_dict(spec.parameter_spec(p, m)[0], pin_frames_per_phoneme=FRAMES_PER_PHONEME)
+    batch = synth.ljspeech_batch(batch=BATCH, s_max=100, s_step=2, mode="infer", seed=seed)
+    frames = int(batch["src_lens"].sum()) * FRAMES_PER_PHONEME
+    return (p, m, t), sd, batch, frames
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_forward_timer(cfgs, sd, batch, frames, budget_s=20.0, min_iters=2):
+    """Times oracle.comp_trans_tts_forward on all host threads; returns (frames/s, iters, threads)."""
+    from oracle import ctts_oracle as O
+    p, m, t = cfgs
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    args = (batch["speakers"], batch["texts"], batch["src_lens"], batch["max_src_len"])
+    with torch.no_grad():
+        O.comp_trans_tts_forward(sd, p, m, t, *args)  # warm-up
+        times = []
+        t_end = time.perf_counter() + budget_s
+        while len(times) < min_iters or (time.perf_counter() < t_end and len(times) < 8):
+            t0 = time.perf_counter()
+            O.comp_trans_tts_forward(sd, p, m, t, *args)
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return frames / med, len(times), threads, med
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfgs, sd, batch, frames = build_workload(seed=0)
+    steps = max(args.steps, 1)
+    from oracle import ctts_oracle as O
+    p, m, t = cfgs
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    a = (batch["speakers"], batch["texts"], batch["src_lens"], batch["max_src_len"])
+    with torch.no_grad():
+        for _ in range(max(min(args.warmup, 2), 1)):
+            O.comp_trans_tts_forward(sd, p, m, t, *a)
+        steps = min(steps, 10)  # ~2.5 s per step on 8 cores: bounded so the run ends within a few minutes
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.comp_trans_tts_forward(sd, p, m, t, *a)
+        dt = time.perf_counter() - t0
+    value = frames * steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "transformer_fs2 + supervised duration, LJSpeech shape, batch 16, S 100..70, "
+                               "8 frames/phoneme (M 800, 10880 valid frames), free-running inference",
+                   "device": "host CPU, torch %s" % torch.__version__},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d full forward passes of the batch-16 workload (oracle/ctts_oracle.py)" % steps},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch.distributed as dist
+    import ctts_b200
+    from ctts_b200 import capi, engine
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+
+    cfgs, sd, batch, frames = build_workload(seed=rank)
+    net = ctts_b200.CompTransTTS(*cfgs).eval()
+    net.load_state_dict(sd, strict=True)
+    net.to(dev)
+    dev_in = (batch["speakers"].to(dev), batch["texts"].to(dev), batch["src_lens"].to(dev), batch["max_src_len"])
+    host_in = tuple(x.pin_memory() for x in (batch["speakers"], batch["texts"], batch["src_lens"]))
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)  # > 126 MB L2
+
+    # --- per-launch timing of the dominant kernel (decoder FFN Conv1d k=9), live, on the launching stream ------------
+    ffn_events = []
+    orig_conv = engine.conv_gemm
+
+    def timed_conv(x, w, *a, **k):
+        if k.get("taps", 1) == 9 and x.shape[1] >= 400:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = orig_conv(x, w, *a, **k)
+            e1.record()
+            ffn_events.append((e0, e1))
+            return y
+        return orig_conv(x, w, *a, **k)
+
+    engine.conv_gemm = timed_conv
+
+    def step_device():
+        return net(*dev_in)
+
+    def step_e2e():
+        spk, txt, lens = (h.to(dev, non_blocking=True) for h in host_in)
+        out = net(spk, txt, lens, batch["max_src_len"])
+        mel = out[1].to("cpu", non_blocking=False)
+        ml = out[9].to("cpu")
+        return mel, ml
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total = 0.0
+        launches0 = capi.LAUNCHES
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), capi.LAUNCHES - launches0
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ffn_events.clear()
+    ms_total, launches = timed(step_device, args.steps, args.warmup)
+    ffn_ms = [a.elapsed_time(b) for a, b in ffn_events[-6 * args.steps:]]
+    engine.conv_gemm = orig_conv
+    ms_e2e, _ = timed(step_e2e, args.steps, 2)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        pk = peaks()
+        value = world * frames * args.steps / (ms_total / 1e3)
+        e2e = world * frames * args.steps / (ms_e2e / 1e3)
+        ffn_avg = sum(ffn_ms) / max(len(ffn_ms), 1)
+        ffn_tflops = frames * FFN_FLOP_PER_FRAME / (ffn_avg * 1e-3) / 1e12 if ffn_ms else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "transformer_fs2 + supervised duration (learn_alignment False), LJSpeech shape, "
+                                   "batch 16 per GPU, S 100..70, 8 frames/phoneme (M 800, 10880 valid frames), "
+                                   "free-running inference, random-init weights",
+                       "l2_flush": "256 MiB device write between timed steps", "timing": "CUDA events per step, max over ranks",
+                       "parallelism": "independent shards x%d" % world},
+            "e2e": {"value": e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host_in)),
+                    "d2h_bytes_per_step": int(BATCH * 800 * 80 * 4 + BATCH * 8), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "decoder FFN Conv1d(256->1024,k9)+GELU implicit GEMM (ctts_conv1d_gemm)",
+                         "bound": "tensor", "achieved": ffn_tflops, "peak": pk["tensor"], "unit": "TFLOP/s",
+                         "frac": (ffn_tflops / pk["tensor"]) if ffn_tflops else None, "traffic": None,
+                         "peak_source": pk["src"], "launch_ms": ffn_avg, "launches_timed": len(ffn_ms),
+                         "flops_per_launch": frames * FFN_FLOP_PER_FRAME},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, iters, threads, med = cpu_forward_timer(cfgs, sd, batch, frames)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d full forward passes of the same batch-16 workload on the host "
+                                              "(oracle/ctts_oracle.py, torch fp32, median %.0f ms)" % (iters, med * 1e3)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,54 @@
+// Shared helpers for libctts_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "ctts_b200.h"
+
+namespace ctts {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+#define CTTS_REQUIRE(cond, ...)            \
+    do {                                   \
+        if (!(cond)) {                     \
+            ctts::set_error(__VA_ARGS__);  \
+            return 2;                      \
+        }                                  \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// exact (erf) GELU, tanh etc. -- the reference uses F.gelu (erf form), torch.tanh, relu, x*sigmoid(x)
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case CTTS_ACT_RELU: return fmaxf(v, 0.f);
+        case CTTS_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+        case CTTS_ACT_TANH: return tanhf(v);
+        case CTTS_ACT_SWISH: return v / (1.f + expf(-v));
+        default: return v;
+    }
+}
+
+}  // namespace ctts

@@ -1,0 +1,788 @@
+// libctts_b200: FP32 CUDA-core kernels of the CompTransTTS forward path (sm_100a).
+//
+// These are the kernels that sit UPSTREAM of a quantiser (duration rounding, pitch / energy buckets:
+// SURVEY.md section 7 H1) and therefore must be true FP32, plus the HBM-bound integer / indexing work
+// (LengthRegulator, embeddings).  The tensor-core engine for the decoder / PostNet lives in
+// ctts_gemm_tc.cu.  Reference call sites are cited in include/ctts_b200.h.
+#include "ctts_common.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace ctts {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Running count of flagged entries along T, one warp, written to shared memory.
+// pos[t] = flag[t] ? (# flags in [0..t]) : 0        (utils/tools.py:640-652 with padding_idx 0)
+template <typename FlagFn>
+__device__ __forceinline__ void warp_positions(int T, int* pos, FlagFn flag) {
+    const int lane = threadIdx.x & 31;
+    int running = 0;
+    for (int base = 0; base < T; base += 32) {
+        const int t = base + lane;
+        const bool f = (t < T) && flag(t);
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        const int incl = __popc(m & (0xffffffffu >> (31 - lane)));
+        if (t < T) pos[t] = f ? running + incl : 0;
+        running += __popc(m);
+    }
+}
+
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ table,
+                                    const float* __restrict__ pe, float scale, int S, int C, int vocab,
+                                    float* __restrict__ x, float* __restrict__ word,
+                                    const int64_t* __restrict__ lens) {
+    extern __shared__ int s_pos[];
+    const int b = blockIdx.x;
+    const int64_t* tok = tokens + (size_t)b * S;
+    if (threadIdx.x < 32) warp_positions(S, s_pos, [&](int t) { return tok[t] != 0; });
+    __syncthreads();
+    const int c4 = C >> 2;
+    const int len = lens ? (int)lens[b] : S;
+    for (int i = threadIdx.x; i < S * c4; i += blockDim.x) {
+        const int s = i / c4, c = (i - s * c4) << 2;
+        int64_t id = tok[s];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        float4 e = *reinterpret_cast<const float4*>(table + (size_t)id * C + c);
+        const float4 p = *reinterpret_cast<const float4*>(pe + (size_t)s_pos[s] * C + c);
+        e.x *= scale; e.y *= scale; e.z *= scale; e.w *= scale;
+        const size_t o = ((size_t)b * S + s) * C + c;
+        *reinterpret_cast<float4*>(word + o) = e;
+        *reinterpret_cast<float4*>(x + o) = (s < len) ? make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+__global__ void add_positions_kernel(float* __restrict__ x, const float* __restrict__ pe, const float* __restrict__ alpha,
+                                     const int64_t* __restrict__ lens, int T, int C) {
+    extern __shared__ int s_pos[];
+    const int b = blockIdx.x;
+    float* xb = x + (size_t)b * T * C;
+    if (threadIdx.x < 32) warp_positions(T, s_pos, [&](int t) { return xb[(size_t)t * C] != 0.f; });
+    __syncthreads();
+    const float a = alpha[0];
+    const int len = lens ? (int)lens[b] : T;
+    const int c4 = C >> 2;
+    for (int i = threadIdx.x; i < T * c4; i += blockDim.x) {
+        const int t = i / c4, c = (i - t * c4) << 2;
+        float4 v = *reinterpret_cast<float4*>(xb + (size_t)t * C + c);
+        if (t < len) {
+            const float4 p = *reinterpret_cast<const float4*>(pe + (size_t)s_pos[t] * C + c);
+            v.x += a * p.x; v.y += a * p.y; v.z += a * p.z; v.w += a * p.w;
+        } else {
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        *reinterpret_cast<float4*>(xb + (size_t)t * C + c) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, two-pass moments in FP32.  C <= 1024, C % 4 == 0.
+template <bool SPLIT>
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, const int64_t* __restrict__ lens, int rows,
+                                 int T, int C, float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
+                                 __nv_bfloat16* __restrict__ y_lo) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + (size_t)row * C;
+    float4 v[8];
+    const int n4 = C >> 2;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = lane + i * 32;
+        if (c < n4) {
+            v[i] = reinterpret_cast<const float4*>(xr)[c];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = lane + i * 32;
+        if (c < n4) {
+            const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b2 * b2) + (c2 * c2 + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    bool keep = true;
+    if (lens) {
+        const int b = row / T, t = row - b * T;
+        keep = t < (int)lens[b];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = lane + i * 32;
+        if (c < n4) {
+            const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+            const float4 bb = reinterpret_cast<const float4*>(beta)[c];
+            float4 o;
+            o.x = keep ? (v[i].x - mean) * rstd * g.x + bb.x : 0.f;
+            o.y = keep ? (v[i].y - mean) * rstd * g.y + bb.y : 0.f;
+            o.z = keep ? (v[i].z - mean) * rstd * g.z + bb.z : 0.f;
+            o.w = keep ? (v[i].w - mean) * rstd * g.w + bb.w : 0.f;
+            if (y) reinterpret_cast<float4*>(y + (size_t)row * C)[c] = o;
+            if (SPLIT) {
+                const float f[4] = {o.x, o.y, o.z, o.w};
+                __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    h[k] = __float2bfloat16_rn(f[k]);
+                    l[k] = __float2bfloat16_rn(f[k] - __bfloat162float(h[k]));
+                }
+                *reinterpret_cast<uint2*>(y_hi + (size_t)row * C + 4 * c) = *reinterpret_cast<uint2*>(h);
+                *reinterpret_cast<uint2*>(y_lo + (size_t)row * C + 4 * c) = *reinterpret_cast<uint2*>(l);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Implicit-GEMM Conv1d / Linear in FP32 on the CUDA cores.
+// Tile 128 (t) x 64 (n) x 16 (k); 256 threads, 8x4 outputs per thread.
+constexpr int GM = 128, GN = 64, GK = 16, GPAD = 4;
+
+__global__ void __launch_bounds__(256)
+conv1d_gemm_fp32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                        float alpha, const float* __restrict__ col_scale, const float* __restrict__ col_shift, int act,
+                        const float* __restrict__ residual, const int64_t* __restrict__ lens, int T, int Cin, int N,
+                        int taps, float* __restrict__ y) {
+    __shared__ __align__(16) float As[2][GK][GM + GPAD];
+    __shared__ __align__(16) float Bs[2][GK][GN + GPAD];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int pad = taps >> 1;
+    const int K = taps * Cin;
+    const float* xb = x + (size_t)b * T * Cin;
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float4 ra[2], rb;
+    auto load_gmem = [&](int kk) {
+        const int tap = kk / Cin, c0 = kk - tap * Cin;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int l = tid + it * 256;
+            const int m = l >> 2, kq = l & 3;
+            const int t = t0 + m + tap - pad;
+            ra[it] = (t >= 0 && t < T && (t0 + m) < T)
+                         ? *reinterpret_cast<const float4*>(xb + (size_t)t * Cin + c0 + kq * 4)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        {
+            const int n = tid >> 2, kq = tid & 3;
+            rb = (n0 + n < N) ? *reinterpret_cast<const float4*>(w + (size_t)(n0 + n) * K + kk + kq * 4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_smem = [&](int buf) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int l = tid + it * 256;
+            const int m = l >> 2, kq = l & 3;
+            As[buf][kq * 4 + 0][m] = ra[it].x;
+            As[buf][kq * 4 + 1][m] = ra[it].y;
+            As[buf][kq * 4 + 2][m] = ra[it].z;
+            As[buf][kq * 4 + 3][m] = ra[it].w;
+        }
+        const int n = tid >> 2, kq = tid & 3;
+        Bs[buf][kq * 4 + 0][n] = rb.x;
+        Bs[buf][kq * 4 + 1][n] = rb.y;
+        Bs[buf][kq * 4 + 2][n] = rb.z;
+        Bs[buf][kq * 4 + 3][n] = rb.w;
+    };
+
+    load_gmem(0);
+    store_smem(0);
+    __syncthreads();
+    int buf = 0;
+    for (int kk = 0; kk < K; kk += GK) {
+        const bool more = kk + GK < K;
+        if (more) load_gmem(kk + GK);
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        if (more) {
+            store_smem(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+    const int len = lens ? (int)lens[b] : T;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int t = t0 + ty * 8 + i;
+        if (t >= T) continue;
+        const size_t row = ((size_t)b * T + t) * N;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[n];
+            v *= alpha;
+            if (col_scale) v = v * col_scale[n] + col_shift[n];
+            v = apply_act(v, act);
+            if (residual) v += residual[row + n];
+            y[row + n] = (t < len) ? v : 0.f;
+        }
+    }
+}
+
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int N, int Cin, int taps, float* __restrict__ p) {
+    const size_t total = (size_t)N * Cin * taps;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cin);
+        const int j = (int)((i / Cin) % taps);
+        const size_t n = i / ((size_t)Cin * taps);
+        p[i] = w[(n * Cin + c) * taps + j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Flash-style masked self-attention, FP32.  32 queries per CTA (128 threads: 4 threads per query row,
+// each owning DH/4 output dims), keys streamed in tiles of 32 through shared memory.
+template <int DH>
+__global__ void __launch_bounds__(128)
+attention_fp32_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ lens, int T, int C, float scale,
+                      float* __restrict__ out) {
+    constexpr int LD = DH + 4;
+    constexpr int DPT = DH / 4;
+    extern __shared__ __align__(16) float smem[];
+    float* Qs = smem;
+    float* Ks = Qs + 32 * LD;
+    float* Vs = Ks + 32 * LD;
+    float* Ps = Vs + 32 * LD;  // [32][33]
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 32;
+    const int tid = threadIdx.x, r = tid >> 2, qd = tid & 3;
+    const int len = min((int)lens[b], T);
+    const size_t ld3 = (size_t)3 * C;
+    const float* base = qkv + (size_t)b * T * ld3 + (size_t)h * DH;
+
+    // stage Q (pre-scaled, like the reference: q * head_dim^-0.5 before q k^T)
+    for (int i = tid; i < 32 * (DH / 4); i += 128) {
+        const int rr = i / (DH / 4), c = (i - rr * (DH / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + rr < T) v = *reinterpret_cast<const float4*>(base + (size_t)(q0 + rr) * ld3 + c);
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        *reinterpret_cast<float4*>(Qs + rr * LD + c) = v;
+    }
+    float acc[DPT];
+#pragma unroll
+    for (int i = 0; i < DPT; ++i) acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int k0 = 0; k0 < len; k0 += 32) {
+        __syncthreads();
+        for (int i = tid; i < 32 * (DH / 4); i += 128) {
+            const int rr = i / (DH / 4), c = (i - rr * (DH / 4)) * 4;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (k0 + rr < len) {
+                const float* p = base + (size_t)(k0 + rr) * ld3 + c;
+                kv = *reinterpret_cast<const float4*>(p + C);
+                vv = *reinterpret_cast<const float4*>(p + 2 * C);
+            }
+            *reinterpret_cast<float4*>(Ks + rr * LD + c) = kv;
+            *reinterpret_cast<float4*>(Vs + rr * LD + c) = vv;
+        }
+        __syncthreads();
+        float s[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = 0.f;
+#pragma unroll 4
+        for (int d = 0; d < DH; d += 4) {
+            const float4 q4 = *reinterpret_cast<const float4*>(Qs + r * LD + d);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 k4 = *reinterpret_cast<const float4*>(Ks + (qd + 4 * i) * LD + d);
+                s[i] = fmaf(q4.x, k4.x, s[i]);
+                s[i] = fmaf(q4.y, k4.y, s[i]);
+                s[i] = fmaf(q4.z, k4.z, s[i]);
+                s[i] = fmaf(q4.w, k4.w, s[i]);
+            }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (k0 + qd + 4 * i >= len) s[i] = -INFINITY;
+            mx = fmaxf(mx, s[i]);
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run, mx);  // finite: every tile holds at least one valid key
+        const float corr = expf(m_run - m_new);
+        float ps = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float p = expf(s[i] - m_new);
+            Ps[r * 33 + qd + 4 * i] = p;
+            ps += p;
+        }
+        ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+        ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+        l_run = l_run * corr + ps;
+        m_run = m_new;
+#pragma unroll
+        for (int i = 0; i < DPT; ++i) acc[i] *= corr;
+        __syncwarp();
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const float p = Ps[r * 33 + k];
+#pragma unroll
+            for (int i = 0; i < DPT; i += 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(Vs + k * LD + qd * DPT + i);
+                acc[i + 0] = fmaf(p, v4.x, acc[i + 0]);
+                acc[i + 1] = fmaf(p, v4.y, acc[i + 1]);
+                acc[i + 2] = fmaf(p, v4.z, acc[i + 2]);
+                acc[i + 3] = fmaf(p, v4.w, acc[i + 3]);
+            }
+        }
+        __syncwarp();
+    }
+    const int t = q0 + r;
+    if (t < T) {
+        const bool valid = t < len;
+        const float inv = valid ? 1.f / l_run : 0.f;
+        float* o = out + ((size_t)b * T + t) * C + (size_t)h * DH + qd * DPT;
+#pragma unroll
+        for (int i = 0; i < DPT; i += 4)
+            *reinterpret_cast<float4*>(o + i) = valid ? make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv,
+                                                                    acc[i + 3] * inv)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void decode_durations_kernel(const float* __restrict__ log_d, float d_control, int n, float* __restrict__ dur) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dur[i] = fmaxf(rintf(expf(log_d[i]) - 1.f) * d_control, 0.f);
+}
+
+// One warp per utterance: inclusive scans of the LR repeat counts and of the mel2ph (rounded) durations.
+__global__ void length_scan_kernel(const float* __restrict__ dur_f, const int64_t* __restrict__ dur_i,
+                                   const int64_t* __restrict__ src_lens, int S, int32_t* __restrict__ cum_lr,
+                                   int32_t* __restrict__ cum_m2p, int64_t* __restrict__ mel_len,
+                                   int64_t* __restrict__ m2p_len) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int slen = src_lens ? (int)src_lens[b] : S;
+    int run_a = 0, run_b = 0;
+    for (int base = 0; base < S; base += 32) {
+        const int j = base + lane;
+        int ra = 0, rb = 0;
+        if (j < S) {
+            if (dur_f) {
+                const float d = dur_f[(size_t)b * S + j];
+                ra = max((int)d, 0);                       // int(expand_size): truncation, modules.py:1241-1242
+                rb = (int)rintf(d);                        // torch.round: half-to-even, utils/tools.py:618
+            } else {
+                const int64_t d = dur_i[(size_t)b * S + j];
+                ra = (int)(d > 0 ? d : 0);
+                rb = (int)d;
+            }
+            if (j >= slen) rb = 0;                         // dur * (1 - dur_padding), utils/tools.py:619-620
+        }
+        int ia = ra, ib = rb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ua; ib += ub; }
+        }
+        if (j < S) {
+            cum_lr[(size_t)b * S + j] = run_a + ia;
+            cum_m2p[(size_t)b * S + j] = run_b + ib;
+        }
+        run_a += __shfl_sync(0xffffffffu, ia, 31);
+        run_b += __shfl_sync(0xffffffffu, ib, 31);
+    }
+    if (lane == 0) {
+        mel_len[b] = run_a;
+        if (m2p_len) m2p_len[b] = run_b;
+    }
+}
+
+__device__ __forceinline__ int upper_bound_i32(const int32_t* __restrict__ a, int n, int v) {
+    int lo = 0, hi = n;  // first index with a[idx] > v
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] > v) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// One warp per output frame.
+__global__ void length_expand_kernel(const float* __restrict__ src, const float* __restrict__ table,
+                                     const int64_t* __restrict__ row_index, const int32_t* __restrict__ cum_lr, int S,
+                                     int C, int M, int accumulate, float* __restrict__ out,
+                                     const int32_t* __restrict__ cum_m2p, int64_t* __restrict__ mel2ph, int M2) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t < M) {
+        const int j = upper_bound_i32(cum_lr + (size_t)b * S, S, t);
+        const float* row = nullptr;
+        if (j < S) row = table ? table + (size_t)row_index[(size_t)b * S + j] * C : src + ((size_t)b * S + j) * C;
+        float4* o = reinterpret_cast<float4*>(out + ((size_t)b * M + t) * C);
+        for (int c = lane; c < (C >> 2); c += 32) {
+            float4 v = row ? reinterpret_cast<const float4*>(row)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (accumulate) {
+                const float4 p = o[c];
+                v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+            }
+            o[c] = v;
+        }
+    }
+    if (mel2ph && t < M2 && lane == 0) {
+        const int j = upper_bound_i32(cum_m2p + (size_t)b * S, S, t);
+        mel2ph[(size_t)b * M2 + t] = (j < S) ? (int64_t)(j + 1) : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+}
+
+__device__ __forceinline__ int64_t f0_to_coarse_dev(float f0) {
+    // utils/pitch_tools.py:20-36, all arithmetic in fp32 like the torch branch
+    const float mel_min = (float)(1127.0 * 0.06899287148695143);  // 1127*ln(1+50/700)
+    const float mel_span = (float)(1127.0 * 0.9444616088408514 - 1127.0 * 0.06899287148695143);  // ln(1+1100/700)
+    float m = 1127.f * logf(1.f + f0 / 700.f);
+    if (m > 0.f) m = (m - mel_min) * 254.f / mel_span + 1.f;
+    if (m <= 1.f) m = 1.f;
+    if (m > 255.f) m = 255.f;
+    return (int64_t)(m + 0.5f);
+}
+
+__global__ void __launch_bounds__(256)
+cwt_to_pitch_kernel(const float* __restrict__ cwt, int cwt_stride, const float* __restrict__ scale_w,
+                    const float* __restrict__ mean, const float* __restrict__ stdv, int stat_stride, float std_scale,
+                    float eps, const float* __restrict__ uv_src, int use_uv, int T, float* __restrict__ f0_norm,
+                    float* __restrict__ f0_denorm, int64_t* __restrict__ pitch_idx) {
+    extern __shared__ float rec[];
+    __shared__ float red[8];
+    const int b = blockIdx.x;
+    const float* cb = cwt + (size_t)b * T * cwt_stride;
+    float w[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) w[i] = scale_w[i];
+    float s = 0.f;
+    for (int t = threadIdx.x; t < T; t += 256) {
+        const float* c = cb + (size_t)t * cwt_stride;
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) a += c[i] * w[i];
+        rec[t] = a;
+        s += a;
+    }
+    const float mu = block_sum_256(s, red) / (float)T;
+    float q = 0.f;
+    for (int t = threadIdx.x; t < T; t += 256) {
+        const float d = rec[t] - mu;
+        q += d * d;
+    }
+    const float sd = sqrtf(block_sum_256(q, red) / (float)(T - 1));  // torch.std: unbiased
+    const float m_b = mean[(size_t)b * stat_stride];
+    const float s_b = stdv[(size_t)b * stat_stride] * std_scale;
+    for (int t = threadIdx.x; t < T; t += 256) {
+        const float z = (rec[t] - mu) / sd;
+        const float f0 = expf(z * s_b + m_b);
+        const float fn = log2f(f0 + eps);
+        bool uv = false;
+        if (use_uv) uv = uv_src ? (uv_src[(size_t)b * T + t] > 0.f) : (cb[(size_t)t * cwt_stride + 10] > 0.f);
+        const float fd = uv ? 0.f : exp2f(fn);
+        const size_t o = (size_t)b * T + t;
+        if (f0_norm) f0_norm[o] = fn;
+        f0_denorm[o] = fd;
+        pitch_idx[o] = f0_to_coarse_dev(fd);
+    }
+}
+
+__global__ void f0_to_pitch_kernel(const float* __restrict__ f0n, const float* __restrict__ uv, int n,
+                                   float* __restrict__ f0_denorm, int64_t* __restrict__ pitch_idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float fd = (uv && uv[i] > 0.f) ? 0.f : exp2f(f0n[i]);
+    f0_denorm[i] = fd;
+    pitch_idx[i] = f0_to_coarse_dev(fd);
+}
+
+__global__ void gather_add_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, int rows, int C,
+                                  int table_rows, float* __restrict__ x) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    int64_t id = idx[row];
+    id = id < 0 ? 0 : (id >= table_rows ? table_rows - 1 : id);
+    const float4* src = reinterpret_cast<const float4*>(table + (size_t)id * C);
+    float4* dst = reinterpret_cast<float4*>(x + (size_t)row * C);
+    for (int c = lane; c < (C >> 2); c += 32) {
+        float4 v = dst[c];
+        const float4 e = src[c];
+        v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+        dst[c] = v;
+    }
+}
+
+__global__ void bucketize_kernel(const float* __restrict__ v, float v_scale, const float* __restrict__ bins, int n_bins,
+                                 int n, int64_t* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = v[i] * v_scale;
+    int lo = 0, hi = n_bins;  // first index with bins[idx] >= x  (torch.bucketize, right=False)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (bins[mid] >= x) hi = mid; else lo = mid + 1;
+    }
+    idx[i] = lo;
+}
+
+__global__ void add_row_broadcast_kernel(const float* __restrict__ x, const float* __restrict__ row, int T, int C,
+                                         size_t total4, float* __restrict__ y) {
+    const int c4 = C >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t tok = i / c4;
+        const int c = (int)(i - tok * c4);
+        const size_t b = tok / T;
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        const float4 r = reinterpret_cast<const float4*>(row + b * C)[c];
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+}  // namespace ctts
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace ctts;
+
+template <int DH>
+static int launch_attention(const float* qkv, const int64_t* lens, int B, int T, int C, int H, float scale, float* out,
+                            cudaStream_t st) {
+    const size_t sm = (size_t)(3 * 32 * (DH + 4) + 32 * 33) * sizeof(float);
+    cudaFuncSetAttribute(attention_fp32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    dim3 grid((T + 31) / 32, H, B);
+    attention_fp32_kernel<DH><<<grid, 128, sm, st>>>(qkv, lens, T, C, scale, out);
+    return check_launch("attention");
+}
+
+extern "C" {
+
+int ctts_abi_version(void) { return CTTS_ABI_VERSION; }
+const char* ctts_last_error(void) { return g_err; }
+
+int ctts_device_arch(void) {
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed (no CUDA device?)"); return -1; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return major * 10 + minor;
+}
+
+int ctts_embed_tokens(const int64_t* tokens, const float* table, const float* pe, int pe_rows, float embed_scale,
+                      int B, int S, int C, int vocab, float* x, float* word, const int64_t* lens, void* stream) {
+    CTTS_REQUIRE(B > 0 && S > 0 && C % 4 == 0, "embed_tokens: bad shape B=%d S=%d C=%d", B, S, C);
+    CTTS_REQUIRE(pe_rows > S, "embed_tokens: positional table has %d rows, need > %d", pe_rows, S);
+    CTTS_REQUIRE((size_t)S * 4 <= 200 * 1024, "embed_tokens: S=%d too long", S);
+    const size_t sm = (size_t)S * sizeof(int);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(embed_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    embed_tokens_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(tokens, table, pe, embed_scale, S, C, vocab, x, word, lens);
+    return check_launch("embed_tokens");
+}
+
+int ctts_add_positions(float* x, const float* pe, int pe_rows, const float* alpha, const int64_t* lens, int B, int T,
+                       int C, void* stream) {
+    CTTS_REQUIRE(B > 0 && T > 0 && C % 4 == 0, "add_positions: bad shape B=%d T=%d C=%d", B, T, C);
+    CTTS_REQUIRE(pe_rows > T, "add_positions: positional table has %d rows, need > %d", pe_rows, T);
+    CTTS_REQUIRE((size_t)T * 4 <= 200 * 1024, "add_positions: T=%d too long", T);
+    const size_t sm = (size_t)T * sizeof(int);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(add_positions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    add_positions_kernel<<<B, 512, sm, (cudaStream_t)stream>>>(x, pe, alpha, lens, T, C);
+    return check_launch("add_positions");
+}
+
+static int layernorm_impl(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B,
+                          int T, int C, float* y, void* y_hi, void* y_lo, void* stream) {
+    CTTS_REQUIRE(C % 4 == 0 && C <= 1024, "layernorm: C=%d unsupported (need C %% 4 == 0, C <= 1024)", C);
+    const int rows = B * T;
+    CTTS_REQUIRE(rows > 0, "layernorm: empty input");
+    const int grid = (rows + 7) / 8;
+    if (y_hi)
+        layernorm_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, lens, rows, T, C, y,
+                                                                        (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
+    else
+        layernorm_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, lens, rows, T, C, y,
+                                                                         nullptr, nullptr);
+    return check_launch("layernorm");
+}
+
+int ctts_layernorm(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B, int T,
+                   int C, float* y, void* stream) {
+    CTTS_REQUIRE(y != nullptr, "layernorm: y is NULL");
+    return layernorm_impl(x, gamma, beta, eps, lens, B, T, C, y, nullptr, nullptr, stream);
+}
+
+int ctts_layernorm_split(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B,
+                         int T, int C, float* y, void* y_hi, void* y_lo, void* stream) {
+    CTTS_REQUIRE(y_hi && y_lo, "layernorm_split: y_hi / y_lo are NULL");
+    return layernorm_impl(x, gamma, beta, eps, lens, B, T, C, y, y_hi, y_lo, stream);
+}
+
+int ctts_conv1d_gemm(const float* x, const float* w, const float* bias, float alpha, const float* col_scale,
+                     const float* col_shift, int act, const float* residual, const int64_t* lens, int B, int T,
+                     int Cin, int N, int taps, float* y, void* stream) {
+    CTTS_REQUIRE(B > 0 && T > 0 && N > 0 && taps >= 1 && (taps & 1), "conv1d_gemm: bad shape B=%d T=%d N=%d taps=%d", B,
+                 T, N, taps);
+    CTTS_REQUIRE(Cin % 16 == 0, "conv1d_gemm: Cin=%d must be a multiple of 16", Cin);
+    CTTS_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), "conv1d_gemm: col_scale/col_shift must come together");
+    dim3 grid((T + GM - 1) / GM, (N + GN - 1) / GN, B);
+    conv1d_gemm_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, alpha, col_scale, col_shift, act,
+                                                                    residual, lens, T, Cin, N, taps, y);
+    return check_launch("conv1d_gemm");
+}
+
+int ctts_pack_conv_weight(const float* w, int N, int Cin, int taps, float* packed, void* stream) {
+    const size_t total = (size_t)N * Cin * taps;
+    CTTS_REQUIRE(total > 0, "pack_conv_weight: empty");
+    const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    pack_conv_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, N, Cin, taps, packed);
+    return check_launch("pack_conv_weight");
+}
+
+int ctts_attention(const float* qkv, const int64_t* lens, int B, int T, int C, int H, float scale, float* out,
+                   void* stream) {
+    CTTS_REQUIRE(B > 0 && T > 0 && H > 0 && C % H == 0, "attention: bad shape B=%d T=%d C=%d H=%d", B, T, C, H);
+    CTTS_REQUIRE(lens != nullptr, "attention: lens is NULL");
+    const int dh = C / H;
+    switch (dh) {
+        case 128: return launch_attention<128>(qkv, lens, B, T, C, H, scale, out, (cudaStream_t)stream);
+        case 64: return launch_attention<64>(qkv, lens, B, T, C, H, scale, out, (cudaStream_t)stream);
+        case 32: return launch_attention<32>(qkv, lens, B, T, C, H, scale, out, (cudaStream_t)stream);
+        default: set_error("attention: head_dim %d unsupported (32, 64, 128)", dh); return 2;
+    }
+}
+
+int ctts_decode_durations(const float* log_d, float d_control, int n, float* dur, void* stream) {
+    CTTS_REQUIRE(n > 0, "decode_durations: empty");
+    decode_durations_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(log_d, d_control, n, dur);
+    return check_launch("decode_durations");
+}
+
+int ctts_length_scan(const float* dur_f32, const int64_t* dur_i64, const int64_t* src_lens, int B, int S,
+                     int32_t* cum_lr, int32_t* cum_m2p, int64_t* mel_len, void* stream) {
+    CTTS_REQUIRE((dur_f32 != nullptr) != (dur_i64 != nullptr), "length_scan: exactly one of dur_f32 / dur_i64");
+    CTTS_REQUIRE(B > 0 && S > 0, "length_scan: bad shape");
+    // mel_len has room for 2*B entries: [0,B) = LR lengths, [B,2B) = mel2ph lengths
+    length_scan_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(dur_f32, dur_i64, src_lens, S, cum_lr, cum_m2p, mel_len,
+                                                           mel_len + B);
+    return check_launch("length_scan");
+}
+
+int ctts_length_expand(const float* src, const float* table, const int64_t* row_index, const int32_t* cum_lr, int B,
+                       int S, int C, int M, int accumulate, float* out, const int32_t* cum_m2p, int64_t* mel2ph, int M2,
+                       void* stream) {
+    CTTS_REQUIRE((src != nullptr) != (table != nullptr), "length_expand: exactly one of src / table");
+    CTTS_REQUIRE(table == nullptr || row_index != nullptr, "length_expand: table needs row_index");
+    CTTS_REQUIRE(C % 4 == 0 && M > 0, "length_expand: bad shape C=%d M=%d", C, M);
+    const int rows = M > M2 ? M : (mel2ph ? M2 : M);
+    dim3 grid((rows + 7) / 8, B);
+    length_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, table, row_index, cum_lr, S, C, M, accumulate, out,
+                                                                 cum_m2p, mel2ph, M2);
+    return check_launch("length_expand");
+}
+
+int ctts_cwt_to_pitch(const float* cwt, int cwt_stride, const float* scale_w, const float* mean, const float* std,
+                      int stat_stride, float std_scale, float eps, const float* uv_src, int use_uv, int B, int T,
+                      float* f0_norm, float* f0_denorm, int64_t* pitch_idx, void* stream) {
+    CTTS_REQUIRE(B > 0 && T > 1, "cwt_to_pitch: need T > 1 (unbiased std), got B=%d T=%d", B, T);
+    CTTS_REQUIRE(cwt_stride >= 10 && (uv_src || !use_uv || cwt_stride >= 11), "cwt_to_pitch: cwt_stride=%d", cwt_stride);
+    const size_t sm = (size_t)T * sizeof(float);
+    CTTS_REQUIRE(sm <= 200 * 1024, "cwt_to_pitch: T=%d too long", T);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(cwt_to_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cwt_to_pitch_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(cwt, cwt_stride, scale_w, mean, std, stat_stride, std_scale,
+                                                              eps, uv_src, use_uv, T, f0_norm, f0_denorm, pitch_idx);
+    return check_launch("cwt_to_pitch");
+}
+
+int ctts_f0_to_pitch(const float* f0_norm, const float* uv_src, int n, float* f0_denorm, int64_t* pitch_idx,
+                     void* stream) {
+    CTTS_REQUIRE(n > 0, "f0_to_pitch: empty");
+    f0_to_pitch_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(f0_norm, uv_src, n, f0_denorm, pitch_idx);
+    return check_launch("f0_to_pitch");
+}
+
+int ctts_gather_add(const float* table, const int64_t* idx, int rows, int C, int table_rows, float* x, void* stream) {
+    CTTS_REQUIRE(rows > 0 && C % 4 == 0, "gather_add: bad shape");
+    gather_add_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(table, idx, rows, C, table_rows, x);
+    return check_launch("gather_add");
+}
+
+int ctts_bucketize(const float* v, float v_scale, const float* bins, int n_bins, int n, int64_t* idx, void* stream) {
+    CTTS_REQUIRE(n > 0 && n_bins > 0, "bucketize: bad shape");
+    bucketize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(v, v_scale, bins, n_bins, n, idx);
+    return check_launch("bucketize");
+}
+
+int ctts_add_row_broadcast(const float* x, const float* row, int B, int T, int C, float* y, void* stream) {
+    CTTS_REQUIRE(C % 4 == 0, "add_row_broadcast: C %% 4 != 0");
+    const size_t total4 = (size_t)B * T * (C / 4);
+    const int grid = (int)((total4 + 255) / 256 < 8192 ? (total4 + 255) / 256 : 8192);
+    add_row_broadcast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, row, T, C, total4, y);
+    return check_launch("add_row_broadcast");
+}
+
+int ctts_split_bf16(const float* x, size_t n, void* hi, void* lo, void* stream) {
+    CTTS_REQUIRE(n > 0, "split_bf16: empty");
+    const int grid = (int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192);
+    split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    return check_launch("split_bf16");
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+"""ctypes binding of libctts_b200.so (the C ABI declared in include/ctts_b200.h).
+
+There is deliberately no fallback: if the shared library is missing, was not built for this
+machine, or the device is not sm_100+, every entry point raises -- the product path must never
+silently run on PyTorch eager or on the CPU oracle.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libctts_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SWISH = 0, 1, 2, 3, 4
+
+_P, _I, _F, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# name -> argtypes, in the order of include/ctts_b200.h (restype is int unless noted)
+SIGNATURES = {
+    "ctts_abi_version": [],
+    "ctts_last_error": [],
+    "ctts_device_arch": [],
+    "ctts_embed_tokens": [_P, _P, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P, _P],
+    "ctts_add_positions": [_P, _P, _I, _P, _P, _I, _I, _I, _P],
+    "ctts_layernorm": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _P],
+    "ctts_conv1d_gemm": [_P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "ctts_pack_conv_weight": [_P, _I, _I, _I, _P, _P],
+    "ctts_attention": [_P, _P, _I, _I, _I, _I, _F, _P, _P],
+    "ctts_decode_durations": [_P, _F, _I, _P, _P],
+    "ctts_length_scan": [_P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "ctts_length_expand": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
+    "ctts_cwt_to_pitch": [_P, _I, _P, _P, _P, _I, _F, _F, _P, _I, _I, _I, _P, _P, _P, _P],
+    "ctts_f0_to_pitch": [_P, _P, _I, _P, _P, _P],
+    "ctts_gather_add": [_P, _P, _I, _I, _I, _P, _P],
+    "ctts_bucketize": [_P, _F, _P, _I, _I, _P, _P],
+    "ctts_add_row_broadcast": [_P, _P, _I, _I, _I, _P, _P],
+    "ctts_gemm_bf16x3": [_P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "ctts_split_bf16": [_P, _Z, _P, _P, _P],
+    "ctts_layernorm_split": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _P, _P, _P],
+}
+
+_lib = None
+
+
+class CttsError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and set the prototypes.  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CttsError("libctts_b200.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU / eager fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_char_p if name == "ctts_last_error" else ctypes.c_int
+    if lib.ctts_abi_version() != 1:
+        raise CttsError("libctts_b200.so ABI %d, binding expects 1" % lib.ctts_abi_version())
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+LAUNCHES = 0          # number of kernel-launching entry points called so far (bench.py reports the delta)
+TIMING_HOOK = None    # optional callable(name, args) -> context manager, used by bench.py to time one op class
+
+
+def call(name, *args):
+    """Call an entry point with torch tensors (-> device pointers) / python scalars; raise on error."""
+    global LAUNCHES
+    lib = load()
+    LAUNCHES += 1
+    conv = [(_ptr(a) if (a is None or hasattr(a, "data_ptr")) else a) for a in args]
+    rc = getattr(lib, name)(*conv)
+    if rc != 0:
+        raise CttsError("%s failed (%d): %s" % (name, rc, lib.ctts_last_error().decode()))
+
+
+_arch_checked = False
+
+
+def require_device():
+    """Fail loudly unless a CUDA device of compute capability >= 10.0 is current."""
+    global _arch_checked
+    if _arch_checked:
+        return
+    lib = load()
+    arch = lib.ctts_device_arch()
+    if arch < 0:
+        raise CttsError("no usable CUDA device: %s" % lib.ctts_last_error().decode())
+    if arch < 100:
+        raise CttsError("libctts_b200 is built for sm_100a only; current device is sm_%d" % arch)
+    _arch_checked = True

@@ -1,0 +1,377 @@
+"""Host-side orchestration of the CompTransTTS forward path over libctts_b200's C ABI.
+
+PyTorch is used for device memory (torch.empty on the caching allocator), the current stream and
+trivial shape bookkeeping only; every arithmetic step of the path is a kernel of libctts_b200
+reached through `capi.call` with raw device pointers.  Function names mirror the reference's
+modules; file:line citations point at the reference code each function stands in for.
+"""
+import math
+
+import torch
+
+from . import capi
+from .capi import ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH
+
+_ACTS = {"gelu": ACT_GELU, "relu": ACT_RELU, "none": ACT_NONE, "tanh": ACT_TANH}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def _i64(t):
+    return t if (t.dtype == torch.int64 and t.is_contiguous()) else t.long().contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# thin op wrappers (shape checking lives in the C layer; these only allocate outputs)
+# ---------------------------------------------------------------------------------------------
+def conv_gemm(x, w, bias=None, alpha=1.0, bn=None, act=ACT_NONE, residual=None, lens=None, taps=1, out=None):
+    """y = epilogue(conv1d_k(x) or linear(x)); x [B,T,Cin] fp32, w packed [N, taps*Cin]."""
+    B, T, Cin = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == taps * Cin, (tuple(w.shape), taps, Cin)
+    y = out if out is not None else torch.empty(B, T, N, device=x.device, dtype=torch.float32)
+    capi.call("ctts_conv1d_gemm", x, w, bias, float(alpha), bn[0] if bn else None, bn[1] if bn else None, int(act),
+              residual, lens, B, T, Cin, N, taps, y, _stream())
+    return y
+
+
+def layernorm(x, gamma, beta, eps, lens=None):
+    B, T, C = x.shape
+    y = torch.empty_like(x)
+    capi.call("ctts_layernorm", x, gamma, beta, float(eps), lens, B, T, C, y, _stream())
+    return y
+
+
+def attention(qkv, lens, n_head):
+    B, T, C3 = qkv.shape
+    C = C3 // 3
+    out = torch.empty(B, T, C, device=qkv.device, dtype=torch.float32)
+    capi.call("ctts_attention", qkv, lens, B, T, C, n_head, 1.0 / math.sqrt(C // n_head), out, _stream())
+    return out
+
+
+def pad_mask(lens, max_len):
+    """utils/tools.py:188-196 (bool bookkeeping tensor handed back to the caller; True = padding)."""
+    return torch.arange(int(max_len), device=lens.device)[None, :] >= lens[:, None]
+
+
+# ---------------------------------------------------------------------------------------------
+# prepared (device-resident, kernel-layout) weights
+# ---------------------------------------------------------------------------------------------
+class Prepared:
+    """Kernel-layout copies of the parameters: packed conv weights, folded BatchNorm, sinusoid tables.
+
+    Rebuilt whenever a parameter's storage or version changes (load_state_dict, .to(device), an
+    optimizer step), so the nn.Module stays the single source of truth.
+    """
+
+    def __init__(self, module):
+        self.module = module
+        self.sig = None
+        self.w = {}
+        self.pe = {}
+
+    def _signature(self, P):
+        return tuple((k, v.data_ptr(), v._version) for k, v in P.items())
+
+    def params(self):
+        P = {k: v for k, v in self.module.named_parameters()}
+        P.update({k: v for k, v in self.module.named_buffers()})
+        sig = self._signature(P)
+        if sig != self.sig:
+            self._build(P)
+            self.sig = sig
+        return P
+
+    def _build(self, P):
+        self.w = {}
+        st = _stream()
+        with torch.no_grad():
+            for name, t in P.items():
+                if t.dim() == 3 and t.dtype == torch.float32 and not name.endswith("position_enc"):
+                    n, cin, taps = t.shape
+                    packed = torch.empty(n, taps * cin, device=t.device, dtype=torch.float32)
+                    capi.call("ctts_pack_conv_weight", _f32(t), n, cin, taps, packed, st)
+                    self.w[name] = packed
+            for i in range(5):  # eval-mode BatchNorm1d folded to a per-channel affine (modules.py:140-148)
+                pre = "postnet.convolutions.%d.1." % i
+                if pre + "weight" in P:
+                    scale = P[pre + "weight"] / torch.sqrt(P[pre + "running_var"] + 1e-5)
+                    shift = P[pre + "bias"] - P[pre + "running_mean"] * scale
+                    self.w[pre + "fold"] = (scale.float().contiguous(), shift.float().contiguous())
+            self.w["cwt_scale_w"] = ((torch.arange(0, 10).float() + 1 + 2.5) ** (-2.5)).to(
+                next(iter(P.values())).device)  # utils/pitch_tools.py:260
+
+    def table_fs2(self, dim, rows, device):
+        """fairseq-style [sin | cos] table (blocks.py:66-83); row 0 zero; grows on demand (:88-95)."""
+        key = ("fs2", dim, str(device))
+        tab = self.pe.get(key)
+        if tab is None or tab.shape[0] < rows:
+            rows = max(rows, 2048)
+            half = dim // 2
+            step = math.log(10000) / (half - 1)
+            freq = torch.exp(torch.arange(half, dtype=torch.float) * -step)
+            ang = torch.arange(rows, dtype=torch.float).unsqueeze(1) * freq.unsqueeze(0)
+            tab = torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)
+            tab[0, :] = 0
+            tab = tab.to(device).contiguous()
+            self.pe[key] = tab
+        return tab
+
+
+# ---------------------------------------------------------------------------------------------
+# transformer_fs2 blocks
+# ---------------------------------------------------------------------------------------------
+def _fft_layers_fs2(prep, P, pre, x, lens, n_layers, n_head, kernel, act):
+    """EncSALayer x n + final LayerNorm (transformer_fs2.py:60-66,176-200).  x is updated in place."""
+    W = prep.w
+    for i in range(n_layers):
+        lp = "%slayers.%d.op." % (pre, i)
+        h = layernorm(x, P[lp + "layer_norm1.weight"], P[lp + "layer_norm1.bias"], 1e-12)
+        qkv = conv_gemm(h, P[lp + "self_attn.in_proj_weight"])
+        a = attention(qkv, lens, n_head)
+        conv_gemm(a, P[lp + "self_attn.out_proj.weight"], residual=x, lens=lens, out=x)
+        h = layernorm(x, P[lp + "layer_norm2.weight"], P[lp + "layer_norm2.bias"], 1e-12)
+        f = conv_gemm(h, W[lp + "ffn.ffn_1.weight"], P[lp + "ffn.ffn_1.bias"], alpha=kernel ** -0.5, act=act,
+                      taps=kernel)
+        conv_gemm(f, P[lp + "ffn.ffn_2.weight"], P[lp + "ffn.ffn_2.bias"], residual=x, lens=lens, out=x)
+    return layernorm(x, P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-5, lens)
+
+
+def encoder_fs2(prep, P, cfg, tokens, src_lens):
+    """TextEncoder.forward, transformer_fs2.py:100-119."""
+    c = cfg["transformer_fs2"]
+    B, S = tokens.shape
+    C = c["encoder_hidden"]
+    table = P["encoder.embed_tokens.weight"]
+    pe = prep.table_fs2(C, S + 1, tokens.device)
+    x = torch.empty(B, S, C, device=tokens.device, dtype=torch.float32)
+    word = torch.empty_like(x)
+    capi.call("ctts_embed_tokens", tokens, table, pe, pe.shape[0], math.sqrt(C), B, S, C, table.shape[0], x, word,
+              src_lens, _stream())
+    act = _ACTS[cfg["variance_predictor"]["ffn_act"]]
+    x = _fft_layers_fs2(prep, P, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"], c["ffn_kernel_size"],
+                        act)
+    return x, word
+
+
+def decoder_fs2(prep, P, cfg, x, mel_lens):
+    """Decoder = FFTBlocks with learnable-scale sinusoid positions, transformer_fs2.py:47-72,122-134.
+    `x` must be a private buffer: it is overwritten."""
+    c = cfg["transformer_fs2"]
+    B, T, C = x.shape
+    pe = prep.table_fs2(C, T + 1, x.device)
+    capi.call("ctts_add_positions", x, pe, pe.shape[0], P["decoder.pos_embed_alpha"], mel_lens, B, T, C, _stream())
+    act = _ACTS[cfg["variance_predictor"]["ffn_act"]]
+    return _fft_layers_fs2(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
+                           c["ffn_kernel_size"], act)
+
+
+# ---------------------------------------------------------------------------------------------
+# variance adaptor
+# ---------------------------------------------------------------------------------------------
+def _predictor_stack(prep, P, pre, x, n_layers, kernel, lens):
+    """[pad, Conv1d, ReLU, LayerNorm(channels), Dropout] x n (modules.py:1277-1288,1330-1338)."""
+    for l in range(n_layers):
+        h = conv_gemm(x, prep.w["%sconv.%d.1.weight" % (pre, l)], P["%sconv.%d.1.bias" % (pre, l)], act=ACT_RELU,
+                      taps=kernel)
+        x = layernorm(h, P["%sconv.%d.3.weight" % (pre, l)], P["%sconv.%d.3.bias" % (pre, l)], 1e-12, lens)
+    return x
+
+
+def duration_predictor(prep, P, cfg, x, src_lens):
+    """DurationPredictor.forward, modules.py:1299-1310 -> log-durations [B, S]."""
+    vp = cfg["variance_predictor"]
+    pre = "variance_adaptor.duration_predictor."
+    h = _predictor_stack(prep, P, pre, x, vp["dur_predictor_layers"], vp["dur_predictor_kernel"], src_lens)
+    out = conv_gemm(h, P[pre + "linear.weight"], P[pre + "linear.bias"], lens=src_lens)
+    return out.squeeze(-1)
+
+
+def pitch_style_predictor(prep, P, cfg, pre, xs, alpha=1.0):
+    """PitchPredictor / EnergyPredictor.forward, modules.py:1343-1356.  `xs` is overwritten."""
+    vp = cfg["variance_predictor"]
+    B, T, C = xs.shape
+    pe = prep.table_fs2(C, T + 1, xs.device)
+    capi.call("ctts_add_positions", xs, pe, pe.shape[0], P[pre + "pos_embed_alpha"], None, B, T, C, _stream())
+    h = _predictor_stack(prep, P, pre, xs, vp["predictor_layers"], vp["predictor_kernel"], None)
+    return conv_gemm(h, P[pre + "linear.weight"], P[pre + "linear.bias"], alpha=alpha)
+
+
+def length_regulate(x, dur, src_lens, max_len, need_mel2ph):
+    """LengthRegulator (modules.py:1222-1249) + dur_to_mel2ph (utils/tools.py:598-628).
+
+    Returns (expanded [B,M,C], mel_len [B] i64, mel2ph [B,M2] i64 or None, cum_lr).  When max_len is
+    None the two maxima are read back from the device: the only host sync of the forward path."""
+    B, S, C = x.shape
+    dev = x.device
+    cum_lr = torch.empty(B, S, device=dev, dtype=torch.int32)
+    cum_m2p = torch.empty(B, S, device=dev, dtype=torch.int32)
+    lens2 = torch.empty(2 * B, device=dev, dtype=torch.int64)
+    if dur.is_floating_point():
+        capi.call("ctts_length_scan", _f32(dur), None, src_lens, B, S, cum_lr, cum_m2p, lens2, _stream())
+    else:
+        capi.call("ctts_length_scan", None, _i64(dur), src_lens, B, S, cum_lr, cum_m2p, lens2, _stream())
+    mel_len = lens2[:B]
+    if max_len is None or need_mel2ph:
+        maxes = lens2.view(2, B).max(dim=1).values.tolist()  # host sync (D2H of two integers)
+        M = int(max_len) if max_len is not None else int(maxes[0])
+        M2 = int(maxes[1])
+    else:
+        M, M2 = int(max_len), 0
+    if M <= 0:
+        raise capi.CttsError("length_regulate: every duration is zero (empty mel)")
+    out = torch.empty(B, M, C, device=dev, dtype=torch.float32)
+    mel2ph = torch.empty(B, M2, device=dev, dtype=torch.int64) if (need_mel2ph and M2 > 0) else None
+    capi.call("ctts_length_expand", x, None, None, cum_lr, B, S, C, M, 0, out, cum_m2p, mel2ph, M2 if mel2ph is not None
+              else 0, _stream())
+    return out, mel_len, mel2ph, cum_lr
+
+
+def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_lens, src_mask, mel, mel_lens, mel_mask,
+                     max_len, pitch_target, energy_target, duration_target, attn_prior, p_control, e_control, d_control,
+                     step):
+    """VarianceAdaptor.forward (prosody 'none'), modules.py:962-1114."""
+    if attn_prior is not None:
+        raise NotImplementedError("unsupervised duration modelling (aligner + MAS) is not built yet "
+                                  "(SURVEY.md section 8a A16/A17)")
+    pitch_cfg = pcfg["preprocessing"]["pitch"]
+    B, S, C = text.shape
+    st = _stream()
+    if spk is not None:
+        x = torch.empty_like(text)
+        capi.call("ctts_add_row_broadcast", text, _f32(spk), B, S, C, x, st)
+    else:
+        x = text
+    log_d = duration_predictor(prep, P, cfg, x, src_lens)
+    x_org = x
+
+    if duration_target is not None:
+        assert not cfg["duration_modeling"]["learn_alignment"] and attn_prior is None
+        xe, mel_len, _, cum_lr = length_regulate(x, duration_target, src_lens, max_len, False)
+        duration_rounded = duration_target
+        mel2ph = None
+    else:
+        assert attn_prior is None and duration_target is None
+        duration_rounded = torch.empty_like(log_d)
+        capi.call("ctts_decode_durations", log_d, float(d_control), B * S, duration_rounded, st)
+        xe, mel_len, mel2ph, cum_lr = length_regulate(x, duration_rounded, src_lens, max_len, True)
+        mel_mask = pad_mask(mel_len, xe.shape[1])
+    M = xe.shape[1]
+
+    x_sum = xe.clone()
+    pitch_pred = energy_pred = None
+    if cfg["variance_embedding"]["use_pitch_embed"]:
+        pre = "variance_adaptor."
+        h = conv_gemm(xe, P[pre + "cwt_predictor.0.weight"], P[pre + "cwt_predictor.0.bias"])
+        cwt = pitch_style_predictor(prep, P, cfg, pre + "cwt_predictor.1.", h, alpha=p_control)
+        first = x_org[:, 0, :].contiguous().view(1, B, C)
+        s = conv_gemm(first, P[pre + "cwt_stats_layers.0.weight"], P[pre + "cwt_stats_layers.0.bias"], act=ACT_RELU)
+        s = conv_gemm(s, P[pre + "cwt_stats_layers.2.weight"], P[pre + "cwt_stats_layers.2.bias"], act=ACT_RELU)
+        stats = conv_gemm(s, P[pre + "cwt_stats_layers.4.weight"], P[pre + "cwt_stats_layers.4.bias"]).view(B, 2)
+        f0_denorm = torch.empty(B, M, device=x.device, dtype=torch.float32)
+        idx = torch.empty(B, M, device=x.device, dtype=torch.int64)
+        use_uv = 1 if pitch_cfg["use_uv"] else 0
+        assert pitch_cfg["pitch_norm"] == "log", "only pitch_norm 'log' (the shipped configs) is built"
+        if pitch_target is not None:
+            m2p = pitch_target["mel2ph"]
+            assert m2p.shape[1] == M, "mel2ph length %d != regulated length %d" % (m2p.shape[1], M)
+            f0n = torch.empty(B, M, device=x.device, dtype=torch.float32)
+            spec = _f32(pitch_target["cwt_spec"])
+            capi.call("ctts_cwt_to_pitch", spec, spec.shape[-1], prep.w["cwt_scale_w"], _f32(pitch_target["f0_mean"]),
+                      _f32(pitch_target["f0_std"]), 1, 1.0, float(pitch_cfg["pitch_norm_eps"]),
+                      _f32(pitch_target["uv"]), use_uv, B, M, f0n, f0_denorm, idx, st)
+            pitch_target["f0"] = f0n
+            pitch_target["f0_cwt"] = f0n
+        else:
+            assert mel2ph is not None and mel2ph.shape[1] == M, "mel2ph / regulated length mismatch"
+            capi.call("ctts_cwt_to_pitch", cwt, cwt.shape[-1], prep.w["cwt_scale_w"], stats, stats[:, 1:], 2,
+                      float(cfg["variance_predictor"]["cwt_std_scale"]), float(pitch_cfg["pitch_norm_eps"]), None,
+                      use_uv, B, M, None, f0_denorm, idx, st)
+        emb = P[pre + "pitch_embed.weight"]
+        capi.call("ctts_gather_add", emb, idx, B * M, C, emb.shape[0], x_sum, st)
+        pitch_pred = {"pitch_pred": None, "f0_denorm": f0_denorm, "cwt": cwt, "f0_mean": stats[:, 0],
+                      "f0_std": stats[:, 1]}
+    if cfg["variance_embedding"]["use_energy_embed"]:
+        pre = "variance_adaptor."
+        level = pcfg["preprocessing"]["energy"]["feature"]
+        bins = P[pre + "energy_bins"]
+        emb = P[pre + "energy_embedding.weight"]
+        if level == "frame_level":
+            pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", xe.clone(),
+                                         alpha=1.0 if energy_target is not None else e_control).squeeze(-1)
+            src_vals = _f32(energy_target) if energy_target is not None else pred
+            eidx = torch.empty(B, M, device=x.device, dtype=torch.int64)
+            capi.call("ctts_bucketize", src_vals, 1.0, bins, bins.shape[0], B * M, eidx, st)
+            capi.call("ctts_gather_add", emb, eidx, B * M, C, emb.shape[0], x_sum, st)
+        else:
+            pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", x_org.clone(),
+                                         alpha=1.0 if energy_target is not None else e_control).squeeze(-1)
+            src_vals = _f32(energy_target) if energy_target is not None else pred
+            eidx = torch.empty(B, S, device=x.device, dtype=torch.int64)
+            capi.call("ctts_bucketize", src_vals, 1.0, bins, bins.shape[0], B * S, eidx, st)
+            capi.call("ctts_length_expand", None, emb, eidx, cum_lr, B, S, C, M, 1, x_sum, None, None, 0, st)
+        energy_pred = pred
+    return (x_sum, pitch_target, pitch_pred, energy_target, energy_pred, log_d, duration_rounded, mel_len, mel_mask,
+            (None, None, None, None), None)
+
+
+# ---------------------------------------------------------------------------------------------
+def mel_head(prep, P, dec):
+    """mel_linear + PostNet + residual (CompTransTTS.py:133-135, modules.py:140-148; eval-mode BN folded)."""
+    mel = conv_gemm(dec, P["mel_linear.weight"], P["mel_linear.bias"])
+    h = mel
+    for i in range(5):
+        pre = "postnet.convolutions.%d." % i
+        h = conv_gemm(h, prep.w[pre + "0.conv.weight"], P[pre + "0.conv.bias"], bn=prep.w[pre + "1.fold"],
+                      act=ACT_TANH if i < 4 else ACT_NONE, residual=mel if i == 4 else None, taps=5)
+    return mel, h
+
+
+def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None, p_targets=None,
+            e_targets=None, d_targets=None, attn_priors=None, spker_embeds=None, p_control=1.0, e_control=1.0,
+            d_control=1.0, step=None):
+    """CompTransTTS.forward, model/CompTransTTS.py:64-152.  Returns the reference's 14-tuple."""
+    capi.require_device()
+    if not texts.is_cuda:
+        raise capi.CttsError("CompTransTTS (B200) runs on CUDA tensors only; got %s -- there is no CPU path"
+                             % texts.device)
+    pcfg, cfg, tcfg = module.preprocess_config, module.model_config, module.train_config
+    prep = module._prepared
+    P = prep.params()
+    texts = _i64(texts)
+    src_lens = _i64(src_lens)
+    src_masks = pad_mask(src_lens, max_src_len)
+    mel_masks = None
+    if mel_lens is not None:
+        mel_lens = _i64(mel_lens)
+        mel_masks = pad_mask(mel_lens, max_mel_len)
+    block = cfg["block_type"]
+    if block != "transformer_fs2":
+        raise NotImplementedError("block_type %r: kernels not built yet" % block)
+    enc, word = encoder_fs2(prep, P, cfg, texts, src_lens)
+
+    spk = None
+    if module.has_speaker_emb:
+        if module.embedder_type == "none":
+            spk = P["speaker_emb.weight"][_i64(speakers)]
+        else:
+            assert spker_embeds is not None, "Speaker embedding should not be None"
+            Bs = spker_embeds.shape[0]
+            spk = conv_gemm(_f32(spker_embeds).view(1, Bs, -1), P["speaker_emb.weight"], P["speaker_emb.bias"]).view(
+                Bs, -1)
+
+    (x, p_targets, p_pred, e_targets, e_pred, log_d, d_rounded, mel_lens, mel_masks, attn_outs, prosody) = \
+        variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, enc, word, src_lens, src_masks, mels, mel_lens, mel_masks,
+                         max_mel_len, p_targets, e_targets, d_targets, attn_priors, p_control, e_control, d_control,
+                         step)
+    dec = decoder_fs2(prep, P, cfg, x, mel_lens)
+    mel, post = mel_head(prep, P, dec)
+    return (mel, post, p_pred, e_pred, log_d, d_rounded, src_masks, mel_masks, src_lens, mel_lens, attn_outs, prosody,
+            p_targets, e_targets)

@@ -1,0 +1,94 @@
+"""`CompTransTTS`: the reference's Python API surface over the B200 kernels.
+
+Same constructor, same `forward` signature and 14-tuple, same state_dict key names as
+model/CompTransTTS.py:12-152, so `utils/model.py:get_model`, `train.py`, `evaluate.py` and
+`synthesize.py` of the reference can use this class in place of theirs.
+The module tree only exists to carry parameters under the reference's names; the forward pass
+is `engine.forward`, which calls libctts_b200 through its C ABI.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import engine, spec
+
+
+class _Node(nn.Module):
+    """Anonymous container: the parameter names are the contract, not the class tree."""
+
+
+def _attach(root, name, tensor, kind):
+    parts = name.split(".")
+    node = root
+    for p in parts[:-1]:
+        nxt = node._modules.get(p)
+        if nxt is None:
+            nxt = _Node()
+            node.add_module(p, nxt)
+        node = nxt
+    if kind == "buffer":
+        node.register_buffer(parts[-1], tensor)
+    else:
+        node.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=(kind == "param")))
+
+
+def _initial(shape, init):
+    """Initialisers equivalent in distribution to the reference's (blocks.py:10-23,255-298 and torch defaults)."""
+    if init == "count":
+        return torch.zeros((), dtype=torch.long)
+    if init == "ones":
+        return torch.ones(shape)
+    if init == "zeros":
+        return torch.zeros(shape)
+    if init == "normal01":
+        return torch.randn(shape)
+    if init.startswith("linspace") or init.startswith("logspace"):
+        _, lo, hi = init.split(":")
+        if init.startswith("logspace"):
+            return torch.exp(torch.linspace(math.log(float(lo)), math.log(float(hi)), shape[0]))
+        return torch.linspace(float(lo), float(hi), shape[0])
+    if init.startswith("emb"):
+        d = int(init.split(":")[1])
+        t = torch.randn(shape) * d ** -0.5
+        t[0] = 0
+        return t
+    if init.startswith("default"):
+        bound = 1.0 / math.sqrt(int(init.split(":")[1]))
+        return (torch.rand(shape) * 2 - 1) * bound
+    if init.startswith("xavier"):
+        gain = spec.gain_of(init.split(":")[1] if ":" in init else "")
+        t = torch.empty(shape)
+        nn.init.xavier_uniform_(t, gain=gain)
+        return t
+    raise ValueError(init)
+
+
+class CompTransTTS(nn.Module):
+    """ CompTransTTS (B200-native).  Reference: model/CompTransTTS.py:12-152. """
+
+    def __init__(self, preprocess_config, model_config, train_config):
+        super().__init__()
+        self.preprocess_config = preprocess_config
+        self.model_config = model_config
+        self.train_config = train_config
+        entries, d_enc, d_dec = spec.parameter_spec(preprocess_config, model_config)
+        for name, shape, kind, init in entries:
+            _attach(self, name, _initial(shape, init), kind)
+        self.d_encoder, self.d_decoder = d_enc, d_dec
+        self.has_speaker_emb = bool(model_config["multi_speaker"])
+        self.embedder_type = preprocess_config["preprocessing"].get("speaker_embedder", "none") \
+            if self.has_speaker_emb else None
+        self._prepared = engine.Prepared(self)
+
+    def forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
+                p_targets=None, e_targets=None, d_targets=None, attn_priors=None, spker_embeds=None, p_control=1.0,
+                e_control=1.0, d_control=1.0, step=None):
+        if self.training:
+            raise NotImplementedError(
+                "training-mode forward (dropout, batch-statistics BatchNorm, backward kernels) is not built yet; "
+                "call .eval() -- SURVEY.md section 7 step 7")
+        with torch.no_grad():
+            return engine.forward(self, speakers, texts, src_lens, max_src_len, mels, mel_lens, max_mel_len,
+                                  p_targets, e_targets, d_targets, attn_priors, spker_embeds, p_control, e_control,
+                                  d_control, step)

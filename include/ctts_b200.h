@@ -1,0 +1,184 @@
+/*
+ * ctts_b200.h -- C ABI of libctts_b200.so: hand-written sm_100a kernels for the CompTransTTS
+ * acoustic-model forward path (reference: keonlee9420/Comprehensive-Transformer-TTS).
+ *
+ * The reference has no FFI layer: its numerics are PyTorch ATen calls made from Python
+ * (SURVEY.md section 8b).  Each entry point below replaces one group of those calls; the
+ * reference call site it replaces is cited as file:line (paths relative to the reference root).
+ * The Python binding a maintainer would add is a ctypes stub -- see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`; the caller owns all
+ *    memory (PyTorch's allocator in practice); nothing is allocated or retained by the library
+ *    except cached TMA descriptors;
+ *  - activations are row-major fp32 "token-major" tensors [B, T, C]; lengths are int64 [B]
+ *    (the reference's `src_lens` / `mel_lens`); a row t of utterance b is padding iff
+ *    t >= lens[b] (utils/tools.py:188-196);
+ *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no host sync
+ *    (the one exception is documented at ctts_length_scan);
+ *  - every function returns 0 on success, non-zero on error; ctts_last_error() then returns a
+ *    thread-local message.  There is no CPU fallback anywhere.
+ */
+#ifndef CTTS_B200_H
+#define CTTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTTS_ABI_VERSION 1
+
+/* activation selector for ctts_conv1d_gemm */
+enum { CTTS_ACT_NONE = 0, CTTS_ACT_RELU = 1, CTTS_ACT_GELU = 2, CTTS_ACT_TANH = 3, CTTS_ACT_SWISH = 4 };
+
+/* arithmetic selector for ctts_conv1d_gemm */
+enum {
+    CTTS_MATH_FP32 = 0,   /* CUDA-core FP32 FMA: used upstream of every quantiser      */
+    CTTS_MATH_BF16X3 = 1  /* tcgen05 kind::f16, operands split bf16 hi+lo, 3 MMAs, FP32 accumulate   */
+};
+
+int ctts_abi_version(void);
+const char* ctts_last_error(void);
+/* compute capability major*10+minor of the current device; the library refuses to run below 100 */
+int ctts_device_arch(void);
+
+/* ---- phoneme embedding + sinusoidal positions -------------------------------------------
+ * transformer_fs2.py:113-119 (TextEncoder.forward_embedding), blocks.py:85-104, utils/tools.py:640-652.
+ *   pos[b,s]  = (# of non-zero tokens in tokens[b,0..s]) if tokens[b,s] != 0 else 0
+ *   word      = embed_scale * table[tokens]
+ *   x         = (word + pe[pos]) * keep          (keep: s < lens[b]; FFTBlocks.forward :60; lens may be NULL)
+ * pe is the [pe_rows, C] sinusoid table (row 0 = zeros); pe_rows must be > S.  `word` is not masked
+ * (it is the reference's second return value, consumed by the aligner).
+ */
+int ctts_embed_tokens(const int64_t* tokens, const float* table, const float* pe, int pe_rows, float embed_scale,
+                      int B, int S, int C, int vocab, float* x, float* word, const int64_t* lens, void* stream);
+
+/* ---- x = (x + alpha * pe[pos(x[..., 0] != 0)]) [* keep] -----------------------------------------
+ * FFTBlocks.forward transformer_fs2.py:54-60 (decoder positions) and PitchPredictor.forward
+ * modules.py:1349-1350.  `alpha` is a device scalar (the learnable pos_embed_alpha).  If lens != NULL
+ * rows t >= lens[b] are zeroed afterwards (the `* nonpadding_mask_TB` of :60).  In place.
+ */
+int ctts_add_positions(float* x, const float* pe, int pe_rows, const float* alpha, const int64_t* lens, int B, int T,
+                       int C, void* stream);
+
+/* ---- y = LayerNorm_C(x) * gamma + beta [* keep] -------------------------------------------
+ * blocks.py:137-156 (eps 1e-12), transformer_fs2.py:41,65-66 (final nn.LayerNorm eps 1e-5).
+ * x, y: [B*T, C].  lens may be NULL.
+ */
+int ctts_layernorm(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B, int T,
+                   int C, float* y, void* stream);
+
+/* ---- the dense workhorse: Conv1d(k taps, "same" zero padding) / Linear as an implicit GEMM --------
+ *   acc[b,t,n] = sum_{j<taps} sum_{c<Cin} x[b, t + j - taps/2, c] * w[n, j*Cin + c]      (x = 0 outside [0,T))
+ *   v          = (acc + bias[n]) * alpha
+ *   v          = v * col_scale[n] + col_shift[n]          (folded eval-mode BatchNorm1d)
+ *   v          = act(v) + residual[b,t,n]
+ *   y[b,t,n]   = lens ? (t < lens[b] ? v : 0) : v
+ * bias / col_scale / col_shift / residual / lens may be NULL.  `w` is the PACKED weight
+ * [N, taps*Cin] produced by ctts_pack_conv_weight.  Replaces nn.Conv1d / nn.Linear at:
+ * transformer_fs2.py:226-238 (FFN), F.multi_head_attention_forward in/out projections (:385-394),
+ * modules.py:1299-1310,1343-1356 (predictor stacks), modules.py:140-148 (PostNet), CompTransTTS.py:133
+ * (mel_linear), modules.py:1195-1196 (aligner projections).
+ * math = CTTS_MATH_FP32: Cin % 16 == 0.  math = CTTS_MATH_BF16X3: see ctts_gemm_bf16x3.
+ */
+int ctts_conv1d_gemm(const float* x, const float* w, const float* bias, float alpha, const float* col_scale,
+                     const float* col_shift, int act, const float* residual, const int64_t* lens, int B, int T,
+                     int Cin, int N, int taps, float* y, void* stream);
+
+/* torch Conv1d weight [N, Cin, taps] -> packed [N, taps*Cin] (tap-major).  taps == 1: plain copy. */
+int ctts_pack_conv_weight(const float* w, int N, int Cin, int taps, float* packed, void* stream);
+
+/* ---- masked multi-head self-attention (softmax(q k^T * scale + key_padding_mask) v) ---------------
+ * transformer_fs2.py:385-394 -> F.multi_head_attention_forward; transformer.py:233-252.
+ * qkv: [B, T, 3*C] (q | k | v, heads contiguous inside each C), head_dim = C / H in {32, 64, 128}.
+ * Keys s >= lens[b] are excluded; query rows t >= lens[b] produce zeros (they are zeroed by the block's
+ * pad mask in the reference, transformer_fs2.py:192).  Scores are never materialised.
+ */
+int ctts_attention(const float* qkv, const int64_t* lens, int B, int T, int C, int H, float scale, float* out,
+                   void* stream);
+
+/* ---- duration decoding: clamp(round(exp(logd) - 1) * d_control, min 0)   modules.py:1060-1063 ---- */
+int ctts_decode_durations(const float* log_d, float d_control, int n, float* dur, void* stream);
+
+/* ---- LengthRegulator scan (integer; bit-exact) -----------------------------------------
+ * modules.py:1222-1249 + utils/tools.py:598-628.  Either dur_f32 or dur_i64 is non-NULL, [B, S].
+ *   reps[b,j]   = max(int(dur[b,j]), 0)                 (LR: truncation toward zero)
+ *   cum_lr[b,j] = sum_{i<=j} reps[b,i]        mel_len[b] = cum_lr[b,S-1]
+ *   cum_m2p[b,j]= sum_{i<=j} round(dur[b,i]) * (j < src_lens[b])    (dur_to_mel2ph: half-to-even rounding)
+ * cum_lr / cum_m2p: int32 [B, S]; mel_len: int64 [2*B]: [0,B) = LR lengths (the reference's mel_len),
+ * [B,2B) = sum of the rounded durations (the length of mel2ph).  The caller reads the maxima back to size the
+ * output when the reference's max_len is None -- the single host sync of the inference path
+ * (the reference has B*S of them, modules.py:1241).
+ */
+int ctts_length_scan(const float* dur_f32, const int64_t* dur_i64, const int64_t* src_lens, int B, int S,
+                     int32_t* cum_lr, int32_t* cum_m2p, int64_t* mel_len, void* stream);
+
+/* ---- LengthRegulator expand ----------------------------------------------------------
+ *   j = the phoneme with cum_lr[b,j-1] <= t < cum_lr[b,j]
+ *   row = table ? table[row_index[b,j]] : src[b,j]          ([*, C] fp32)
+ *   out[b,t,:] = (accumulate ? out[b,t,:] : 0) + (j exists ? row : 0)
+ * mel2ph (nullable, int64 [B, M2]) = 1-based index from cum_m2p, 0 beyond the end (utils/tools.py:627).
+ * Used for x (modules.py:1064) and, with table = energy_embedding.weight and row_index = bucket ids,
+ * for the phoneme-level energy embedding (modules.py:1099).
+ */
+int ctts_length_expand(const float* src, const float* table, const int64_t* row_index, const int32_t* cum_lr,
+                       int B, int S, int C, int M, int accumulate, float* out, const int32_t* cum_m2p,
+                       int64_t* mel2ph, int M2, void* stream);
+
+/* ---- pitch: CWT spectrogram -> f0 -> mel-scale bucket -> (optional) embedding add ---------------
+ * modules.py:907-938 + utils/pitch_tools.py:258-294 (cwt2f0_norm), :69-82 (denorm_f0), :27-36 (f0_to_coarse).
+ *   rec[b,t] = sum_i cwt[b,t,i] * scale_w[i]   (i < 10; cwt row stride = cwt_stride floats)
+ *   rec      = (rec - mean_t rec) / std_t rec  (over all T frames, unbiased)
+ *   f0n      = log2(exp(rec * (std[b]*std_scale) + mean[b]) + eps)
+ *   uv       = uv_src ? (uv_src[b,t] > 0) : (cwt[b,t,10] > 0)   (use_uv; uv_from_cwt selects)
+ *   f0d      = uv ? 0 : 2^f0n                -> f0_denorm[b,t];  f0_norm (nullable) receives f0n
+ *   idx      = f0_to_coarse(f0d)             -> pitch_idx[b,t] (int64)
+ * stats: [B,2] rows (mean, std) with element stride given by stats_stride (2 for the MLP output,
+ * or separate arrays via mean/std pointers).
+ */
+int ctts_cwt_to_pitch(const float* cwt, int cwt_stride, const float* scale_w, const float* mean, const float* std,
+                      int stat_stride, float std_scale, float eps, const float* uv_src, int use_uv, int B, int T,
+                      float* f0_norm, float* f0_denorm, int64_t* pitch_idx, void* stream);
+
+/* f0 given (teacher forcing): f0_denorm = uv ? 0 : 2^f0 ; idx = coarse(f0_denorm).  modules.py:933-938 */
+int ctts_f0_to_pitch(const float* f0_norm, const float* uv_src, int n, float* f0_denorm, int64_t* pitch_idx,
+                     void* stream);
+
+/* x[r,:] += table[idx[r],:]   (nn.Embedding + add; modules.py:938,1089) */
+int ctts_gather_add(const float* table, const int64_t* idx, int rows, int C, int table_rows, float* x, void* stream);
+
+/* idx[i] = #{ bins[k] < v[i] }  == torch.bucketize(v, bins) (right=False); modules.py:954-958 */
+int ctts_bucketize(const float* v, float v_scale, const float* bins, int n_bins, int n, int64_t* idx, void* stream);
+
+/* y = x + spk[b] broadcast over T (modules.py:985-988) */
+int ctts_add_row_broadcast(const float* x, const float* row, int B, int T, int C, float* y, void* stream);
+
+/* ---- tcgen05 tensor-core GEMM (the decoder / PostNet engine) ---------------------------------
+ * Same contract as ctts_conv1d_gemm but the operands are bf16 hi/lo planes:
+ *   x_hi, x_lo : [B, T, Cin] bf16, x ~= x_hi + x_lo     (written by the producing kernel's epilogue)
+ *   w_hi, w_lo : [N, taps*Cin] bf16 packed planes (ctts_split_bf16 of the packed fp32 weight)
+ *   acc = x_hi*w_hi + x_hi*w_lo + x_lo*w_hi   (three tcgen05.mma per k-slice, FP32 accumulate in TMEM)
+ * The epilogue is identical; additionally y_hi / y_lo (nullable) receive the bf16 split of y so
+ * the next GEMM can consume it without a separate pass.  Requirements: Cin % 64 == 0, N % 16 == 0.
+ * Tiles are fetched with TMA from 3-D tensor maps over [B, T, Cin]; the conv halo (rows t < 0 or
+ * t >= T) is produced by TMA out-of-bounds zero fill.
+ */
+int ctts_gemm_bf16x3(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                     float alpha, const float* col_scale, const float* col_shift, int act, const float* residual,
+                     const int64_t* lens, int B, int T, int Cin, int N, int taps, float* y, void* y_hi, void* y_lo,
+                     void* stream);
+
+/* fp32 -> (bf16 hi, bf16 lo) with hi = rn(x), lo = rn(x - hi) */
+int ctts_split_bf16(const float* x, size_t n, void* hi, void* lo, void* stream);
+
+/* LayerNorm whose output is written as fp32 (nullable) and as bf16 hi/lo planes */
+int ctts_layernorm_split(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B,
+                         int T, int C, float* y, void* y_hi, void* y_lo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTTS_B200_H */

@@ -1,0 +1,504 @@
+"""CPU oracle for the CompTransTTS acoustic-model forward path.  TEST INFRASTRUCTURE -- NOT PRODUCT.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU legs (`cpu_baseline`,
+`--impl reference`) may import this file.  The product path (`comprehensive-transformer-tts_b200/`)
+never does, and fails loudly when its CUDA library is missing.
+
+What it is: a plain fp32 PyTorch-CPU restatement, written as pure functions over a flat
+state_dict (`name -> tensor`, the reference's own key names), of what the
+reference computes in `CompTransTTS.forward` (model/CompTransTTS.py:64-152).  The numerics of
+the individual ops (conv1d, linear, layer_norm, softmax, gelu, bucketize) are torch's, exactly as
+in the reference, whose arithmetic also lives in torch (pinned torch==1.7.0,
+requirements.txt:24; this image has torch 2.11).  Each function cites the reference lines it
+follows.
+
+Parity pin: the reference has no tests and no golden vectors.  The pin is
+therefore created here: `tests/golden/make_golden.py` imports the UNMODIFIED reference from
+`/root/reference` in the build container, loads the same synthetic state_dict into it and into
+this oracle, and commits the reference's outputs under `tests/golden/*.npz`;
+`tests/test_oracle_golden.py` checks this file against those fixtures (CPU, no reference
+needed), and `tests/test_oracle_vs_reference.py` re-checks against the live reference whenever
+`/root/reference` exists.
+
+Scope: block types transformer_fs2 / transformer / fastformer / conformer; prosody "none";
+inference (free-running), supervised teacher-forced, and unsupervised (aligner + MAS) branches
+of the VarianceAdaptor.  Dropout is identity (eval mode); BatchNorm uses running statistics.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers (utils/tools.py)
+# ----------------------------------------------------------------------------------------------
+def pad_mask_from_lengths(lengths, max_len=None):
+    """True = padding.  utils/tools.py:188-196."""
+    if max_len is None:
+        max_len = int(lengths.max().item())
+    ids = torch.arange(max_len, device=lengths.device)[None, :]
+    return ids >= lengths[:, None]
+
+
+def positions_of(flag_src, padding_idx=0):
+    """utils/tools.py:640-652 -- running count of non-pad entries, pads keep `padding_idx`."""
+    keep = flag_src.ne(padding_idx).int()
+    return (torch.cumsum(keep, dim=1).type_as(keep) * keep).long() + padding_idx
+
+
+def sinusoid_table_fs2(n_rows, dim, padding_idx=0):
+    """fairseq-style [sin | cos] table.  model/transformers/blocks.py:66-83."""
+    half = dim // 2
+    step = math.log(10000) / (half - 1)
+    freq = torch.exp(torch.arange(half, dtype=torch.float) * -step)
+    ang = torch.arange(n_rows, dtype=torch.float).unsqueeze(1) * freq.unsqueeze(0)
+    tab = torch.cat([torch.sin(ang), torch.cos(ang)], dim=1).view(n_rows, -1)
+    if dim % 2 == 1:
+        tab = torch.cat([tab, torch.zeros(n_rows, 1)], dim=1)
+    tab[padding_idx, :] = 0
+    return tab
+
+
+def sinusoid_table_interleaved(n_position, d_hid):
+    """Interleaved sin/cos table computed in float64 then cast.  blocks.py:26-46."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)[None, :]
+    tab = pos / np.power(10000, 2 * (j // 2) / d_hid)
+    tab[:, 0::2] = np.sin(tab[:, 0::2])
+    tab[:, 1::2] = np.cos(tab[:, 1::2])
+    return torch.FloatTensor(tab)
+
+
+def fs2_positional(flag_src, dim, init_size):
+    """SinusoidalPositionalEmbedding.forward, blocks.py:85-104: table grows to seq_len+1 if needed."""
+    seq_len = flag_src.shape[1]
+    tab = sinusoid_table_fs2(max(init_size, seq_len + 1), dim, 0)
+    pos = positions_of(flag_src, 0)
+    return tab.index_select(0, pos.reshape(-1)).view(flag_src.shape[0], seq_len, dim)
+
+
+def durations_to_mel2ph(dur, dur_padding=None):
+    """utils/tools.py:598-628 with alpha = 1: frame -> 1-based phoneme index, 0 beyond sum(dur)."""
+    dur = torch.round(dur.float()).long()
+    if dur_padding is not None:
+        dur = dur * (1 - dur_padding.long())
+    csum = torch.cumsum(dur, 1)
+    prev = F.pad(csum, [1, -1])
+    total = int(dur.sum(-1).max().item())
+    t = torch.arange(total)[None, None]
+    hit = (t >= prev[:, :, None]) & (t < csum[:, :, None])
+    idx = torch.arange(1, dur.shape[1] + 1)[None, :, None]
+    return (idx * hit.long()).sum(1)
+
+
+def length_regulate(x, duration, max_len=None):
+    """LengthRegulator.LR/expand (model/modules.py:1222-1249) + pad (utils/tools.py:577-595).
+
+    Row j of utterance b is repeated max(int(duration[b, j]), 0) times (truncation, not
+    rounding), rows are zero padded to `max_len` (or the batch maximum).  Returns the expanded
+    tensor and the per-utterance lengths (before padding).
+    """
+    reps = duration.to(torch.float64).trunc().clamp(min=0).long() if duration.is_floating_point() \
+        else duration.clamp(min=0).long()
+    lens = reps.sum(1)
+    out_len = int(max_len) if max_len else int(lens.max().item())
+    B, S = reps.shape
+    out = x.new_zeros(B, out_len, x.shape[-1])
+    for b in range(B):
+        idx = torch.repeat_interleave(torch.arange(S), reps[b])
+        n = idx.numel()
+        if n > out_len:
+            raise RuntimeError("length_regulate: expanded length %d exceeds max_len %d (the reference's "
+                               "F.pad with a negative amount would crop; not exercised)" % (n, out_len))
+        out[b, :n] = x[b, idx]
+    return out, lens
+
+
+# ----------------------------------------------------------------------------------------------
+# transformer_fs2 blocks (model/transformers/transformer_fs2.py)
+# ----------------------------------------------------------------------------------------------
+def _mha_fs2(P, pre, x, pad_mask, n_head):
+    """EncSALayer's self-attention: F.multi_head_attention_forward with in_proj_weight [3C, C],
+    no biases, key_padding_mask (transformer_fs2.py:385-394).  x: [B, T, C]."""
+    B, T, C = x.shape
+    dh = C // n_head
+    qkv = F.linear(x, P[pre + "self_attn.in_proj_weight"])
+    q, k, v = qkv.split(C, dim=-1)
+    q = q.view(B, T, n_head, dh).transpose(1, 2) * (1.0 / math.sqrt(dh))
+    k = k.view(B, T, n_head, dh).transpose(1, 2)
+    v = v.view(B, T, n_head, dh).transpose(1, 2)
+    s = torch.matmul(q, k.transpose(-1, -2))
+    s = s.masked_fill(pad_mask[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    o = torch.matmul(p, v).transpose(1, 2).reshape(B, T, C)
+    return F.linear(o, P[pre + "self_attn.out_proj.weight"])
+
+
+def _ffn_fs2(P, pre, x, kernel_size, act="gelu"):
+    """TransformerFFNLayer.forward, transformer_fs2.py:220-239 (padding SAME)."""
+    h = F.conv1d(x.transpose(1, 2), P[pre + "ffn.ffn_1.weight"], P[pre + "ffn.ffn_1.bias"],
+                 padding=kernel_size // 2).transpose(1, 2)
+    h = h * kernel_size ** -0.5
+    if act == "gelu":
+        h = F.gelu(h)
+    elif act == "relu":
+        h = F.relu(h)
+    else:
+        raise NotImplementedError(act)
+    return F.linear(h, P[pre + "ffn.ffn_2.weight"], P[pre + "ffn.ffn_2.bias"])
+
+
+def fft_blocks_fs2(P, pre, x, pad_mask, n_layers, n_head, kernel_size, use_pos, init_size, act="gelu",
+                   taps=None):
+    """FFTBlocks.forward (transformer_fs2.py:47-72) + EncSALayer.forward (:176-200). x: [B,T,C]."""
+    keep = (~pad_mask).float()[:, :, None]
+    C = x.shape[-1]
+    if use_pos:
+        x = x + P[pre + "pos_embed_alpha"] * fs2_positional(x[..., 0], C, init_size)
+    x = x * keep
+    for i in range(n_layers):
+        lp = "%slayers.%d.op." % (pre, i)
+        h = F.layer_norm(x, (C,), P[lp + "layer_norm1.weight"], P[lp + "layer_norm1.bias"], 1e-12)
+        x = (x + _mha_fs2(P, lp, h, pad_mask, n_head)) * keep
+        h = F.layer_norm(x, (C,), P[lp + "layer_norm2.weight"], P[lp + "layer_norm2.bias"], 1e-12)
+        x = (x + _ffn_fs2(P, lp, h, kernel_size, act)) * keep
+        if taps is not None:
+            taps["%slayers.%d" % (pre, i)] = x
+    x = F.layer_norm(x, (C,), P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-5) * keep
+    return x
+
+
+def encoder_fs2(P, cfg, tokens, pad_mask, taps=None):
+    """TextEncoder.forward / forward_embedding, transformer_fs2.py:100-119."""
+    c = cfg["transformer_fs2"]
+    C = c["encoder_hidden"]
+    word = math.sqrt(C) * F.embedding(tokens, P["encoder.embed_tokens.weight"], padding_idx=0)
+    x = word + fs2_positional(tokens, C, cfg["max_seq_len"])
+    x = fft_blocks_fs2(P, "encoder.", x, pad_mask, c["encoder_layer"], c["encoder_head"], c["ffn_kernel_size"],
+                       False, 0, cfg["variance_predictor"]["ffn_act"], taps)
+    return x, word
+
+
+def decoder_fs2(P, cfg, x, pad_mask, taps=None):
+    """Decoder (FFTBlocks with positional embedding, init_size 2*max_seq_len), transformer_fs2.py:122-134."""
+    c = cfg["transformer_fs2"]
+    return fft_blocks_fs2(P, "decoder.", x, pad_mask, c["decoder_layer"], c["decoder_head"], c["ffn_kernel_size"],
+                          True, cfg["max_seq_len"] * 2, cfg["variance_predictor"]["ffn_act"], taps), pad_mask
+
+
+# ----------------------------------------------------------------------------------------------
+# variance adaptor (model/modules.py)
+# ----------------------------------------------------------------------------------------------
+def _conv_relu_ln_stack(P, pre, xs, n_layers, kernel, pad_mask=None):
+    """The [ConstantPad1d, Conv1d, ReLU, LayerNorm(dim=1, eps 1e-12), Dropout] stacks of
+    DurationPredictor (modules.py:1277-1288, 1299-1304) and PitchPredictor (:1330-1338, 1351-1352).
+    xs: [B, T, C] (kept token-major here; the reference transposes to [B, C, T])."""
+    for l in range(n_layers):
+        w = P["%sconv.%d.1.weight" % (pre, l)]
+        h = F.conv1d(xs.transpose(1, 2), w, P["%sconv.%d.1.bias" % (pre, l)], padding=(kernel - 1) // 2)
+        h = F.relu(h).transpose(1, 2)
+        xs = F.layer_norm(h, (h.shape[-1],), P["%sconv.%d.3.weight" % (pre, l)], P["%sconv.%d.3.bias" % (pre, l)],
+                          1e-12)
+        if pad_mask is not None:
+            xs = xs * (~pad_mask).float()[:, :, None]
+    return xs
+
+
+def duration_predictor(P, cfg, x, src_mask):
+    """DurationPredictor.forward (dur_loss 'mse'), modules.py:1299-1310 -> log durations [B, S]."""
+    vp = cfg["variance_predictor"]
+    pre = "variance_adaptor.duration_predictor."
+    h = _conv_relu_ln_stack(P, pre, x, vp["dur_predictor_layers"], vp["dur_predictor_kernel"], src_mask)
+    out = F.linear(h, P[pre + "linear.weight"], P[pre + "linear.bias"])
+    return (out * (~src_mask).float()[:, :, None]).squeeze(-1)
+
+
+def pitch_style_predictor(P, cfg, pre, xs):
+    """PitchPredictor.forward (also EnergyPredictor), modules.py:1343-1356.  xs: [B, T, idim]."""
+    vp = cfg["variance_predictor"]
+    xs = xs + P[pre + "pos_embed_alpha"] * fs2_positional(xs[..., 0], xs.shape[-1], 4096)
+    h = _conv_relu_ln_stack(P, pre, xs, vp["predictor_layers"], vp["predictor_kernel"], None)
+    return F.linear(h, P[pre + "linear.weight"], P[pre + "linear.bias"])
+
+
+F0_BIN, F0_MAX, F0_MIN = 256, 1100.0, 50.0
+
+
+def f0_to_coarse(f0):
+    """utils/pitch_tools.py:20-36 (torch branch): mel-scale bucket index in [1, 255]."""
+    mel_min = 1127 * np.log(1 + F0_MIN / 700)
+    mel_max = 1127 * np.log(1 + F0_MAX / 700)
+    f0_mel = 1127 * (1 + f0 / 700).log()
+    pos = f0_mel > 0
+    f0_mel = torch.where(pos, (f0_mel - mel_min) * (F0_BIN - 2) / (mel_max - mel_min) + 1, f0_mel)
+    f0_mel = torch.where(f0_mel <= 1, torch.ones_like(f0_mel), f0_mel)
+    f0_mel = torch.where(f0_mel > F0_BIN - 1, torch.full_like(f0_mel, F0_BIN - 1), f0_mel)
+    return (f0_mel + 0.5).long()
+
+
+def cwt_to_f0_norm(cwt_spec, mean, std, n_frames, pitch_cfg):
+    """cwt2f0_norm -> cwt2f0 -> inverse_cwt_torch -> norm_f0, utils/pitch_tools.py:258-294,39-48.
+    The standardisation runs over ALL (padded) frames with the unbiased std."""
+    n_scales = cwt_spec.shape[-1]
+    b = (torch.arange(0, n_scales).float()[None, None, :] + 1 + 2.5) ** (-2.5)
+    rec = (cwt_spec * b).sum(-1)
+    rec = (rec - rec.mean(-1, keepdim=True)) / rec.std(-1, keepdim=True)
+    f0 = (rec * std[:, None] + mean[:, None]).exp()
+    if n_frames > f0.shape[1]:
+        f0 = torch.cat([f0] + [f0[:, -1:]] * (n_frames - f0.shape[1]), 1)
+    if pitch_cfg["pitch_norm"] == "standard":
+        f0 = (f0 - pitch_cfg["f0_mean"]) / pitch_cfg["f0_std"]
+    if pitch_cfg["pitch_norm"] == "log":
+        f0 = torch.log2(f0 + pitch_cfg["pitch_norm_eps"])
+    return f0
+
+
+def denorm_f0(f0, uv, pitch_cfg, pitch_padding=None):
+    """utils/pitch_tools.py:69-82."""
+    if pitch_cfg["pitch_norm"] == "standard":
+        f0 = f0 * pitch_cfg["f0_std"] + pitch_cfg["f0_mean"]
+    if pitch_cfg["pitch_norm"] == "log":
+        f0 = 2 ** f0
+    if uv is not None and pitch_cfg["use_uv"]:
+        f0 = torch.where(uv > 0, torch.zeros_like(f0), f0)
+    if pitch_padding is not None:
+        f0 = torch.where(pitch_padding, torch.zeros_like(f0), f0)
+    return f0
+
+
+def pitch_embedding_cwt(P, cfg, pcfg, decoder_inp, f0, uv, mel2ph, control, x_org):
+    """get_pitch_embedding, pitch_type == 'cwt' branch, modules.py:890-948."""
+    pitch_cfg = pcfg["preprocessing"]["pitch"]
+    pre = "variance_adaptor."
+    h = F.linear(decoder_inp, P[pre + "cwt_predictor.0.weight"], P[pre + "cwt_predictor.0.bias"])
+    cwt = pitch_style_predictor(P, cfg, pre + "cwt_predictor.1.", h) * control
+    s = F.relu(F.linear(x_org[:, 0, :], P[pre + "cwt_stats_layers.0.weight"], P[pre + "cwt_stats_layers.0.bias"]))
+    s = F.relu(F.linear(s, P[pre + "cwt_stats_layers.2.weight"], P[pre + "cwt_stats_layers.2.bias"]))
+    stats = F.linear(s, P[pre + "cwt_stats_layers.4.weight"], P[pre + "cwt_stats_layers.4.bias"])
+    f0_mean, f0_std = stats[:, 0], stats[:, 1]
+    if f0 is None:
+        std = f0_std * cfg["variance_predictor"]["cwt_std_scale"]
+        f0 = cwt_to_f0_norm(cwt[:, :, :10], f0_mean, std, mel2ph.shape[1], pitch_cfg)
+        if pitch_cfg["use_uv"]:
+            uv = cwt[:, :, -1] > 0
+    f0_denorm = denorm_f0(f0, uv, pitch_cfg, None)
+    emb = F.embedding(f0_to_coarse(f0_denorm), P[pre + "pitch_embed.weight"], padding_idx=0)
+    pred = {"pitch_pred": None, "f0_denorm": f0_denorm, "cwt": cwt, "f0_mean": f0_mean, "f0_std": f0_std}
+    return pred, emb
+
+
+def energy_embedding(P, cfg, x, target, control):
+    """get_energy_embedding, modules.py:950-960."""
+    pre = "variance_adaptor."
+    pred = pitch_style_predictor(P, cfg, pre + "energy_predictor.", x).squeeze(-1)
+    if target is not None:
+        idx = torch.bucketize(target, P[pre + "energy_bins"])
+    else:
+        pred = pred * control
+        idx = torch.bucketize(pred, P[pre + "energy_bins"])
+    return pred, F.embedding(idx, P[pre + "energy_embedding.weight"], padding_idx=0)
+
+
+# --- unsupervised duration modelling: AlignmentEncoder + MAS -----------------------------------
+def alignment_encoder(P, queries, keys, src_mask, attn_prior, temperature, speaker_embed=None):
+    """AlignmentEncoder.forward, modules.py:1176-1213.  queries [B,80,M] (mel), keys [B,C,S]."""
+    pre = "variance_adaptor.aligner."
+    if speaker_embed is not None:
+        keys = keys + F.linear(speaker_embed, P[pre + "key_spk_proj.linear.weight"])[:, :, None]
+        queries = queries + F.linear(speaker_embed, P[pre + "query_spk_proj.linear.weight"])[:, :, None]
+    k = F.conv1d(keys, P[pre + "key_proj.0.conv.weight"], P[pre + "key_proj.0.conv.bias"], padding=1)
+    k = F.conv1d(F.relu(k), P[pre + "key_proj.2.conv.weight"], P[pre + "key_proj.2.conv.bias"])
+    q = F.conv1d(queries, P[pre + "query_proj.0.conv.weight"], P[pre + "query_proj.0.conv.bias"], padding=1)
+    q = F.conv1d(F.relu(q), P[pre + "query_proj.2.conv.weight"], P[pre + "query_proj.2.conv.bias"])
+    q = F.conv1d(F.relu(q), P[pre + "query_proj.4.conv.weight"], P[pre + "query_proj.4.conv.bias"])
+    attn = (q[:, :, :, None] - k[:, :, None]) ** 2
+    attn = -temperature * attn.sum(1, keepdim=True)
+    if attn_prior is not None:
+        attn = F.log_softmax(attn, dim=3) + torch.log(attn_prior[:, None] + 1e-8)
+    logprob = attn.clone()
+    attn = attn.masked_fill(src_mask[:, None, None, :], float("-inf"))
+    return F.softmax(attn, dim=3), logprob
+
+
+def mas_width1(attn_map):
+    """mas_width1, modules.py:36-64 (numba in the reference; plain numpy loops here, small cases).
+    attn_map: [M, S] probabilities.  Returns the 0/1 monotonic path matrix."""
+    M, S = attn_map.shape
+    with np.errstate(divide="ignore"):
+        a = np.log(attn_map)
+    a[0, 1:] = -np.inf
+    log_p = np.zeros_like(a)
+    log_p[0] = a[0]
+    prev = np.zeros((M, S), dtype=np.int64)
+    for i in range(1, M):
+        left = np.concatenate([[-np.inf], log_p[i - 1, :-1]]).astype(a.dtype)
+        take_left = left >= log_p[i - 1]
+        take_left[0] = False
+        best = np.where(take_left, left, log_p[i - 1])
+        log_p[i] = a[i] + best
+        prev[i] = np.arange(S) - take_left.astype(np.int64)
+    opt = np.zeros_like(a)
+    j = S - 1
+    for i in range(M - 1, -1, -1):
+        opt[i, j] = 1
+        j = prev[i, j]
+    opt[0, j] = 1
+    return opt
+
+
+def binarize_attention(attn, in_lens, out_lens):
+    """binarize_attention_parallel / b_mas, modules.py:66-75, 863-872."""
+    a = attn.detach().cpu().numpy()
+    out = np.zeros_like(a)
+    for b in range(a.shape[0]):
+        m, s = int(out_lens[b]), int(in_lens[b])
+        out[b, 0, :m, :s] = mas_width1(a[b, 0, :m, :s].copy())
+    return torch.from_numpy(out)
+
+
+def phoneme_level_energy(duration, src_len, energy_frame):
+    """VarianceAdaptor.get_phoneme_level_energy (modules.py:882-888) + utils/tools.py:56-66 + pad_1D."""
+    B = duration.shape[0]
+    rows = []
+    for b in range(B):
+        d = duration[b, : int(src_len[b])].int().numpy()
+        e = energy_frame[b].numpy().copy()
+        pos = 0
+        for i, di in enumerate(d):
+            e[i] = np.mean(e[pos: pos + di]) if di > 0 else 0
+            pos += di
+        rows.append(e[: len(d)])
+    L = max(len(r) for r in rows)
+    out = np.zeros((B, L), dtype=np.float32)
+    for b, r in enumerate(rows):
+        out[b, : len(r)] = r
+    return torch.from_numpy(out)
+
+
+def variance_adaptor(P, pcfg, cfg, tcfg, speaker_embedding, text, text_embedding, src_len, src_mask, mel, mel_len,
+                     mel_mask, max_len, pitch_target, energy_target, duration_target, attn_prior,
+                     p_control, e_control, d_control, step):
+    """VarianceAdaptor.forward, prosody model 'none', modules.py:962-1114."""
+    assert cfg["prosody_modeling"]["model_type"] == "none"
+    assert pcfg["preprocessing"]["pitch"]["pitch_type"] == "cwt"
+    learn_alignment = cfg["duration_modeling"]["learn_alignment"]
+    x = text.clone()
+    if speaker_embedding is not None:
+        x = x + speaker_embedding.unsqueeze(1)
+    log_d = duration_predictor(P, cfg, x, src_mask)
+
+    attn_soft = attn_hard = attn_hard_dur = attn_logprob = None
+    if attn_prior is not None:
+        assert learn_alignment and duration_target is None and mel is not None
+        attn_soft, attn_logprob = alignment_encoder(
+            P, mel.transpose(1, 2), text_embedding.transpose(1, 2), src_mask, attn_prior.transpose(1, 2),
+            cfg["duration_modeling"]["aligner_temperature"], speaker_embedding)
+        attn_hard = binarize_attention(attn_soft, src_len, mel_len)
+        attn_hard_dur = attn_hard.sum(2)[:, 0, :]
+    attn_out = (attn_soft, attn_hard, attn_hard_dur, attn_logprob)
+
+    x_org = x.clone()
+    if attn_prior is not None:
+        if step < tcfg["duration"]["binarization_start_steps"]:
+            x = torch.bmm(attn_soft.squeeze(1), x)
+        else:
+            x, mel_len = length_regulate(x, attn_hard_dur, max_len)
+        duration_rounded = attn_hard_dur
+        pitch_target["mel2ph"] = durations_to_mel2ph(duration_rounded, src_mask)[:, :max_len]
+    elif duration_target is not None:
+        assert not learn_alignment
+        x, mel_len = length_regulate(x, duration_target, max_len)
+        duration_rounded = duration_target
+    else:
+        duration_rounded = torch.clamp(torch.round(torch.exp(log_d) - 1) * d_control, min=0)
+        x, mel_len = length_regulate(x, duration_rounded, max_len)
+        mel_mask = pad_mask_from_lengths(mel_len)
+        mel2ph = durations_to_mel2ph(duration_rounded, src_mask)
+
+    x_sum = x.clone()
+    pitch_pred = energy_pred = None
+    if cfg["variance_embedding"]["use_pitch_embed"]:
+        if pitch_target is not None:
+            mel2ph = pitch_target["mel2ph"]
+            pitch_target["f0"] = cwt_to_f0_norm(pitch_target["cwt_spec"], pitch_target["f0_mean"],
+                                                pitch_target["f0_std"], mel2ph.shape[1],
+                                                pcfg["preprocessing"]["pitch"])
+            pitch_target["f0_cwt"] = pitch_target["f0"]
+            pitch_pred, p_emb = pitch_embedding_cwt(P, cfg, pcfg, x, pitch_target["f0"], pitch_target["uv"],
+                                                    mel2ph, p_control, x_org)
+        else:
+            pitch_pred, p_emb = pitch_embedding_cwt(P, cfg, pcfg, x, None, None, mel2ph, p_control, x_org)
+        x_sum = x_sum + p_emb
+    if cfg["variance_embedding"]["use_energy_embed"]:
+        level = pcfg["preprocessing"]["energy"]["feature"]
+        if level == "frame_level":
+            energy_pred, e_emb = energy_embedding(P, cfg, x, energy_target, e_control)
+            x_sum = x_sum + e_emb
+        else:
+            if attn_prior is not None:
+                energy_target = phoneme_level_energy(attn_hard_dur, src_len, energy_target)
+            energy_pred, e_emb = energy_embedding(P, cfg, x_org, energy_target, e_control)
+            x_sum = x_sum + length_regulate(e_emb, duration_rounded, max_len)[0]
+    return (x_sum, pitch_target, pitch_pred, energy_target, energy_pred, log_d, duration_rounded, mel_len, mel_mask,
+            attn_out, None)
+
+
+# ----------------------------------------------------------------------------------------------
+# mel head (model/CompTransTTS.py:133-135, model/modules.py:78-148)
+# ----------------------------------------------------------------------------------------------
+def postnet(P, x):
+    """PostNet.forward in eval mode (BatchNorm1d running stats, dropout off), modules.py:140-148."""
+    h = x.transpose(1, 2)
+    for i in range(5):
+        pre = "postnet.convolutions.%d." % i
+        h = F.conv1d(h, P[pre + "0.conv.weight"], P[pre + "0.conv.bias"], padding=2)
+        h = F.batch_norm(h, P[pre + "1.running_mean"], P[pre + "1.running_var"], P[pre + "1.weight"],
+                         P[pre + "1.bias"], False, 0.1, 1e-5)
+        if i < 4:
+            h = torch.tanh(h)
+    return h.transpose(1, 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# top level (model/CompTransTTS.py:64-152)
+# ----------------------------------------------------------------------------------------------
+def comp_trans_tts_forward(P, pcfg, cfg, tcfg, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None,
+                           max_mel_len=None, p_targets=None, e_targets=None, d_targets=None, attn_priors=None,
+                           spker_embeds=None, p_control=1.0, e_control=1.0, d_control=1.0, step=None, taps=None):
+    """Returns the reference's 14-tuple.  `taps`, if a dict, receives intermediate activations."""
+    block = cfg["block_type"]
+    src_masks = pad_mask_from_lengths(src_lens, max_src_len)
+    mel_masks = pad_mask_from_lengths(mel_lens, max_mel_len) if mel_lens is not None else None
+    if block == "transformer_fs2":
+        enc, word = encoder_fs2(P, cfg, texts, src_masks, taps)
+    else:
+        from . import ctts_oracle_blocks as OB
+        enc, word = OB.ENCODERS[block](P, cfg, texts, src_masks, taps)
+    if taps is not None:
+        taps["encoder_out"] = enc
+    spk = None
+    if cfg["multi_speaker"]:
+        if pcfg["preprocessing"]["speaker_embedder"] == "none":
+            spk = F.embedding(speakers, P["speaker_emb.weight"])
+        else:
+            assert spker_embeds is not None, "Speaker embedding should not be None"
+            spk = F.linear(spker_embeds, P["speaker_emb.weight"], P["speaker_emb.bias"])
+    (x, p_targets, p_pred, e_targets, e_pred, log_d, d_rounded, mel_lens, mel_masks, attn_outs, prosody) = \
+        variance_adaptor(P, pcfg, cfg, tcfg, spk, enc, word, src_lens, src_masks, mels, mel_lens, mel_masks,
+                         max_mel_len, p_targets, e_targets, d_targets, attn_priors, p_control, e_control, d_control,
+                         step)
+    if taps is not None:
+        taps["decoder_in"] = x
+    if block == "transformer_fs2":
+        dec, mel_masks = decoder_fs2(P, cfg, x, mel_masks, taps)
+    else:
+        from . import ctts_oracle_blocks as OB
+        dec, mel_masks = OB.DECODERS[block](P, cfg, x, mel_masks, taps)
+    if taps is not None:
+        taps["decoder_out"] = dec
+    mel = F.linear(dec, P["mel_linear.weight"], P["mel_linear.bias"])
+    post = postnet(P, mel) + mel
+    return (mel, post, p_pred, e_pred, log_d, d_rounded, src_masks, mel_masks, src_lens, mel_lens, attn_outs, prosody,
+            p_targets, e_targets)

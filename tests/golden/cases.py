@@ -1,0 +1,70 @@
+"""Definition of the golden cases (shared by make_golden.py, the CPU oracle tests and the GPU parity tests).
+
+Every case is fully determined by this table: weights come from `synth.synthetic_state_dict`
+(seeded by tensor name), inputs from `synth.ljspeech_batch` (seeded), so the fixtures only have to
+store the REFERENCE's outputs.
+"""
+CASES = {
+    # BASELINE.json configs[0]: transformer_fs2, LJSpeech config, batch 2, seq_len ~100, free-running inference.
+    # Durations are pinned to 3 frames / phoneme (the random-init duration predictor would emit ~0 frames).
+    "fs2_infer_c1": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="infer",
+                         batch=2, s_max=100, s_step=9, pin=3, seed=0),
+    # supervised / teacher-forced branch (modules.py:1054-1057): explicit durations U[1,15], pitch / energy targets
+    "fs2_teacher": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="teacher",
+                        batch=3, s_max=40, s_step=7, pin=None, seed=1),
+}
+
+TAP_STRIDE = 4  # intermediate activations are stored for every 4th row only
+
+# names of the arrays stored per case (prefix "ref.")
+TUPLE_NAMES = ["mel", "postnet_mel", "p_predictions", "e_predictions", "log_d_predictions", "d_rounded", "src_masks",
+               "mel_masks", "src_lens", "mel_lens", "attn_outs", "prosody_info", "p_targets", "e_targets"]
+
+
+def build_case(name):
+    """(configs, state_dict, batch) for a case -- importable without the reference."""
+    from ctts_b200 import configs, spec, synth
+    c = CASES[name]
+    p, m, t = configs.builtin_configs(c["dataset"], block_type=c["block_type"], learn_alignment=c["learn_alignment"])
+    entries, _, _ = spec.parameter_spec(p, m)
+    sd = synth.synthetic_state_dict(entries, pin_frames_per_phoneme=c["pin"])
+    batch = synth.ljspeech_batch(batch=c["batch"], s_max=c["s_max"], s_step=c["s_step"], mode=c["mode"],
+                                 seed=c["seed"], spk_dim=512 if c["dataset"] == "VCTK" else None)
+    return (p, m, t), sd, batch
+
+
+def flatten_outputs(out):
+    """14-tuple -> {name: numpy array} (None entries dropped, nested dict / tuple flattened with dots)."""
+    import numpy as np
+    import torch
+    flat = {}
+
+    def put(key, v):
+        if v is None:
+            return
+        if isinstance(v, dict):
+            for k in sorted(v):
+                put(key + "." + k, v[k])
+        elif isinstance(v, (tuple, list)):
+            for i, x in enumerate(v):
+                put("%s.%d" % (key, i), x)
+        elif isinstance(v, torch.Tensor):
+            flat[key] = v.detach().cpu().numpy()
+        else:
+            flat[key] = np.asarray(v)
+
+    for n, v in zip(TUPLE_NAMES, out):
+        put(n, v)
+    return flat
+
+
+def call_kwargs(batch):
+    """Positional / keyword arguments of CompTransTTS.forward from a synth batch (deep-copied targets)."""
+    import copy
+    b = copy.deepcopy(batch)
+    args = (b["speakers"], b["texts"], b["src_lens"], b["max_src_len"])
+    kw = {k: b[k] for k in ("mels", "mel_lens", "max_mel_len", "p_targets", "e_targets", "d_targets", "attn_priors",
+                            "spker_embeds") if k in b}
+    if "attn_priors" in kw:
+        kw["step"] = 120000
+    return args, kw

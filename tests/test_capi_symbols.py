@@ -1,0 +1,56 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/ctts_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ctts_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctts_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_path():
+    syms = declared_symbols()
+    for need in ("ctts_conv1d_gemm", "ctts_attention", "ctts_length_scan", "ctts_length_expand", "ctts_layernorm",
+                 "ctts_gemm_bf16x3", "ctts_cwt_to_pitch", "ctts_embed_tokens"):
+        assert need in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from ctts_b200 import capi
+    if not os.path.exists(capi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), "libctts_b200.so does not export %s" % s
+    assert sorted(capi.SIGNATURES) == declared_symbols(), "capi.SIGNATURES and the header disagree"
+    assert capi.load().ctts_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """The product path must refuse CPU tensors instead of silently computing somewhere else."""
+    import torch
+    import ctts_b200
+    p, m, t = ctts_b200.builtin_configs("LJSpeech", learn_alignment=False)
+    m["transformer_fs2"]["encoder_layer"] = 1
+    m["transformer_fs2"]["decoder_layer"] = 1
+    net = ctts_b200.CompTransTTS(p, m, t).eval()
+    with pytest.raises(Exception):
+        net(torch.zeros(1, dtype=torch.long), torch.ones(1, 4, dtype=torch.long), torch.tensor([4]), 4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "comprehensive-transformer-tts_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                for line in txt.splitlines():
+                    assert not re.match(r"\s*(from|import)\s+oracle", line), "%s imports the oracle" % f

@@ -1,0 +1,222 @@
+"""GPU: every kernel of libctts_b200, called through the C ABI, against the CPU oracle / plain fp32 torch.
+
+Tolerances: FP32 kernels 2e-5 abs + 1e-4 rel (summation-order noise only); integer / index results bit-exact.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from ctts_b200 import capi, engine  # noqa: E402
+from oracle import ctts_oracle as O  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def g(seed):
+    gen = torch.Generator()
+    gen.manual_seed(seed)
+    return gen
+
+
+def close(a, b, atol=2e-5, rtol=1e-4, msg=""):
+    np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), atol=atol, rtol=rtol, err_msg=msg)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("B,T,Cin,N,taps,act", [
+    (2, 37, 256, 768, 1, "none"), (3, 100, 256, 1024, 9, "gelu"), (2, 130, 1024, 256, 1, "none"),
+    (2, 300, 80, 512, 5, "tanh"), (2, 129, 512, 80, 5, "none"), (4, 64, 256, 1, 1, "none"),
+    (2, 50, 128, 256, 5, "relu"), (1, 16, 256, 11, 1, "none"), (2, 257, 256, 256, 3, "relu"),
+])
+def test_conv1d_gemm_fp32(B, T, Cin, N, taps, act):
+    x = torch.randn(B, T, Cin, generator=g(1))
+    w = torch.randn(N, Cin, taps, generator=g(2)) / math.sqrt(Cin * taps)
+    bias = torch.randn(N, generator=g(3))
+    res = torch.randn(B, T, N, generator=g(4))
+    lens = torch.tensor([max(T - 7 * b, 1) for b in range(B)])
+    sc, sh = torch.rand(N, generator=g(5)) + 0.5, torch.randn(N, generator=g(6))
+    alpha = 0.37
+    ref = F.conv1d(x.transpose(1, 2), w, bias, padding=taps // 2).transpose(1, 2) * alpha
+    ref = ref * sc + sh
+    ref = {"none": lambda v: v, "gelu": F.gelu, "tanh": torch.tanh, "relu": F.relu}[act](ref) + res
+    ref = ref * (torch.arange(T)[None, :] < lens[:, None]).float()[:, :, None]
+    wd = w.to(DEV)
+    packed = torch.empty(N, taps * Cin, device=DEV)
+    capi.call("ctts_pack_conv_weight", wd, N, Cin, taps, packed, stream())
+    assert torch.equal(packed.cpu(), w.permute(0, 2, 1).reshape(N, -1))
+    y = engine.conv_gemm(x.to(DEV), packed, bias.to(DEV), alpha=alpha, bn=(sc.to(DEV), sh.to(DEV)),
+                         act=engine._ACTS[act], residual=res.to(DEV), lens=lens.to(DEV), taps=taps)
+    close(y, ref, atol=5e-5)
+
+
+def test_conv1d_gemm_rejects_bad_shapes():
+    x = torch.zeros(1, 8, 24, device=DEV)
+    w = torch.zeros(8, 24, device=DEV)
+    with pytest.raises(capi.CttsError):
+        engine.conv_gemm(x, w)  # Cin % 16 != 0
+
+
+@pytest.mark.parametrize("rows,C,eps", [(77, 256, 1e-12), (300, 128, 1e-5), (5, 1024, 1e-12), (64, 80, 1e-5)])
+def test_layernorm(rows, C, eps):
+    x = torch.randn(1, rows, C, generator=g(7)) * 3 + 1
+    x[0, 3] = 0  # LN(0) = beta
+    gm, bt = torch.randn(C, generator=g(8)), torch.randn(C, generator=g(9))
+    lens = torch.tensor([rows - 2])
+    ref = F.layer_norm(x, (C,), gm, bt, eps)
+    y = engine.layernorm(x.to(DEV), gm.to(DEV), bt.to(DEV), eps)
+    close(y, ref)
+    assert torch.allclose(y[0, 3].cpu(), bt, atol=1e-6)
+    y2 = engine.layernorm(x.to(DEV), gm.to(DEV), bt.to(DEV), eps, lens.to(DEV))
+    ref2 = ref.clone()
+    ref2[0, rows - 2:] = 0
+    close(y2, ref2)
+
+
+@pytest.mark.parametrize("B,T,C,H", [(3, 100, 256, 2), (2, 333, 256, 2), (2, 70, 256, 8), (1, 33, 128, 2)])
+def test_attention(B, T, C, H):
+    qkv = torch.randn(B, T, 3 * C, generator=g(10))
+    lens = torch.tensor([max(T - 13 * b, 1) for b in range(B)])
+    dh = C // H
+    q, k, v = qkv.split(C, -1)
+    q = q.view(B, T, H, dh).transpose(1, 2) / math.sqrt(dh)
+    k = k.view(B, T, H, dh).transpose(1, 2)
+    v = v.view(B, T, H, dh).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    pad = torch.arange(T)[None, :] >= lens[:, None]
+    s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, C)
+    ref = ref * (~pad).float()[:, :, None]
+    out = engine.attention(qkv.to(DEV), lens.to(DEV), H)
+    close(out, ref, atol=3e-5)
+
+
+def test_embed_and_positions():
+    B, S, C, V = 3, 50, 256, 361
+    tok = torch.randint(1, V, (B, S), generator=g(11))
+    lens = torch.tensor([50, 41, 7])
+    for b in range(B):
+        tok[b, lens[b]:] = 0
+    tok[0, 5] = 0  # an in-sequence pad symbol: position must not advance (utils/tools.py:640-652)
+    table = torch.randn(V, C, generator=g(12))
+    table[0] = 0
+    pe = O.sinusoid_table_fs2(2048, C)
+    x = torch.empty(B, S, C, device=DEV)
+    word = torch.empty(B, S, C, device=DEV)
+    capi.call("ctts_embed_tokens", tok.to(DEV), table.to(DEV), pe.to(DEV), 2048, 16.0, B, S, C, V, x, word,
+              lens.to(DEV), stream())
+    w_ref = 16.0 * F.embedding(tok, table)
+    x_ref = (w_ref + O.fs2_positional(tok, C, 1000)) * (torch.arange(S)[None] < lens[:, None]).float()[:, :, None]
+    close(word, w_ref, atol=1e-6)
+    close(x, x_ref, atol=1e-6)
+    # decoder-style positions from x[..., 0] != 0, scaled by a device scalar, then masked
+    h = torch.randn(B, S, C, generator=g(13))
+    h[1, 4, 0] = 0
+    alpha = torch.tensor([0.73])
+    ref = (h + alpha * O.fs2_positional(h[..., 0], C, 2000)) * (torch.arange(S)[None] < lens[:, None]).float()[:, :, None]
+    hd = h.to(DEV).clone()
+    capi.call("ctts_add_positions", hd, pe.to(DEV), 2048, alpha.to(DEV), lens.to(DEV), B, S, C, stream())
+    close(hd, ref, atol=1e-6)
+
+
+def test_decode_durations_half_to_even():
+    logd = torch.log(torch.tensor([1.5, 2.5, 3.5, 4.4999, 0.2, 9.0, 1.0, 1.49]) + 1.0)
+    out = torch.empty_like(logd, device=DEV)
+    capi.call("ctts_decode_durations", logd.to(DEV), 1.0, logd.numel(), out, stream())
+    ref = torch.clamp(torch.round(torch.exp(logd) - 1) * 1.0, min=0)
+    assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_length_regulator_bit_exact(seed):
+    """LengthRegulator + dur_to_mel2ph against the oracle's loop restatement: bit-exact, incl. zero durations,
+    fractional (d_control != 1) durations where LR truncates but mel2ph rounds, all-zero rows and max_len padding."""
+    gen = g(100 + seed)
+    B, S, C = 5, 37, 64
+    x = torch.randn(B, S, C, generator=gen)
+    src_lens = torch.tensor([37, 30, 22, 9, 1])
+    if seed % 2 == 0:
+        dur = torch.randint(0, 9, (B, S), generator=gen)
+    else:
+        dur = torch.clamp(torch.round(torch.rand(B, S, generator=gen) * 8) * (0.5 + 0.25 * seed), min=0)
+    dur = dur * (torch.arange(S)[None] < src_lens[:, None])
+    if seed == 2:
+        dur[3] = 0
+    ref_x, ref_len = O.length_regulate(x, dur, None)
+    ref_m2p = O.durations_to_mel2ph(dur, torch.arange(S)[None] >= src_lens[:, None])
+    out, mel_len, m2p, _ = engine.length_regulate(x.to(DEV), dur.to(DEV), src_lens.to(DEV), None, True)
+    assert torch.equal(mel_len.cpu(), ref_len)
+    assert torch.equal(out.cpu(), ref_x)
+    assert torch.equal(m2p.cpu(), ref_m2p)
+    M = int(ref_len.max()) + 11
+    out2, _, _, _ = engine.length_regulate(x.to(DEV), dur.to(DEV), src_lens.to(DEV), M, False)
+    ref2, _ = O.length_regulate(x, dur, M)
+    assert torch.equal(out2.cpu(), ref2)
+
+
+def test_length_regulator_full_size_properties():
+    """BASELINE full size (B 16, S 100, 8 frames/phoneme): size-independent properties -- every output row is a copy
+    of the row its mel2ph names, row counts per phoneme equal the durations, rows past mel_len are zero."""
+    B, S, C = 16, 100, 256
+    x = torch.randn(B, S, C, generator=g(5), device="cpu").to(DEV)
+    src_lens = torch.tensor([100 - 2 * b for b in range(B)], device=DEV)
+    dur = (torch.arange(S, device=DEV)[None] < src_lens[:, None]).float() * 8
+    out, mel_len, m2p, _ = engine.length_regulate(x, dur, src_lens, None, True)
+    assert out.shape == (B, 800, C) and mel_len.tolist() == [8 * int(s) for s in src_lens]
+    idx = (m2p - 1).clamp(min=0)
+    gathered = torch.gather(x, 1, idx[:, :, None].expand(-1, -1, C)) * (m2p > 0)[:, :, None]
+    assert torch.equal(out, gathered)
+    counts = torch.zeros(B, S + 1, dtype=torch.long, device=DEV).scatter_add(1, m2p, torch.ones_like(m2p))[:, 1:]
+    assert torch.equal(counts, dur.long())
+
+
+def test_cwt_to_pitch_and_buckets():
+    B, T = 3, 211
+    cwt = torch.randn(B, T, 11, generator=g(20))
+    mean = torch.tensor([5.3, 5.0, 5.6])
+    std = torch.tensor([0.4, 0.3, 0.5])
+    cfg = dict(pitch_norm="log", pitch_norm_eps=1e-9, use_uv=True)
+    f0n = O.cwt_to_f0_norm(cwt[:, :, :10], mean, std * 0.8, T, cfg)
+    uv = cwt[:, :, -1] > 0
+    f0d = O.denorm_f0(f0n, uv, cfg)
+    idx_ref = O.f0_to_coarse(f0d)
+    w = ((torch.arange(0, 10).float() + 1 + 2.5) ** (-2.5)).to(DEV)
+    f0n_d = torch.empty(B, T, device=DEV)
+    f0d_d = torch.empty(B, T, device=DEV)
+    idx = torch.empty(B, T, dtype=torch.long, device=DEV)
+    capi.call("ctts_cwt_to_pitch", cwt.to(DEV), 11, w, mean.to(DEV), std.to(DEV), 1, 0.8, 1e-9, None, 1, B, T, f0n_d,
+              f0d_d, idx, stream())
+    close(f0n_d, f0n, atol=1e-5)
+    close(f0d_d, f0d, atol=1e-3, rtol=1e-5)
+    flips = int((idx.cpu() != idx_ref).sum())
+    assert flips == 0, "%d pitch-bucket flips" % flips
+    assert len(idx_ref.unique()) > 20
+    # teacher-forced variant: uv from targets, stats stride 1
+    uvt = (torch.rand(B, T, generator=g(21)) < 0.3).float()
+    capi.call("ctts_cwt_to_pitch", cwt[:, :, :10].contiguous().to(DEV), 10, w, mean.to(DEV), std.to(DEV), 1, 1.0, 1e-9,
+              uvt.to(DEV), 1, B, T, f0n_d, f0d_d, idx, stream())
+    f0n2 = O.cwt_to_f0_norm(cwt[:, :, :10], mean, std, T, cfg)
+    assert int((idx.cpu() != O.f0_to_coarse(O.denorm_f0(f0n2, uvt, cfg))).sum()) == 0
+
+
+def test_bucketize_and_gather():
+    bins = torch.linspace(-1.43, 8.18, 255)
+    v = torch.cat([torch.randn(1000, generator=g(30)) * 2 + 2, bins[::17], torch.tensor([-5.0, 20.0])])
+    idx = torch.empty(v.numel(), dtype=torch.long, device=DEV)
+    capi.call("ctts_bucketize", v.to(DEV), 1.0, bins.to(DEV), 255, v.numel(), idx, stream())
+    assert torch.equal(idx.cpu(), torch.bucketize(v, bins))
+    table = torch.randn(256, 64, generator=g(31))
+    x = torch.randn(v.numel(), 64, generator=g(32))
+    xd = x.to(DEV).clone()
+    capi.call("ctts_gather_add", table.to(DEV), idx, v.numel(), 64, 256, xd, stream())
+    assert torch.equal(xd.cpu(), x + table[idx.cpu()])
