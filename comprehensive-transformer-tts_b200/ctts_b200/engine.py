@@ -41,6 +41,57 @@ def conv_gemm(x, w, bias=None, alpha=1.0, bn=None, act=ACT_NONE, residual=None, 
     return y
 
 
+class Planes:
+    """A [B, T, C] activation (or [N, K] weight) stored as two bf16 planes: value ~= hi + lo (16 mantissa bits)."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @staticmethod
+    def empty(B, T, C, device):
+        return Planes(torch.empty(B, T, C, device=device, dtype=torch.bfloat16),
+                      torch.empty(B, T, C, device=device, dtype=torch.bfloat16))
+
+
+def split_planes(x):
+    """fp32 tensor -> Planes (ctts_split_bf16)."""
+    x = _f32(x)
+    p = Planes(torch.empty(x.shape, device=x.device, dtype=torch.bfloat16),
+               torch.empty(x.shape, device=x.device, dtype=torch.bfloat16))
+    capi.call("ctts_split_bf16", x, x.numel(), p.hi, p.lo, _stream())
+    return p
+
+
+def gemm_tc(xp, wp, bias=None, alpha=1.0, bn=None, act=ACT_NONE, residual=None, lens=None, taps=1, out=None,
+            want_fp32=True, want_planes=False):
+    """tcgen05 bf16x3 implicit-GEMM conv / linear.  xp: Planes [B,T,Cin]; wp: Planes [N, taps*Cin].
+    Returns (y fp32 or None, Planes or None)."""
+    B, T, Cin = xp.shape
+    N = wp.shape[0]
+    assert wp.shape[1] == taps * Cin, (tuple(wp.shape), taps, Cin)
+    y = out if out is not None else (torch.empty(B, T, N, device=xp.hi.device, dtype=torch.float32) if want_fp32
+                                     else None)
+    yp = Planes.empty(B, T, N, xp.hi.device) if want_planes else None
+    capi.call("ctts_gemm_bf16x3", xp.hi, xp.lo, wp.hi, wp.lo, bias, float(alpha), bn[0] if bn else None,
+              bn[1] if bn else None, int(act), residual, lens, B, T, Cin, N, taps, y, yp.hi if yp else None,
+              yp.lo if yp else None, _stream())
+    return y, yp
+
+
+def layernorm_planes(x, gamma, beta, eps, lens=None, want_fp32=False):
+    """LayerNorm whose result is written as bf16 hi/lo planes (and optionally fp32)."""
+    B, T, C = x.shape
+    y = torch.empty_like(x) if want_fp32 else None
+    yp = Planes.empty(B, T, C, x.device)
+    capi.call("ctts_layernorm_split", x, gamma, beta, float(eps), lens, B, T, C, y, yp.hi, yp.lo, _stream())
+    return y, yp
+
+
 def layernorm(x, gamma, beta, eps, lens=None):
     B, T, C = x.shape
     y = torch.empty_like(x)
@@ -105,6 +156,14 @@ class Prepared:
                     scale = P[pre + "weight"] / torch.sqrt(P[pre + "running_var"] + 1e-5)
                     shift = P[pre + "bias"] - P[pre + "running_mean"] * scale
                     self.w[pre + "fold"] = (scale.float().contiguous(), shift.float().contiguous())
+            if self.module.decoder_math == "bf16x3":
+                # bf16 hi/lo planes of every weight on the tensor-core part of the path (decoder, mel head)
+                for name, t in P.items():
+                    if not (name.startswith("decoder.") or name.startswith("postnet.") or name.startswith("mel_linear.")):
+                        continue
+                    if name.endswith("weight") and t.dim() in (2, 3):
+                        src = self.w[name] if t.dim() == 3 else _f32(t)
+                        self.w[name + "#planes"] = split_planes(src)
             self.w["cwt_scale_w"] = ((torch.arange(0, 10).float() + 1 + 2.5) ** (-2.5)).to(
                 next(iter(P.values())).device)  # utils/pitch_tools.py:260
 
@@ -161,16 +220,36 @@ def encoder_fs2(prep, P, cfg, tokens, src_lens):
     return x, word
 
 
-def decoder_fs2(prep, P, cfg, x, mel_lens):
+def _fft_layers_fs2_tc(prep, P, pre, x, lens, n_layers, n_head, kernel, act):
+    """Same block as _fft_layers_fs2 with the four dense contractions on tcgen05 (bf16x3); attention, LayerNorm and
+    the residual stream stay FP32.  Returns (final LN fp32, final LN planes)."""
+    W = prep.w
+    for i in range(n_layers):
+        lp = "%slayers.%d.op." % (pre, i)
+        _, hp = layernorm_planes(x, P[lp + "layer_norm1.weight"], P[lp + "layer_norm1.bias"], 1e-12)
+        qkv, _ = gemm_tc(hp, W[lp + "self_attn.in_proj_weight#planes"])
+        a = attention(qkv, lens, n_head)
+        gemm_tc(split_planes(a), W[lp + "self_attn.out_proj.weight#planes"], residual=x, lens=lens, out=x)
+        _, hp = layernorm_planes(x, P[lp + "layer_norm2.weight"], P[lp + "layer_norm2.bias"], 1e-12)
+        _, fp = gemm_tc(hp, W[lp + "ffn.ffn_1.weight#planes"], P[lp + "ffn.ffn_1.bias"], alpha=kernel ** -0.5, act=act,
+                        taps=kernel, want_fp32=False, want_planes=True)
+        gemm_tc(fp, W[lp + "ffn.ffn_2.weight#planes"], P[lp + "ffn.ffn_2.bias"], residual=x, lens=lens, out=x)
+    return layernorm_planes(x, P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-5, lens, want_fp32=True)
+
+
+def decoder_fs2(prep, P, cfg, x, mel_lens, math="fp32"):
     """Decoder = FFTBlocks with learnable-scale sinusoid positions, transformer_fs2.py:47-72,122-134.
-    `x` must be a private buffer: it is overwritten."""
+    `x` must be a private buffer: it is overwritten.  Returns (dec fp32, dec planes or None)."""
     c = cfg["transformer_fs2"]
     B, T, C = x.shape
     pe = prep.table_fs2(C, T + 1, x.device)
     capi.call("ctts_add_positions", x, pe, pe.shape[0], P["decoder.pos_embed_alpha"], mel_lens, B, T, C, _stream())
     act = _ACTS[cfg["variance_predictor"]["ffn_act"]]
+    if math == "bf16x3":
+        return _fft_layers_fs2_tc(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
+                                  c["ffn_kernel_size"], act)
     return _fft_layers_fs2(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
-                           c["ffn_kernel_size"], act)
+                           c["ffn_kernel_size"], act), None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -323,8 +402,17 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
 
 
 # ---------------------------------------------------------------------------------------------
-def mel_head(prep, P, dec):
+def mel_head(prep, P, dec, dec_planes=None):
     """mel_linear + PostNet + residual (CompTransTTS.py:133-135, modules.py:140-148; eval-mode BN folded)."""
+    if dec_planes is not None:
+        mel, hp = gemm_tc(dec_planes, prep.w["mel_linear.weight#planes"], P["mel_linear.bias"], want_planes=True)
+        post = None
+        for i in range(5):
+            pre = "postnet.convolutions.%d." % i
+            post, hp = gemm_tc(hp, prep.w[pre + "0.conv.weight#planes"], P[pre + "0.conv.bias"], bn=prep.w[pre + "1.fold"],
+                               act=ACT_TANH if i < 4 else ACT_NONE, residual=mel if i == 4 else None, taps=5,
+                               want_fp32=(i == 4), want_planes=(i < 4))
+        return mel, post
     mel = conv_gemm(dec, P["mel_linear.weight"], P["mel_linear.bias"])
     h = mel
     for i in range(5):
@@ -371,7 +459,7 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, enc, word, src_lens, src_masks, mels, mel_lens, mel_masks,
                          max_mel_len, p_targets, e_targets, d_targets, attn_priors, p_control, e_control, d_control,
                          step)
-    dec = decoder_fs2(prep, P, cfg, x, mel_lens)
-    mel, post = mel_head(prep, P, dec)
+    dec, dec_planes = decoder_fs2(prep, P, cfg, x, mel_lens, module.decoder_math)
+    mel, post = mel_head(prep, P, dec, dec_planes)
     return (mel, post, p_pred, e_pred, log_d, d_rounded, src_masks, mel_masks, src_lens, mel_lens, attn_outs, prosody,
             p_targets, e_targets)

@@ -7,6 +7,7 @@ The module tree only exists to carry parameters under the reference's names; the
 is `engine.forward`, which calls libctts_b200 through its C ABI.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -79,6 +80,11 @@ class CompTransTTS(nn.Module):
         self.has_speaker_emb = bool(model_config["multi_speaker"])
         self.embedder_type = preprocess_config["preprocessing"].get("speaker_embedder", "none") \
             if self.has_speaker_emb else None
+        # arithmetic of the decoder / mel head (downstream of every quantiser): "bf16x3" = tcgen05 tensor cores with
+        # bf16 hi/lo operand planes, "fp32" = CUDA-core FMA (same kernels as the encoder / predictors)
+        self.decoder_math = os.environ.get("CTTS_DECODER_MATH", "bf16x3")
+        if self.decoder_math not in ("bf16x3", "fp32"):
+            raise ValueError("CTTS_DECODER_MATH must be 'bf16x3' or 'fp32'")
         self._prepared = engine.Prepared(self)
 
     def forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
