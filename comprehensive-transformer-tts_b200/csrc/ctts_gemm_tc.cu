@@ -40,6 +40,17 @@ struct Epilogue {
     int act;
 };
 
+// Operand / output addressing.  z = blockIdx.x / tiles_per_utt is the "utterance" index of a plain conv (z = b) or the
+// (b, head) pair of the attention GEMMs (z = b*mod + head).
+struct Addr {
+    int mod;                  // heads per batch element (1 for conv / linear)
+    int a_div, a_c0, a_step;  // A tile coords: (a_c0 + (z % mod)*a_step + k, t, z / a_div)
+    int w_div, w_c0, w_step;  // W tile coords: (w_c0 + (z % mod)*w_step + k, n, z / w_div)
+    int lens_div;             // pad-mask length = lens[z / lens_div]
+    int ldy;                  // output row stride (elements)
+    long long y_outer, y_inner;  // output offset = (z / mod)*y_outer + (z % mod)*y_inner + t*ldy + n
+};
+
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -131,7 +142,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                   const Epilogue ep, int T, int Cin, int N, int taps, int tiles_per_utt) {
+                   const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps, int tiles_per_utt) {
     using S = Smem<BLOCK_N, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must be 1024-byte aligned in the shared address space
@@ -142,8 +153,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x / tiles_per_utt;
-    const int t0 = (blockIdx.x - b * tiles_per_utt) * BLOCK_M;
+    const int z = blockIdx.x / tiles_per_utt;
+    const int t0 = (blockIdx.x - z * tiles_per_utt) * BLOCK_M;
+    const int zh = z % ad.mod;
     const int n0 = blockIdx.y * BLOCK_N;
     const int kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
     const int num_kb = taps * kb_per_tap;
@@ -183,10 +195,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const int tap = kb / kb_per_tap;
                 const int c0 = (kb - tap * kb_per_tap) * BLOCK_K;
                 uint8_t* st = smem + s * S::STAGE_BYTES;
-                tma_load_3d(&tm_a_hi, &full_bar[s], st, c0, t0 + tap - pad, b);
-                tma_load_3d(&tm_a_lo, &full_bar[s], st + A_TILE_BYTES, c0, t0 + tap - pad, b);
-                tma_load_2d(&tm_b_hi, &full_bar[s], st + 2 * A_TILE_BYTES, tap * Cin + c0, n0);
-                tma_load_2d(&tm_b_lo, &full_bar[s], st + 2 * A_TILE_BYTES + S::B_TILE_BYTES, tap * Cin + c0, n0);
+                const int ca = ad.a_c0 + zh * ad.a_step + c0, za = z / ad.a_div;
+                const int cw = ad.w_c0 + zh * ad.w_step + tap * Cin + c0, zw = z / ad.w_div;
+                tma_load_3d(&tm_a_hi, &full_bar[s], st, ca, t0 + tap - pad, za);
+                tma_load_3d(&tm_a_lo, &full_bar[s], st + A_TILE_BYTES, ca, t0 + tap - pad, za);
+                tma_load_3d(&tm_b_hi, &full_bar[s], st + 2 * A_TILE_BYTES, cw, n0, zw);
+                tma_load_3d(&tm_b_lo, &full_bar[s], st + 2 * A_TILE_BYTES + S::B_TILE_BYTES, cw, n0, zw);
             }
         }
     } else if (warp == 1) {
@@ -221,10 +235,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int t = t0 + row;
         mbar_wait(accum_bar, 0);
         tcgen05_fence_after();
-        const int len = ep.lens ? (int)ep.lens[b] : T;
+        const int len = ep.lens ? (int)ep.lens[z / ad.lens_div] : T;
         const bool in_range = t < T;
         const bool keep = t < len;
-        const size_t rowoff = ((size_t)b * T + (in_range ? t : 0)) * (size_t)N;
+        const size_t rowoff = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner +
+                              (size_t)(in_range ? t : 0) * (size_t)ad.ldy;
 #pragma unroll 1
         for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
             uint32_t r[32];
@@ -309,25 +324,31 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
     return 0;
 }
 
+struct Operand {          // a bf16 hi/lo plane pair viewed as a 3-D tensor [d2][d1][d0] (d0 contiguous)
+    const void* hi;
+    const void* lo;
+    cuuint64_t d0, d1, d2;   // extents (elements)
+    cuuint64_t s1, s2;       // strides of d1 / d2 in elements
+};
+
 template <int BLOCK_N, int STAGES>
-static int launch(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const Epilogue& ep, int B, int T,
-                  int Cin, int N, int taps, cudaStream_t st) {
+static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin, int N,
+                  int taps, cudaStream_t st) {
     using S = Smem<BLOCK_N, STAGES>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    const cuuint64_t K = (cuuint64_t)taps * Cin;
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)B};
-        cuuint64_t str[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)T * Cin * 2};
+        cuuint64_t dims[3] = {A.d0, A.d1, A.d2};
+        cuuint64_t str[2] = {A.s1 * 2, A.s2 * 2};
         cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
-        if (int e = make_map(&ma_hi, x_hi, 3, dims, str, box, "x_hi")) return e;
-        if (int e = make_map(&ma_lo, x_lo, 3, dims, str, box, "x_lo")) return e;
+        if (int e = make_map(&ma_hi, A.hi, 3, dims, str, box, "a_hi")) return e;
+        if (int e = make_map(&ma_lo, A.lo, 3, dims, str, box, "a_lo")) return e;
     }
     {
-        cuuint64_t dims[2] = {K, (cuuint64_t)N};
-        cuuint64_t str[1] = {K * 2};
-        cuuint32_t box[2] = {BLOCK_K, BLOCK_N};
-        if (int e = make_map(&mb_hi, w_hi, 2, dims, str, box, "w_hi")) return e;
-        if (int e = make_map(&mb_lo, w_lo, 2, dims, str, box, "w_lo")) return e;
+        cuuint64_t dims[3] = {W.d0, W.d1, W.d2};
+        cuuint64_t str[2] = {W.s1 * 2, W.s2 * 2};
+        cuuint32_t box[3] = {BLOCK_K, BLOCK_N, 1};
+        if (int e = make_map(&mb_hi, W.hi, 3, dims, str, box, "w_hi")) return e;
+        if (int e = make_map(&mb_lo, W.lo, 3, dims, str, box, "w_lo")) return e;
     }
     auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES>;
     static bool configured = false;
@@ -339,9 +360,79 @@ static int launch(const void* x_hi, const void* x_lo, const void* w_hi, const vo
         configured = true;
     }
     const int tiles_per_utt = (T + BLOCK_M - 1) / BLOCK_M;
-    dim3 grid(B * tiles_per_utt, (N + BLOCK_N - 1) / BLOCK_N);
-    kern<<<grid, 192, S::TOTAL, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep, T, Cin, N, taps, tiles_per_utt);
+    dim3 grid(Z * tiles_per_utt, (N + BLOCK_N - 1) / BLOCK_N);
+    kern<<<grid, 192, S::TOTAL, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep, ad, T, Cin, N, taps, tiles_per_utt);
     return check_launch("gemm_bf16x3");
+}
+
+static int launch_auto(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin, int N,
+                       int taps, cudaStream_t st) {
+    if (N >= 512 && N % 256 == 0) return launch<256, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+    return launch<128, 3>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+}
+
+// ---- attention helpers: masked softmax over materialised scores, V transpose ----------------------------------------
+// S: [Z, T, Tp] fp32 (already scaled).  P planes: softmax over keys < len, zeros elsewhere (incl. the Tp padding).
+__global__ void softmax_planes_kernel(const float* __restrict__ S, const int64_t* __restrict__ lens, int H, int T, int Tp,
+                                      int rows, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // over Z*T
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int z = row / T;
+    const int t = row - z * T;
+    const int len = min((int)lens[z / H], T);
+    const float* s = S + (size_t)row * Tp;
+    __nv_bfloat16* oh = p_hi + (size_t)row * Tp;
+    __nv_bfloat16* ol = p_lo + (size_t)row * Tp;
+    if (t >= len) {
+        for (int j = lane * 4; j < Tp; j += 128) {
+            *reinterpret_cast<uint2*>(oh + j) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(ol + j) = make_uint2(0u, 0u);
+        }
+        return;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < len; j += 32) mx = fmaxf(mx, s[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < len; j += 32) sum += expf(s[j] - mx);
+    const float inv = 1.f / warp_sum(sum);
+    for (int j = lane * 4; j < Tp; j += 128) {
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float p = (j + e < len) ? expf(s[j + e] - mx) * inv : 0.f;
+            h[e] = __float2bfloat16_rn(p);
+            l[e] = __float2bfloat16_rn(p - __bfloat162float(h[e]));
+        }
+        *reinterpret_cast<uint2*>(oh + j) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(ol + j) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+// qkv planes [B, T, 3C] -> Vt planes [B*H, DH, Tp] (keys contiguous, zero padded): the K-major B operand of P.V
+__global__ void transpose_v_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restrict__ q_lo, int T,
+                                   int Tp, int C, int H, int DH, __nv_bfloat16* __restrict__ vt_hi,
+                                   __nv_bfloat16* __restrict__ vt_lo) {
+    __shared__ __nv_bfloat16 th[32][34], tl[32][34];
+    const int z = blockIdx.z, b = z / H, h = z % H;
+    const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int t = t0 + i;
+        const size_t src = ((size_t)b * T + t) * (size_t)(3 * C) + 2 * C + h * DH + d0 + tx;
+        th[i][tx] = (t < T) ? q_hi[src] : __float2bfloat16(0.f);
+        tl[i][tx] = (t < T) ? q_lo[src] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int d = d0 + i, t = t0 + tx;
+        if (t < Tp) {
+            const size_t dst = ((size_t)z * DH + d) * (size_t)Tp + t;
+            vt_hi[dst] = th[tx][i];
+            vt_lo[dst] = tl[tx][i];
+        }
+    }
 }
 
 }  // namespace ctts
@@ -362,7 +453,55 @@ extern "C" int ctts_gemm_bf16x3(const void* x_hi, const void* x_lo, const void* 
     CTTS_REQUIRE((((uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)w_hi | (uintptr_t)w_lo) & 15) == 0,
                  "gemm_bf16x3: operand planes must be 16-byte aligned");
     Epilogue ep{bias, col_scale, col_shift, residual, lens, y, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, alpha, act};
+    const cuuint64_t K = (cuuint64_t)taps * Cin;
+    Operand A{x_hi, x_lo, (cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)Cin, (cuuint64_t)T * Cin};
+    Operand W{w_hi, w_lo, K, (cuuint64_t)N, 1, K, K * (cuuint64_t)N};
+    Addr ad{1, 1, 0, 0, 0x7fffffff, 0, 0, 1, N, (long long)T * N, 0};
+    return launch_auto(A, W, ep, ad, B, T, Cin, N, taps, (cudaStream_t)stream);
+}
+
+extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, const int64_t* lens, int B, int T, int C,
+                                     int H, float scale, float* scores, void* p_hi, void* p_lo, void* vt_hi, void* vt_lo,
+                                     void* out_hi, void* out_lo, float* out_f32, void* stream) {
+    CTTS_REQUIRE(B > 0 && T > 0 && H > 0 && C % H == 0, "attention_bf16x3: bad shape B=%d T=%d C=%d H=%d", B, T, C, H);
+    const int DH = C / H;
+    CTTS_REQUIRE(DH % 64 == 0, "attention_bf16x3: head_dim %d must be a multiple of 64", DH);
+    CTTS_REQUIRE(lens && scores && p_hi && p_lo && vt_hi && vt_lo, "attention_bf16x3: NULL workspace");
+    CTTS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr) && (out_hi || out_f32), "attention_bf16x3: bad outputs");
     cudaStream_t st = (cudaStream_t)stream;
-    if (N >= 512 && N % 256 == 0) return launch<256, 2>(x_hi, x_lo, w_hi, w_lo, ep, B, T, Cin, N, taps, st);
-    return launch<128, 3>(x_hi, x_lo, w_hi, w_lo, ep, B, T, Cin, N, taps, st);
+    const int Tp = (T + 7) & ~7;
+    const int Z = B * H;
+    const cuuint64_t C3 = (cuuint64_t)3 * C;
+    // 1. S[z, t, s] = scale * q[z,t,:] . k[z,s,:]      (A = q columns, W = k columns of the same qkv planes)
+    {
+        Operand A{qkv_hi, qkv_lo, C3, (cuuint64_t)T, (cuuint64_t)B, C3, (cuuint64_t)T * C3};
+        Operand W = A;
+        Epilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, scores, nullptr, nullptr, scale, CTTS_ACT_NONE};
+        Addr ad{H, H, 0, DH, H, C, DH, 1, Tp, (long long)H * T * Tp, (long long)T * Tp};
+        if (int e = launch_auto(A, W, ep, ad, Z, T, DH, Tp, 1, st)) return e;
+    }
+    // 2. Vt planes
+    {
+        dim3 grid((Tp + 31) / 32, DH / 32, Z);
+        transpose_v_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv_hi, (const __nv_bfloat16*)qkv_lo, T, Tp, C, H, DH,
+                                                 (__nv_bfloat16*)vt_hi, (__nv_bfloat16*)vt_lo);
+        if (int e = check_launch("transpose_v")) return e;
+    }
+    // 3. P = softmax over keys < len of S, written as bf16 hi/lo planes
+    {
+        const int rows = Z * T;
+        softmax_planes_kernel<<<(rows + 7) / 8, 256, 0, st>>>(scores, lens, H, T, Tp, rows, (__nv_bfloat16*)p_hi,
+                                                             (__nv_bfloat16*)p_lo);
+        if (int e = check_launch("softmax_planes")) return e;
+    }
+    // 4. out[b, t, h*DH + d] = sum_s P[z,t,s] * Vt[z,d,s]; rows t >= len are zeroed
+    {
+        Operand A{p_hi, p_lo, (cuuint64_t)Tp, (cuuint64_t)T, (cuuint64_t)Z, (cuuint64_t)Tp, (cuuint64_t)T * Tp};
+        Operand W{vt_hi, vt_lo, (cuuint64_t)Tp, (cuuint64_t)DH, (cuuint64_t)Z, (cuuint64_t)Tp, (cuuint64_t)DH * Tp};
+        Epilogue ep{nullptr, nullptr, nullptr, nullptr, lens, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, 1.f,
+                    CTTS_ACT_NONE};
+        Addr ad{H, 1, 0, 0, 1, 0, 0, H, C, (long long)T * C, (long long)DH};
+        if (int e = launch_auto(A, W, ep, ad, Z, T, Tp, DH, 1, st)) return e;
+    }
+    return 0;
 }

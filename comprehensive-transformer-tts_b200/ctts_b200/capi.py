@@ -34,6 +34,7 @@ SIGNATURES = {
     "ctts_bucketize": [_P, _F, _P, _I, _I, _P, _P],
     "ctts_add_row_broadcast": [_P, _P, _I, _I, _I, _P, _P],
     "ctts_gemm_bf16x3": [_P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "ctts_attention_bf16x3": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "ctts_split_bf16": [_P, _Z, _P, _P, _P],
     "ctts_layernorm_split": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _P, _P, _P],
 }

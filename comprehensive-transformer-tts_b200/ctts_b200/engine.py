@@ -107,6 +107,24 @@ def attention(qkv, lens, n_head):
     return out
 
 
+def attention_tc(qkv_planes, lens, n_head):
+    """Tensor-core masked self-attention on bf16 hi/lo planes (ctts_attention_bf16x3); returns output planes."""
+    B, T, C3 = qkv_planes.shape
+    C = C3 // 3
+    dev = qkv_planes.hi.device
+    Tp = (T + 7) // 8 * 8
+    Z = B * n_head
+    scores = torch.empty(Z * T * Tp, device=dev, dtype=torch.float32)
+    p_hi = torch.empty(Z * T * Tp, device=dev, dtype=torch.bfloat16)
+    p_lo = torch.empty_like(p_hi)
+    vt_hi = torch.empty(B * C * Tp, device=dev, dtype=torch.bfloat16)
+    vt_lo = torch.empty_like(vt_hi)
+    out = Planes.empty(B, T, C, dev)
+    capi.call("ctts_attention_bf16x3", qkv_planes.hi, qkv_planes.lo, lens, B, T, C, n_head,
+              1.0 / math.sqrt(C // n_head), scores, p_hi, p_lo, vt_hi, vt_lo, out.hi, out.lo, None, _stream())
+    return out
+
+
 def pad_mask(lens, max_len):
     """utils/tools.py:188-196 (bool bookkeeping tensor handed back to the caller; True = padding)."""
     return torch.arange(int(max_len), device=lens.device)[None, :] >= lens[:, None]
@@ -227,9 +245,9 @@ def _fft_layers_fs2_tc(prep, P, pre, x, lens, n_layers, n_head, kernel, act):
     for i in range(n_layers):
         lp = "%slayers.%d.op." % (pre, i)
         _, hp = layernorm_planes(x, P[lp + "layer_norm1.weight"], P[lp + "layer_norm1.bias"], 1e-12)
-        qkv, _ = gemm_tc(hp, W[lp + "self_attn.in_proj_weight#planes"])
-        a = attention(qkv, lens, n_head)
-        gemm_tc(split_planes(a), W[lp + "self_attn.out_proj.weight#planes"], residual=x, lens=lens, out=x)
+        _, qkvp = gemm_tc(hp, W[lp + "self_attn.in_proj_weight#planes"], want_fp32=False, want_planes=True)
+        ap = attention_tc(qkvp, lens, n_head)
+        gemm_tc(ap, W[lp + "self_attn.out_proj.weight#planes"], residual=x, lens=lens, out=x)
         _, hp = layernorm_planes(x, P[lp + "layer_norm2.weight"], P[lp + "layer_norm2.bias"], 1e-12)
         _, fp = gemm_tc(hp, W[lp + "ffn.ffn_1.weight#planes"], P[lp + "ffn.ffn_1.bias"], alpha=kernel ** -0.5, act=act,
                         taps=kernel, want_fp32=False, want_planes=True)

@@ -30,8 +30,10 @@ def _attach(root, name, tensor, kind):
         node = nxt
     if kind == "buffer":
         node.register_buffer(parts[-1], tensor)
-    else:
-        node.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=(kind == "param")))
+        return tensor
+    param = tensor if isinstance(tensor, nn.Parameter) else nn.Parameter(tensor, requires_grad=(kind == "param"))
+    node.register_parameter(parts[-1], param)
+    return param
 
 
 def _initial(shape, init):
@@ -44,6 +46,20 @@ def _initial(shape, init):
         return torch.zeros(shape)
     if init == "normal01":
         return torch.randn(shape)
+    if init == "normal002":  # fastformer.py:285-290
+        return torch.randn(shape) * 0.02
+    if init == "emb1":
+        t = torch.randn(shape)
+        t[0] = 0
+        return t
+    if init == "sinusoid_interleaved":  # get_sinusoid_encoding_table, blocks.py:26-46
+        import numpy as np
+        _, rows, d = shape
+        pos = np.arange(rows, dtype=np.float64)[:, None]
+        tab = pos / np.power(10000, 2 * (np.arange(d)[None, :] // 2) / d)
+        tab[:, 0::2] = np.sin(tab[:, 0::2])
+        tab[:, 1::2] = np.cos(tab[:, 1::2])
+        return torch.FloatTensor(tab).unsqueeze(0)
     if init.startswith("linspace") or init.startswith("logspace"):
         _, lo, hi = init.split(":")
         if init.startswith("logspace"):
@@ -74,8 +90,12 @@ class CompTransTTS(nn.Module):
         self.model_config = model_config
         self.train_config = train_config
         entries, d_enc, d_dec = spec.parameter_spec(preprocess_config, model_config)
+        made = {}
         for name, shape, kind, init in entries:
-            _attach(self, name, _initial(shape, init), kind)
+            if init.startswith("tie:"):
+                _attach(self, name, made[init[4:]], kind)
+            else:
+                made[name] = _attach(self, name, _initial(shape, init), kind)
         self.d_encoder, self.d_decoder = d_enc, d_dec
         self.has_speaker_emb = bool(model_config["multi_speaker"])
         self.embedder_type = preprocess_config["preprocessing"].get("speaker_embedder", "none") \

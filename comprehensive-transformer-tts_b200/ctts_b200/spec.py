@@ -10,8 +10,9 @@ container modules (`module.py`); the forward pass never walks the tree, it reads
 Entry = (name, shape, kind, init):
   kind  "param" (trainable) | "frozen" (Parameter, requires_grad=False) | "buffer"
   init  "xavier[:gain]" | "default:<fan_in>" (torch's Conv/Linear default: U(+-1/sqrt(fan_in)))
-        | "emb:<dim>" (N(0, dim^-0.5), row 0 zero) | "ones" | "zeros" | "sinusoid" | "linspace:a:b"
-        | "normal01" | "count"
+        | "emb:<dim>" (N(0, dim^-0.5), row 0 zero) | "emb1" (N(0,1), row 0 zero: nn.Embedding(padding_idx=0))
+        | "ones" | "zeros" | "sinusoid_interleaved" | "linspace:a:b" | "normal01" | "normal002" | "count"
+        | "tie:<name>" (the same Parameter object as <name>)
 References: model/transformers/transformer_fs2.py:16-45,75-134,154-218,278-330;
 model/modules.py:78-138,726-861,1117-1174,1252-1298,1313-1341; model/CompTransTTS.py:34-62.
 """

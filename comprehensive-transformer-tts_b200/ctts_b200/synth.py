@@ -33,7 +33,21 @@ def synthetic_state_dict(spec_entries, seed=1234, pin_frames_per_phoneme=None):
     for name, shape, kind, init in spec_entries:
         g = _gen(name, seed)
         leaf = name.rsplit(".", 1)[-1]
-        if init == "count":
+        if init.startswith("tie:"):
+            t = out[init[4:]]
+        elif init == "sinusoid_interleaved":
+            _, rows, d = shape
+            pos = np.arange(rows, dtype=np.float64)[:, None]
+            tab = pos / np.power(10000, 2 * (np.arange(d)[None, :] // 2) / d)
+            tab[:, 0::2] = np.sin(tab[:, 0::2])
+            tab[:, 1::2] = np.cos(tab[:, 1::2])
+            t = torch.FloatTensor(tab).unsqueeze(0)
+        elif init == "emb1":
+            t = torch.randn(shape, generator=g) * 0.1
+            t[0] = 0
+        elif leaf in ("u_bias", "v_bias"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif init == "count":
             t = torch.zeros((), dtype=torch.long)
         elif init.startswith("linspace") or init.startswith("logspace"):
             _, lo, hi = init.split(":")
@@ -57,8 +71,6 @@ def synthetic_state_dict(spec_entries, seed=1234, pin_frames_per_phoneme=None):
             d = int(init.split(":")[1])
             t = torch.randn(shape, generator=g) * d ** -0.5
             t[0] = 0
-        elif init == "sinusoid":
-            t = None  # filled by the module (deterministic table)
         elif init == "normal01":
             t = torch.randn(shape, generator=g)
         else:  # dense / conv weights: variance-preserving

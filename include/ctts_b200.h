@@ -171,6 +171,19 @@ int ctts_gemm_bf16x3(const void* x_hi, const void* x_lo, const void* w_hi, const
                      const int64_t* lens, int B, int T, int Cin, int N, int taps, float* y, void* y_hi, void* y_lo,
                      void* stream);
 
+/* ---- tensor-core masked self-attention (decoder) ---------------------------------------------
+ * Same function as ctts_attention on bf16 hi/lo planes of qkv [B, T, 3C], head_dim % 64 == 0.  Four launches:
+ *   S = scale * q k^T      (tcgen05 bf16x3, batched over (b, head); scores [B*H, T, Tp] fp32, Tp = T rounded up to 8)
+ *   Vt = V^T planes        ([B*H, head_dim, Tp])
+ *   P = softmax over keys < lens[b] of S, as bf16 hi/lo planes (zeros for masked keys / padded query rows)
+ *   out = P V              (tcgen05 bf16x3) -> out_hi/out_lo planes [B, T, C] and/or out_f32; rows t >= lens[b] are zero
+ * Workspaces are the caller's: scores B*H*T*Tp floats, p_hi/p_lo B*H*T*Tp bf16 each, vt_hi/vt_lo B*C*Tp bf16 each.
+ * Replaces transformer_fs2.py:385-394 / transformer.py:233-252 on the decoder (downstream of every quantiser).
+ */
+int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, const int64_t* lens, int B, int T, int C, int H,
+                          float scale, float* scores, void* p_hi, void* p_lo, void* vt_hi, void* vt_lo, void* out_hi,
+                          void* out_lo, float* out_f32, void* stream);
+
 /* fp32 -> (bf16 hi, bf16 lo) with hi = rn(x), lo = rn(x - hi) */
 int ctts_split_bf16(const float* x, size_t n, void* hi, void* lo, void* stream);
 

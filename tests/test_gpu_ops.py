@@ -282,3 +282,25 @@ def test_gemm_bf16x3_full_size_linearity():
     assert (y12 - (y1 + y2)).abs().max().item() < 5e-4
     ref = engine.conv_gemm(x1, w, taps=taps)
     assert (y1 - ref).abs().max().item() < 5e-4
+
+
+@pytest.mark.parametrize("B,T,C,H", [(2, 128, 256, 2), (3, 300, 256, 2), (2, 273, 256, 2), (1, 70, 256, 4), (2, 801, 256, 2)])
+def test_attention_bf16x3(B, T, C, H):
+    """Tensor-core attention (materialised scores, bf16x3 GEMMs) against fp64 softmax attention."""
+    qkv = torch.randn(B, T, 3 * C, generator=g(50))
+    lens = torch.tensor([max(T - 31 * b, 1) for b in range(B)])
+    dh = C // H
+    q, k, v = qkv.double().split(C, -1)
+    q = q.view(B, T, H, dh).transpose(1, 2) / math.sqrt(dh)
+    k = k.view(B, T, H, dh).transpose(1, 2)
+    v = v.view(B, T, H, dh).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    pad = torch.arange(T)[None, :] >= lens[:, None]
+    s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, C)
+    ref = (ref * (~pad).double()[:, :, None]).float()
+    out = engine.attention_tc(engine.split_planes(qkv.to(DEV)), lens.to(DEV), H)
+    got = out.hi.float() + out.lo.float()
+    close(got, ref, atol=1e-4, rtol=1e-4)
+    # and against the FP32 CUDA-core kernel
+    close(got, engine.attention(qkv.to(DEV), lens.to(DEV), H), atol=1e-4, rtol=1e-4)
