@@ -40,11 +40,15 @@ __device__ __forceinline__ void warp_positions(int T, int* pos, FlagFn flag) {
 __global__ void embed_tokens_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ table,
                                     const float* __restrict__ pe, float scale, int S, int C, int vocab,
                                     float* __restrict__ x, float* __restrict__ word,
-                                    const int64_t* __restrict__ lens) {
+                                    const int64_t* __restrict__ lens, int pos_mode) {
     extern __shared__ int s_pos[];
     const int b = blockIdx.x;
     const int64_t* tok = tokens + (size_t)b * S;
-    if (threadIdx.x < 32) warp_positions(S, s_pos, [&](int t) { return tok[t] != 0; });
+    if (pos_mode == 0) {
+        if (threadIdx.x < 32) warp_positions(S, s_pos, [&](int t) { return tok[t] != 0; });
+    } else {
+        for (int t = threadIdx.x; t < S; t += blockDim.x) s_pos[t] = t;  // absolute positions (transformer.py:72-74)
+    }
     __syncthreads();
     const int c4 = C >> 2;
     const int len = lens ? (int)lens[b] : S;
@@ -63,13 +67,17 @@ __global__ void embed_tokens_kernel(const int64_t* __restrict__ tokens, const fl
 }
 
 __global__ void add_positions_kernel(float* __restrict__ x, const float* __restrict__ pe, const float* __restrict__ alpha,
-                                     const int64_t* __restrict__ lens, int T, int C) {
+                                     const int64_t* __restrict__ lens, int T, int C, int pos_mode) {
     extern __shared__ int s_pos[];
     const int b = blockIdx.x;
     float* xb = x + (size_t)b * T * C;
-    if (threadIdx.x < 32) warp_positions(T, s_pos, [&](int t) { return xb[(size_t)t * C] != 0.f; });
+    if (pos_mode == 0) {
+        if (threadIdx.x < 32) warp_positions(T, s_pos, [&](int t) { return xb[(size_t)t * C] != 0.f; });
+    } else {
+        for (int t = threadIdx.x; t < T; t += blockDim.x) s_pos[t] = t;
+    }
     __syncthreads();
-    const float a = alpha[0];
+    const float a = alpha ? alpha[0] : 1.f;
     const int len = lens ? (int)lens[b] : T;
     const int c4 = C >> 2;
     for (int i = threadIdx.x; i < T * c4; i += blockDim.x) {
@@ -155,20 +163,32 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // Tile 128 (t) x 64 (n) x 16 (k); 256 threads, 8x4 outputs per thread.
 constexpr int GM = 128, GN = 64, GK = 16, GPAD = 4;
 
+// Addressing of the FP32 GEMM.  z = blockIdx.z is the utterance (conv / linear) or a (batch, head) pair
+// (zo = z / mod, zh = z % mod) for the batched attention products of the conformer block.
+struct GAddr {
+    int mod;
+    long long x_so, x_sh; int x_ld;   // A row t:  x + zo*x_so + zh*x_sh + t*x_ld
+    long long w_so, w_sh; int w_ld;   // W row n:  w + zo*w_so + zh*w_sh + n*w_ld
+    long long y_so, y_sh; int y_ld;   // y row t:  y + zo*y_so + zh*y_sh + t*y_ld   (residual uses the same)
+    int lens_div;
+};
+
 __global__ void __launch_bounds__(256)
 conv1d_gemm_fp32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                         float alpha, const float* __restrict__ col_scale, const float* __restrict__ col_shift, int act,
                         const float* __restrict__ residual, const int64_t* __restrict__ lens, int T, int Cin, int N,
-                        int taps, float* __restrict__ y) {
+                        int taps, float* __restrict__ y, const GAddr ga) {
     __shared__ __align__(16) float As[2][GK][GM + GPAD];
     __shared__ __align__(16) float Bs[2][GK][GN + GPAD];
     const int b = blockIdx.z;
+    const int zo = b / ga.mod, zh = b - zo * ga.mod;
     const int t0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int pad = taps >> 1;
     const int K = taps * Cin;
-    const float* xb = x + (size_t)b * T * Cin;
+    const float* xb = x + (size_t)zo * ga.x_so + (size_t)zh * ga.x_sh;
+    const float* wb = w + (size_t)zo * ga.w_so + (size_t)zh * ga.w_sh;
 
     float acc[8][4];
 #pragma unroll
@@ -185,12 +205,12 @@ conv1d_gemm_fp32_kernel(const float* __restrict__ x, const float* __restrict__ w
             const int m = l >> 2, kq = l & 3;
             const int t = t0 + m + tap - pad;
             ra[it] = (t >= 0 && t < T && (t0 + m) < T)
-                         ? *reinterpret_cast<const float4*>(xb + (size_t)t * Cin + c0 + kq * 4)
+                         ? *reinterpret_cast<const float4*>(xb + (size_t)t * ga.x_ld + c0 + kq * 4)
                          : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         {
             const int n = tid >> 2, kq = tid & 3;
-            rb = (n0 + n < N) ? *reinterpret_cast<const float4*>(w + (size_t)(n0 + n) * K + kk + kq * 4)
+            rb = (n0 + n < N) ? *reinterpret_cast<const float4*>(wb + (size_t)(n0 + n) * ga.w_ld + kk + kq * 4)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
@@ -237,12 +257,12 @@ conv1d_gemm_fp32_kernel(const float* __restrict__ x, const float* __restrict__ w
         }
     }
 
-    const int len = lens ? (int)lens[b] : T;
+    const int len = lens ? (int)lens[b / ga.lens_div] : T;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int t = t0 + ty * 8 + i;
         if (t >= T) continue;
-        const size_t row = ((size_t)b * T + t) * N;
+        const size_t row = (size_t)zo * ga.y_so + (size_t)zh * ga.y_sh + (size_t)t * ga.y_ld;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
@@ -596,6 +616,150 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, size_t n, __nv_bf
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fastformer additive-attention pooling (fastformer.py:308-322 and 326-336):
+//   s[t,h]  = logits[b,t,h] / sqrt(hs) + (t < len ? -10000 : 0)      (the reference's INVERTED mask, quirk 1)
+//   w       = softmax_t(s);   pooled[b, h*hs + e] = sum_t w[t,h] * values[b,t,h*hs+e]
+// grid (B, Hh/32), 256 threads = 32 heads x 8 time lanes.
+__global__ void __launch_bounds__(256)
+fastformer_pool_kernel(const float* __restrict__ logits, const float* __restrict__ values, const int64_t* __restrict__ lens,
+                       int T, int Hh, int hs, float div, float* __restrict__ pooled) {
+    __shared__ float red[8][32];
+    __shared__ float red2[8][32][4];
+    const int b = blockIdx.x;
+    const int hl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+    const int h = blockIdx.y * 32 + hl;
+    const bool hv = h < Hh;
+    const int len = min((int)lens[b], T);
+    const float* lg = logits + (size_t)b * T * Hh;
+    const float* vl = values + (size_t)b * T * Hh * hs;
+    float mx = -INFINITY;
+    if (hv)
+        for (int t = tl; t < T; t += 8) mx = fmaxf(mx, lg[(size_t)t * Hh + h] / div + (t < len ? -10000.f : 0.f));
+    red[tl][hl] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx = fmaxf(mx, red[i][hl]);
+    __syncthreads();
+    float sum = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (hv)
+        for (int t = tl; t < T; t += 8) {
+            const float e = expf(lg[(size_t)t * Hh + h] / div + (t < len ? -10000.f : 0.f) - mx);
+            sum += e;
+            for (int k = 0; k < hs; ++k) acc[k] += e * vl[((size_t)t * Hh + h) * hs + k];
+        }
+    red[tl][hl] = sum;
+    for (int k = 0; k < 4; ++k) red2[tl][hl][k] = acc[k];
+    __syncthreads();
+    if (tl == 0 && hv) {
+        float s = 0.f, a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 8; ++i) {
+            s += red[i][hl];
+            for (int k = 0; k < 4; ++k) a[k] += red2[i][hl][k];
+        }
+        for (int k = 0; k < hs; ++k) pooled[(size_t)b * Hh * hs + h * hs + k] = a[k] / s;
+    }
+}
+
+// y = op(a, b) [masked]: op 0: a + b, op 1: a * b ; b is either full-size or one row per batch element (b_rowwise)
+__global__ void binary_kernel(const float* __restrict__ a, const float* __restrict__ bb, int op, int b_rowwise,
+                              const int64_t* __restrict__ lens, int T, int C, size_t total4, float* __restrict__ y) {
+    const int c4 = C >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t tok = i / c4;
+        const int c = (int)(i - tok * c4);
+        const size_t bi = tok / T;
+        const int t = (int)(tok - bi * T);
+        float4 v = reinterpret_cast<const float4*>(a)[i];
+        const float4 r = b_rowwise ? reinterpret_cast<const float4*>(bb + bi * C)[c] : reinterpret_cast<const float4*>(bb)[i];
+        if (op == 0) { v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        else { v.x *= r.x; v.y *= r.y; v.z *= r.z; v.w *= r.w; }
+        if (lens && t >= (int)lens[bi]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conformer convolution module, elementwise part (conformer.py:459-469):
+//   glu:   g[b,t,c] = h[b,t,c] * sigmoid(h[b,t,C+c])                         (GLU over the channel dim, blocks.py:123-134)
+//   dwconv: y[b,t,c] = swish( BN( sum_j g[b,t+j-K/2,c] * w[c,j] ) )          (depthwise k=31 'same', eval BatchNorm folded)
+__global__ void glu_kernel(const float* __restrict__ h, int C, size_t rows, float* __restrict__ g) {
+    const size_t total = rows * (size_t)C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / C;
+        const int c = (int)(i - r * C);
+        const float a = h[r * 2 * C + c], gate = h[r * 2 * C + C + c];
+        g[i] = a * (1.f / (1.f + expf(-gate)));
+    }
+}
+
+__global__ void dwconv_bn_swish_kernel(const float* __restrict__ g, const float* __restrict__ w, int K,
+                                       const float* __restrict__ scale, const float* __restrict__ shift, int T, int C,
+                                       float* __restrict__ y) {
+    const int b = blockIdx.z, t = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float* gb = g + (size_t)b * T * C;
+    float acc = 0.f;
+    const int pad = K >> 1;
+    for (int j = 0; j < K; ++j) {
+        const int tt = t + j - pad;
+        if (tt >= 0 && tt < T) acc = fmaf(gb[(size_t)tt * C + c], w[c * K + j], acc);
+    }
+    const float v = acc * scale[c] + shift[c];
+    y[((size_t)b * T + t) * C + c] = v / (1.f + expf(-v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conformer relative-position attention, score assembly (conformer.py:405-431):
+//   score[z,i,j] = (content[z,i,j] + shift(pos)[z,i,j]) / sqrt(d_model);  P = softmax_j(score)  (NO padding mask, quirk 2)
+//   shift(pos)[i,j] = j <= i ? pos[i, T-1-i+j] : (j == i+1 ? 0 : pos[i+1, j-i-2])     (zero-pad + view trick of :423-431)
+// One warp per (z, i) row; P is written with row stride ldp (>= T, zero padded) so that it can feed the P.V GEMM.
+__global__ void relshift_softmax_kernel(const float* __restrict__ content, const float* __restrict__ pos, int T, int ldp,
+                                        float sqrt_dim, size_t rows, float* __restrict__ P) {
+    const size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const size_t z = row / T;
+    const int i = (int)(row - z * T);
+    const float* cz = content + row * (size_t)T;
+    const float* pz = pos + z * (size_t)T * T;
+    float* out = P + row * (size_t)ldp;
+    auto score = [&](int j) {
+        float p;
+        if (j <= i) p = pz[(size_t)i * T + (T - 1 - i + j)];
+        else if (j == i + 1) p = 0.f;
+        else p = pz[(size_t)(i + 1) * T + (j - i - 2)];
+        return (cz[j] + p) / sqrt_dim;
+    };
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, score(j));
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) sum += expf(score(j) - mx);
+    const float inv = 1.f / warp_sum(sum);
+    for (int j = lane; j < ldp; j += 32) out[j] = (j < T) ? expf(score(j) - mx) * inv : 0.f;
+}
+
+// x [B, T, ld_in] (channel offset c0, heads of DH) -> xt [B*H, DH, ldt] (time contiguous, zero padded)
+__global__ void transpose_heads_kernel(const float* __restrict__ x, int T, int ld_in, int c0, int H, int DH, int ldt,
+                                       float* __restrict__ xt) {
+    __shared__ float tile[32][33];
+    const int z = blockIdx.z, b = z / H, h = z % H;
+    const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int t = t0 + i, d = d0 + tx;
+        tile[i][tx] = (t < T && d < DH) ? x[((size_t)b * T + t) * ld_in + c0 + h * DH + d] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int d = d0 + i, t = t0 + tx;
+        if (d < DH && t < ldt) xt[((size_t)z * DH + d) * ldt + t] = tile[tx][i];
+    }
+}
+
 }  // namespace ctts
 
 // =============================================================================================
@@ -627,24 +791,26 @@ int ctts_device_arch(void) {
 }
 
 int ctts_embed_tokens(const int64_t* tokens, const float* table, const float* pe, int pe_rows, float embed_scale,
-                      int B, int S, int C, int vocab, float* x, float* word, const int64_t* lens, void* stream) {
+                      int B, int S, int C, int vocab, float* x, float* word, const int64_t* lens, int pos_mode,
+                      void* stream) {
     CTTS_REQUIRE(B > 0 && S > 0 && C % 4 == 0, "embed_tokens: bad shape B=%d S=%d C=%d", B, S, C);
-    CTTS_REQUIRE(pe_rows > S, "embed_tokens: positional table has %d rows, need > %d", pe_rows, S);
+    CTTS_REQUIRE(pe_rows > S - (pos_mode ? 1 : 0), "embed_tokens: positional table has %d rows, need > %d", pe_rows, S);
     CTTS_REQUIRE((size_t)S * 4 <= 200 * 1024, "embed_tokens: S=%d too long", S);
     const size_t sm = (size_t)S * sizeof(int);
     if (sm > 48 * 1024) cudaFuncSetAttribute(embed_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    embed_tokens_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(tokens, table, pe, embed_scale, S, C, vocab, x, word, lens);
+    embed_tokens_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(tokens, table, pe, embed_scale, S, C, vocab, x, word, lens,
+                                                              pos_mode);
     return check_launch("embed_tokens");
 }
 
 int ctts_add_positions(float* x, const float* pe, int pe_rows, const float* alpha, const int64_t* lens, int B, int T,
-                       int C, void* stream) {
+                       int C, int pos_mode, void* stream) {
     CTTS_REQUIRE(B > 0 && T > 0 && C % 4 == 0, "add_positions: bad shape B=%d T=%d C=%d", B, T, C);
-    CTTS_REQUIRE(pe_rows > T, "add_positions: positional table has %d rows, need > %d", pe_rows, T);
+    CTTS_REQUIRE(pe_rows > T - (pos_mode ? 1 : 0), "add_positions: positional table has %d rows, need > %d", pe_rows, T);
     CTTS_REQUIRE((size_t)T * 4 <= 200 * 1024, "add_positions: T=%d too long", T);
     const size_t sm = (size_t)T * sizeof(int);
     if (sm > 48 * 1024) cudaFuncSetAttribute(add_positions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    add_positions_kernel<<<B, 512, sm, (cudaStream_t)stream>>>(x, pe, alpha, lens, T, C);
+    add_positions_kernel<<<B, 512, sm, (cudaStream_t)stream>>>(x, pe, alpha, lens, T, C, pos_mode);
     return check_launch("add_positions");
 }
 
@@ -683,9 +849,24 @@ int ctts_conv1d_gemm(const float* x, const float* w, const float* bias, float al
     CTTS_REQUIRE(Cin % 16 == 0, "conv1d_gemm: Cin=%d must be a multiple of 16", Cin);
     CTTS_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), "conv1d_gemm: col_scale/col_shift must come together");
     dim3 grid((T + GM - 1) / GM, (N + GN - 1) / GN, B);
+    const GAddr ga{1, (long long)T * Cin, 0, Cin, 0, 0, taps * Cin, (long long)T * N, 0, N, 1};
     conv1d_gemm_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, alpha, col_scale, col_shift, act,
-                                                                    residual, lens, T, Cin, N, taps, y);
+                                                                    residual, lens, T, Cin, N, taps, y, ga);
     return check_launch("conv1d_gemm");
+}
+
+int ctts_batched_gemm_fp32(const float* x, const float* w, float alpha, const int64_t* lens, int lens_div, int Z, int mod,
+                           int T, int K, int N, long long x_so, long long x_sh, int x_ld, long long w_so, long long w_sh,
+                           int w_ld, long long y_so, long long y_sh, int y_ld, float* y, void* stream) {
+    CTTS_REQUIRE(Z > 0 && mod > 0 && T > 0 && N > 0 && K > 0 && K % 16 == 0, "batched_gemm_fp32: bad shape Z=%d T=%d K=%d N=%d",
+                 Z, T, K, N);
+    CTTS_REQUIRE(x_ld % 4 == 0 && w_ld % 4 == 0 && x_so % 4 == 0 && x_sh % 4 == 0 && w_so % 4 == 0 && w_sh % 4 == 0,
+                 "batched_gemm_fp32: operand strides must be multiples of 4 floats");
+    dim3 grid((T + GM - 1) / GM, (N + GN - 1) / GN, Z);
+    const GAddr ga{mod, x_so, x_sh, x_ld, w_so, w_sh, w_ld, y_so, y_sh, y_ld, lens_div > 0 ? lens_div : 1};
+    conv1d_gemm_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, nullptr, alpha, nullptr, nullptr, CTTS_ACT_NONE,
+                                                                    nullptr, lens, T, K, N, 1, y, ga);
+    return check_launch("batched_gemm_fp32");
 }
 
 int ctts_pack_conv_weight(const float* w, int N, int Cin, int taps, float* packed, void* stream) {
@@ -783,6 +964,59 @@ int ctts_split_bf16(const float* x, size_t n, void* hi, void* lo, void* stream) 
     const int grid = (int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192);
     split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
     return check_launch("split_bf16");
+}
+
+int ctts_fastformer_pool(const float* logits, const float* values, const int64_t* lens, int B, int T, int heads, int head_size,
+                         float* pooled, void* stream) {
+    CTTS_REQUIRE(B > 0 && T > 0 && heads > 0 && head_size >= 1 && head_size <= 4, "fastformer_pool: bad shape heads=%d hs=%d",
+                 heads, head_size);
+    CTTS_REQUIRE(lens != nullptr, "fastformer_pool: lens is NULL");
+    dim3 grid(B, (heads + 31) / 32);
+    // the reference divides by python's attention_head_size ** 0.5 (fastformer.py:310,328)
+    fastformer_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, values, lens, T, heads, head_size,
+                                                                   (float)sqrt((double)head_size), pooled);
+    return check_launch("fastformer_pool");
+}
+
+int ctts_binary(const float* a, const float* b, int op, int b_rowwise, const int64_t* lens, int B, int T, int C, float* y,
+                void* stream) {
+    CTTS_REQUIRE(C % 4 == 0 && B > 0 && T > 0 && (op == 0 || op == 1), "binary: bad arguments");
+    const size_t total4 = (size_t)B * T * (C / 4);
+    const int grid = (int)((total4 + 255) / 256 < 8192 ? (total4 + 255) / 256 : 8192);
+    binary_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, op, b_rowwise, lens, T, C, total4, y);
+    return check_launch("binary");
+}
+
+int ctts_glu(const float* h, int rows, int C, float* g, void* stream) {
+    CTTS_REQUIRE(rows > 0 && C > 0, "glu: bad shape");
+    const size_t total = (size_t)rows * C;
+    const int grid = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
+    glu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, C, (size_t)rows, g);
+    return check_launch("glu");
+}
+
+int ctts_dwconv_bn_swish(const float* g, const float* w, int K, const float* scale, const float* shift, int B, int T, int C,
+                         float* y, void* stream) {
+    CTTS_REQUIRE(B > 0 && T > 0 && C > 0 && (K & 1), "dwconv_bn_swish: bad shape");
+    dim3 grid((C + 127) / 128, T, B);
+    dwconv_bn_swish_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(g, w, K, scale, shift, T, C, y);
+    return check_launch("dwconv_bn_swish");
+}
+
+int ctts_relshift_softmax(const float* content, const float* pos, int Z, int T, int ldp, float sqrt_dim, float* P,
+                          void* stream) {
+    CTTS_REQUIRE(Z > 0 && T > 0 && ldp >= T, "relshift_softmax: bad shape");
+    const size_t rows = (size_t)Z * T;
+    relshift_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(content, pos, T, ldp, sqrt_dim, rows,
+                                                                                        P);
+    return check_launch("relshift_softmax");
+}
+
+int ctts_transpose_heads(const float* x, int B, int T, int ld_in, int c0, int H, int DH, int ldt, float* xt, void* stream) {
+    CTTS_REQUIRE(B > 0 && T > 0 && H > 0 && DH > 0 && ldt >= T, "transpose_heads: bad shape");
+    dim3 grid((ldt + 31) / 32, (DH + 31) / 32, B * H);
+    transpose_heads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, T, ld_in, c0, H, DH, ldt, xt);
+    return check_launch("transpose_heads");
 }
 
 }  // extern "C"

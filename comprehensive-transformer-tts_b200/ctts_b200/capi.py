@@ -12,15 +12,15 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libctts_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SWISH = 0, 1, 2, 3, 4
 
-_P, _I, _F, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_P, _I, _F, _Z, _L = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
 
 # name -> argtypes, in the order of include/ctts_b200.h (restype is int unless noted)
 SIGNATURES = {
     "ctts_abi_version": [],
     "ctts_last_error": [],
     "ctts_device_arch": [],
-    "ctts_embed_tokens": [_P, _P, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P, _P],
-    "ctts_add_positions": [_P, _P, _I, _P, _P, _I, _I, _I, _P],
+    "ctts_embed_tokens": [_P, _P, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P, _I, _P],
+    "ctts_add_positions": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "ctts_layernorm": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _P],
     "ctts_conv1d_gemm": [_P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "ctts_pack_conv_weight": [_P, _I, _I, _I, _P, _P],
@@ -33,6 +33,13 @@ SIGNATURES = {
     "ctts_gather_add": [_P, _P, _I, _I, _I, _P, _P],
     "ctts_bucketize": [_P, _F, _P, _I, _I, _P, _P],
     "ctts_add_row_broadcast": [_P, _P, _I, _I, _I, _P, _P],
+    "ctts_batched_gemm_fp32": [_P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _L, _L, _I, _L, _L, _I, _L, _L, _I, _P, _P],
+    "ctts_fastformer_pool": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "ctts_binary": [_P, _P, _I, _I, _P, _I, _I, _I, _P, _P],
+    "ctts_glu": [_P, _I, _I, _P, _P],
+    "ctts_dwconv_bn_swish": [_P, _P, _I, _P, _P, _I, _I, _I, _P, _P],
+    "ctts_relshift_softmax": [_P, _P, _I, _I, _I, _F, _P, _P],
+    "ctts_transpose_heads": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "ctts_gemm_bf16x3": [_P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ctts_attention_bf16x3": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "ctts_split_bf16": [_P, _Z, _P, _P, _P],

@@ -179,9 +179,13 @@ class Prepared:
                 for name, t in P.items():
                     if not (name.startswith("decoder.") or name.startswith("postnet.") or name.startswith("mel_linear.")):
                         continue
-                    if name.endswith("weight") and t.dim() in (2, 3):
+                    if name.endswith("weight") and t.dim() in (2, 3) and t.shape[1] != 1:
                         src = self.w[name] if t.dim() == 3 else _f32(t)
                         self.w[name + "#planes"] = split_planes(src)
+            block = self.module.model_config["block_type"]
+            if block != "transformer_fs2":
+                from . import engine_blocks
+                engine_blocks.PREPARE[block](self, P, self.module.decoder_math == "bf16x3")
             self.w["cwt_scale_w"] = ((torch.arange(0, 10).float() + 1 + 2.5) ** (-2.5)).to(
                 next(iter(P.values())).device)  # utils/pitch_tools.py:260
 
@@ -231,7 +235,7 @@ def encoder_fs2(prep, P, cfg, tokens, src_lens):
     x = torch.empty(B, S, C, device=tokens.device, dtype=torch.float32)
     word = torch.empty_like(x)
     capi.call("ctts_embed_tokens", tokens, table, pe, pe.shape[0], math.sqrt(C), B, S, C, table.shape[0], x, word,
-              src_lens, _stream())
+              src_lens, 0, _stream())
     act = _ACTS[cfg["variance_predictor"]["ffn_act"]]
     x = _fft_layers_fs2(prep, P, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"], c["ffn_kernel_size"],
                         act)
@@ -261,7 +265,7 @@ def decoder_fs2(prep, P, cfg, x, mel_lens, math="fp32"):
     c = cfg["transformer_fs2"]
     B, T, C = x.shape
     pe = prep.table_fs2(C, T + 1, x.device)
-    capi.call("ctts_add_positions", x, pe, pe.shape[0], P["decoder.pos_embed_alpha"], mel_lens, B, T, C, _stream())
+    capi.call("ctts_add_positions", x, pe, pe.shape[0], P["decoder.pos_embed_alpha"], mel_lens, B, T, C, 0, _stream())
     act = _ACTS[cfg["variance_predictor"]["ffn_act"]]
     if math == "bf16x3":
         return _fft_layers_fs2_tc(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
@@ -296,7 +300,7 @@ def pitch_style_predictor(prep, P, cfg, pre, xs, alpha=1.0):
     vp = cfg["variance_predictor"]
     B, T, C = xs.shape
     pe = prep.table_fs2(C, T + 1, xs.device)
-    capi.call("ctts_add_positions", xs, pe, pe.shape[0], P[pre + "pos_embed_alpha"], None, B, T, C, _stream())
+    capi.call("ctts_add_positions", xs, pe, pe.shape[0], P[pre + "pos_embed_alpha"], None, B, T, C, 0, _stream())
     h = _predictor_stack(prep, P, pre, xs, vp["predictor_layers"], vp["predictor_kernel"], None)
     return conv_gemm(h, P[pre + "linear.weight"], P[pre + "linear.bias"], alpha=alpha)
 
@@ -459,9 +463,13 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         mel_lens = _i64(mel_lens)
         mel_masks = pad_mask(mel_lens, max_mel_len)
     block = cfg["block_type"]
-    if block != "transformer_fs2":
-        raise NotImplementedError("block_type %r: kernels not built yet" % block)
-    enc, word = encoder_fs2(prep, P, cfg, texts, src_lens)
+    if block == "transformer_fs2":
+        enc, word = encoder_fs2(prep, P, cfg, texts, src_lens)
+    else:
+        from . import engine_blocks
+        if block not in engine_blocks.ENCODERS:
+            raise NotImplementedError("block_type %r: kernels not built yet" % block)
+        enc, word = engine_blocks.ENCODERS[block](prep, P, cfg, texts, src_lens)
 
     spk = None
     if module.has_speaker_emb:
@@ -477,7 +485,12 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, enc, word, src_lens, src_masks, mels, mel_lens, mel_masks,
                          max_mel_len, p_targets, e_targets, d_targets, attn_priors, p_control, e_control, d_control,
                          step)
-    dec, dec_planes = decoder_fs2(prep, P, cfg, x, mel_lens, module.decoder_math)
+    if block == "transformer_fs2":
+        dec, dec_planes = decoder_fs2(prep, P, cfg, x, mel_lens, module.decoder_math)
+    else:
+        dec, dec_planes = engine_blocks.DECODERS[block](prep, P, cfg, x, mel_lens, module.decoder_math)
+        if module.decoder_math == "bf16x3" and dec_planes is None:
+            dec_planes = split_planes(dec)
     mel, post = mel_head(prep, P, dec, dec_planes)
     return (mel, post, p_pred, e_pred, log_d, d_rounded, src_masks, mel_masks, src_lens, mel_lens, attn_outs, prosody,
             p_targets, e_targets)

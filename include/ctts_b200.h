@@ -50,19 +50,23 @@ int ctts_device_arch(void);
  *   pos[b,s]  = (# of non-zero tokens in tokens[b,0..s]) if tokens[b,s] != 0 else 0
  *   word      = embed_scale * table[tokens]
  *   x         = (word + pe[pos]) * keep          (keep: s < lens[b]; FFTBlocks.forward :60; lens may be NULL)
+ * pos_mode 0: as above (fs2).  pos_mode 1: pos[b,s] = s (absolute; transformer.py:72-74, fastformer.py:62-64,
+ * conformer.py:82-84 with embed_scale 1 and the interleaved sin/cos table).
  * pe is the [pe_rows, C] sinusoid table (row 0 = zeros); pe_rows must be > S.  `word` is not masked
  * (it is the reference's second return value, consumed by the aligner).
  */
 int ctts_embed_tokens(const int64_t* tokens, const float* table, const float* pe, int pe_rows, float embed_scale,
-                      int B, int S, int C, int vocab, float* x, float* word, const int64_t* lens, void* stream);
+                      int B, int S, int C, int vocab, float* x, float* word, const int64_t* lens, int pos_mode,
+                      void* stream);
 
 /* ---- x = (x + alpha * pe[pos(x[..., 0] != 0)]) [* keep] -----------------------------------------
  * FFTBlocks.forward transformer_fs2.py:54-60 (decoder positions) and PitchPredictor.forward
  * modules.py:1349-1350.  `alpha` is a device scalar (the learnable pos_embed_alpha).  If lens != NULL
  * rows t >= lens[b] are zeroed afterwards (the `* nonpadding_mask_TB` of :60).  In place.
+ * pos_mode 1: pos = t (absolute table rows, transformer.py:137-141); alpha may then be NULL (= 1).
  */
 int ctts_add_positions(float* x, const float* pe, int pe_rows, const float* alpha, const int64_t* lens, int B, int T,
-                       int C, void* stream);
+                       int C, int pos_mode, void* stream);
 
 /* ---- y = LayerNorm_C(x) * gamma + beta [* keep] -------------------------------------------
  * blocks.py:137-156 (eps 1e-12), transformer_fs2.py:41,65-66 (final nn.LayerNorm eps 1e-5).
@@ -155,6 +159,46 @@ int ctts_bucketize(const float* v, float v_scale, const float* bins, int n_bins,
 
 /* y = x + spk[b] broadcast over T (modules.py:985-988) */
 int ctts_add_row_broadcast(const float* x, const float* row, int B, int T, int C, float* y, void* stream);
+
+/* ---- FP32 batched GEMM with explicit strides (conformer attention products) ------------
+ *   y[zo,zh][t, n] = alpha * sum_k x[zo,zh][t, k] * w[zo,zh][n, k]        z = zo*mod + zh in [0, Z)
+ * row pointers: x + zo*x_so + zh*x_sh + t*x_ld, w + zo*w_so + zh*w_sh + n*w_ld, y + zo*y_so + zh*y_sh + t*y_ld.
+ * K % 16 == 0.  lens (nullable): rows t >= lens[z / lens_div] are written as zeros.
+ */
+int ctts_batched_gemm_fp32(const float* x, const float* w, float alpha, const int64_t* lens, int lens_div, int Z, int mod,
+                           int T, int K, int N, long long x_so, long long x_sh, int x_ld, long long w_so, long long w_sh,
+                           int w_ld, long long y_so, long long y_sh, int y_ld, float* y, void* stream);
+
+/* ---- fastformer additive attention pooling (fastformer.py:308-322, 326-336) ------------------------
+ *   s[t,h] = logits[b,t,h] / sqrt(head_size) + (t < lens[b] ? -10000 : 0)   -- the reference's inverted mask is kept
+ *   pooled[b, h*head_size + e] = sum_t softmax_t(s)[t,h] * values[b, t, h*head_size + e]
+ * logits [B,T,heads], values [B,T,heads*head_size], pooled [B, heads*head_size]; head_size <= 4.
+ */
+int ctts_fastformer_pool(const float* logits, const float* values, const int64_t* lens, int B, int T, int heads, int head_size,
+                         float* pooled, void* stream);
+
+/* y = a (+|*) b, optionally pad-masked.  op 0 add, 1 multiply; b_rowwise: b is [B, C] broadcast over T. */
+int ctts_binary(const float* a, const float* b, int op, int b_rowwise, const int64_t* lens, int B, int T, int C, float* y,
+                void* stream);
+
+/* ---- conformer convolution module, elementwise stages (conformer.py:459-469) -----------------------
+ * ctts_glu:            g[r, c] = h[r, c] * sigmoid(h[r, C + c])                    h: [rows, 2C]
+ * ctts_dwconv_bn_swish y[b,t,c] = swish(scale[c] * sum_j g[b,t+j-K/2,c] w[c,j] + shift[c])   (eval BatchNorm1d folded)
+ */
+int ctts_glu(const float* h, int rows, int C, float* g, void* stream);
+int ctts_dwconv_bn_swish(const float* g, const float* w, int K, const float* scale, const float* shift, int B, int T, int C,
+                         float* y, void* stream);
+
+/* ---- conformer relative-position attention, score assembly (conformer.py:405-431) ------------------
+ *   P[z,i,:] = softmax_j( (content[z,i,j] + shift(pos)[z,i,j]) / sqrt_dim )   -- no padding mask (quirk kept)
+ *   shift(pos)[i,j] = j <= i ? pos[i, T-1-i+j] : (j == i+1 ? 0 : pos[i+1, j-i-2])
+ * content, pos: [Z, T, T]; P: [Z, T, ldp] (zero padded up to ldp).
+ */
+int ctts_relshift_softmax(const float* content, const float* pos, int Z, int T, int ldp, float sqrt_dim, float* P,
+                          void* stream);
+
+/* x[b, t, c0 + h*DH + d] -> xt[(b*H + h), d, t]  (row stride ldt >= T, zero padded): K-major operand for P.V */
+int ctts_transpose_heads(const float* x, int B, int T, int ld_in, int c0, int H, int DH, int ldt, float* xt, void* stream);
 
 /* ---- tcgen05 tensor-core GEMM (the decoder / PostNet engine) ---------------------------------
  * Same contract as ctts_conv1d_gemm but the operands are bf16 hi/lo planes:

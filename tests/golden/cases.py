@@ -12,6 +12,19 @@ CASES = {
     # supervised / teacher-forced branch (modules.py:1054-1057): explicit durations U[1,15], pitch / energy targets
     "fs2_teacher": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="teacher",
                         batch=3, s_max=40, s_step=7, pin=None, seed=1),
+    # post-LN "transformer" block (model/transformers/transformer.py): free-running and teacher-forced
+    "transformer_infer": dict(dataset="LJSpeech", block_type="transformer", learn_alignment=False, mode="infer",
+                              batch=2, s_max=60, s_step=11, pin=4, seed=2),
+    "transformer_teacher": dict(dataset="LJSpeech", block_type="transformer", learn_alignment=False, mode="teacher",
+                                batch=2, s_max=30, s_step=7, pin=None, seed=3),
+    # fastformer (additive attention with the reference's inverted mask; padded AND unpadded utterances in one batch)
+    "fastformer_infer": dict(dataset="LJSpeech", block_type="fastformer", learn_alignment=False, mode="infer",
+                             batch=2, s_max=60, s_step=11, pin=4, seed=4),
+    # conformer (relative-position attention without padding mask, GLU + depthwise conv + BatchNorm + Swish)
+    "conformer_infer": dict(dataset="LJSpeech", block_type="conformer", learn_alignment=False, mode="infer",
+                            batch=2, s_max=60, s_step=11, pin=4, seed=5),
+    "conformer_teacher": dict(dataset="LJSpeech", block_type="conformer", learn_alignment=False, mode="teacher",
+                              batch=2, s_max=30, s_step=7, pin=None, seed=6),
 }
 
 TAP_STRIDE = 4  # intermediate activations are stored for every 4th row only

@@ -114,7 +114,7 @@ def test_embed_and_positions():
     x = torch.empty(B, S, C, device=DEV)
     word = torch.empty(B, S, C, device=DEV)
     capi.call("ctts_embed_tokens", tok.to(DEV), table.to(DEV), pe.to(DEV), 2048, 16.0, B, S, C, V, x, word,
-              lens.to(DEV), stream())
+              lens.to(DEV), 0, stream())
     w_ref = 16.0 * F.embedding(tok, table)
     x_ref = (w_ref + O.fs2_positional(tok, C, 1000)) * (torch.arange(S)[None] < lens[:, None]).float()[:, :, None]
     close(word, w_ref, atol=1e-6)
@@ -125,7 +125,7 @@ def test_embed_and_positions():
     alpha = torch.tensor([0.73])
     ref = (h + alpha * O.fs2_positional(h[..., 0], C, 2000)) * (torch.arange(S)[None] < lens[:, None]).float()[:, :, None]
     hd = h.to(DEV).clone()
-    capi.call("ctts_add_positions", hd, pe.to(DEV), 2048, alpha.to(DEV), lens.to(DEV), B, S, C, stream())
+    capi.call("ctts_add_positions", hd, pe.to(DEV), 2048, alpha.to(DEV), lens.to(DEV), B, S, C, 0, stream())
     close(hd, ref, atol=1e-6)
 
 
