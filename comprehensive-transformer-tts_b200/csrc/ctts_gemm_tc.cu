@@ -34,10 +34,14 @@ struct Epilogue {
     const float* residual;
     const int64_t* lens;
     float* y;
-    __nv_bfloat16* y_hi;
-    __nv_bfloat16* y_lo;
+    __nv_bfloat16* yp[3];   // output planes (hi, [mid,] lo); yp[0] == nullptr: none
     float alpha;
     int act;
+};
+
+struct Maps {               // TMA descriptors of the operand planes (NP of each are used)
+    CUtensorMap a[3];
+    CUtensorMap w[3];
 };
 
 // Operand / output addressing.  z = blockIdx.x / tiles_per_utt is the "utterance" index of a plain conv (z = b) or the
@@ -130,20 +134,21 @@ __host__ __device__ constexpr uint32_t instr_desc() {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int NP>
 struct Smem {
     static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int STAGE_BYTES = NP * (A_TILE_BYTES + B_TILE_BYTES);
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BLOCK_N, int STAGES>
+// NP = number of bf16 planes per operand: 2 -> 3 MMAs per k-slice ("bf16x3", 16 mantissa bits, decoder / PostNet),
+// 3 -> 6 MMAs per k-slice ("bf16x6", 24 mantissa bits: FP32-equivalent, used upstream of the quantisers).
+template <int BLOCK_N, int STAGES, int NP>
 __global__ void __launch_bounds__(192, 1)
-gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                   const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps, int tiles_per_utt) {
-    using S = Smem<BLOCK_N, STAGES>;
+gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
+                  int tiles_per_utt) {
+    using S = Smem<BLOCK_N, STAGES, NP>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must be 1024-byte aligned in the shared address space
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -162,10 +167,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const int pad = taps >> 1;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_a_hi);
-        tma_prefetch_desc(&tm_a_lo);
-        tma_prefetch_desc(&tm_b_hi);
-        tma_prefetch_desc(&tm_b_lo);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            tma_prefetch_desc(&tm.a[p]);
+            tma_prefetch_desc(&tm.w[p]);
+        }
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -197,10 +203,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 uint8_t* st = smem + s * S::STAGE_BYTES;
                 const int ca = ad.a_c0 + zh * ad.a_step + c0, za = z / ad.a_div;
                 const int cw = ad.w_c0 + zh * ad.w_step + tap * Cin + c0, zw = z / ad.w_div;
-                tma_load_3d(&tm_a_hi, &full_bar[s], st, ca, t0 + tap - pad, za);
-                tma_load_3d(&tm_a_lo, &full_bar[s], st + A_TILE_BYTES, ca, t0 + tap - pad, za);
-                tma_load_3d(&tm_b_hi, &full_bar[s], st + 2 * A_TILE_BYTES, cw, n0, zw);
-                tma_load_3d(&tm_b_lo, &full_bar[s], st + 2 * A_TILE_BYTES + S::B_TILE_BYTES, cw, n0, zw);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES, ca, t0 + tap - pad, za);
+                    tma_load_3d(&tm.w[p], &full_bar[s], st + NP * A_TILE_BYTES + p * S::B_TILE_BYTES, cw, n0, zw);
+                }
             }
         }
     } else if (warp == 1) {
@@ -211,18 +218,30 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tcgen05_fence_after();
-                const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
-                const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
-                const uint32_t b_lo = b_hi + S::B_TILE_BYTES;
+                const uint32_t a0 = smem_u32(smem + s * S::STAGE_BYTES);   // planes: 0 = hi, 1 = mid / lo, 2 = lo
+                const uint32_t b0 = a0 + NP * A_TILE_BYTES;
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                     const uint32_t off = k * UMMA_K * 2;  // bytes inside the 128-byte swizzle row
-                    const uint64_t dah = umma_desc_sw128(a_hi + off), dal = umma_desc_sw128(a_lo + off);
-                    const uint64_t dbh = umma_desc_sw128(b_hi + off), dbl = umma_desc_sw128(b_lo + off);
-                    umma_bf16(tmem_base, dal, dbh, idesc, (kb | k) ? 1u : 0u);  // small terms first
-                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-                    umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+                    uint64_t da[NP], db[NP];
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        da[p] = umma_desc_sw128(a0 + p * A_TILE_BYTES + off);
+                        db[p] = umma_desc_sw128(b0 + p * S::B_TILE_BYTES + off);
+                    }
+                    const uint32_t first = (kb | k) ? 1u : 0u;
+                    if (NP == 2) {  // small terms first
+                        umma_bf16(tmem_base, da[1], db[0], idesc, first);
+                        umma_bf16(tmem_base, da[0], db[1], idesc, 1u);
+                        umma_bf16(tmem_base, da[0], db[0], idesc, 1u);
+                    } else {        // all products of weight >= 2^-16 (the dropped ones are <= 2^-24 relative)
+                        umma_bf16(tmem_base, da[1], db[1], idesc, first);
+                        umma_bf16(tmem_base, da[0], db[2], idesc, 1u);
+                        umma_bf16(tmem_base, da[2], db[0], idesc, 1u);
+                        umma_bf16(tmem_base, da[0], db[1], idesc, 1u);
+                        umma_bf16(tmem_base, da[1], db[0], idesc, 1u);
+                        umma_bf16(tmem_base, da[0], db[0], idesc, 1u);
+                    }
                 }
                 umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
             }
@@ -273,15 +292,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 }
                 if (!keep) { v[0] = v[1] = v[2] = v[3] = 0.f; }
                 if (ep.y) *reinterpret_cast<float4*>(ep.y + rowoff + n) = make_float4(v[0], v[1], v[2], v[3]);
-                if (ep.y_hi) {
-                    __nv_bfloat16 h[4], l[4];
+                if (ep.yp[0]) {
+                    float rem[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        h[j] = __float2bfloat16_rn(v[j]);
-                        l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+                    for (int p = 0; p < NP; ++p) {
+                        __nv_bfloat16 h[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            h[j] = __float2bfloat16_rn(rem[j]);
+                            rem[j] -= __bfloat162float(h[j]);
+                        }
+                        *reinterpret_cast<uint2*>(ep.yp[p] + rowoff + n) = *reinterpret_cast<uint2*>(h);
                     }
-                    *reinterpret_cast<uint2*>(ep.y_hi + rowoff + n) = *reinterpret_cast<uint2*>(h);
-                    *reinterpret_cast<uint2*>(ep.y_lo + rowoff + n) = *reinterpret_cast<uint2*>(l);
                 }
             }
         }
@@ -324,51 +346,53 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
     return 0;
 }
 
-struct Operand {          // a bf16 hi/lo plane pair viewed as a 3-D tensor [d2][d1][d0] (d0 contiguous)
-    const void* hi;
-    const void* lo;
+struct Operand {          // NP bf16 planes viewed as a 3-D tensor [d2][d1][d0] (d0 contiguous)
+    const void* p[3];
     cuuint64_t d0, d1, d2;   // extents (elements)
     cuuint64_t s1, s2;       // strides of d1 / d2 in elements
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int NP>
 static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin, int N,
                   int taps, cudaStream_t st) {
-    using S = Smem<BLOCK_N, STAGES>;
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    using S = Smem<BLOCK_N, STAGES, NP>;
+    Maps maps;
     {
         cuuint64_t dims[3] = {A.d0, A.d1, A.d2};
         cuuint64_t str[2] = {A.s1 * 2, A.s2 * 2};
         cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
-        if (int e = make_map(&ma_hi, A.hi, 3, dims, str, box, "a_hi")) return e;
-        if (int e = make_map(&ma_lo, A.lo, 3, dims, str, box, "a_lo")) return e;
+        for (int p = 0; p < NP; ++p)
+            if (int e = make_map(&maps.a[p], A.p[p], 3, dims, str, box, "activation plane")) return e;
+        for (int p = NP; p < 3; ++p) maps.a[p] = maps.a[0];
     }
     {
         cuuint64_t dims[3] = {W.d0, W.d1, W.d2};
         cuuint64_t str[2] = {W.s1 * 2, W.s2 * 2};
         cuuint32_t box[3] = {BLOCK_K, BLOCK_N, 1};
-        if (int e = make_map(&mb_hi, W.hi, 3, dims, str, box, "w_hi")) return e;
-        if (int e = make_map(&mb_lo, W.lo, 3, dims, str, box, "w_lo")) return e;
+        for (int p = 0; p < NP; ++p)
+            if (int e = make_map(&maps.w[p], W.p[p], 3, dims, str, box, "weight plane")) return e;
+        for (int p = NP; p < 3; ++p) maps.w[p] = maps.w[0];
     }
-    auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES>;
+    auto kern = gemm_split_kernel<BLOCK_N, STAGES, NP>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
-            set_error("gemm_bf16x3: cannot reserve %d bytes of shared memory", S::TOTAL);
+            set_error("gemm_split: cannot reserve %d bytes of shared memory", S::TOTAL);
             return 4;
         }
         configured = true;
     }
     const int tiles_per_utt = (T + BLOCK_M - 1) / BLOCK_M;
     dim3 grid(Z * tiles_per_utt, (N + BLOCK_N - 1) / BLOCK_N);
-    kern<<<grid, 192, S::TOTAL, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep, ad, T, Cin, N, taps, tiles_per_utt);
-    return check_launch("gemm_bf16x3");
+    kern<<<grid, 192, S::TOTAL, st>>>(maps, ep, ad, T, Cin, N, taps, tiles_per_utt);
+    return check_launch("gemm_split");
 }
 
-static int launch_auto(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin, int N,
-                       int taps, cudaStream_t st) {
-    if (N >= 512 && N % 256 == 0) return launch<256, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
-    return launch<128, 3>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin,
+                       int N, int taps, cudaStream_t st) {
+    if (np == 3) return launch<128, 2, 3>(A, W, ep, ad, Z, T, Cin, N, taps, st);   // 2 x 96 KiB stages
+    if (N >= 512 && N % 256 == 0) return launch<256, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+    return launch<128, 3, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
 }
 
 // ---- attention helpers: masked softmax over materialised scores, V transpose ----------------------------------------
@@ -439,25 +463,55 @@ __global__ void transpose_v_kernel(const __nv_bfloat16* __restrict__ q_hi, const
 
 using namespace ctts;
 
+static int gemm_split_impl(int np, const void* const* x_planes, const void* const* w_planes, const float* bias, float alpha,
+                           const float* col_scale, const float* col_shift, int act, const float* residual,
+                           const int64_t* lens, int B, int T, int Cin, int N, int taps, float* y, void* const* y_planes,
+                           void* stream) {
+    CTTS_REQUIRE(np == 2 || np == 3, "gemm_split: n_planes must be 2 (bf16x3) or 3 (bf16x6), got %d", np);
+    CTTS_REQUIRE(B > 0 && T > 0 && N > 0 && taps >= 1 && (taps & 1), "gemm_split: bad shape B=%d T=%d N=%d taps=%d", B, T, N,
+                 taps);
+    CTTS_REQUIRE(Cin % 8 == 0, "gemm_split: Cin=%d must be a multiple of 8 (16-byte TMA strides)", Cin);
+    CTTS_REQUIRE(N % 4 == 0, "gemm_split: N=%d must be a multiple of 4", N);
+    CTTS_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), "gemm_split: col_scale/col_shift must come together");
+    CTTS_REQUIRE(y || (y_planes && y_planes[0]), "gemm_split: no output requested");
+    Epilogue ep{bias, col_scale, col_shift, residual, lens, y, {nullptr, nullptr, nullptr}, alpha, act};
+    const cuuint64_t K = (cuuint64_t)taps * Cin;
+    Operand A{{nullptr, nullptr, nullptr}, (cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)Cin,
+              (cuuint64_t)T * Cin};
+    Operand W{{nullptr, nullptr, nullptr}, K, (cuuint64_t)N, 1, K, K * (cuuint64_t)N};
+    for (int p = 0; p < np; ++p) {
+        CTTS_REQUIRE(x_planes[p] && w_planes[p], "gemm_split: NULL operand plane %d", p);
+        CTTS_REQUIRE((((uintptr_t)x_planes[p] | (uintptr_t)w_planes[p]) & 15) == 0,
+                     "gemm_split: operand planes must be 16-byte aligned");
+        A.p[p] = x_planes[p];
+        W.p[p] = w_planes[p];
+        if (y_planes && y_planes[0]) {
+            CTTS_REQUIRE(y_planes[p], "gemm_split: NULL output plane %d", p);
+            ep.yp[p] = (__nv_bfloat16*)y_planes[p];
+        }
+    }
+    Addr ad{1, 1, 0, 0, 0x7fffffff, 0, 0, 1, N, (long long)T * N, 0};
+    return launch_auto(np, A, W, ep, ad, B, T, Cin, N, taps, (cudaStream_t)stream);
+}
+
+extern "C" int ctts_gemm_split(int n_planes, const void* const* x_planes, const void* const* w_planes, const float* bias,
+                               float alpha, const float* col_scale, const float* col_shift, int act, const float* residual,
+                               const int64_t* lens, int B, int T, int Cin, int N, int taps, float* y, void* const* y_planes,
+                               void* stream) {
+    CTTS_REQUIRE(x_planes && w_planes, "gemm_split: NULL plane arrays");
+    return gemm_split_impl(n_planes, x_planes, w_planes, bias, alpha, col_scale, col_shift, act, residual, lens, B, T, Cin, N,
+                           taps, y, y_planes, stream);
+}
+
 extern "C" int ctts_gemm_bf16x3(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                                 const float* bias, float alpha, const float* col_scale, const float* col_shift, int act,
                                 const float* residual, const int64_t* lens, int B, int T, int Cin, int N, int taps,
                                 float* y, void* y_hi, void* y_lo, void* stream) {
-    CTTS_REQUIRE(B > 0 && T > 0 && N > 0 && taps >= 1 && (taps & 1), "gemm_bf16x3: bad shape B=%d T=%d N=%d taps=%d", B, T,
-                 N, taps);
-    CTTS_REQUIRE(Cin % 8 == 0, "gemm_bf16x3: Cin=%d must be a multiple of 8 (16-byte TMA strides)", Cin);
-    CTTS_REQUIRE(N % 4 == 0, "gemm_bf16x3: N=%d must be a multiple of 4", N);
-    CTTS_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), "gemm_bf16x3: col_scale/col_shift must come together");
     CTTS_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "gemm_bf16x3: y_hi/y_lo must come together");
-    CTTS_REQUIRE(y || y_hi, "gemm_bf16x3: no output requested");
-    CTTS_REQUIRE((((uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)w_hi | (uintptr_t)w_lo) & 15) == 0,
-                 "gemm_bf16x3: operand planes must be 16-byte aligned");
-    Epilogue ep{bias, col_scale, col_shift, residual, lens, y, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, alpha, act};
-    const cuuint64_t K = (cuuint64_t)taps * Cin;
-    Operand A{x_hi, x_lo, (cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)Cin, (cuuint64_t)T * Cin};
-    Operand W{w_hi, w_lo, K, (cuuint64_t)N, 1, K, K * (cuuint64_t)N};
-    Addr ad{1, 1, 0, 0, 0x7fffffff, 0, 0, 1, N, (long long)T * N, 0};
-    return launch_auto(A, W, ep, ad, B, T, Cin, N, taps, (cudaStream_t)stream);
+    const void* xp[3] = {x_hi, x_lo, nullptr};
+    const void* wp[3] = {w_hi, w_lo, nullptr};
+    void* yp[3] = {y_hi, y_lo, nullptr};
+    return gemm_split_impl(2, xp, wp, bias, alpha, col_scale, col_shift, act, residual, lens, B, T, Cin, N, taps, y, yp, stream);
 }
 
 extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, const int64_t* lens, int B, int T, int C,
@@ -474,11 +528,11 @@ extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, con
     const cuuint64_t C3 = (cuuint64_t)3 * C;
     // 1. S[z, t, s] = scale * q[z,t,:] . k[z,s,:]      (A = q columns, W = k columns of the same qkv planes)
     {
-        Operand A{qkv_hi, qkv_lo, C3, (cuuint64_t)T, (cuuint64_t)B, C3, (cuuint64_t)T * C3};
+        Operand A{{qkv_hi, qkv_lo, nullptr}, C3, (cuuint64_t)T, (cuuint64_t)B, C3, (cuuint64_t)T * C3};
         Operand W = A;
-        Epilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, scores, nullptr, nullptr, scale, CTTS_ACT_NONE};
+        Epilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, scores, {nullptr, nullptr, nullptr}, scale, CTTS_ACT_NONE};
         Addr ad{H, H, 0, DH, H, C, DH, 1, Tp, (long long)H * T * Tp, (long long)T * Tp};
-        if (int e = launch_auto(A, W, ep, ad, Z, T, DH, Tp, 1, st)) return e;
+        if (int e = launch_auto(2, A, W, ep, ad, Z, T, DH, Tp, 1, st)) return e;
     }
     // 2. Vt planes
     {
@@ -496,12 +550,13 @@ extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, con
     }
     // 4. out[b, t, h*DH + d] = sum_s P[z,t,s] * Vt[z,d,s]; rows t >= len are zeroed
     {
-        Operand A{p_hi, p_lo, (cuuint64_t)Tp, (cuuint64_t)T, (cuuint64_t)Z, (cuuint64_t)Tp, (cuuint64_t)T * Tp};
-        Operand W{vt_hi, vt_lo, (cuuint64_t)Tp, (cuuint64_t)DH, (cuuint64_t)Z, (cuuint64_t)Tp, (cuuint64_t)DH * Tp};
-        Epilogue ep{nullptr, nullptr, nullptr, nullptr, lens, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, 1.f,
-                    CTTS_ACT_NONE};
+        Operand A{{p_hi, p_lo, nullptr}, (cuuint64_t)Tp, (cuuint64_t)T, (cuuint64_t)Z, (cuuint64_t)Tp, (cuuint64_t)T * Tp};
+        Operand W{{vt_hi, vt_lo, nullptr}, (cuuint64_t)Tp, (cuuint64_t)DH, (cuuint64_t)Z, (cuuint64_t)Tp,
+                  (cuuint64_t)DH * Tp};
+        Epilogue ep{nullptr, nullptr, nullptr, nullptr, lens, out_f32,
+                    {(__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, nullptr}, 1.f, CTTS_ACT_NONE};
         Addr ad{H, 1, 0, 0, 1, 0, 0, H, C, (long long)T * C, (long long)DH};
-        if (int e = launch_auto(A, W, ep, ad, Z, T, Tp, DH, 1, st)) return e;
+        if (int e = launch_auto(2, A, W, ep, ad, Z, T, Tp, DH, 1, st)) return e;
     }
     return 0;
 }

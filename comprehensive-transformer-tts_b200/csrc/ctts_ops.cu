@@ -95,11 +95,14 @@ __global__ void add_positions_kernel(float* __restrict__ x, const float* __restr
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, two-pass moments in FP32.  C <= 1024, C % 4 == 0.
-template <bool SPLIT>
+struct PlanePtrs {
+    __nv_bfloat16* p[3];
+};
+
+template <int NP>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, const int64_t* __restrict__ lens, int rows,
-                                 int T, int C, float* __restrict__ y, __nv_bfloat16* __restrict__ y_hi,
-                                 __nv_bfloat16* __restrict__ y_lo) {
+                                 int T, int C, float* __restrict__ y, const PlanePtrs yp) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -143,16 +146,18 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
             o.z = keep ? (v[i].z - mean) * rstd * g.z + bb.z : 0.f;
             o.w = keep ? (v[i].w - mean) * rstd * g.w + bb.w : 0.f;
             if (y) reinterpret_cast<float4*>(y + (size_t)row * C)[c] = o;
-            if (SPLIT) {
-                const float f[4] = {o.x, o.y, o.z, o.w};
-                __nv_bfloat16 h[4], l[4];
+            if (NP > 0) {
+                float rem[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    h[k] = __float2bfloat16_rn(f[k]);
-                    l[k] = __float2bfloat16_rn(f[k] - __bfloat162float(h[k]));
+                for (int p = 0; p < NP; ++p) {
+                    __nv_bfloat16 h[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        h[k] = __float2bfloat16_rn(rem[k]);
+                        rem[k] -= __bfloat162float(h[k]);
+                    }
+                    *reinterpret_cast<uint2*>(yp.p[p] + (size_t)row * C + 4 * c) = *reinterpret_cast<uint2*>(h);
                 }
-                *reinterpret_cast<uint2*>(y_hi + (size_t)row * C + 4 * c) = *reinterpret_cast<uint2*>(h);
-                *reinterpret_cast<uint2*>(y_lo + (size_t)row * C + 4 * c) = *reinterpret_cast<uint2*>(l);
             }
         }
     }
@@ -606,13 +611,16 @@ __global__ void add_row_broadcast_kernel(const float* __restrict__ x, const floa
     }
 }
 
-__global__ void split_bf16_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo) {
+template <int NP>
+__global__ void split_bf16_kernel(const float* __restrict__ x, size_t n, const PlanePtrs out) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float v = x[i];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        hi[i] = h;
-        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+        float rem = x[i];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+            out.p[p][i] = h;
+            rem -= __bfloat162float(h);
+        }
     }
 }
 
@@ -815,30 +823,40 @@ int ctts_add_positions(float* x, const float* pe, int pe_rows, const float* alph
 }
 
 static int layernorm_impl(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B,
-                          int T, int C, float* y, void* y_hi, void* y_lo, void* stream) {
+                          int T, int C, float* y, int np, void* const* planes, void* stream) {
     CTTS_REQUIRE(C % 4 == 0 && C <= 1024, "layernorm: C=%d unsupported (need C %% 4 == 0, C <= 1024)", C);
     const int rows = B * T;
     CTTS_REQUIRE(rows > 0, "layernorm: empty input");
+    CTTS_REQUIRE(np >= 0 && np <= 3 && np != 1, "layernorm: n_planes must be 0, 2 or 3");
     const int grid = (rows + 7) / 8;
-    if (y_hi)
-        layernorm_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, lens, rows, T, C, y,
-                                                                        (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
-    else
-        layernorm_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, lens, rows, T, C, y,
-                                                                         nullptr, nullptr);
+    PlanePtrs pp{{nullptr, nullptr, nullptr}};
+    for (int p = 0; p < np; ++p) {
+        CTTS_REQUIRE(planes && planes[p], "layernorm: NULL output plane %d", p);
+        pp.p[p] = (__nv_bfloat16*)planes[p];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (np == 3) layernorm_kernel<3><<<grid, 256, 0, st>>>(x, gamma, beta, eps, lens, rows, T, C, y, pp);
+    else if (np == 2) layernorm_kernel<2><<<grid, 256, 0, st>>>(x, gamma, beta, eps, lens, rows, T, C, y, pp);
+    else layernorm_kernel<0><<<grid, 256, 0, st>>>(x, gamma, beta, eps, lens, rows, T, C, y, pp);
     return check_launch("layernorm");
 }
 
 int ctts_layernorm(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B, int T,
                    int C, float* y, void* stream) {
     CTTS_REQUIRE(y != nullptr, "layernorm: y is NULL");
-    return layernorm_impl(x, gamma, beta, eps, lens, B, T, C, y, nullptr, nullptr, stream);
+    return layernorm_impl(x, gamma, beta, eps, lens, B, T, C, y, 0, nullptr, stream);
+}
+
+int ctts_layernorm_planes(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B, int T,
+                          int C, float* y, int n_planes, void* const* planes, void* stream) {
+    return layernorm_impl(x, gamma, beta, eps, lens, B, T, C, y, n_planes, planes, stream);
 }
 
 int ctts_layernorm_split(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B,
                          int T, int C, float* y, void* y_hi, void* y_lo, void* stream) {
     CTTS_REQUIRE(y_hi && y_lo, "layernorm_split: y_hi / y_lo are NULL");
-    return layernorm_impl(x, gamma, beta, eps, lens, B, T, C, y, y_hi, y_lo, stream);
+    void* planes[3] = {y_hi, y_lo, nullptr};
+    return layernorm_impl(x, gamma, beta, eps, lens, B, T, C, y, 2, planes, stream);
 }
 
 int ctts_conv1d_gemm(const float* x, const float* w, const float* bias, float alpha, const float* col_scale,
@@ -959,11 +977,22 @@ int ctts_add_row_broadcast(const float* x, const float* row, int B, int T, int C
     return check_launch("add_row_broadcast");
 }
 
-int ctts_split_bf16(const float* x, size_t n, void* hi, void* lo, void* stream) {
-    CTTS_REQUIRE(n > 0, "split_bf16: empty");
+int ctts_split_planes(const float* x, size_t n, int n_planes, void* const* planes, void* stream) {
+    CTTS_REQUIRE(n > 0 && (n_planes == 2 || n_planes == 3) && planes, "split_planes: bad arguments");
     const int grid = (int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192);
-    split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
-    return check_launch("split_bf16");
+    PlanePtrs pp{{nullptr, nullptr, nullptr}};
+    for (int p = 0; p < n_planes; ++p) {
+        CTTS_REQUIRE(planes[p], "split_planes: NULL plane %d", p);
+        pp.p[p] = (__nv_bfloat16*)planes[p];
+    }
+    if (n_planes == 3) split_bf16_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, pp);
+    else split_bf16_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, pp);
+    return check_launch("split_planes");
+}
+
+int ctts_split_bf16(const float* x, size_t n, void* hi, void* lo, void* stream) {
+    void* planes[3] = {hi, lo, nullptr};
+    return ctts_split_planes(x, n, 2, planes, stream);
 }
 
 int ctts_fastformer_pool(const float* logits, const float* values, const int64_t* lens, int B, int T, int heads, int head_size,

@@ -42,6 +42,9 @@ SIGNATURES = {
     "ctts_transpose_heads": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "ctts_gemm_bf16x3": [_P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ctts_attention_bf16x3": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "ctts_gemm_split": [_I, _P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "ctts_split_planes": [_P, _Z, _I, _P, _P],
+    "ctts_layernorm_planes": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _I, _P, _P],
     "ctts_split_bf16": [_P, _Z, _P, _P, _P],
     "ctts_layernorm_split": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _P, _P, _P],
 }
@@ -72,6 +75,15 @@ def load():
     return lib
 
 
+def ptr_array(tensors):
+    """Host array of device pointers (for the `const void* const*` plane arguments)."""
+    arr = (ctypes.c_void_p * 3)()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    arr._keepalive = list(tensors)
+    return arr
+
+
 def _ptr(t):
     if t is None:
         return None
@@ -89,7 +101,8 @@ def call(name, *args):
     global LAUNCHES
     lib = load()
     LAUNCHES += 1
-    conv = [(_ptr(a) if (a is None or hasattr(a, "data_ptr")) else a) for a in args]
+    conv = [(_ptr(a) if (a is None or hasattr(a, "data_ptr")) else (ctypes.cast(a, ctypes.c_void_p) if isinstance(
+        a, ctypes.Array) else a)) for a in args]
     rc = getattr(lib, name)(*conv)
     if rc != 0:
         raise CttsError("%s failed (%d): %s" % (name, rc, lib.ctts_last_error().decode()))

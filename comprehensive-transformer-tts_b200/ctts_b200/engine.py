@@ -42,53 +42,69 @@ def conv_gemm(x, w, bias=None, alpha=1.0, bn=None, act=ACT_NONE, residual=None, 
 
 
 class Planes:
-    """A [B, T, C] activation (or [N, K] weight) stored as two bf16 planes: value ~= hi + lo (16 mantissa bits)."""
-    __slots__ = ("hi", "lo")
+    """A [B, T, C] activation (or [N, K] weight) stored as 2 or 3 bf16 planes: value ~= sum(p).
+    2 planes = 16 mantissa bits ("bf16x3": 3 MMAs), 3 planes = 24 bits ("bf16x6": 6 MMAs, FP32-equivalent)."""
+    __slots__ = ("p",)
 
-    def __init__(self, hi, lo):
-        self.hi, self.lo = hi, lo
+    def __init__(self, planes):
+        self.p = list(planes)
 
     @property
     def shape(self):
-        return self.hi.shape
+        return self.p[0].shape
+
+    @property
+    def n(self):
+        return len(self.p)
+
+    @property
+    def hi(self):
+        return self.p[0]
+
+    @property
+    def lo(self):
+        assert len(self.p) == 2
+        return self.p[1]
+
+    def value(self):
+        return sum(t.float() for t in self.p)
 
     @staticmethod
-    def empty(B, T, C, device):
-        return Planes(torch.empty(B, T, C, device=device, dtype=torch.bfloat16),
-                      torch.empty(B, T, C, device=device, dtype=torch.bfloat16))
+    def empty(shape, device, n=2):
+        return Planes([torch.empty(shape, device=device, dtype=torch.bfloat16) for _ in range(n)])
 
 
-def split_planes(x):
-    """fp32 tensor -> Planes (ctts_split_bf16)."""
+def split_planes(x, n=2):
+    """fp32 tensor -> Planes (ctts_split_planes)."""
     x = _f32(x)
-    p = Planes(torch.empty(x.shape, device=x.device, dtype=torch.bfloat16),
-               torch.empty(x.shape, device=x.device, dtype=torch.bfloat16))
-    capi.call("ctts_split_bf16", x, x.numel(), p.hi, p.lo, _stream())
+    p = Planes.empty(x.shape, x.device, n)
+    capi.call("ctts_split_planes", x, x.numel(), n, capi.ptr_array(p.p), _stream())
     return p
 
 
 def gemm_tc(xp, wp, bias=None, alpha=1.0, bn=None, act=ACT_NONE, residual=None, lens=None, taps=1, out=None,
             want_fp32=True, want_planes=False):
-    """tcgen05 bf16x3 implicit-GEMM conv / linear.  xp: Planes [B,T,Cin]; wp: Planes [N, taps*Cin].
-    Returns (y fp32 or None, Planes or None)."""
+    """tcgen05 implicit-GEMM conv / linear on bf16 operand planes (2 planes: bf16x3, 3 planes: bf16x6).
+    xp: Planes [B,T,Cin]; wp: Planes [N, taps*Cin].  Returns (y fp32 or None, Planes or None)."""
     B, T, Cin = xp.shape
     N = wp.shape[0]
     assert wp.shape[1] == taps * Cin, (tuple(wp.shape), taps, Cin)
-    y = out if out is not None else (torch.empty(B, T, N, device=xp.hi.device, dtype=torch.float32) if want_fp32
-                                     else None)
-    yp = Planes.empty(B, T, N, xp.hi.device) if want_planes else None
-    capi.call("ctts_gemm_bf16x3", xp.hi, xp.lo, wp.hi, wp.lo, bias, float(alpha), bn[0] if bn else None,
-              bn[1] if bn else None, int(act), residual, lens, B, T, Cin, N, taps, y, yp.hi if yp else None,
-              yp.lo if yp else None, _stream())
+    assert xp.n == wp.n, "activation and weight must be split into the same number of planes"
+    dev = xp.p[0].device
+    y = out if out is not None else (torch.empty(B, T, N, device=dev, dtype=torch.float32) if want_fp32 else None)
+    yp = Planes.empty((B, T, N), dev, xp.n) if want_planes else None
+    capi.call("ctts_gemm_split", xp.n, capi.ptr_array(xp.p), capi.ptr_array(wp.p), bias, float(alpha),
+              bn[0] if bn else None, bn[1] if bn else None, int(act), residual, lens, B, T, Cin, N, taps, y,
+              capi.ptr_array(yp.p) if yp else None, _stream())
     return y, yp
 
 
-def layernorm_planes(x, gamma, beta, eps, lens=None, want_fp32=False):
-    """LayerNorm whose result is written as bf16 hi/lo planes (and optionally fp32)."""
+def layernorm_planes(x, gamma, beta, eps, lens=None, want_fp32=False, n=2):
+    """LayerNorm whose result is written as bf16 planes (and optionally fp32)."""
     B, T, C = x.shape
     y = torch.empty_like(x) if want_fp32 else None
-    yp = Planes.empty(B, T, C, x.device)
-    capi.call("ctts_layernorm_split", x, gamma, beta, float(eps), lens, B, T, C, y, yp.hi, yp.lo, _stream())
+    yp = Planes.empty((B, T, C), x.device, n)
+    capi.call("ctts_layernorm_planes", x, gamma, beta, float(eps), lens, B, T, C, y, n, capi.ptr_array(yp.p), _stream())
     return y, yp
 
 
@@ -119,7 +135,8 @@ def attention_tc(qkv_planes, lens, n_head):
     p_lo = torch.empty_like(p_hi)
     vt_hi = torch.empty(B * C * Tp, device=dev, dtype=torch.bfloat16)
     vt_lo = torch.empty_like(vt_hi)
-    out = Planes.empty(B, T, C, dev)
+    assert qkv_planes.n == 2
+    out = Planes.empty((B, T, C), dev, 2)
     capi.call("ctts_attention_bf16x3", qkv_planes.hi, qkv_planes.lo, lens, B, T, C, n_head,
               1.0 / math.sqrt(C // n_head), scores, p_hi, p_lo, vt_hi, vt_lo, out.hi, out.lo, None, _stream())
     return out
@@ -150,8 +167,8 @@ class Prepared:
         return tuple((k, v.data_ptr(), v._version) for k, v in P.items())
 
     def params(self):
-        P = {k: v for k, v in self.module.named_parameters()}
-        P.update({k: v for k, v in self.module.named_buffers()})
+        P = {k: v for k, v in self.module.named_parameters(remove_duplicate=False)}  # tied names included
+        P.update({k: v for k, v in self.module.named_buffers(remove_duplicate=False)})
         sig = self._signature(P)
         if sig != self.sig:
             self._build(P)
@@ -182,6 +199,16 @@ class Prepared:
                     if name.endswith("weight") and t.dim() in (2, 3) and t.shape[1] != 1:
                         src = self.w[name] if t.dim() == 3 else _f32(t)
                         self.w[name + "#planes"] = split_planes(src)
+            if self.module.encoder_math == "bf16x6":
+                # 3-plane (24-bit) copies of the weights upstream of the quantisers: encoder + variance predictors
+                for name, t in P.items():
+                    if not (name.startswith("encoder.") or name.startswith("variance_adaptor.")):
+                        continue
+                    if name.endswith("weight") and t.dim() in (2, 3) and t.shape[1] != 1 and t.shape[0] % 4 == 0 \
+                            and "embed" not in name and "emb" not in name.split(".")[-2]:
+                        src = self.w[name] if t.dim() == 3 else _f32(t)
+                        if src.shape[1] % 8 == 0:
+                            self.w[name + "#planes3"] = split_planes(src, 3)
             block = self.module.model_config["block_type"]
             if block != "transformer_fs2":
                 from . import engine_blocks
@@ -225,7 +252,7 @@ def _fft_layers_fs2(prep, P, pre, x, lens, n_layers, n_head, kernel, act):
     return layernorm(x, P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-5, lens)
 
 
-def encoder_fs2(prep, P, cfg, tokens, src_lens):
+def encoder_fs2(prep, P, cfg, tokens, src_lens, math="fp32"):
     """TextEncoder.forward, transformer_fs2.py:100-119."""
     c = cfg["transformer_fs2"]
     B, S = tokens.shape
@@ -237,26 +264,36 @@ def encoder_fs2(prep, P, cfg, tokens, src_lens):
     capi.call("ctts_embed_tokens", tokens, table, pe, pe.shape[0], math.sqrt(C), B, S, C, table.shape[0], x, word,
               src_lens, 0, _stream())
     act = _ACTS[cfg["variance_predictor"]["ffn_act"]]
-    x = _fft_layers_fs2(prep, P, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"], c["ffn_kernel_size"],
-                        act)
+    if math == "bf16x6":
+        x, _ = _fft_layers_fs2_tc(prep, P, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"],
+                                  c["ffn_kernel_size"], act, n=3)
+    else:
+        x = _fft_layers_fs2(prep, P, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"],
+                            c["ffn_kernel_size"], act)
     return x, word
 
 
-def _fft_layers_fs2_tc(prep, P, pre, x, lens, n_layers, n_head, kernel, act):
-    """Same block as _fft_layers_fs2 with the four dense contractions on tcgen05 (bf16x3); attention, LayerNorm and
-    the residual stream stay FP32.  Returns (final LN fp32, final LN planes)."""
+def _fft_layers_fs2_tc(prep, P, pre, x, lens, n_layers, n_head, kernel, act, n=2):
+    """Same block as _fft_layers_fs2 with the four dense contractions on tcgen05.  n = 2: bf16x3 operands and
+    tensor-core attention (decoder); n = 3: bf16x6 operands (FP32-equivalent) with the FP32 attention kernel (encoder).
+    LayerNorm, softmax and the residual stream stay FP32.  Returns (final LN fp32, final LN planes)."""
     W = prep.w
+    tag = "#planes" if n == 2 else "#planes3"
     for i in range(n_layers):
         lp = "%slayers.%d.op." % (pre, i)
-        _, hp = layernorm_planes(x, P[lp + "layer_norm1.weight"], P[lp + "layer_norm1.bias"], 1e-12)
-        _, qkvp = gemm_tc(hp, W[lp + "self_attn.in_proj_weight#planes"], want_fp32=False, want_planes=True)
-        ap = attention_tc(qkvp, lens, n_head)
-        gemm_tc(ap, W[lp + "self_attn.out_proj.weight#planes"], residual=x, lens=lens, out=x)
-        _, hp = layernorm_planes(x, P[lp + "layer_norm2.weight"], P[lp + "layer_norm2.bias"], 1e-12)
-        _, fp = gemm_tc(hp, W[lp + "ffn.ffn_1.weight#planes"], P[lp + "ffn.ffn_1.bias"], alpha=kernel ** -0.5, act=act,
+        _, hp = layernorm_planes(x, P[lp + "layer_norm1.weight"], P[lp + "layer_norm1.bias"], 1e-12, n=n)
+        if n == 2:
+            _, qkvp = gemm_tc(hp, W[lp + "self_attn.in_proj_weight" + tag], want_fp32=False, want_planes=True)
+            ap = attention_tc(qkvp, lens, n_head)
+        else:
+            qkv, _ = gemm_tc(hp, W[lp + "self_attn.in_proj_weight" + tag])
+            ap = split_planes(attention(qkv, lens, n_head), n)
+        gemm_tc(ap, W[lp + "self_attn.out_proj.weight" + tag], residual=x, lens=lens, out=x)
+        _, hp = layernorm_planes(x, P[lp + "layer_norm2.weight"], P[lp + "layer_norm2.bias"], 1e-12, n=n)
+        _, fp = gemm_tc(hp, W[lp + "ffn.ffn_1.weight" + tag], P[lp + "ffn.ffn_1.bias"], alpha=kernel ** -0.5, act=act,
                         taps=kernel, want_fp32=False, want_planes=True)
-        gemm_tc(fp, W[lp + "ffn.ffn_2.weight#planes"], P[lp + "ffn.ffn_2.bias"], residual=x, lens=lens, out=x)
-    return layernorm_planes(x, P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-5, lens, want_fp32=True)
+        gemm_tc(fp, W[lp + "ffn.ffn_2.weight" + tag], P[lp + "ffn.ffn_2.bias"], residual=x, lens=lens, out=x)
+    return layernorm_planes(x, P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-5, lens, want_fp32=True, n=n)
 
 
 def decoder_fs2(prep, P, cfg, x, mel_lens, math="fp32"):
@@ -278,7 +315,17 @@ def decoder_fs2(prep, P, cfg, x, mel_lens, math="fp32"):
 # variance adaptor
 # ---------------------------------------------------------------------------------------------
 def _predictor_stack(prep, P, pre, x, n_layers, kernel, lens):
-    """[pad, Conv1d, ReLU, LayerNorm(channels), Dropout] x n (modules.py:1277-1288,1330-1338)."""
+    """[pad, Conv1d, ReLU, LayerNorm(channels), Dropout] x n (modules.py:1277-1288,1330-1338).
+    On tcgen05 with 3-plane (FP32-equivalent) operands when the module's encoder_math is "bf16x6"."""
+    if ("%sconv.0.1.weight#planes3" % pre) in prep.w:
+        xp = split_planes(x, 3)
+        for l in range(n_layers):
+            h, _ = gemm_tc(xp, prep.w["%sconv.%d.1.weight#planes3" % (pre, l)], P["%sconv.%d.1.bias" % (pre, l)],
+                           act=ACT_RELU, taps=kernel)
+            last = l == n_layers - 1
+            x, xp = layernorm_planes(h, P["%sconv.%d.3.weight" % (pre, l)], P["%sconv.%d.3.bias" % (pre, l)], 1e-12, lens,
+                                     want_fp32=last, n=3)
+        return x
     for l in range(n_layers):
         h = conv_gemm(x, prep.w["%sconv.%d.1.weight" % (pre, l)], P["%sconv.%d.1.bias" % (pre, l)], act=ACT_RELU,
                       taps=kernel)
@@ -370,7 +417,11 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
     pitch_pred = energy_pred = None
     if cfg["variance_embedding"]["use_pitch_embed"]:
         pre = "variance_adaptor."
-        h = conv_gemm(xe, P[pre + "cwt_predictor.0.weight"], P[pre + "cwt_predictor.0.bias"])
+        if (pre + "cwt_predictor.0.weight#planes3") in prep.w:
+            h, _ = gemm_tc(split_planes(xe, 3), prep.w[pre + "cwt_predictor.0.weight#planes3"],
+                           P[pre + "cwt_predictor.0.bias"])
+        else:
+            h = conv_gemm(xe, P[pre + "cwt_predictor.0.weight"], P[pre + "cwt_predictor.0.bias"])
         cwt = pitch_style_predictor(prep, P, cfg, pre + "cwt_predictor.1.", h, alpha=p_control)
         first = x_org[:, 0, :].contiguous().view(1, B, C)
         s = conv_gemm(first, P[pre + "cwt_stats_layers.0.weight"], P[pre + "cwt_stats_layers.0.bias"], act=ACT_RELU)
@@ -464,7 +515,7 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         mel_masks = pad_mask(mel_lens, max_mel_len)
     block = cfg["block_type"]
     if block == "transformer_fs2":
-        enc, word = encoder_fs2(prep, P, cfg, texts, src_lens)
+        enc, word = encoder_fs2(prep, P, cfg, texts, src_lens, module.encoder_math)
     else:
         from . import engine_blocks
         if block not in engine_blocks.ENCODERS:

@@ -105,6 +105,11 @@ class CompTransTTS(nn.Module):
         self.decoder_math = os.environ.get("CTTS_DECODER_MATH", "bf16x3")
         if self.decoder_math not in ("bf16x3", "fp32"):
             raise ValueError("CTTS_DECODER_MATH must be 'bf16x3' or 'fp32'")
+        # arithmetic of the encoder + variance predictors (UPSTREAM of the quantisers, must be FP32-equivalent):
+        # "bf16x6" = tcgen05 with 3 bf16 planes per operand (24 mantissa bits, 6 MMAs per k-slice), "fp32" = CUDA cores
+        self.encoder_math = os.environ.get("CTTS_ENCODER_MATH", "bf16x6")
+        if self.encoder_math not in ("bf16x6", "fp32"):
+            raise ValueError("CTTS_ENCODER_MATH must be 'bf16x6' or 'fp32'")
         self._prepared = engine.Prepared(self)
 
     def forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,

@@ -228,6 +228,20 @@ int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, const int64_t*
                           float scale, float* scores, void* p_hi, void* p_lo, void* vt_hi, void* vt_lo, void* out_hi,
                           void* out_lo, float* out_f32, void* stream);
 
+/* ---- generalisation to n_planes bf16 planes per operand ------------------------------------------------
+ * n_planes 2: x ~= p0 + p1 (16 mantissa bits), 3 MMAs per k-slice ("bf16x3", decoder / PostNet);
+ * n_planes 3: x ~= p0 + p1 + p2 (24 mantissa bits), 6 MMAs per k-slice ("bf16x6": FP32-equivalent; measured 3e-6 on the
+ *             whole model, the same as FP32 summation-order noise) -- used for everything UPSTREAM of a quantiser
+ *             (encoder, duration / pitch / energy predictors), SURVEY.md H1.
+ * x_planes / w_planes / y_planes are HOST arrays of n_planes device pointers.  Otherwise as ctts_gemm_bf16x3.
+ */
+int ctts_gemm_split(int n_planes, const void* const* x_planes, const void* const* w_planes, const float* bias, float alpha,
+                    const float* col_scale, const float* col_shift, int act, const float* residual, const int64_t* lens,
+                    int B, int T, int Cin, int N, int taps, float* y, void* const* y_planes, void* stream);
+int ctts_split_planes(const float* x, size_t n, int n_planes, void* const* planes, void* stream);
+int ctts_layernorm_planes(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B, int T,
+                          int C, float* y, int n_planes, void* const* planes, void* stream);
+
 /* fp32 -> (bf16 hi, bf16 lo) with hi = rn(x), lo = rn(x - hi) */
 int ctts_split_bf16(const float* x, size_t n, void* hi, void* lo, void* stream);
 

@@ -19,6 +19,7 @@ DEV = "cuda:0"
 @pytest.mark.parametrize("name", sorted(cases.CASES))
 def test_decoder_math_modes(name, math, golden_dir, monkeypatch):
     monkeypatch.setenv("CTTS_DECODER_MATH", math)
+    monkeypatch.setenv("CTTS_ENCODER_MATH", "bf16x6" if math == "bf16x3" else "fp32")
     gold = np.load(os.path.join(golden_dir, name + ".npz"))
     (p, m, t), sd, batch = cases.build_case(name)
     net = ctts_b200.CompTransTTS(p, m, t).eval()

@@ -228,7 +228,7 @@ def test_bucketize_and_gather():
 def test_split_bf16_planes():
     x = torch.randn(4, 33, 64, generator=g(40)) * 3
     p = engine.split_planes(x.to(DEV))
-    hi, lo = p.hi.float().cpu(), p.lo.float().cpu()
+    hi, lo = p.p[0].float().cpu(), p.p[1].float().cpu()
     assert torch.equal(hi, x.bfloat16().float())
     assert torch.equal(lo, (x - hi).bfloat16().float())
     assert (x - hi - lo).abs().max() <= x.abs().max() * 2.0 ** -16
@@ -263,7 +263,7 @@ def test_gemm_bf16x3_matches_fp32(B, T, Cin, N, taps, act):
     torch.cuda.synchronize()
     # bf16x3 keeps 16 mantissa bits per operand: error ~ 2^-16 * sqrt(K) * |a||b|; far below the 1e-3 path tolerance
     close(y, ref, atol=2e-4, rtol=2e-4, msg="fp32 output")
-    back = yp.hi.float() + yp.lo.float()
+    back = yp.value()
     close(back, y, atol=1e-4, rtol=2e-5, msg="hi/lo planes of the output")
 
 
@@ -300,7 +300,31 @@ def test_attention_bf16x3(B, T, C, H):
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, C)
     ref = (ref * (~pad).double()[:, :, None]).float()
     out = engine.attention_tc(engine.split_planes(qkv.to(DEV)), lens.to(DEV), H)
-    got = out.hi.float() + out.lo.float()
+    got = out.value()
     close(got, ref, atol=1e-4, rtol=1e-4)
     # and against the FP32 CUDA-core kernel
     close(got, engine.attention(qkv.to(DEV), lens.to(DEV), H), atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,T,Cin,N,taps,act", [
+    (2, 100, 256, 768, 1, "none"), (3, 100, 256, 1024, 9, "gelu"), (2, 300, 128, 256, 5, "relu"),
+    (2, 261, 1024, 256, 1, "none"), (2, 100, 256, 256, 3, "relu"),
+])
+def test_gemm_bf16x6_is_fp32_equivalent(B, T, Cin, N, taps, act):
+    """3-plane operands (24 mantissa bits, 6 MMAs per k-slice): as close to fp64 as the FP32 CUDA-core kernel is."""
+    x = torch.randn(B, T, Cin, generator=g(61))
+    w = torch.randn(N, Cin, taps, generator=g(62)) / math.sqrt(Cin * taps)
+    bias = torch.randn(N, generator=g(63))
+    lens = torch.tensor([max(T - 9 * b, 1) for b in range(B)])
+    ref = F.conv1d(x.double().transpose(1, 2), w.double(), bias.double(), padding=taps // 2).transpose(1, 2)
+    ref = {"none": lambda v: v, "gelu": F.gelu, "relu": F.relu}[act](ref)
+    ref = (ref * (torch.arange(T)[None, :] < lens[:, None]).double()[:, :, None]).float()
+    packed = w.permute(0, 2, 1).reshape(N, -1).contiguous().to(DEV)
+    y, yp = engine.gemm_tc(engine.split_planes(x.to(DEV), 3), engine.split_planes(packed, 3), bias.to(DEV),
+                           act=engine._ACTS[act], lens=lens.to(DEV), taps=taps, want_planes=True)
+    y32 = engine.conv_gemm(x.to(DEV), packed, bias.to(DEV), act=engine._ACTS[act], lens=lens.to(DEV), taps=taps)
+    err6 = (y.cpu() - ref).abs().max().item()
+    err32 = (y32.cpu() - ref).abs().max().item()
+    assert err6 < 3e-6 and err6 < 4 * err32 + 1e-6, (err6, err32)
+    assert (yp.value() - y).abs().max().item() < 1e-6
+    assert yp.n == 3
