@@ -180,9 +180,16 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // whole warp: TMEM allocation (BLOCK_N fp32 columns x 128 lanes)
+    // NP == 3 keeps FOUR accumulators: the tensor core adds each MMA into the FP32 accumulator with truncation, so the
+    // error of one accumulator grows linearly with its number of MMA steps (measured 2e-5 at K = 256 with one
+    // accumulator).  The dominant hi*hi products are therefore spread round-robin over three accumulators and the five
+    // small products go to a fourth; the epilogue adds the four in FP32 (round-to-nearest).
+    constexpr int NACC = (NP == 3) ? 4 : 1;
+    constexpr uint32_t TMEM_COLS = NACC * BLOCK_N;
+    static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
+    if (warp == 1) {  // whole warp: TMEM allocation (TMEM_COLS fp32 columns x 128 lanes)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)BLOCK_N)
+                     "r"(TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -235,12 +242,13 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                         umma_bf16(tmem_base, da[0], db[1], idesc, 1u);
                         umma_bf16(tmem_base, da[0], db[0], idesc, 1u);
                     } else {        // all products of weight >= 2^-16 (the dropped ones are <= 2^-24 relative)
-                        umma_bf16(tmem_base, da[1], db[1], idesc, first);
-                        umma_bf16(tmem_base, da[0], db[2], idesc, 1u);
-                        umma_bf16(tmem_base, da[2], db[0], idesc, 1u);
-                        umma_bf16(tmem_base, da[0], db[1], idesc, 1u);
-                        umma_bf16(tmem_base, da[1], db[0], idesc, 1u);
-                        umma_bf16(tmem_base, da[0], db[0], idesc, 1u);
+                        const uint32_t small_acc = tmem_base + 3 * BLOCK_N;
+                        umma_bf16(small_acc, da[1], db[1], idesc, first);
+                        umma_bf16(small_acc, da[0], db[2], idesc, 1u);
+                        umma_bf16(small_acc, da[2], db[0], idesc, 1u);
+                        umma_bf16(small_acc, da[0], db[1], idesc, 1u);
+                        umma_bf16(small_acc, da[1], db[0], idesc, 1u);
+                        umma_bf16(tmem_base + (uint32_t)(kb % 3) * BLOCK_N, da[0], db[0], idesc, (kb >= 3 || k > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
@@ -263,6 +271,17 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
         for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
+            if (NP == 3) {  // add the small-term accumulator and the other (used) main accumulators
+                const int n_main = num_kb < 3 ? num_kb : 3;
+#pragma unroll 1
+                for (int a = 1; a < 4; ++a) {
+                    if (a < 3 && a >= n_main) continue;
+                    uint32_t r2[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BLOCK_N + chunk * 32), r2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                }
+            }
             if (!in_range) continue;
             const int nb = n0 + chunk * 32;
 #pragma unroll
@@ -312,8 +331,7 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N)
-                     : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 

@@ -768,6 +768,134 @@ __global__ void transpose_heads_kernel(const float* __restrict__ x, int T, int l
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// AlignmentEncoder score assembly (modules.py:1198-1212), one warp per (b, mel frame):
+//   d[s]     = -temperature * sum_c (q[b,m,c] - k[b,s,c])^2
+//   logprob  = log_softmax_s(d) (over ALL S key columns, padded ones included -- quirk 7) + log(prior[b,s,m] + 1e-8)
+//   soft     = softmax_s(logprob with -inf at s >= src_len)
+// q: [B, M, C], k: [B, S, C], prior: [B, S, M] (the caller's layout, read transposed), outputs [B, M, S].
+__global__ void __launch_bounds__(256)
+aligner_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ prior,
+                         const int64_t* __restrict__ src_lens, float temperature, int M, int S, int C,
+                         float* __restrict__ soft, float* __restrict__ logprob) {
+    extern __shared__ float sm[];
+    float* ks = sm;                 // [C][S+1] transposed keys
+    float* qs = sm + (size_t)C * (S + 1);   // [8][C]
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * 8 + warp;
+    for (int i = threadIdx.x; i < S * C; i += 256) {
+        const int s_ = i / C, c = i - s_ * C;
+        ks[c * (S + 1) + s_] = k[((size_t)b * S + s_) * C + c];
+    }
+    if (m < M)
+        for (int c = lane; c < C; c += 32) qs[warp * C + c] = q[((size_t)b * M + m) * C + c];
+    __syncthreads();
+    if (m >= M) return;
+    const int slen = min((int)src_lens[b], S);
+    const float* qr = qs + warp * C;
+    float* lp = logprob + ((size_t)b * M + m) * S;
+    float* so = soft + ((size_t)b * M + m) * S;
+    // pass 1: distances -> lp (temporarily), running max for the log-softmax
+    float mx = -INFINITY;
+    for (int s_ = lane; s_ < S; s_ += 32) {
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float d = qr[c] - ks[c * (S + 1) + s_];
+            acc += d * d;
+        }
+        const float v = -temperature * acc;
+        lp[s_] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s_ = lane; s_ < S; s_ += 32) sum += expf(lp[s_] - mx);
+    const float lse = mx + logf(warp_sum(sum));
+    float mx2 = -INFINITY;
+    for (int s_ = lane; s_ < S; s_ += 32) {
+        const float v = (lp[s_] - lse) + logf(prior[((size_t)b * S + s_) * M + m] + 1e-8f);
+        lp[s_] = v;
+        if (s_ < slen) mx2 = fmaxf(mx2, v);
+    }
+    mx2 = warp_max(mx2);
+    float sum2 = 0.f;
+    for (int s_ = lane; s_ < slen; s_ += 32) sum2 += expf(lp[s_] - mx2);
+    const float inv = 1.f / warp_sum(sum2);
+    for (int s_ = lane; s_ < S; s_ += 32) so[s_] = (s_ < slen) ? expf(lp[s_] - mx2) * inv : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Monotonic alignment search (mas_width1 / b_mas, modules.py:36-75), one CTA per utterance.
+//   a = log(attn[:M_b, :S_b]); a[0, 1:] = -inf; log_p[i,j] = a[i,j] + max(log_p[i-1,j], log_p[i-1,j-1]) (tie -> j-1, `>=`)
+//   backtrack from column S_b-1 of the last row.  prev: workspace uint8 [B, M, S] (1 = came from j-1).
+// Outputs: hard [B, M, S] 0/1 (zero outside the valid rectangle), dur [B, S] = column sums (attn_hard.sum(2)).
+__global__ void __launch_bounds__(1024)
+mas_kernel(const float* __restrict__ attn, const int64_t* __restrict__ src_lens, const int64_t* __restrict__ mel_lens, int M,
+           int S, uint8_t* __restrict__ prev, float* __restrict__ hard, float* __restrict__ dur) {
+    extern __shared__ float rowbuf[];  // 2 x S
+    const int b = blockIdx.x;
+    const int Sb = min((int)src_lens[b], S), Mb = min((int)mel_lens[b], M);
+    const float* ab = attn + (size_t)b * M * S;
+    uint8_t* pb = prev + (size_t)b * M * S;
+    float* hb = hard + (size_t)b * M * S;
+    for (size_t i = threadIdx.x; i < (size_t)M * S; i += blockDim.x) hb[i] = 0.f;
+    for (int j = threadIdx.x; j < S; j += blockDim.x) dur[(size_t)b * S + j] = 0.f;
+    float* cur = rowbuf;
+    float* nxt = rowbuf + S;
+    for (int j = threadIdx.x; j < Sb; j += blockDim.x) cur[j] = (j == 0) ? logf(ab[0]) : -INFINITY;
+    __syncthreads();
+    for (int i = 1; i < Mb; ++i) {
+        for (int j = threadIdx.x; j < Sb; j += blockDim.x) {
+            float best = cur[j];
+            uint8_t from_left = 0;
+            if (j >= 1 && cur[j - 1] >= cur[j]) { best = cur[j - 1]; from_left = 1; }
+            nxt[j] = logf(ab[(size_t)i * S + j]) + best;
+            pb[(size_t)i * S + j] = from_left;
+        }
+        __syncthreads();
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    if (threadIdx.x == 0 && Mb > 0 && Sb > 0) {
+        float* db = dur + (size_t)b * S;
+        int j = Sb - 1;
+        for (int i = Mb - 1; i >= 0; --i) {
+            hb[(size_t)i * S + j] = 1.f;
+            db[j] += 1.f;
+            if (i > 0) j -= pb[(size_t)i * S + j];
+        }
+        // `opt[0, curr_text_idx] = 1` after the loop with prev_ind[0, :] == 0 -> column 0 (modules.py:63)
+        if (hb[0] != 1.f) { hb[0] = 1.f; db[0] += 1.f; }
+    }
+}
+
+// Phoneme-level averaging of a frame-level feature by hard durations, IN PLACE and sequentially like the reference
+// (utils/tools.py:56-66 via modules.py:882-888): out[b, i] = mean(e[pos:pos+d_i]) if d_i > 0 else 0, pos += d_i,
+// where `e` is the frame array being overwritten as it goes.  One thread per utterance (S <= a few hundred).
+__global__ void phoneme_energy_kernel(const float* __restrict__ dur, const int64_t* __restrict__ src_lens,
+                                      const float* __restrict__ energy, int B, int S, int M, float* __restrict__ work,
+                                      float* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float* e = work + (size_t)b * M;
+    for (int t = 0; t < M; ++t) e[t] = energy[(size_t)b * M + t];
+    const int slen = min((int)src_lens[b], S);
+    int pos = 0;
+    for (int i = 0; i < slen; ++i) {
+        const int d = (int)dur[(size_t)b * S + i];
+        float v = 0.f;
+        if (d > 0) {
+            float acc = 0.f;
+            for (int t = pos; t < pos + d && t < M; ++t) acc += e[t];
+            v = acc / (float)d;
+        }
+        if (i < M) e[i] = v;
+        pos += d;
+    }
+    for (int i = 0; i < S; ++i) out[(size_t)b * S + i] = (i < slen && i < M) ? e[i] : 0.f;
+}
+
 }  // namespace ctts
 
 // =============================================================================================
@@ -1046,6 +1174,36 @@ int ctts_transpose_heads(const float* x, int B, int T, int ld_in, int c0, int H,
     dim3 grid((ldt + 31) / 32, (DH + 31) / 32, B * H);
     transpose_heads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, T, ld_in, c0, H, DH, ldt, xt);
     return check_launch("transpose_heads");
+}
+
+int ctts_aligner_attention(const float* q, const float* k, const float* prior, const int64_t* src_lens, float temperature, int B,
+                           int M, int S, int C, float* soft, float* logprob, void* stream) {
+    CTTS_REQUIRE(B > 0 && M > 0 && S > 0 && C > 0 && src_lens && prior, "aligner_attention: bad arguments");
+    const size_t sm = ((size_t)C * (S + 1) + 8 * (size_t)C) * sizeof(float);
+    CTTS_REQUIRE(sm <= 200 * 1024, "aligner_attention: S=%d too long for the shared-memory key tile", S);
+    if (sm > 48 * 1024)
+        cudaFuncSetAttribute(aligner_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    dim3 grid((M + 7) / 8, B);
+    aligner_attention_kernel<<<grid, 256, sm, (cudaStream_t)stream>>>(q, k, prior, src_lens, temperature, M, S, C, soft,
+                                                                      logprob);
+    return check_launch("aligner_attention");
+}
+
+int ctts_mas(const float* attn, const int64_t* src_lens, const int64_t* mel_lens, int B, int M, int S, uint8_t* prev_workspace,
+             float* hard, float* dur, void* stream) {
+    CTTS_REQUIRE(B > 0 && M > 0 && S > 0 && src_lens && mel_lens && prev_workspace, "mas: bad arguments");
+    const size_t sm = 2 * (size_t)S * sizeof(float);
+    CTTS_REQUIRE(sm <= 48 * 1024, "mas: S=%d too long", S);
+    const int threads = S >= 1024 ? 1024 : ((S + 31) / 32) * 32;
+    mas_kernel<<<B, threads, sm, (cudaStream_t)stream>>>(attn, src_lens, mel_lens, M, S, prev_workspace, hard, dur);
+    return check_launch("mas");
+}
+
+int ctts_phoneme_energy(const float* dur, const int64_t* src_lens, const float* energy, int B, int S, int M, float* workspace,
+                        float* out, void* stream) {
+    CTTS_REQUIRE(B > 0 && S > 0 && M > 0 && workspace, "phoneme_energy: bad arguments");
+    phoneme_energy_kernel<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream>>>(dur, src_lens, energy, B, S, M, workspace, out);
+    return check_launch("phoneme_energy");
 }
 
 }  // extern "C"

@@ -252,7 +252,7 @@ def _fft_layers_fs2(prep, P, pre, x, lens, n_layers, n_head, kernel, act):
     return layernorm(x, P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-5, lens)
 
 
-def encoder_fs2(prep, P, cfg, tokens, src_lens, math="fp32"):
+def encoder_fs2(prep, P, cfg, tokens, src_lens, math_mode="fp32"):
     """TextEncoder.forward, transformer_fs2.py:100-119."""
     c = cfg["transformer_fs2"]
     B, S = tokens.shape
@@ -264,7 +264,7 @@ def encoder_fs2(prep, P, cfg, tokens, src_lens, math="fp32"):
     capi.call("ctts_embed_tokens", tokens, table, pe, pe.shape[0], math.sqrt(C), B, S, C, table.shape[0], x, word,
               src_lens, 0, _stream())
     act = _ACTS[cfg["variance_predictor"]["ffn_act"]]
-    if math == "bf16x6":
+    if math_mode == "bf16x6":
         x, _ = _fft_layers_fs2_tc(prep, P, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"],
                                   c["ffn_kernel_size"], act, n=3)
     else:
@@ -296,7 +296,7 @@ def _fft_layers_fs2_tc(prep, P, pre, x, lens, n_layers, n_head, kernel, act, n=2
     return layernorm_planes(x, P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-5, lens, want_fp32=True, n=n)
 
 
-def decoder_fs2(prep, P, cfg, x, mel_lens, math="fp32"):
+def decoder_fs2(prep, P, cfg, x, mel_lens, math_mode="fp32"):
     """Decoder = FFTBlocks with learnable-scale sinusoid positions, transformer_fs2.py:47-72,122-134.
     `x` must be a private buffer: it is overwritten.  Returns (dec fp32, dec planes or None)."""
     c = cfg["transformer_fs2"]
@@ -304,7 +304,7 @@ def decoder_fs2(prep, P, cfg, x, mel_lens, math="fp32"):
     pe = prep.table_fs2(C, T + 1, x.device)
     capi.call("ctts_add_positions", x, pe, pe.shape[0], P["decoder.pos_embed_alpha"], mel_lens, B, T, C, 0, _stream())
     act = _ACTS[cfg["variance_predictor"]["ffn_act"]]
-    if math == "bf16x3":
+    if math_mode == "bf16x3":
         return _fft_layers_fs2_tc(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
                                   c["ffn_kernel_size"], act)
     return _fft_layers_fs2(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
@@ -352,7 +352,35 @@ def pitch_style_predictor(prep, P, cfg, pre, xs, alpha=1.0):
     return conv_gemm(h, P[pre + "linear.weight"], P[pre + "linear.bias"], alpha=alpha)
 
 
-def length_regulate(x, dur, src_lens, max_len, need_mel2ph):
+def alignment_encoder(prep, P, cfg, mel, text_embedding, src_lens, attn_prior, spk):
+    """AlignmentEncoder.forward, modules.py:1176-1213.  mel [B,M,80], text_embedding [B,S,C] (token-major), attn_prior
+    [B,S,M].  Returns (attn_soft, attn_logprob) as [B,1,M,S]."""
+    pre = "variance_adaptor.aligner."
+    B, M, _ = mel.shape
+    S = text_embedding.shape[1]
+    st = _stream()
+    keys, queries = text_embedding, mel
+    if spk is not None:
+        ks = conv_gemm(_f32(spk).view(1, B, -1), P[pre + "key_spk_proj.linear.weight"]).view(B, -1)
+        qs = conv_gemm(_f32(spk).view(1, B, -1), P[pre + "query_spk_proj.linear.weight"]).view(B, -1)
+        k2 = torch.empty_like(keys)
+        capi.call("ctts_add_row_broadcast", keys, ks, B, S, keys.shape[2], k2, st)
+        q2 = torch.empty_like(queries)
+        capi.call("ctts_add_row_broadcast", queries, qs, B, M, queries.shape[2], q2, st)
+        keys, queries = k2, q2
+    k = conv_gemm(keys, prep.w[pre + "key_proj.0.conv.weight"], P[pre + "key_proj.0.conv.bias"], act=ACT_RELU, taps=3)
+    k = conv_gemm(k, prep.w[pre + "key_proj.2.conv.weight"], P[pre + "key_proj.2.conv.bias"])
+    q = conv_gemm(queries, prep.w[pre + "query_proj.0.conv.weight"], P[pre + "query_proj.0.conv.bias"], act=ACT_RELU, taps=3)
+    q = conv_gemm(q, prep.w[pre + "query_proj.2.conv.weight"], P[pre + "query_proj.2.conv.bias"], act=ACT_RELU)
+    q = conv_gemm(q, prep.w[pre + "query_proj.4.conv.weight"], P[pre + "query_proj.4.conv.bias"])
+    soft = torch.empty(B, 1, M, S, device=mel.device, dtype=torch.float32)
+    logprob = torch.empty(B, 1, M, S, device=mel.device, dtype=torch.float32)
+    capi.call("ctts_aligner_attention", q, k, attn_prior, src_lens, float(cfg["duration_modeling"]["aligner_temperature"]),
+              B, M, S, q.shape[2], soft, logprob, st)
+    return soft, logprob
+
+
+def length_regulate(x, dur, src_lens, max_len, need_mel2ph, expand=True):
     """LengthRegulator (modules.py:1222-1249) + dur_to_mel2ph (utils/tools.py:598-628).
 
     Returns (expanded [B,M,C], mel_len [B] i64, mel2ph [B,M2] i64 or None, cum_lr).  When max_len is
@@ -375,10 +403,15 @@ def length_regulate(x, dur, src_lens, max_len, need_mel2ph):
         M, M2 = int(max_len), 0
     if M <= 0:
         raise capi.CttsError("length_regulate: every duration is zero (empty mel)")
-    out = torch.empty(B, M, C, device=dev, dtype=torch.float32)
     mel2ph = torch.empty(B, M2, device=dev, dtype=torch.int64) if (need_mel2ph and M2 > 0) else None
-    capi.call("ctts_length_expand", x, None, None, cum_lr, B, S, C, M, 0, out, cum_m2p, mel2ph, M2 if mel2ph is not None
-              else 0, _stream())
+    if expand:
+        out = torch.empty(B, M, C, device=dev, dtype=torch.float32)
+        capi.call("ctts_length_expand", x, None, None, cum_lr, B, S, C, M, 0, out, cum_m2p, mel2ph,
+                  M2 if mel2ph is not None else 0, _stream())
+    else:  # only the frame -> phoneme map is wanted (soft-upsampling branch)
+        out = torch.empty(B, 1, C, device=dev, dtype=torch.float32)
+        capi.call("ctts_length_expand", x, None, None, cum_lr, B, S, C, 1, 0, out, cum_m2p, mel2ph,
+                  M2 if mel2ph is not None else 0, _stream())
     return out, mel_len, mel2ph, cum_lr
 
 
@@ -386,9 +419,6 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
                      max_len, pitch_target, energy_target, duration_target, attn_prior, p_control, e_control, d_control,
                      step):
     """VarianceAdaptor.forward (prosody 'none'), modules.py:962-1114."""
-    if attn_prior is not None:
-        raise NotImplementedError("unsupervised duration modelling (aligner + MAS) is not built yet "
-                                  "(SURVEY.md section 8a A16/A17)")
     pitch_cfg = pcfg["preprocessing"]["pitch"]
     B, S, C = text.shape
     st = _stream()
@@ -400,11 +430,39 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
     log_d = duration_predictor(prep, P, cfg, x, src_lens)
     x_org = x
 
-    if duration_target is not None:
+    attn_out = (None, None, None, None)
+    mel2ph = None
+    if attn_prior is not None:
+        # unsupervised duration modelling: AlignmentEncoder + monotonic alignment search (modules.py:1031-1053)
+        assert cfg["duration_modeling"]["learn_alignment"] and duration_target is None and mel is not None
+        attn_soft, attn_logprob = alignment_encoder(prep, P, cfg, _f32(mel), text_embedding, src_lens, _f32(attn_prior), spk)
+        M_in = mel.shape[1]
+        prev_ws = torch.empty(B * M_in * S, device=x.device, dtype=torch.uint8)
+        attn_hard = torch.empty(B, 1, M_in, S, device=x.device, dtype=torch.float32)
+        attn_hard_dur = torch.empty(B, S, device=x.device, dtype=torch.float32)
+        capi.call("ctts_mas", attn_soft, src_lens, mel_lens, B, M_in, S, prev_ws, attn_hard, attn_hard_dur, st)
+        attn_out = (attn_soft, attn_hard, attn_hard_dur, attn_logprob)
+        duration_rounded = attn_hard_dur
+        if step < tcfg["duration"]["binarization_start_steps"]:
+            # soft upsampling x = bmm(A_soft, x) (modules.py:1047-1049); mel_len stays the caller's
+            Sp = (S + 15) // 16 * 16
+            a_pad = torch.zeros(B, M_in, Sp, device=x.device, dtype=torch.float32)
+            a_pad[:, :, :S] = attn_soft[:, 0]
+            xt = torch.empty(B, C, Sp, device=x.device, dtype=torch.float32)
+            capi.call("ctts_transpose_heads", x, B, S, C, 0, 1, C, Sp, xt, st)
+            xe = torch.empty(B, M_in, C, device=x.device, dtype=torch.float32)
+            capi.call("ctts_batched_gemm_fp32", a_pad, xt, 1.0, None, 1, B, 1, M_in, Sp, C, M_in * Sp, 0, Sp, C * Sp, 0, Sp,
+                      M_in * C, 0, C, xe, st)
+            _, _, m2p, cum_lr = length_regulate(x, duration_rounded, src_lens, max_len, True, expand=False)
+            mel_len = mel_lens
+        else:
+            xe, mel_len, m2p, cum_lr = length_regulate(x, duration_rounded, src_lens, max_len, True)
+        m2p = m2p if m2p is not None else torch.zeros(B, 0, device=x.device, dtype=torch.int64)
+        pitch_target["mel2ph"] = m2p[:, :max_len]
+    elif duration_target is not None:
         assert not cfg["duration_modeling"]["learn_alignment"] and attn_prior is None
         xe, mel_len, _, cum_lr = length_regulate(x, duration_target, src_lens, max_len, False)
         duration_rounded = duration_target
-        mel2ph = None
     else:
         assert attn_prior is None and duration_target is None
         duration_rounded = torch.empty_like(log_d)
@@ -463,6 +521,12 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
             capi.call("ctts_bucketize", src_vals, 1.0, bins, bins.shape[0], B * M, eidx, st)
             capi.call("ctts_gather_add", emb, eidx, B * M, C, emb.shape[0], x_sum, st)
         else:
+            if attn_prior is not None:  # frame-level target -> phoneme level by the hard durations (modules.py:1096-1097)
+                et = _f32(energy_target)
+                M_e = et.shape[1]
+                work = torch.empty(B * M_e, device=x.device, dtype=torch.float32)
+                energy_target = torch.empty(B, S, device=x.device, dtype=torch.float32)
+                capi.call("ctts_phoneme_energy", attn_out[2], src_lens, et, B, S, M_e, work, energy_target, st)
             pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", x_org.clone(),
                                          alpha=1.0 if energy_target is not None else e_control).squeeze(-1)
             src_vals = _f32(energy_target) if energy_target is not None else pred
@@ -471,7 +535,7 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
             capi.call("ctts_length_expand", None, emb, eidx, cum_lr, B, S, C, M, 1, x_sum, None, None, 0, st)
         energy_pred = pred
     return (x_sum, pitch_target, pitch_pred, energy_target, energy_pred, log_d, duration_rounded, mel_len, mel_mask,
-            (None, None, None, None), None)
+            attn_out, None)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -160,6 +160,24 @@ int ctts_bucketize(const float* v, float v_scale, const float* bins, int n_bins,
 /* y = x + spk[b] broadcast over T (modules.py:985-988) */
 int ctts_add_row_broadcast(const float* x, const float* row, int B, int T, int C, float* y, void* stream);
 
+/* ---- unsupervised duration modelling (learn_alignment: True) --------------------------------------
+ * ctts_aligner_attention  AlignmentEncoder.forward score assembly, modules.py:1198-1212.  q [B,M,C] / k [B,S,C] are the
+ *   projected mel / text features (the conv stacks run through ctts_conv1d_gemm), prior [B,S,M] is the caller's
+ *   attn_priors (read transposed).  soft, logprob: [B,M,S] (= the reference's [B,1,M,S]).  The first log_softmax runs
+ *   over ALL S columns, the mask is applied only before the second softmax (reference quirk, kept).
+ * ctts_mas                 binarize_attention_parallel / b_mas / mas_width1, modules.py:36-75,863-872: monotonic Viterbi
+ *   path per utterance on log(attn); hard [B,M,S] 0/1, dur [B,S] = hard.sum(M).  prev_workspace: B*M*S bytes.
+ *   Replaces the reference's D2H copy + numba CPU loop + H2D copy per training step.
+ * ctts_phoneme_energy      get_phoneme_level_energy, modules.py:882-888 + utils/tools.py:56-66 (sequential, in place).
+ *   workspace: B*M floats; out [B,S].
+ */
+int ctts_aligner_attention(const float* q, const float* k, const float* prior, const int64_t* src_lens, float temperature, int B,
+                           int M, int S, int C, float* soft, float* logprob, void* stream);
+int ctts_mas(const float* attn, const int64_t* src_lens, const int64_t* mel_lens, int B, int M, int S, uint8_t* prev_workspace,
+             float* hard, float* dur, void* stream);
+int ctts_phoneme_energy(const float* dur, const int64_t* src_lens, const float* energy, int B, int S, int M, float* workspace,
+                        float* out, void* stream);
+
 /* ---- FP32 batched GEMM with explicit strides (conformer attention products) ------------
  *   y[zo,zh][t, n] = alpha * sum_k x[zo,zh][t, k] * w[zo,zh][n, k]        z = zo*mod + zh in [0, Z)
  * row pointers: x + zo*x_so + zh*x_sh + t*x_ld, w + zo*w_so + zh*w_sh + n*w_ld, y + zo*y_so + zh*y_sh + t*y_ld.

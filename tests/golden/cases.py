@@ -25,6 +25,10 @@ CASES = {
                             batch=2, s_max=60, s_step=11, pin=4, seed=5),
     "conformer_teacher": dict(dataset="LJSpeech", block_type="conformer", learn_alignment=False, mode="teacher",
                               batch=2, s_max=30, s_step=7, pin=None, seed=6),
+    # unsupervised duration modelling: AlignmentEncoder + MAS + hard-duration upsampling + phoneme-level energy from
+    # frame-level targets (learn_alignment True, attn_priors given, step 120000 > binarization_start_steps)
+    "fs2_unsup": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=True, mode="unsup",
+                      batch=3, s_max=30, s_step=7, pin=None, seed=7),
 }
 
 TAP_STRIDE = 4  # intermediate activations are stored for every 4th row only

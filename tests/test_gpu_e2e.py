@@ -19,7 +19,8 @@ from oracle import ctts_oracle as O  # noqa: E402
 
 DEV = "cuda:0"
 MEL_ATOL, MEL_RTOL = 1e-3, 1e-2
-EXACT = ("d_rounded", "mel_lens", "src_lens", "src_masks", "mel_masks", "p_targets.mel2ph")
+EXACT = ("d_rounded", "mel_lens", "src_lens", "src_masks", "mel_masks", "p_targets.mel2ph",
+         "attn_outs.1", "attn_outs.2")  # attn_hard (MAS path) and attn_hard_dur are integer-valued: bit-exact
 
 
 def to_dev(v):

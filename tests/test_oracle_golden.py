@@ -10,7 +10,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "gol
 import cases  # noqa: E402
 from oracle import ctts_oracle as O  # noqa: E402
 
-EXACT = ("d_rounded", "mel_lens", "src_lens", "src_masks", "mel_masks", "p_targets.mel2ph")
+EXACT = ("d_rounded", "mel_lens", "src_lens", "src_masks", "mel_masks", "p_targets.mel2ph",
+         "attn_outs.1", "attn_outs.2")  # attn_hard (MAS path) and attn_hard_dur are integer-valued: bit-exact
 
 
 def run_oracle(name):
