@@ -205,7 +205,6 @@ def main():
             return fn(x, w, *a, **k)
         return wrapper
 
-    engine.conv_gemm, engine.gemm_tc = timed(orig_conv), timed(orig_tc)
     ffn_kernel = ("ctts_gemm_bf16x3 (tcgen05, bf16 hi/lo x3)" if net.decoder_math == "bf16x3"
                   else "ctts_conv1d_gemm (FP32 CUDA cores)")
 
@@ -245,11 +244,21 @@ def main():
         return float(t.item()), capi.LAUNCHES - launches0
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ffn_events.clear()
     ms_total, launches = run_timed(step_device, args.steps, args.warmup)
+    ms_e2e, _ = run_timed(step_e2e, args.steps, 2)
+    # per-launch duration of the dominant kernel: the same steps again with graph replay off (a replayed graph cannot
+    # be instrumented from the host), CUDA events around each launch on the launching stream, L2 flushed between steps
+    graphs_were_on = net.use_cuda_graphs
+    net.use_cuda_graphs = False
+    engine.conv_gemm, engine.gemm_tc = timed(orig_conv), timed(orig_tc)
+    ffn_events.clear()
+    _, eager_launches = run_timed(step_device, args.steps, 1)
+    torch.cuda.synchronize()
     ffn_ms = [a.elapsed_time(b) for a, b in ffn_events[-6 * args.steps:]]
     engine.conv_gemm, engine.gemm_tc = orig_conv, orig_tc
-    ms_e2e, _ = run_timed(step_e2e, args.steps, 2)
+    net.use_cuda_graphs = graphs_were_on
+    if graphs_were_on:
+        launches = eager_launches   # kernels per step are the same; replayed steps do not pass through capi.call
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -267,7 +276,8 @@ def main():
                                    "batch 16 per GPU, S 100..70, 8 frames/phoneme (M 800, 10880 valid frames), "
                                    "free-running inference, random-init weights",
                        "l2_flush": "256 MiB device write between timed steps", "timing": "CUDA events per step, max over ranks",
-                       "parallelism": "independent shards x%d" % world},
+                       "parallelism": "independent shards x%d" % world,
+                       "cuda_graphs": bool(net.use_cuda_graphs)},
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host_in)),
                     "d2h_bytes_per_step": int(BATCH * 800 * 80 * 4 + BATCH * 8), "ms_per_step": ms_e2e / args.steps},
@@ -277,6 +287,7 @@ def main():
                          "bound": "tensor", "achieved": ffn_tflops, "peak": pk["tensor"], "unit": "TFLOP/s",
                          "frac": (ffn_tflops / pk["tensor"]) if ffn_tflops else None, "traffic": None,
                          "peak_source": pk["src"], "launch_ms": ffn_avg, "launches_timed": len(ffn_ms),
+                         "launch_timing": "CUDA events around each launch, eager re-run of the timed steps",
                          "flops_per_launch": frames * FFN_FLOP_PER_FRAME},
         }
         if world == 1 and not args.no_cpu_baseline:

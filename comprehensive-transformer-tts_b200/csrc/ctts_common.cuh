@@ -21,6 +21,14 @@ inline int check_launch(const char* what) {
     return 0;
 }
 
+// Raise a kernel's dynamic shared-memory limit only when a launch needs more than was granted before (never while a
+// graph capture re-runs a launch of the same size: the first, eager pass has already done it).
+void ensure_smem_impl(const void* kernel, size_t bytes);
+template <typename K>
+inline void ensure_smem(K kernel, size_t bytes) {
+    ensure_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 #define CTTS_REQUIRE(cond, ...)            \
     do {                                   \
         if (!(cond)) {                     \

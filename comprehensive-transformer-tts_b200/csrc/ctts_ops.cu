@@ -9,9 +9,21 @@
 #include <math.h>
 #include <string.h>
 
+#include <unordered_map>
+
 namespace ctts {
 
 static thread_local char g_err[512] = "";
+
+void ensure_smem_impl(const void* kernel, size_t bytes) {
+    static std::unordered_map<const void*, size_t> granted;
+    size_t& g = granted[kernel];
+    if (g == 0) g = 48 * 1024;
+    if (bytes > g) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        g = bytes;
+    }
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -896,6 +908,72 @@ __global__ void phoneme_energy_kernel(const float* __restrict__ dur, const int64
     for (int i = 0; i < S; ++i) out[(size_t)b * S + i] = (i < slen && i < M) ? e[i] : 0.f;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bidirectional single-layer GRU recurrence (nn.GRU, gates r|z|n; modules.py:620-640), one CTA per (utterance, direction).
+//   gi  = x W_ih^T + b_ih          precomputed for every step by the dense GEMM          [B, T, 3H]
+//   gh  = h W_hh^T + b_hh;  r = s(gi_r + gh_r); z = s(gi_z + gh_z); n = tanh(gi_n + r * gh_n);  h' = (1-z) n + z h
+// The recurrent weights live transposed in shared memory ([H][3H], 192 KiB at H = 128) for the whole sequence.
+// Like the reference, the recurrence runs over ALL T steps (padded phonemes included: no packing).
+__global__ void gru_bidir_kernel(const float* __restrict__ gi_f, const float* __restrict__ gi_b,
+                                 const float* __restrict__ whh_f, const float* __restrict__ bhh_f,
+                                 const float* __restrict__ whh_b, const float* __restrict__ bhh_b, int T, int H,
+                                 float* __restrict__ out, float* __restrict__ h_final) {
+    extern __shared__ float sm[];
+    const int G = 3 * H;
+    float* wt = sm;              // [H][G]
+    float* hs = wt + (size_t)H * G;   // [H]
+    float* gh = hs + H;          // [G]
+    const int b = blockIdx.x, dir = blockIdx.y;
+    const float* whh = dir ? whh_b : whh_f;
+    const float* bhh = dir ? bhh_b : bhh_f;
+    const float* gi = (dir ? gi_b : gi_f) + (size_t)b * T * G;
+    const int j = threadIdx.x;   // 0 .. G-1
+    for (int i = j; i < H * G; i += G) {
+        const int row = i / H, k = i - row * H;      // whh[row][k]
+        wt[(size_t)k * G + row] = whh[i];
+    }
+    if (j < H) hs[j] = 0.f;
+    const float bj = bhh[j];
+    __syncthreads();
+    for (int step = 0; step < T; ++step) {
+        const int t = dir ? (T - 1 - step) : step;
+        float acc = bj;
+#pragma unroll 8
+        for (int k = 0; k < H; ++k) acc = fmaf(wt[(size_t)k * G + j], hs[k], acc);
+        gh[j] = acc;
+        __syncthreads();
+        float hn = 0.f;
+        if (j < H) {
+            const float* g = gi + (size_t)t * G;
+            const float r = 1.f / (1.f + expf(-(g[j] + gh[j])));
+            const float z = 1.f / (1.f + expf(-(g[H + j] + gh[H + j])));
+            const float n = tanhf(g[2 * H + j] + r * gh[2 * H + j]);
+            hn = (1.f - z) * n + z * hs[j];
+            out[((size_t)b * T + t) * (2 * H) + dir * H + j] = hn;
+        }
+        __syncthreads();
+        if (j < H) hs[j] = hn;
+        __syncthreads();
+    }
+    if (j < H) h_final[(size_t)b * 2 * H + dir * H + j] = hs[j];
+}
+
+// y[r, n] = sum_{k<K} x[r,k] w[n,k] + bias[n] (+ residual[r,n]); tiny K (the 4-d phoneme prosody code, modules.py:861)
+__global__ void linear_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                     const float* __restrict__ residual, size_t rows, int K, int N, float* __restrict__ y) {
+    const size_t total = rows * (size_t)N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / N;
+        const int n = (int)(i - r * N);
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc = fmaf(x[r * K + k], w[(size_t)n * K + k], acc);
+        if (bias) acc += bias[n];
+        if (residual) acc += residual[i];
+        y[i] = acc;
+    }
+}
+
 }  // namespace ctts
 
 // =============================================================================================
@@ -907,7 +985,7 @@ template <int DH>
 static int launch_attention(const float* qkv, const int64_t* lens, int B, int T, int C, int H, float scale, float* out,
                             cudaStream_t st) {
     const size_t sm = (size_t)(3 * 32 * (DH + 4) + 32 * 33) * sizeof(float);
-    cudaFuncSetAttribute(attention_fp32_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    ensure_smem(attention_fp32_kernel<DH>, sm);
     dim3 grid((T + 31) / 32, H, B);
     attention_fp32_kernel<DH><<<grid, 128, sm, st>>>(qkv, lens, T, C, scale, out);
     return check_launch("attention");
@@ -933,7 +1011,7 @@ int ctts_embed_tokens(const int64_t* tokens, const float* table, const float* pe
     CTTS_REQUIRE(pe_rows > S - (pos_mode ? 1 : 0), "embed_tokens: positional table has %d rows, need > %d", pe_rows, S);
     CTTS_REQUIRE((size_t)S * 4 <= 200 * 1024, "embed_tokens: S=%d too long", S);
     const size_t sm = (size_t)S * sizeof(int);
-    if (sm > 48 * 1024) cudaFuncSetAttribute(embed_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    ensure_smem(embed_tokens_kernel, sm);
     embed_tokens_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(tokens, table, pe, embed_scale, S, C, vocab, x, word, lens,
                                                               pos_mode);
     return check_launch("embed_tokens");
@@ -945,7 +1023,7 @@ int ctts_add_positions(float* x, const float* pe, int pe_rows, const float* alph
     CTTS_REQUIRE(pe_rows > T - (pos_mode ? 1 : 0), "add_positions: positional table has %d rows, need > %d", pe_rows, T);
     CTTS_REQUIRE((size_t)T * 4 <= 200 * 1024, "add_positions: T=%d too long", T);
     const size_t sm = (size_t)T * sizeof(int);
-    if (sm > 48 * 1024) cudaFuncSetAttribute(add_positions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    ensure_smem(add_positions_kernel, sm);
     add_positions_kernel<<<B, 512, sm, (cudaStream_t)stream>>>(x, pe, alpha, lens, T, C, pos_mode);
     return check_launch("add_positions");
 }
@@ -1072,7 +1150,7 @@ int ctts_cwt_to_pitch(const float* cwt, int cwt_stride, const float* scale_w, co
     CTTS_REQUIRE(cwt_stride >= 10 && (uv_src || !use_uv || cwt_stride >= 11), "cwt_to_pitch: cwt_stride=%d", cwt_stride);
     const size_t sm = (size_t)T * sizeof(float);
     CTTS_REQUIRE(sm <= 200 * 1024, "cwt_to_pitch: T=%d too long", T);
-    if (sm > 48 * 1024) cudaFuncSetAttribute(cwt_to_pitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    ensure_smem(cwt_to_pitch_kernel, sm);
     cwt_to_pitch_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(cwt, cwt_stride, scale_w, mean, std, stat_stride, std_scale,
                                                               eps, uv_src, use_uv, T, f0_norm, f0_denorm, pitch_idx);
     return check_launch("cwt_to_pitch");
@@ -1181,8 +1259,7 @@ int ctts_aligner_attention(const float* q, const float* k, const float* prior, c
     CTTS_REQUIRE(B > 0 && M > 0 && S > 0 && C > 0 && src_lens && prior, "aligner_attention: bad arguments");
     const size_t sm = ((size_t)C * (S + 1) + 8 * (size_t)C) * sizeof(float);
     CTTS_REQUIRE(sm <= 200 * 1024, "aligner_attention: S=%d too long for the shared-memory key tile", S);
-    if (sm > 48 * 1024)
-        cudaFuncSetAttribute(aligner_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    ensure_smem(aligner_attention_kernel, sm);
     dim3 grid((M + 7) / 8, B);
     aligner_attention_kernel<<<grid, 256, sm, (cudaStream_t)stream>>>(q, k, prior, src_lens, temperature, M, S, C, soft,
                                                                       logprob);
@@ -1204,6 +1281,27 @@ int ctts_phoneme_energy(const float* dur, const int64_t* src_lens, const float* 
     CTTS_REQUIRE(B > 0 && S > 0 && M > 0 && workspace, "phoneme_energy: bad arguments");
     phoneme_energy_kernel<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream>>>(dur, src_lens, energy, B, S, M, workspace, out);
     return check_launch("phoneme_energy");
+}
+
+int ctts_gru_bidir(const float* gi_fwd, const float* gi_bwd, const float* w_hh_fwd, const float* b_hh_fwd,
+                   const float* w_hh_bwd, const float* b_hh_bwd, int B, int T, int H, float* out, float* h_final,
+                   void* stream) {
+    CTTS_REQUIRE(B > 0 && T > 0 && H > 0 && 3 * H <= 1024, "gru_bidir: bad shape B=%d T=%d H=%d", B, T, H);
+    const size_t sm = ((size_t)H * 3 * H + H + 3 * H) * sizeof(float);
+    CTTS_REQUIRE(sm <= 227 * 1024, "gru_bidir: hidden size %d does not fit the shared-memory weight tile", H);
+    ensure_smem(gru_bidir_kernel, sm);
+    gru_bidir_kernel<<<dim3(B, 2), 3 * H, sm, (cudaStream_t)stream>>>(gi_fwd, gi_bwd, w_hh_fwd, b_hh_fwd, w_hh_bwd, b_hh_bwd,
+                                                                      T, H, out, h_final);
+    return check_launch("gru_bidir");
+}
+
+int ctts_linear_smallk(const float* x, const float* w, const float* bias, const float* residual, int rows, int K, int N,
+                       float* y, void* stream) {
+    CTTS_REQUIRE(rows > 0 && K > 0 && K <= 64 && N > 0, "linear_smallk: bad shape");
+    const size_t total = (size_t)rows * N;
+    const int grid = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
+    linear_smallk_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, residual, (size_t)rows, K, N, y);
+    return check_launch("linear_smallk");
 }
 
 }  // extern "C"

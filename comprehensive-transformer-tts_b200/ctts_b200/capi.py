@@ -33,6 +33,8 @@ SIGNATURES = {
     "ctts_gather_add": [_P, _P, _I, _I, _I, _P, _P],
     "ctts_bucketize": [_P, _F, _P, _I, _I, _P, _P],
     "ctts_add_row_broadcast": [_P, _P, _I, _I, _I, _P, _P],
+    "ctts_gru_bidir": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "ctts_linear_smallk": [_P, _P, _P, _P, _I, _I, _I, _P, _P],
     "ctts_aligner_attention": [_P, _P, _P, _P, _F, _I, _I, _I, _I, _P, _P, _P],
     "ctts_mas": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "ctts_phoneme_energy": [_P, _P, _P, _I, _I, _I, _P, _P, _P],

@@ -352,6 +352,32 @@ def pitch_style_predictor(prep, P, cfg, pre, xs, alpha=1.0):
     return conv_gemm(h, P[pre + "linear.weight"], P[pre + "linear.bias"], alpha=alpha)
 
 
+def prosody_predictor(prep, P, cfg, pre, x, phoneme_level):
+    """ParallelProsodyPredictor.forward, modules.py:630-648: (conv k3 + ReLU + LayerNorm 1e-5) x 2, bi-GRU over all S
+    steps, bottleneck Linear.  FP32 (it feeds the duration / pitch / energy quantisers)."""
+    k = cfg["prosody_modeling"]["liu2021"]["predictor_kernel_size"]
+    B, S, E = x.shape
+    st = _stream()
+    h = x
+    for i in (1, 2):
+        if i == 2 and k != 3:
+            raise NotImplementedError("conv1d_2 uses padding=1: only predictor_kernel_size 3 is 'same' (modules.py:610)")
+        c = conv_gemm(h, prep.w[pre + "conv_layer.conv1d_%d.conv.weight" % i], P[pre + "conv_layer.conv1d_%d.conv.bias" % i],
+                      act=ACT_RELU, taps=k)
+        h = layernorm(c, P[pre + "conv_layer.layer_norm_%d.weight" % i], P[pre + "conv_layer.layer_norm_%d.bias" % i], 1e-5)
+    gi_f = conv_gemm(h, P[pre + "gru.weight_ih_l0"], P[pre + "gru.bias_ih_l0"])
+    gi_b = conv_gemm(h, P[pre + "gru.weight_ih_l0_reverse"], P[pre + "gru.bias_ih_l0_reverse"])
+    Hd = P[pre + "gru.weight_hh_l0"].shape[1]
+    mem = torch.empty(B, S, 2 * Hd, device=x.device, dtype=torch.float32)
+    h_fin = torch.empty(B, 2 * Hd, device=x.device, dtype=torch.float32)
+    capi.call("ctts_gru_bidir", gi_f, gi_b, P[pre + "gru.weight_hh_l0"], P[pre + "gru.bias_hh_l0"],
+              P[pre + "gru.weight_hh_l0_reverse"], P[pre + "gru.bias_hh_l0_reverse"], B, S, Hd, mem, h_fin, st)
+    if phoneme_level:
+        return conv_gemm(mem, P[pre + "predictor_bottleneck.weight"], P[pre + "predictor_bottleneck.bias"])
+    return conv_gemm(h_fin.view(1, B, 2 * Hd), P[pre + "predictor_bottleneck.weight"],
+                     P[pre + "predictor_bottleneck.bias"]).view(B, 1, -1)
+
+
 def alignment_encoder(prep, P, cfg, mel, text_embedding, src_lens, attn_prior, spk):
     """AlignmentEncoder.forward, modules.py:1176-1213.  mel [B,M,80], text_embedding [B,S,C] (token-major), attn_prior
     [B,S,M].  Returns (attn_soft, attn_logprob) as [B,1,M,S]."""
@@ -415,11 +441,23 @@ def length_regulate(x, dur, src_lens, max_len, need_mel2ph, expand=True):
     return out, mel_len, mel2ph, cum_lr
 
 
-def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_lens, src_mask, mel, mel_lens, mel_mask,
-                     max_len, pitch_target, energy_target, duration_target, attn_prior, p_control, e_control, d_control,
-                     step):
-    """VarianceAdaptor.forward (prosody 'none'), modules.py:962-1114."""
-    pitch_cfg = pcfg["preprocessing"]["pitch"]
+def length_scan(dur, src_lens, B, S, device):
+    """ctts_length_scan: (cum_lr, cum_m2p, lens2) with lens2[:B] = LR lengths, lens2[B:] = mel2ph lengths."""
+    cum_lr = torch.empty(B, S, device=device, dtype=torch.int32)
+    cum_m2p = torch.empty(B, S, device=device, dtype=torch.int32)
+    lens2 = torch.empty(2 * B, device=device, dtype=torch.int64)
+    if dur.is_floating_point():
+        capi.call("ctts_length_scan", _f32(dur), None, src_lens, B, S, cum_lr, cum_m2p, lens2, _stream())
+    else:
+        capi.call("ctts_length_scan", None, _i64(dur), src_lens, B, S, cum_lr, cum_m2p, lens2, _stream())
+    return cum_lr, cum_m2p, lens2
+
+
+def variance_stage_a(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_lens, mel, mel_lens, duration_target,
+                     attn_prior, d_control):
+    """VarianceAdaptor.forward up to the point where the regulated length must be known on the host
+    (modules.py:962-1063): speaker add, liu2021 predictors, duration predictor, aligner + MAS, duration decoding and the
+    LengthRegulator scan.  No host synchronisation: capturable in a CUDA graph."""
     B, S, C = text.shape
     st = _stream()
     if spk is not None:
@@ -427,11 +465,26 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
         capi.call("ctts_add_row_broadcast", text, _f32(spk), B, S, C, x, st)
     else:
         x = text
+    prosody_info = None
+    model_type = cfg["prosody_modeling"]["model_type"]
+    if model_type == "liu2021":
+        # eval mode: the parallel predictors stand in for the reference encoders (modules.py:1002-1023)
+        pre = "variance_adaptor."
+        u_vec = prosody_predictor(prep, P, cfg, pre + "utterance_prosody_predictor.", x, False)       # [B, 1, 256]
+        u_add = conv_gemm(u_vec.view(1, B, -1), P[pre + "utterance_prosody_prj.weight"],
+                          P[pre + "utterance_prosody_prj.bias"]).view(B, -1)
+        x2 = torch.empty_like(x)
+        capi.call("ctts_add_row_broadcast", x, u_add, B, S, C, x2, st)
+        p_vec = prosody_predictor(prep, P, cfg, pre + "phoneme_prosody_predictor.", x2, True)        # [B, S, 4]
+        x = torch.empty_like(x2)
+        capi.call("ctts_linear_smallk", p_vec, P[pre + "phoneme_prosody_prj.weight"], P[pre + "phoneme_prosody_prj.bias"],
+                  x2, B * S, p_vec.shape[-1], C, x, st)
+        prosody_info = (None, None, u_vec, p_vec, None)
+    elif model_type != "none":
+        raise NotImplementedError("prosody model %r" % model_type)
     log_d = duration_predictor(prep, P, cfg, x, src_lens)
-    x_org = x
 
     attn_out = (None, None, None, None)
-    mel2ph = None
     if attn_prior is not None:
         # unsupervised duration modelling: AlignmentEncoder + monotonic alignment search (modules.py:1031-1053)
         assert cfg["duration_modeling"]["learn_alignment"] and duration_target is None and mel is not None
@@ -443,31 +496,56 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
         capi.call("ctts_mas", attn_soft, src_lens, mel_lens, B, M_in, S, prev_ws, attn_hard, attn_hard_dur, st)
         attn_out = (attn_soft, attn_hard, attn_hard_dur, attn_logprob)
         duration_rounded = attn_hard_dur
-        if step < tcfg["duration"]["binarization_start_steps"]:
-            # soft upsampling x = bmm(A_soft, x) (modules.py:1047-1049); mel_len stays the caller's
-            Sp = (S + 15) // 16 * 16
-            a_pad = torch.zeros(B, M_in, Sp, device=x.device, dtype=torch.float32)
-            a_pad[:, :, :S] = attn_soft[:, 0]
-            xt = torch.empty(B, C, Sp, device=x.device, dtype=torch.float32)
-            capi.call("ctts_transpose_heads", x, B, S, C, 0, 1, C, Sp, xt, st)
-            xe = torch.empty(B, M_in, C, device=x.device, dtype=torch.float32)
-            capi.call("ctts_batched_gemm_fp32", a_pad, xt, 1.0, None, 1, B, 1, M_in, Sp, C, M_in * Sp, 0, Sp, C * Sp, 0, Sp,
-                      M_in * C, 0, C, xe, st)
-            _, _, m2p, cum_lr = length_regulate(x, duration_rounded, src_lens, max_len, True, expand=False)
-            mel_len = mel_lens
-        else:
-            xe, mel_len, m2p, cum_lr = length_regulate(x, duration_rounded, src_lens, max_len, True)
-        m2p = m2p if m2p is not None else torch.zeros(B, 0, device=x.device, dtype=torch.int64)
-        pitch_target["mel2ph"] = m2p[:, :max_len]
     elif duration_target is not None:
         assert not cfg["duration_modeling"]["learn_alignment"] and attn_prior is None
-        xe, mel_len, _, cum_lr = length_regulate(x, duration_target, src_lens, max_len, False)
         duration_rounded = duration_target
     else:
-        assert attn_prior is None and duration_target is None
         duration_rounded = torch.empty_like(log_d)
         capi.call("ctts_decode_durations", log_d, float(d_control), B * S, duration_rounded, st)
-        xe, mel_len, mel2ph, cum_lr = length_regulate(x, duration_rounded, src_lens, max_len, True)
+    cum_lr, cum_m2p, lens2 = length_scan(duration_rounded, src_lens, B, S, x.device)
+    return dict(x=x, log_d=log_d, duration_rounded=duration_rounded, cum_lr=cum_lr, cum_m2p=cum_m2p, lens2=lens2,
+                attn_out=attn_out, prosody_info=prosody_info)
+
+
+def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, max_len, M, M2, pitch_target,
+                     energy_target, attn_prior, p_control, e_control, step):
+    """The rest of VarianceAdaptor.forward once the regulated length M (and the mel2ph length M2) are known
+    (modules.py:1044-1114): upsampling, pitch / energy embeddings."""
+    pitch_cfg = pcfg["preprocessing"]["pitch"]
+    x = a["x"]
+    x_org = x
+    B, S, C = x.shape
+    st = _stream()
+    dev = x.device
+    cum_lr, cum_m2p = a["cum_lr"], a["cum_m2p"]
+    need_m2p = attn_prior is not None or a.get("free_running", False)
+    mel2ph = torch.empty(B, M2, device=dev, dtype=torch.int64) if (need_m2p and M2 > 0) else None
+    soft = attn_prior is not None and step < tcfg["duration"]["binarization_start_steps"]
+    if soft:
+        # soft upsampling x = bmm(A_soft, x) (modules.py:1047-1049); mel_len stays the caller's
+        attn_soft = a["attn_out"][0]
+        M_in = attn_soft.shape[2]
+        Sp = (S + 15) // 16 * 16
+        a_pad = torch.zeros(B, M_in, Sp, device=dev, dtype=torch.float32)
+        a_pad[:, :, :S] = attn_soft[:, 0]
+        xt = torch.empty(B, C, Sp, device=dev, dtype=torch.float32)
+        capi.call("ctts_transpose_heads", x, B, S, C, 0, 1, C, Sp, xt, st)
+        xe = torch.empty(B, M_in, C, device=dev, dtype=torch.float32)
+        capi.call("ctts_batched_gemm_fp32", a_pad, xt, 1.0, None, 1, B, 1, M_in, Sp, C, M_in * Sp, 0, Sp, C * Sp, 0, Sp,
+                  M_in * C, 0, C, xe, st)
+        dummy = torch.empty(B, 1, C, device=dev, dtype=torch.float32)   # only the frame -> phoneme map is wanted
+        capi.call("ctts_length_expand", x, None, None, cum_lr, B, S, C, 1, 0, dummy, cum_m2p, mel2ph,
+                  M2 if mel2ph is not None else 0, st)
+        mel_len = mel_lens
+    else:
+        xe = torch.empty(B, M, C, device=dev, dtype=torch.float32)
+        capi.call("ctts_length_expand", x, None, None, cum_lr, B, S, C, M, 0, xe, cum_m2p, mel2ph,
+                  M2 if mel2ph is not None else 0, st)
+        mel_len = a["lens2"][:B]
+    if attn_prior is not None:
+        m2p = mel2ph if mel2ph is not None else torch.zeros(B, 0, device=dev, dtype=torch.int64)
+        pitch_target["mel2ph"] = m2p[:, :max_len]
+    if a.get("free_running", False):
         mel_mask = pad_mask(mel_len, xe.shape[1])
     M = xe.shape[1]
 
@@ -485,14 +563,14 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
         s = conv_gemm(first, P[pre + "cwt_stats_layers.0.weight"], P[pre + "cwt_stats_layers.0.bias"], act=ACT_RELU)
         s = conv_gemm(s, P[pre + "cwt_stats_layers.2.weight"], P[pre + "cwt_stats_layers.2.bias"], act=ACT_RELU)
         stats = conv_gemm(s, P[pre + "cwt_stats_layers.4.weight"], P[pre + "cwt_stats_layers.4.bias"]).view(B, 2)
-        f0_denorm = torch.empty(B, M, device=x.device, dtype=torch.float32)
-        idx = torch.empty(B, M, device=x.device, dtype=torch.int64)
+        f0_denorm = torch.empty(B, M, device=dev, dtype=torch.float32)
+        idx = torch.empty(B, M, device=dev, dtype=torch.int64)
         use_uv = 1 if pitch_cfg["use_uv"] else 0
         assert pitch_cfg["pitch_norm"] == "log", "only pitch_norm 'log' (the shipped configs) is built"
         if pitch_target is not None:
             m2p = pitch_target["mel2ph"]
             assert m2p.shape[1] == M, "mel2ph length %d != regulated length %d" % (m2p.shape[1], M)
-            f0n = torch.empty(B, M, device=x.device, dtype=torch.float32)
+            f0n = torch.empty(B, M, device=dev, dtype=torch.float32)
             spec = _f32(pitch_target["cwt_spec"])
             capi.call("ctts_cwt_to_pitch", spec, spec.shape[-1], prep.w["cwt_scale_w"], _f32(pitch_target["f0_mean"]),
                       _f32(pitch_target["f0_std"]), 1, 1.0, float(pitch_cfg["pitch_norm_eps"]),
@@ -517,25 +595,24 @@ def variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, text, text_embedding, src_le
             pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", xe.clone(),
                                          alpha=1.0 if energy_target is not None else e_control).squeeze(-1)
             src_vals = _f32(energy_target) if energy_target is not None else pred
-            eidx = torch.empty(B, M, device=x.device, dtype=torch.int64)
+            eidx = torch.empty(B, M, device=dev, dtype=torch.int64)
             capi.call("ctts_bucketize", src_vals, 1.0, bins, bins.shape[0], B * M, eidx, st)
             capi.call("ctts_gather_add", emb, eidx, B * M, C, emb.shape[0], x_sum, st)
         else:
             if attn_prior is not None:  # frame-level target -> phoneme level by the hard durations (modules.py:1096-1097)
                 et = _f32(energy_target)
                 M_e = et.shape[1]
-                work = torch.empty(B * M_e, device=x.device, dtype=torch.float32)
-                energy_target = torch.empty(B, S, device=x.device, dtype=torch.float32)
-                capi.call("ctts_phoneme_energy", attn_out[2], src_lens, et, B, S, M_e, work, energy_target, st)
+                work = torch.empty(B * M_e, device=dev, dtype=torch.float32)
+                energy_target = torch.empty(B, S, device=dev, dtype=torch.float32)
+                capi.call("ctts_phoneme_energy", a["attn_out"][2], src_lens, et, B, S, M_e, work, energy_target, st)
             pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", x_org.clone(),
                                          alpha=1.0 if energy_target is not None else e_control).squeeze(-1)
             src_vals = _f32(energy_target) if energy_target is not None else pred
-            eidx = torch.empty(B, S, device=x.device, dtype=torch.int64)
+            eidx = torch.empty(B, S, device=dev, dtype=torch.int64)
             capi.call("ctts_bucketize", src_vals, 1.0, bins, bins.shape[0], B * S, eidx, st)
             capi.call("ctts_length_expand", None, emb, eidx, cum_lr, B, S, C, M, 1, x_sum, None, None, 0, st)
         energy_pred = pred
-    return (x_sum, pitch_target, pitch_pred, energy_target, energy_pred, log_d, duration_rounded, mel_len, mel_mask,
-            attn_out, None)
+    return (x_sum, pitch_target, pitch_pred, energy_target, energy_pred, mel_len, mel_mask)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -559,6 +636,95 @@ def mel_head(prep, P, dec, dec_planes=None):
     return mel, h
 
 
+# ---------------------------------------------------------------------------------------------
+# CUDA-graph plumbing: the forward is two capturable stages around its single host sync
+# ---------------------------------------------------------------------------------------------
+def _flatten(prefix, v, out):
+    if v is None:
+        return
+    if torch.is_tensor(v):
+        out[prefix] = v
+    elif isinstance(v, dict):
+        for k in v:
+            _flatten(prefix + "." + k if prefix else k, v[k], out)
+    elif isinstance(v, (tuple, list)):
+        for i, x in enumerate(v):
+            _flatten("%s.%d" % (prefix, i), x, out)
+
+
+def _tree_map(fn, v):
+    if torch.is_tensor(v):
+        return fn(v)
+    if isinstance(v, dict):
+        return {k: _tree_map(fn, x) for k, x in v.items()}
+    if isinstance(v, tuple):
+        return tuple(_tree_map(fn, x) for x in v)
+    if isinstance(v, list):
+        return [_tree_map(fn, x) for x in v]
+    return v
+
+
+class GraphCache:
+    """Shape-keyed cache of captured stages.  A stage is run eagerly the first time a key is seen (this also warms the
+    lazily built tables and kernel attributes), captured into a CUDA graph the second time, and replayed afterwards:
+    at the bench shape the step is otherwise bound by ~120 Python/ctypes launches, not by the GPU."""
+
+    def __init__(self, max_entries=16):
+        self.entries = {}
+        self.max_entries = max_entries
+        self.pool = None
+
+    def clear(self):
+        self.entries.clear()
+
+    def run(self, key, fn, tensor_inputs, table=None):
+        """fn(inputs_dict) -> pytree.  Returns (outputs, sub_table or None).  Outputs of a replayed graph are static
+        buffers (valid until the next replay of the same key)."""
+        table = self.entries if table is None else table
+        e = table.get(key)
+        if e is None:
+            if len(table) >= self.max_entries:
+                table.pop(next(iter(table)))
+            table[key] = False
+            return fn(tensor_inputs), None
+        if e is False:
+            static = {k: v.clone() for k, v in tensor_inputs.items()}
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            if self.pool is None:
+                self.pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(g, pool=self.pool):
+                out = fn(static)
+            e = table[key] = (g, static, out, {})
+        g, static, out, sub = e
+        for k, v in tensor_inputs.items():
+            static[k].copy_(v, non_blocking=True)
+        g.replay()
+        return out, sub
+
+
+def _encode(module, prep, P, cfg, texts, src_lens):
+    block = cfg["block_type"]
+    if block == "transformer_fs2":
+        return encoder_fs2(prep, P, cfg, texts, src_lens, module.encoder_math)
+    from . import engine_blocks
+    if block not in engine_blocks.ENCODERS:
+        raise NotImplementedError("block_type %r: kernels not built yet" % block)
+    return engine_blocks.ENCODERS[block](prep, P, cfg, texts, src_lens)
+
+
+def _decode(module, prep, P, cfg, x, mel_lens):
+    block = cfg["block_type"]
+    if block == "transformer_fs2":
+        dec, dec_planes = decoder_fs2(prep, P, cfg, x, mel_lens, module.decoder_math)
+    else:
+        from . import engine_blocks
+        dec, dec_planes = engine_blocks.DECODERS[block](prep, P, cfg, x, mel_lens, module.decoder_math)
+        if module.decoder_math == "bf16x3" and dec_planes is None:
+            dec_planes = split_planes(dec)
+    return mel_head(prep, P, dec, dec_planes)
+
+
 def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None, p_targets=None,
             e_targets=None, d_targets=None, attn_priors=None, spker_embeds=None, p_control=1.0, e_control=1.0,
             d_control=1.0, step=None):
@@ -569,43 +735,94 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
                              % texts.device)
     pcfg, cfg, tcfg = module.preprocess_config, module.model_config, module.train_config
     prep = module._prepared
+    sig_before = prep.sig
     P = prep.params()
+    graphs = module._graphs if module.use_cuda_graphs else None
+    if graphs is not None and prep.sig is not sig_before:
+        graphs.clear()   # weights were re-laid-out: captured graphs point at stale buffers
     texts = _i64(texts)
     src_lens = _i64(src_lens)
+    B, S = texts.shape
+    free_running = attn_priors is None and d_targets is None
+    soft = attn_priors is not None and step < tcfg["duration"]["binarization_start_steps"]
+
+    # ---- stage A: encoder, speaker / prosody, duration model, LengthRegulator scan ------------------------------------
+    in_a = {}
+    _flatten("", dict(speakers=speakers if module.has_speaker_emb and module.embedder_type == "none" else None,
+                      texts=texts, src_lens=src_lens, mels=mels if attn_priors is not None else None,
+                      mel_lens=_i64(mel_lens) if mel_lens is not None else None, d_targets=d_targets,
+                      attn_priors=attn_priors,
+                      spker_embeds=spker_embeds if module.has_speaker_emb and module.embedder_type != "none" else None),
+             in_a)
+
+    def stage_a(t):
+        enc, word = _encode(module, prep, P, cfg, t["texts"], t["src_lens"])
+        spk = None
+        if module.has_speaker_emb:
+            if module.embedder_type == "none":
+                spk = P["speaker_emb.weight"][_i64(t["speakers"])]
+            else:
+                assert "spker_embeds" in t, "Speaker embedding should not be None"
+                Bs = t["spker_embeds"].shape[0]
+                spk = conv_gemm(_f32(t["spker_embeds"]).view(1, Bs, -1), P["speaker_emb.weight"],
+                                P["speaker_emb.bias"]).view(Bs, -1)
+        a = variance_stage_a(prep, P, pcfg, cfg, tcfg, spk, enc, word, t["src_lens"], t.get("mels"), t.get("mel_lens"),
+                             t.get("d_targets"), t.get("attn_priors"), d_control)
+        a["free_running"] = free_running
+        return a
+
+    key_a = ("A", float(d_control), tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(in_a.items())))
+    if graphs is not None:
+        a, sub = graphs.run(key_a, stage_a, in_a)
+    else:
+        a, sub = stage_a(in_a), None
+
+    # ---- the single host sync: the regulated lengths --------------------------------------------------------------
+    need_m2p = attn_priors is not None or free_running
+    if max_mel_len is None or need_m2p:
+        maxes = a["lens2"].view(2, B).max(dim=1).values.tolist()
+        M = int(max_mel_len) if max_mel_len is not None else int(maxes[0])
+        M2 = int(maxes[1])
+    else:
+        M, M2 = int(max_mel_len), 0
+    if soft:
+        M = int(mels.shape[1])
+    if M <= 0:
+        raise capi.CttsError("length_regulate: every duration is zero (empty mel)")
+
+    # ---- stage B: upsampling, pitch / energy embeddings, decoder, mel head ------------------------------------------
     src_masks = pad_mask(src_lens, max_src_len)
-    mel_masks = None
-    if mel_lens is not None:
-        mel_lens = _i64(mel_lens)
-        mel_masks = pad_mask(mel_lens, max_mel_len)
-    block = cfg["block_type"]
-    if block == "transformer_fs2":
-        enc, word = encoder_fs2(prep, P, cfg, texts, src_lens, module.encoder_math)
-    else:
-        from . import engine_blocks
-        if block not in engine_blocks.ENCODERS:
-            raise NotImplementedError("block_type %r: kernels not built yet" % block)
-        enc, word = engine_blocks.ENCODERS[block](prep, P, cfg, texts, src_lens)
+    mel_masks = pad_mask(_i64(mel_lens), max_mel_len) if mel_lens is not None else None
+    in_b = {}
+    _flatten("", dict(p_targets=p_targets, e_targets=e_targets, mel_lens=_i64(mel_lens) if mel_lens is not None else None),
+             in_b)
+    a_live = a   # static buffers of graph A when it was replayed, plain tensors otherwise
 
-    spk = None
-    if module.has_speaker_emb:
-        if module.embedder_type == "none":
-            spk = P["speaker_emb.weight"][_i64(speakers)]
-        else:
-            assert spker_embeds is not None, "Speaker embedding should not be None"
-            Bs = spker_embeds.shape[0]
-            spk = conv_gemm(_f32(spker_embeds).view(1, Bs, -1), P["speaker_emb.weight"], P["speaker_emb.bias"]).view(
-                Bs, -1)
+    def stage_b(t):
+        pt = None
+        if p_targets is not None:
+            pt = {k[len("p_targets."):]: v for k, v in t.items() if k.startswith("p_targets.")}
+        xs, pt, p_pred, e_t, e_pred, mel_len, mel_mask = variance_stage_b(
+            prep, P, pcfg, cfg, tcfg, a_live, a_src_lens[0], t.get("mel_lens"), None, max_mel_len, M, M2, pt,
+            t.get("e_targets"), attn_priors, p_control, e_control, step)
+        mel, post = _decode(module, prep, P, cfg, xs, mel_len)
+        return dict(mel=mel, post=post, p_pred=p_pred, e_pred=e_pred, mel_len=mel_len, mel_mask=mel_mask, p_targets=pt,
+                    e_targets=e_t)
 
-    (x, p_targets, p_pred, e_targets, e_pred, log_d, d_rounded, mel_lens, mel_masks, attn_outs, prosody) = \
-        variance_adaptor(prep, P, pcfg, cfg, tcfg, spk, enc, word, src_lens, src_masks, mels, mel_lens, mel_masks,
-                         max_mel_len, p_targets, e_targets, d_targets, attn_priors, p_control, e_control, d_control,
-                         step)
-    if block == "transformer_fs2":
-        dec, dec_planes = decoder_fs2(prep, P, cfg, x, mel_lens, module.decoder_math)
+    a_src_lens = [src_lens]
+    key_b = ("B", M, M2, float(p_control), float(e_control), bool(soft), max_mel_len,
+             tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(in_b.items())))
+    if graphs is not None and sub is not None:
+        # graph B reads graph A's static outputs in place; its own inputs are the caller's targets
+        a_src_lens[0] = graphs.entries[key_a][1]["src_lens"]
+        o, _ = graphs.run(key_b, stage_b, in_b, table=sub)
     else:
-        dec, dec_planes = engine_blocks.DECODERS[block](prep, P, cfg, x, mel_lens, module.decoder_math)
-        if module.decoder_math == "bf16x3" and dec_planes is None:
-            dec_planes = split_planes(dec)
-    mel, post = mel_head(prep, P, dec, dec_planes)
-    return (mel, post, p_pred, e_pred, log_d, d_rounded, src_masks, mel_masks, src_lens, mel_lens, attn_outs, prosody,
-            p_targets, e_targets)
+        o = stage_b(in_b)
+    if graphs is not None and sub is not None:
+        # hand out private copies: the static buffers are overwritten by the next replay
+        o = _tree_map(lambda v: v.clone(), o)
+        a = _tree_map(lambda v: v.clone(), {k: a[k] for k in ("log_d", "duration_rounded", "attn_out", "prosody_info")})
+    mel_masks_out = o["mel_mask"] if o["mel_mask"] is not None else mel_masks
+    d_rounded = d_targets if (d_targets is not None and attn_priors is None) else a["duration_rounded"]
+    return (o["mel"], o["post"], o["p_pred"], o["e_pred"], a["log_d"], d_rounded, src_masks, mel_masks_out, src_lens,
+            o["mel_len"], a["attn_out"], a["prosody_info"], o["p_targets"], o["e_targets"])

@@ -46,6 +46,8 @@ def _initial(shape, init):
         return torch.zeros(shape)
     if init == "normal01":
         return torch.randn(shape)
+    if init == "normal05":  # STL token embeddings, modules.py:470
+        return torch.randn(shape) * 0.5
     if init == "normal002":  # fastformer.py:285-290
         return torch.randn(shape) * 0.02
     if init == "emb1":
@@ -110,6 +112,9 @@ class CompTransTTS(nn.Module):
         self.encoder_math = os.environ.get("CTTS_ENCODER_MATH", "bf16x6")
         if self.encoder_math not in ("bf16x6", "fp32"):
             raise ValueError("CTTS_ENCODER_MATH must be 'bf16x6' or 'fp32'")
+        # CUDA graphs: the forward is captured as two stages around its single host sync (engine.GraphCache)
+        self.use_cuda_graphs = os.environ.get("CTTS_CUDA_GRAPHS", "1") != "0"
+        self._graphs = engine.GraphCache()
         self._prepared = engine.Prepared(self)
 
     def forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,

@@ -144,9 +144,73 @@ def _variance_adaptor(out, pcfg, cfg, d_model):
         if cfg["multi_speaker"]:
             out.append((a + "key_spk_proj.linear.weight", (d_model, d_model), "param", "xavier"))
             out.append((a + "query_spk_proj.linear.weight", (mel, d_model), "param", "xavier"))
-    if cfg["prosody_modeling"]["model_type"] != "none":
-        raise NotImplementedError("prosody_modeling.model_type %r is not built yet (SURVEY.md section 8a A19)"
-                                  % cfg["prosody_modeling"]["model_type"])
+    model_type = cfg["prosody_modeling"]["model_type"]
+    if model_type == "liu2021":
+        _liu2021(out, pcfg, cfg)
+    elif model_type != "none":
+        # du2021 (GMM-MDN) is out of scope: SURVEY.md section 2 row 2
+        raise NotImplementedError("prosody_modeling.model_type %r is not built" % model_type)
+
+
+def _liu2021(out, pcfg, cfg):
+    """Implicit prosody modelling (Liu et al. 2021): modules.py:332-648, 840-861; coordconv.py:140-159.
+    The two reference encoders (mel -> prosody) only run in training mode (modules.py:1005-1007) but their
+    parameters are part of every checkpoint, so they are registered here as well."""
+    c = cfg["prosody_modeling"]["liu2021"]
+    E = cfg["transformer"]["encoder_hidden"]
+    mel = pcfg["preprocessing"]["mel"]["n_mel_channels"]
+    g = c["ref_enc_gru_size"]
+    filt = [1] + list(c["ref_enc_filters"])
+    kh, kw = c["ref_enc_size"]
+    L = mel
+    for _ in range(len(filt) - 1):      # ReferenceEncoder.calculate_channels(L, 3, 2, 1, K)
+        L = (L - 3 + 2 * 1) // 2 + 1
+    for enc in ("utterance_prosody_encoder", "phoneme_prosody_encoder"):
+        p = "variance_adaptor.%s.encoder." % enc
+        for i in range(len(filt) - 1):
+            fan = filt[i] * kh * kw
+            out.append((p + "convs.%d.weight" % i, (filt[i + 1], filt[i], kh, kw), "param", "default:%d" % fan))
+            out.append((p + "convs.%d.bias" % i, (filt[i + 1],), "param", "default:%d" % fan))
+            if i == 0:  # CoordConv2d keeps the parent Conv2d's tensors AND its own conv (+2 coords +1 radius)
+                fan = (filt[0] + 3) * kh * kw
+                out.append((p + "convs.0.conv.weight", (filt[1], filt[0] + 3, kh, kw), "param", "default:%d" % fan))
+                out.append((p + "convs.0.conv.bias", (filt[1],), "param", "default:%d" % fan))
+        for i in range(len(filt) - 1):
+            _bn(out, p + "bns.%d" % i, filt[i + 1])
+        _gru(out, p + "gru", filt[-1] * L, g, False)
+        q = "variance_adaptor.%s." % enc
+        if enc == "utterance_prosody_encoder":
+            _lin(out, q + "encoder_prj", E // 2, g)
+            out.append((q + "stl.embed", (c["token_num"], E), "param", "normal05"))
+            out.append((q + "stl.attention.W_query.weight", (E, E // 2), "param", "default:%d" % (E // 2)))
+            out.append((q + "stl.attention.W_key.weight", (E, E), "param", "default:%d" % E))
+            out.append((q + "stl.attention.W_value.weight", (E, E), "param", "default:%d" % E))
+            _lin(out, q + "encoder_bottleneck", c["bottleneck_size_u"], E)
+        else:
+            out.append((q + "linears.0.linear.weight", (E, E), "param", "xavier"))
+            out.append((q + "linears.1.linear.weight", (E, E), "param", "xavier"))
+            _lin(out, q + "encoder_prj", 2 * E, g)
+            _lin(out, q + "encoder_bottleneck", c["bottleneck_size_p"], E)
+    for name, bott in (("utterance_prosody_predictor", c["bottleneck_size_u"]),
+                       ("phoneme_prosody_predictor", c["bottleneck_size_p"])):
+        p = "variance_adaptor.%s." % name
+        k = c["predictor_kernel_size"]
+        _conv(out, p + "conv_layer.conv1d_1.conv", E, E, k, init="xavier")
+        _ln(out, p + "conv_layer.layer_norm_1", E)
+        _conv(out, p + "conv_layer.conv1d_2.conv", E, E, k, init="xavier")
+        _ln(out, p + "conv_layer.layer_norm_2", E)
+        _gru(out, p + "gru", E, E // 2, True)
+        _lin(out, p + "predictor_bottleneck", bott, E)
+    _lin(out, "variance_adaptor.utterance_prosody_prj", E, c["bottleneck_size_u"])
+    _lin(out, "variance_adaptor.phoneme_prosody_prj", E, c["bottleneck_size_p"])
+
+
+def _gru(out, name, in_size, hidden, bidirectional):
+    for suffix in ([""] + (["_reverse"] if bidirectional else [])):
+        out.append((name + ".weight_ih_l0" + suffix, (3 * hidden, in_size), "param", "default:%d" % hidden))
+        out.append((name + ".weight_hh_l0" + suffix, (3 * hidden, hidden), "param", "default:%d" % hidden))
+        out.append((name + ".bias_ih_l0" + suffix, (3 * hidden,), "param", "default:%d" % hidden))
+        out.append((name + ".bias_hh_l0" + suffix, (3 * hidden,), "param", "default:%d" % hidden))
 
 
 def _postnet(out):

@@ -65,7 +65,7 @@ def synthetic_state_dict(spec_entries, seed=1234, pin_frames_per_phoneme=None):
             t = torch.full(shape, 0.7) + 0.1 * torch.randn(shape, generator=g)
         elif init == "ones":  # LN / BN scale
             t = 1.0 + 0.1 * torch.randn(shape, generator=g)
-        elif leaf == "bias" or init == "zeros":
+        elif leaf.startswith("bias") or init == "zeros":
             t = 0.05 * torch.randn(shape, generator=g)
         elif init.startswith("emb"):
             d = int(init.split(":")[1])
@@ -73,6 +73,8 @@ def synthetic_state_dict(spec_entries, seed=1234, pin_frames_per_phoneme=None):
             t[0] = 0
         elif init == "normal01":
             t = torch.randn(shape, generator=g)
+        elif init == "normal05":
+            t = 0.5 * torch.randn(shape, generator=g)
         else:  # dense / conv weights: variance-preserving
             fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
             t = torch.randn(shape, generator=g) / math.sqrt(fan_in)

@@ -160,6 +160,18 @@ int ctts_bucketize(const float* v, float v_scale, const float* bins, int n_bins,
 /* y = x + spk[b] broadcast over T (modules.py:985-988) */
 int ctts_add_row_broadcast(const float* x, const float* row, int B, int T, int C, float* y, void* stream);
 
+/* ---- liu2021 implicit prosody predictors (eval path; modules.py:572-648, 1002-1023) ----------------------
+ * ctts_gru_bidir      recurrence of a bidirectional single-layer nn.GRU (gates r|z|n).  gi_* = x W_ih^T + b_ih for every
+ *                     step ([B,T,3H], produced by ctts_conv1d_gemm); out [B,T,2H] (fwd | bwd), h_final [B,2H].  Runs over
+ *                     all T (padded) steps like the reference (no packing).  3H <= 1024; W_hh^T lives in shared memory.
+ * ctts_linear_smallk  y = x W^T + b (+ residual) for tiny K (the 4-d phoneme prosody code -> 256, modules.py:861).
+ */
+int ctts_gru_bidir(const float* gi_fwd, const float* gi_bwd, const float* w_hh_fwd, const float* b_hh_fwd,
+                   const float* w_hh_bwd, const float* b_hh_bwd, int B, int T, int H, float* out, float* h_final,
+                   void* stream);
+int ctts_linear_smallk(const float* x, const float* w, const float* bias, const float* residual, int rows, int K, int N,
+                       float* y, void* stream);
+
 /* ---- unsupervised duration modelling (learn_alignment: True) --------------------------------------
  * ctts_aligner_attention  AlignmentEncoder.forward score assembly, modules.py:1198-1212.  q [B,M,C] / k [B,S,C] are the
  *   projected mel / text features (the conv stacks run through ctts_conv1d_gemm), prior [B,S,M] is the caller's

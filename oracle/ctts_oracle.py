@@ -301,6 +301,45 @@ def energy_embedding(P, cfg, x, target, control):
     return pred, F.embedding(idx, P[pre + "energy_embedding.weight"], padding_idx=0)
 
 
+def _gru_direction(x, w_ih, w_hh, b_ih, b_hh, reverse):
+    """One direction of nn.GRU (batch_first), gates ordered r, z, n; runs over every (padded) step."""
+    B, T, _ = x.shape
+    Hd = w_hh.shape[1]
+    gi = F.linear(x, w_ih, b_ih)
+    h = x.new_zeros(B, Hd)
+    outs = [None] * T
+    steps = range(T - 1, -1, -1) if reverse else range(T)
+    for t in steps:
+        gh = F.linear(h, w_hh, b_hh)
+        i_r, i_z, i_n = gi[:, t].chunk(3, 1)
+        h_r, h_z, h_n = gh.chunk(3, 1)
+        r = torch.sigmoid(i_r + h_r)
+        z = torch.sigmoid(i_z + h_z)
+        n = torch.tanh(i_n + r * h_n)
+        h = (1 - z) * n + z * h
+        outs[t] = h
+    return torch.stack(outs, 1), h
+
+
+def parallel_prosody_predictor(P, cfg, pre, x, phoneme_level):
+    """ParallelProsodyPredictor.forward, modules.py:630-648 (conv k3 + ReLU + LN(1e-5) twice, bi-GRU, bottleneck)."""
+    k = cfg["prosody_modeling"]["liu2021"]["predictor_kernel_size"]
+    E = x.shape[-1]
+    h = x
+    for i in (1, 2):
+        pad = (k - 1) // 2 if i == 1 else 1
+        h = F.conv1d(h.transpose(1, 2), P[pre + "conv_layer.conv1d_%d.conv.weight" % i],
+                     P[pre + "conv_layer.conv1d_%d.conv.bias" % i], padding=pad).transpose(1, 2)
+        h = F.layer_norm(F.relu(h), (E,), P[pre + "conv_layer.layer_norm_%d.weight" % i],
+                         P[pre + "conv_layer.layer_norm_%d.bias" % i], 1e-5)
+    fw, h_f = _gru_direction(h, P[pre + "gru.weight_ih_l0"], P[pre + "gru.weight_hh_l0"], P[pre + "gru.bias_ih_l0"],
+                             P[pre + "gru.bias_hh_l0"], False)
+    bw, h_b = _gru_direction(h, P[pre + "gru.weight_ih_l0_reverse"], P[pre + "gru.weight_hh_l0_reverse"],
+                             P[pre + "gru.bias_ih_l0_reverse"], P[pre + "gru.bias_hh_l0_reverse"], True)
+    vec = torch.cat([fw, bw], -1) if phoneme_level else torch.cat([h_f, h_b], -1).unsqueeze(1)
+    return F.linear(vec, P[pre + "predictor_bottleneck.weight"], P[pre + "predictor_bottleneck.bias"])
+
+
 # --- unsupervised duration modelling: AlignmentEncoder + MAS -----------------------------------
 def alignment_encoder(P, queries, keys, src_mask, attn_prior, temperature, speaker_embed=None):
     """AlignmentEncoder.forward, modules.py:1176-1213.  queries [B,80,M] (mel), keys [B,C,S]."""
@@ -380,13 +419,23 @@ def phoneme_level_energy(duration, src_len, energy_frame):
 def variance_adaptor(P, pcfg, cfg, tcfg, speaker_embedding, text, text_embedding, src_len, src_mask, mel, mel_len,
                      mel_mask, max_len, pitch_target, energy_target, duration_target, attn_prior,
                      p_control, e_control, d_control, step):
-    """VarianceAdaptor.forward, prosody model 'none', modules.py:962-1114."""
-    assert cfg["prosody_modeling"]["model_type"] == "none"
+    """VarianceAdaptor.forward (prosody model 'none' or 'liu2021' in eval mode), modules.py:962-1114."""
+    assert cfg["prosody_modeling"]["model_type"] in ("none", "liu2021")
     assert pcfg["preprocessing"]["pitch"]["pitch_type"] == "cwt"
     learn_alignment = cfg["duration_modeling"]["learn_alignment"]
     x = text.clone()
     if speaker_embedding is not None:
         x = x + speaker_embedding.unsqueeze(1)
+    prosody_info = None
+    if cfg["prosody_modeling"]["model_type"] == "liu2021":
+        # eval mode: the predictors stand in for the reference encoders (modules.py:1002-1023)
+        u_vec = parallel_prosody_predictor(P, cfg, "variance_adaptor.utterance_prosody_predictor.", x, False)
+        x = x + F.linear(u_vec, P["variance_adaptor.utterance_prosody_prj.weight"],
+                         P["variance_adaptor.utterance_prosody_prj.bias"])
+        p_vec = parallel_prosody_predictor(P, cfg, "variance_adaptor.phoneme_prosody_predictor.", x, True)
+        x = x + F.linear(p_vec, P["variance_adaptor.phoneme_prosody_prj.weight"],
+                         P["variance_adaptor.phoneme_prosody_prj.bias"])
+        prosody_info = (None, None, u_vec, p_vec, None)
     log_d = duration_predictor(P, cfg, x, src_mask)
 
     attn_soft = attn_hard = attn_hard_dur = attn_logprob = None
@@ -442,7 +491,7 @@ def variance_adaptor(P, pcfg, cfg, tcfg, speaker_embedding, text, text_embedding
             energy_pred, e_emb = energy_embedding(P, cfg, x_org, energy_target, e_control)
             x_sum = x_sum + length_regulate(e_emb, duration_rounded, max_len)[0]
     return (x_sum, pitch_target, pitch_pred, energy_target, energy_pred, log_d, duration_rounded, mel_len, mel_mask,
-            attn_out, None)
+            attn_out, prosody_info)
 
 
 # ----------------------------------------------------------------------------------------------

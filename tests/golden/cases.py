@@ -29,6 +29,13 @@ CASES = {
     # frame-level targets (learn_alignment True, attn_priors given, step 120000 > binarization_start_steps)
     "fs2_unsup": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=True, mode="unsup",
                       batch=3, s_max=30, s_step=7, pin=None, seed=7),
+    # BASELINE configs[3] family: fastformer, VCTK config (multi-speaker, DeepSpeaker 512-d embeddings -> Linear),
+    # unsupervised alignment with speaker-conditioned aligner projections
+    "fastformer_vctk_unsup": dict(dataset="VCTK", block_type="fastformer", learn_alignment=True, mode="unsup",
+                                  batch=3, s_max=24, s_step=5, pin=None, seed=8),
+    # BASELINE configs[4] family: transformer_fs2 + liu2021 implicit prosody (eval: conv + bi-GRU predictors)
+    "fs2_liu2021_infer": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="infer",
+                              batch=2, s_max=40, s_step=9, pin=4, seed=9, prosody="liu2021"),
 }
 
 TAP_STRIDE = 4  # intermediate activations are stored for every 4th row only
@@ -42,7 +49,8 @@ def build_case(name):
     """(configs, state_dict, batch) for a case -- importable without the reference."""
     from ctts_b200 import configs, spec, synth
     c = CASES[name]
-    p, m, t = configs.builtin_configs(c["dataset"], block_type=c["block_type"], learn_alignment=c["learn_alignment"])
+    p, m, t = configs.builtin_configs(c["dataset"], block_type=c["block_type"], learn_alignment=c["learn_alignment"],
+                                      prosody=c.get("prosody"))
     entries, _, _ = spec.parameter_spec(p, m)
     sd = synth.synthetic_state_dict(entries, pin_frames_per_phoneme=c["pin"])
     batch = synth.ljspeech_batch(batch=c["batch"], s_max=c["s_max"], s_step=c["s_step"], mode=c["mode"],

@@ -31,6 +31,8 @@ def run_reference(name):
     rp, rm, rt = reference_configs(c["dataset"])
     rm["block_type"] = c["block_type"]
     rm["duration_modeling"]["learn_alignment"] = c["learn_alignment"]
+    if c.get("prosody"):
+        rm["prosody_modeling"]["model_type"] = c["prosody"]
     net = ref_model.CompTransTTS(rp, rm, rt).eval()
     net.load_state_dict(sd, strict=True)
     taps = {}
