@@ -175,6 +175,7 @@ def main():
     import torch.distributed as dist
     import ctts_b200
     from ctts_b200 import capi, engine
+    from ctts_b200 import dist as cdist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -238,10 +239,7 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t = torch.tensor([total], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), capi.LAUNCHES - launches0
+        return cdist.max_over_ranks(total, dev, world), capi.LAUNCHES - launches0
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, launches = run_timed(step_device, args.steps, args.warmup)

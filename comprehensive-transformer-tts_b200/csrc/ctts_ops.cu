@@ -78,30 +78,48 @@ __global__ void embed_tokens_kernel(const int64_t* __restrict__ tokens, const fl
     }
 }
 
-__global__ void add_positions_kernel(float* __restrict__ x, const float* __restrict__ pe, const float* __restrict__ alpha,
-                                     const int64_t* __restrict__ lens, int T, int C, int pos_mode) {
-    extern __shared__ int s_pos[];
+// grid (B, ceil(T / 64)): every CTA re-derives the running position count up to its own 64-row chunk with warp
+// ballots (T strided loads of x[b,t,0], cheap) and then updates its rows -- one CTA per utterance left 132 SMs idle.
+constexpr int POS_ROWS = 64;
+__global__ void add_positions_kernel(const float* __restrict__ x, const float* __restrict__ pe,
+                                     const float* __restrict__ alpha, const int64_t* __restrict__ lens, int T, int C,
+                                     int pos_mode, float* __restrict__ y) {
+    __shared__ int s_pos[POS_ROWS];
     const int b = blockIdx.x;
-    float* xb = x + (size_t)b * T * C;
+    const int r0 = blockIdx.y * POS_ROWS;
+    const int r1 = min(r0 + POS_ROWS, T);
+    const float* xb = x + (size_t)b * T * C;
+    float* yb = y + (size_t)b * T * C;
     if (pos_mode == 0) {
-        if (threadIdx.x < 32) warp_positions(T, s_pos, [&](int t) { return xb[(size_t)t * C] != 0.f; });
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            int running = 0;
+            for (int base = 0; base < r1; base += 32) {
+                const int t = base + lane;
+                const bool f = (t < r1) && xb[(size_t)t * C] != 0.f;
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                const int incl = __popc(m & (0xffffffffu >> (31 - lane)));
+                if (t >= r0 && t < r1) s_pos[t - r0] = f ? running + incl : 0;
+                running += __popc(m);
+            }
+        }
     } else {
-        for (int t = threadIdx.x; t < T; t += blockDim.x) s_pos[t] = t;
+        for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) s_pos[t - r0] = t;
     }
     __syncthreads();
     const float a = alpha ? alpha[0] : 1.f;
     const int len = lens ? (int)lens[b] : T;
     const int c4 = C >> 2;
-    for (int i = threadIdx.x; i < T * c4; i += blockDim.x) {
-        const int t = i / c4, c = (i - t * c4) << 2;
-        float4 v = *reinterpret_cast<float4*>(xb + (size_t)t * C + c);
+    for (int i = threadIdx.x; i < (r1 - r0) * c4; i += blockDim.x) {
+        const int t = r0 + i / c4, c = (i % c4) << 2;
+        float4 v = *reinterpret_cast<const float4*>(xb + (size_t)t * C + c);
         if (t < len) {
-            const float4 p = *reinterpret_cast<const float4*>(pe + (size_t)s_pos[t] * C + c);
+            const float4 p = *reinterpret_cast<const float4*>(pe + (size_t)s_pos[t - r0] * C + c);
             v.x += a * p.x; v.y += a * p.y; v.z += a * p.z; v.w += a * p.w;
         } else {
             v = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        *reinterpret_cast<float4*>(xb + (size_t)t * C + c) = v;
+        *reinterpret_cast<float4*>(yb + (size_t)t * C + c) = v;
     }
 }
 
@@ -1017,14 +1035,13 @@ int ctts_embed_tokens(const int64_t* tokens, const float* table, const float* pe
     return check_launch("embed_tokens");
 }
 
-int ctts_add_positions(float* x, const float* pe, int pe_rows, const float* alpha, const int64_t* lens, int B, int T,
-                       int C, int pos_mode, void* stream) {
+int ctts_add_positions(const float* x, const float* pe, int pe_rows, const float* alpha, const int64_t* lens, int B, int T,
+                       int C, int pos_mode, float* y, void* stream) {
+    CTTS_REQUIRE(y != nullptr && y != x, "add_positions: y must be a separate buffer (CTAs re-read x[..., 0] of earlier rows)");
     CTTS_REQUIRE(B > 0 && T > 0 && C % 4 == 0, "add_positions: bad shape B=%d T=%d C=%d", B, T, C);
     CTTS_REQUIRE(pe_rows > T - (pos_mode ? 1 : 0), "add_positions: positional table has %d rows, need > %d", pe_rows, T);
-    CTTS_REQUIRE((size_t)T * 4 <= 200 * 1024, "add_positions: T=%d too long", T);
-    const size_t sm = (size_t)T * sizeof(int);
-    ensure_smem(add_positions_kernel, sm);
-    add_positions_kernel<<<B, 512, sm, (cudaStream_t)stream>>>(x, pe, alpha, lens, T, C, pos_mode);
+    dim3 grid(B, (T + POS_ROWS - 1) / POS_ROWS);
+    add_positions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, pe, alpha, lens, T, C, pos_mode, y);
     return check_launch("add_positions");
 }
 

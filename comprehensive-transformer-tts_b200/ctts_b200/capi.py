@@ -20,7 +20,7 @@ SIGNATURES = {
     "ctts_last_error": [],
     "ctts_device_arch": [],
     "ctts_embed_tokens": [_P, _P, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P, _I, _P],
-    "ctts_add_positions": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "ctts_add_positions": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P],
     "ctts_layernorm": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _P],
     "ctts_conv1d_gemm": [_P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "ctts_pack_conv_weight": [_P, _I, _I, _I, _P, _P],

@@ -302,7 +302,8 @@ def decoder_fs2(prep, P, cfg, x, mel_lens, math_mode="fp32"):
     c = cfg["transformer_fs2"]
     B, T, C = x.shape
     pe = prep.table_fs2(C, T + 1, x.device)
-    capi.call("ctts_add_positions", x, pe, pe.shape[0], P["decoder.pos_embed_alpha"], mel_lens, B, T, C, 0, _stream())
+    xin, x = x, torch.empty_like(x)
+    capi.call("ctts_add_positions", xin, pe, pe.shape[0], P["decoder.pos_embed_alpha"], mel_lens, B, T, C, 0, x, _stream())
     act = _ACTS[cfg["variance_predictor"]["ffn_act"]]
     if math_mode == "bf16x3":
         return _fft_layers_fs2_tc(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
@@ -343,12 +344,13 @@ def duration_predictor(prep, P, cfg, x, src_lens):
 
 
 def pitch_style_predictor(prep, P, cfg, pre, xs, alpha=1.0):
-    """PitchPredictor / EnergyPredictor.forward, modules.py:1343-1356.  `xs` is overwritten."""
+    """PitchPredictor / EnergyPredictor.forward, modules.py:1343-1356."""
     vp = cfg["variance_predictor"]
     B, T, C = xs.shape
     pe = prep.table_fs2(C, T + 1, xs.device)
-    capi.call("ctts_add_positions", xs, pe, pe.shape[0], P[pre + "pos_embed_alpha"], None, B, T, C, 0, _stream())
-    h = _predictor_stack(prep, P, pre, xs, vp["predictor_layers"], vp["predictor_kernel"], None)
+    xp = torch.empty_like(xs)
+    capi.call("ctts_add_positions", xs, pe, pe.shape[0], P[pre + "pos_embed_alpha"], None, B, T, C, 0, xp, _stream())
+    h = _predictor_stack(prep, P, pre, xp, vp["predictor_layers"], vp["predictor_kernel"], None)
     return conv_gemm(h, P[pre + "linear.weight"], P[pre + "linear.bias"], alpha=alpha)
 
 
@@ -592,7 +594,7 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
         bins = P[pre + "energy_bins"]
         emb = P[pre + "energy_embedding.weight"]
         if level == "frame_level":
-            pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", xe.clone(),
+            pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", xe,
                                          alpha=1.0 if energy_target is not None else e_control).squeeze(-1)
             src_vals = _f32(energy_target) if energy_target is not None else pred
             eidx = torch.empty(B, M, device=dev, dtype=torch.int64)
@@ -605,7 +607,7 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
                 work = torch.empty(B * M_e, device=dev, dtype=torch.float32)
                 energy_target = torch.empty(B, S, device=dev, dtype=torch.float32)
                 capi.call("ctts_phoneme_energy", a["attn_out"][2], src_lens, et, B, S, M_e, work, energy_target, st)
-            pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", x_org.clone(),
+            pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", x_org,
                                          alpha=1.0 if energy_target is not None else e_control).squeeze(-1)
             src_vals = _f32(energy_target) if energy_target is not None else pred
             eidx = torch.empty(B, S, device=dev, dtype=torch.int64)

@@ -50,8 +50,9 @@ def embed_abs(prep, P, cfg, d, tokens):
 def add_abs_positions(prep, P, cfg, key, x):
     B, T, C = x.shape
     pe = abs_table(prep, P, key, T, C, cfg["max_seq_len"], x.device)
-    capi.call("ctts_add_positions", x, pe, pe.shape[0], None, None, B, T, C, 1, _stream())
-    return x
+    y = torch.empty_like(x)
+    capi.call("ctts_add_positions", x, pe, pe.shape[0], None, None, B, T, C, 1, y, _stream())
+    return y
 
 
 # ---------------------------------------------------------------------------------------------
@@ -105,7 +106,7 @@ def encoder_transformer(prep, P, cfg, tokens, src_lens):
 
 def decoder_transformer(prep, P, cfg, x, mel_lens, math_mode):
     c = cfg["transformer"]
-    add_abs_positions(prep, P, cfg, "decoder.position_enc", x)
+    x = add_abs_positions(prep, P, cfg, "decoder.position_enc", x)
     return _stack_transformer(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
                               c["conv_kernel_size"], math_mode == "bf16x3")
 
@@ -184,7 +185,7 @@ def encoder_fastformer(prep, P, cfg, tokens, src_lens):
 
 def decoder_fastformer(prep, P, cfg, x, mel_lens, math_mode):
     c = cfg["transformer"]
-    add_abs_positions(prep, P, cfg, "decoder.position_enc", x)
+    x = add_abs_positions(prep, P, cfg, "decoder.position_enc", x)
     heads = c["decoder_hidden"] // c["decoder_head"]
     return _stack_fastformer(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], heads, c["conv_kernel_size"],
                              math_mode == "bf16x3"), None
@@ -294,7 +295,7 @@ def encoder_conformer(prep, P, cfg, tokens, src_lens):
 
 def decoder_conformer(prep, P, cfg, x, mel_lens, math_mode):
     c = cfg["conformer"]
-    add_abs_positions(prep, P, cfg, "decoder.position_enc", x)
+    x = add_abs_positions(prep, P, cfg, "decoder.position_enc", x)
     return _stack_conformer(prep, P, cfg, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
                             c["conv_kernel_size"], math_mode == "bf16x3"), None
 

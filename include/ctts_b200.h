@@ -59,14 +59,14 @@ int ctts_embed_tokens(const int64_t* tokens, const float* table, const float* pe
                       int B, int S, int C, int vocab, float* x, float* word, const int64_t* lens, int pos_mode,
                       void* stream);
 
-/* ---- x = (x + alpha * pe[pos(x[..., 0] != 0)]) [* keep] -----------------------------------------
+/* ---- y = (x + alpha * pe[pos(x[..., 0] != 0)]) [* keep]   (out of place: y != x) -----------------------
  * FFTBlocks.forward transformer_fs2.py:54-60 (decoder positions) and PitchPredictor.forward
  * modules.py:1349-1350.  `alpha` is a device scalar (the learnable pos_embed_alpha).  If lens != NULL
- * rows t >= lens[b] are zeroed afterwards (the `* nonpadding_mask_TB` of :60).  In place.
+ * rows t >= lens[b] are zeroed afterwards (the `* nonpadding_mask_TB` of :60).
  * pos_mode 1: pos = t (absolute table rows, transformer.py:137-141); alpha may then be NULL (= 1).
  */
-int ctts_add_positions(float* x, const float* pe, int pe_rows, const float* alpha, const int64_t* lens, int B, int T,
-                       int C, int pos_mode, void* stream);
+int ctts_add_positions(const float* x, const float* pe, int pe_rows, const float* alpha, const int64_t* lens, int B, int T,
+                       int C, int pos_mode, float* y, void* stream);
 
 /* ---- y = LayerNorm_C(x) * gamma + beta [* keep] -------------------------------------------
  * blocks.py:137-156 (eps 1e-12), transformer_fs2.py:41,65-66 (final nn.LayerNorm eps 1e-5).

@@ -124,8 +124,8 @@ def test_embed_and_positions():
     h[1, 4, 0] = 0
     alpha = torch.tensor([0.73])
     ref = (h + alpha * O.fs2_positional(h[..., 0], C, 2000)) * (torch.arange(S)[None] < lens[:, None]).float()[:, :, None]
-    hd = h.to(DEV).clone()
-    capi.call("ctts_add_positions", hd, pe.to(DEV), 2048, alpha.to(DEV), lens.to(DEV), B, S, C, 0, stream())
+    hd = torch.empty(B, S, C, device=DEV)
+    capi.call("ctts_add_positions", h.to(DEV), pe.to(DEV), 2048, alpha.to(DEV), lens.to(DEV), B, S, C, 0, hd, stream())
     close(hd, ref, atol=1e-6)
 
 
