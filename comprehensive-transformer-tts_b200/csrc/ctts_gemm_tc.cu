@@ -19,6 +19,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace ctts {
 
@@ -26,6 +27,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // bf16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int STG_LD = 36;    // floats per row of the epilogue transpose tile (16-byte aligned, conflict-free)
 
 struct Epilogue {
     const float* bias;
@@ -91,6 +93,27 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5, %6}], [%2], %3;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -139,15 +162,22 @@ struct Smem {
     static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = NP * (A_TILE_BYTES + B_TILE_BYTES);
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+    static constexpr int STAGING_OFFSET = BAR_OFFSET + 128;                 // 4 epilogue warps x 32 x STG_LD floats
+    static constexpr int TOTAL = STAGING_OFFSET + 4 * 32 * STG_LD * 4 + 1024;   // + alignment slack
 };
 
 // NP = number of bf16 planes per operand: 2 -> 3 MMAs per k-slice ("bf16x3", 16 mantissa bits, decoder / PostNet),
 // 3 -> 6 MMAs per k-slice ("bf16x6", 24 mantissa bits: FP32-equivalent, used upstream of the quantisers).
-template <int BLOCK_N, int STAGES, int NP>
+//
+// CM = CTAs per cluster along M (1 or 2).  With CM = 2 the two CTAs work on neighbouring 128-row tiles of the SAME
+// n-tile, so the weight tile is identical: each CTA fetches half of it and TMA-multicasts it into both CTAs' shared
+// memory.  The kernel is bound by L2 -> SM traffic (96 KiB per k-block at 128x256, measured 5.8 TB/s); multicast cuts
+// it to 64 KiB.  A stage may only be overwritten once BOTH CTAs' MMAs have drained it: tcgen05.commit is multicast to
+// both CTAs' empty barriers (count CM).
+template <int BLOCK_N, int STAGES, int NP, int CM>
 __global__ void __launch_bounds__(192, 1)
 gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
-                  int tiles_per_utt) {
+                  int tiles_per_utt, int Z) {
     using S = Smem<BLOCK_N, STAGES, NP>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must be 1024-byte aligned in the shared address space
@@ -158,7 +188,9 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int z = blockIdx.x / tiles_per_utt;
+    const uint32_t cta_rank = (CM > 1) ? cluster_ctarank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CM) - 1u);
+    const int z = blockIdx.x / tiles_per_utt;   // may be >= Z for the padding CTA of an odd grid (CM = 2)
     const int t0 = (blockIdx.x - z * tiles_per_utt) * BLOCK_M;
     const int zh = z % ad.mod;
     const int n0 = blockIdx.y * BLOCK_N;
@@ -175,7 +207,7 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CM);
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -195,6 +227,7 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CM > 1) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast into them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -213,7 +246,14 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
                     tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES, ca, t0 + tap - pad, za);
-                    tma_load_3d(&tm.w[p], &full_bar[s], st + NP * A_TILE_BYTES + p * S::B_TILE_BYTES, cw, n0, zw);
+                    uint8_t* wdst = st + NP * A_TILE_BYTES + p * S::B_TILE_BYTES;
+                    if (CM == 1) {
+                        tma_load_3d(&tm.w[p], &full_bar[s], wdst, cw, n0, zw);
+                    } else {   // my half of the weight tile, delivered to both CTAs of the cluster
+                        constexpr int HALF_ROWS = BLOCK_N / CM;
+                        tma_load_3d_mc(&tm.w[p], &full_bar[s], wdst + cta_rank * (HALF_ROWS * BLOCK_K * 2), cw,
+                                       n0 + (int)cta_rank * HALF_ROWS, zw, kMask);
+                    }
                 }
             }
         }
@@ -251,22 +291,26 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                         umma_bf16(tmem_base + (uint32_t)(kb % 3) * BLOCK_N, da[0], db[0], idesc, (kb >= 3 || k > 0) ? 1u : 0u);
                     }
                 }
-                umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+                if (CM == 1) umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+                else umma_commit_mc(&empty_bar[s], kMask);
             }
             umma_commit(accum_bar);          // accumulator complete
         }
     } else {
         // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ------------------------------------
+        // tcgen05.ld hands every thread ONE ROW of 32 accumulator columns; written out like that, a warp store touches
+        // 32 different lines (measured: 4x write amplification, the epilogue cost 10x the mainloop at K = 256).  Each
+        // 32x32 chunk is therefore transposed through a private shared-memory tile: afterwards 8 lanes cover the 32
+        // columns of a row with float4s, so every global load / store instruction moves whole 128-byte rows.
         const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int t = t0 + row;
+        float* stg = reinterpret_cast<float*>(smem + S::STAGING_OFFSET) + (warp - 2) * (32 * STG_LD);
         mbar_wait(accum_bar, 0);
         tcgen05_fence_after();
-        const int len = ep.lens ? (int)ep.lens[z / ad.lens_div] : T;
-        const bool in_range = t < T;
-        const bool keep = t < len;
-        const size_t rowoff = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner +
-                              (size_t)(in_range ? t : 0) * (size_t)ad.ldy;
+        const bool tile_valid = z < Z;
+        const int len = (ep.lens && tile_valid) ? (int)ep.lens[z / ad.lens_div] : T;
+        const size_t tilebase = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner;
+        const int c4 = (lane & 7) * 4;          // my 4 columns inside the chunk
+        const int rsub = lane >> 3;             // my row inside each group of 4 rows
 #pragma unroll 1
         for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
             uint32_t r[32];
@@ -282,35 +326,44 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                     for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
                 }
             }
-            if (!in_range) continue;
-            const int nb = n0 + chunk * 32;
+            const int n = n0 + chunk * 32 + c4;
+            if (n0 + chunk * 32 >= N) break;   // warp-uniform: the remaining chunks lie beyond N
+            __syncwarp();
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                const int n = nb + g4 * 4;
-                if (n >= N) break;
-                float v[4];
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) =
+                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+            __syncwarp();
+            if (!tile_valid || n >= N) continue;
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bb;
+            if (ep.bias) bb = *reinterpret_cast<const float4*>(ep.bias + n);
+            if (ep.col_scale) {
+                sc = *reinterpret_cast<const float4*>(ep.col_scale + n);
+                sh = *reinterpret_cast<const float4*>(ep.col_shift + n);
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[g4 * 4 + j]);
-                if (ep.bias) {
-                    const float4 bb = *reinterpret_cast<const float4*>(ep.bias + n);
-                    v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] *= ep.alpha;
+            for (int i = 0; i < 8; ++i) {
+                const int rr = rsub + 4 * i;
+                const int t = t0 + q * 32 + rr;
+                if (t >= T) continue;
+                const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + c4);
+                float v[4] = {a4.x, a4.y, a4.z, a4.w};
+                v[0] = (v[0] + bb.x) * ep.alpha; v[1] = (v[1] + bb.y) * ep.alpha;
+                v[2] = (v[2] + bb.z) * ep.alpha; v[3] = (v[3] + bb.w) * ep.alpha;
                 if (ep.col_scale) {
-                    const float4 sc = *reinterpret_cast<const float4*>(ep.col_scale + n);
-                    const float4 sh = *reinterpret_cast<const float4*>(ep.col_shift + n);
                     v[0] = v[0] * sc.x + sh.x; v[1] = v[1] * sc.y + sh.y;
                     v[2] = v[2] * sc.z + sh.z; v[3] = v[3] * sc.w + sh.w;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], ep.act);
+                const size_t off = tilebase + (size_t)t * (size_t)ad.ldy + (size_t)n;
                 if (ep.residual) {
-                    const float4 rr = *reinterpret_cast<const float4*>(ep.residual + rowoff + n);
-                    v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+                    const float4 rs = *reinterpret_cast<const float4*>(ep.residual + off);
+                    v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
                 }
-                if (!keep) { v[0] = v[1] = v[2] = v[3] = 0.f; }
-                if (ep.y) *reinterpret_cast<float4*>(ep.y + rowoff + n) = make_float4(v[0], v[1], v[2], v[3]);
+                if (t >= len) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+                if (ep.y) *reinterpret_cast<float4*>(ep.y + off) = make_float4(v[0], v[1], v[2], v[3]);
                 if (ep.yp[0]) {
                     float rem[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
@@ -321,7 +374,7 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                             h[j] = __float2bfloat16_rn(rem[j]);
                             rem[j] -= __bfloat162float(h[j]);
                         }
-                        *reinterpret_cast<uint2*>(ep.yp[p] + rowoff + n) = *reinterpret_cast<uint2*>(h);
+                        *reinterpret_cast<uint2*>(ep.yp[p] + off) = *reinterpret_cast<uint2*>(h);
                     }
                 }
             }
@@ -329,6 +382,7 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
         tcgen05_fence_before();
     }
     __syncthreads();
+    if (CM > 1) cluster_sync_all();   // do not exit (or free TMEM) while the peer can still signal / write into this CTA
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -370,7 +424,7 @@ struct Operand {          // NP bf16 planes viewed as a 3-D tensor [d2][d1][d0] 
     cuuint64_t s1, s2;       // strides of d1 / d2 in elements
 };
 
-template <int BLOCK_N, int STAGES, int NP>
+template <int BLOCK_N, int STAGES, int NP, int CM>
 static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin, int N,
                   int taps, cudaStream_t st) {
     using S = Smem<BLOCK_N, STAGES, NP>;
@@ -386,12 +440,12 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
     {
         cuuint64_t dims[3] = {W.d0, W.d1, W.d2};
         cuuint64_t str[2] = {W.s1 * 2, W.s2 * 2};
-        cuuint32_t box[3] = {BLOCK_K, BLOCK_N, 1};
+        cuuint32_t box[3] = {BLOCK_K, BLOCK_N / CM, 1};   // CM = 2: every CTA fetches (and multicasts) half of the tile
         for (int p = 0; p < NP; ++p)
             if (int e = make_map(&maps.w[p], W.p[p], 3, dims, str, box, "weight plane")) return e;
         for (int p = NP; p < 3; ++p) maps.w[p] = maps.w[0];
     }
-    auto kern = gemm_split_kernel<BLOCK_N, STAGES, NP>;
+    auto kern = gemm_split_kernel<BLOCK_N, STAGES, NP, CM>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
@@ -401,16 +455,42 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
         configured = true;
     }
     const int tiles_per_utt = (T + BLOCK_M - 1) / BLOCK_M;
-    dim3 grid(Z * tiles_per_utt, (N + BLOCK_N - 1) / BLOCK_N);
-    kern<<<grid, 192, S::TOTAL, st>>>(maps, ep, ad, T, Cin, N, taps, tiles_per_utt);
+    const int gx = ((Z * tiles_per_utt + CM - 1) / CM) * CM;   // an odd grid gets one padding CTA (it computes, never stores)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, (N + BLOCK_N - 1) / BLOCK_N, 1);
+    cfg.blockDim = dim3(192, 1, 1);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CM;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kern, maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z);
+    if (err != cudaSuccess) {
+        set_error("gemm_split launch: %s", cudaGetErrorString(err));
+        return 1;
+    }
     return check_launch("gemm_split");
 }
 
 static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin,
                        int N, int taps, cudaStream_t st) {
-    if (np == 3) return launch<128, 2, 3>(A, W, ep, ad, Z, T, Cin, N, taps, st);   // 2 x 96 KiB stages
-    if (N >= 512 && N % 256 == 0) return launch<256, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
-    return launch<128, 3, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+    // weights shared by all utterances (conv / linear: w_div huge) can be multicast across a 2-CTA cluster along M
+    static const bool use_cluster = getenv("CTTS_NO_CLUSTER") == nullptr;
+    const bool shared_w = use_cluster && ad.w_div == 0x7fffffff && (long long)Z * ((T + BLOCK_M - 1) / BLOCK_M) >= 2;
+    if (np == 3) {
+        if (shared_w) return launch<128, 2, 3, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+        return launch<128, 2, 3, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st);   // 2 x 96 KiB stages
+    }
+    if (N >= 512 && N % 256 == 0) {
+        if (shared_w) return launch<256, 2, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+        return launch<256, 2, 2, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+    }
+    if (shared_w) return launch<128, 3, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+    return launch<128, 3, 2, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st);
 }
 
 // ---- attention helpers: masked softmax over materialised scores, V transpose ----------------------------------------
