@@ -39,6 +39,7 @@ struct Epilogue {
     __nv_bfloat16* yp[3];   // output planes (hi, [mid,] lo); yp[0] == nullptr: none
     float alpha;
     int act;
+    long long* dbg;         // optional per-CTA cycle stamps {start, setup done, accumulator ready, epilogue done}
 };
 
 struct Maps {               // TMA descriptors of the operand planes (NP of each are used)
@@ -162,9 +163,68 @@ struct Smem {
     static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = NP * (A_TILE_BYTES + B_TILE_BYTES);
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int STAGING_OFFSET = BAR_OFFSET + 128;                 // 4 epilogue warps x 32 x STG_LD floats
-    static constexpr int TOTAL = STAGING_OFFSET + 4 * 32 * STG_LD * 4 + 1024;   // + alignment slack
+    static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;   // + alignment slack
+    static_assert(8 * 32 * STG_LD * 4 <= STAGE_BYTES, "the epilogue's transpose tiles reuse the first pipeline stage");
 };
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+    if (ACT == CTTS_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == CTTS_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    if (ACT == CTTS_ACT_TANH) return tanhf(v);
+    if (ACT == CTTS_ACT_SWISH) return v / (1.f + expf(-v));
+    return v;
+}
+
+// Second half of the epilogue for one transposed 32x32 chunk: this lane owns 4 columns (n .. n+3) of 8 rows.
+template <int NP, int ACT>
+__device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg, int c4, int rsub, int trow0, int T, int len,
+                                            int n, size_t tilebase, int ldy) {
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bb;
+    if (ep.bias) bb = *reinterpret_cast<const float4*>(ep.bias + n);
+    const bool affine = ep.col_scale != nullptr;
+    if (affine) {
+        sc = *reinterpret_cast<const float4*>(ep.col_scale + n);
+        sh = *reinterpret_cast<const float4*>(ep.col_shift + n);
+    }
+    const float alpha = ep.alpha;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int t = trow0 + 4 * i;
+        if (t >= T) break;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + (rsub + 4 * i) * STG_LD + c4);
+        float v[4] = {(a4.x + bb.x) * alpha, (a4.y + bb.y) * alpha, (a4.z + bb.z) * alpha, (a4.w + bb.w) * alpha};
+        if (affine) {
+            v[0] = v[0] * sc.x + sh.x; v[1] = v[1] * sc.y + sh.y;
+            v[2] = v[2] * sc.z + sh.z; v[3] = v[3] * sc.w + sh.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = act_fn<ACT>(v[j]);
+        const size_t off = tilebase + (size_t)t * (size_t)ldy + (size_t)n;
+        if (ep.residual) {
+            const float4 rs = *reinterpret_cast<const float4*>(ep.residual + off);
+            v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
+        }
+        if (t >= len) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+        if (ep.y) *reinterpret_cast<float4*>(ep.y + off) = make_float4(v[0], v[1], v[2], v[3]);
+        if (ep.yp[0]) {
+            float rem[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                __nv_bfloat162 h01 = __floats2bfloat162_rn(rem[0], rem[1]);
+                __nv_bfloat162 h23 = __floats2bfloat162_rn(rem[2], rem[3]);
+                if (p + 1 < NP) {
+                    rem[0] -= __low2float(h01); rem[1] -= __high2float(h01);
+                    rem[2] -= __low2float(h23); rem[3] -= __high2float(h23);
+                }
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(ep.yp[p] + off) = pk;
+            }
+        }
+    }
+}
 
 // NP = number of bf16 planes per operand: 2 -> 3 MMAs per k-slice ("bf16x3", 16 mantissa bits, decoder / PostNet),
 // 3 -> 6 MMAs per k-slice ("bf16x6", 24 mantissa bits: FP32-equivalent, used upstream of the quantisers).
@@ -175,7 +235,7 @@ struct Smem {
 // it to 64 KiB.  A stage may only be overwritten once BOTH CTAs' MMAs have drained it: tcgen05.commit is multicast to
 // both CTAs' empty barriers (count CM).
 template <int BLOCK_N, int STAGES, int NP, int CM>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
                   int tiles_per_utt, int Z) {
     using S = Smem<BLOCK_N, STAGES, NP>;
@@ -188,6 +248,7 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long clk_start = ep.dbg ? clock64() : 0;
     const uint32_t cta_rank = (CM > 1) ? cluster_ctarank() : 0u;
     constexpr uint16_t kMask = (uint16_t)((1u << CM) - 1u);
     const int z = blockIdx.x / tiles_per_utt;   // may be >= Z for the padding CTA of an odd grid (CM = 2)
@@ -297,22 +358,27 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
             umma_commit(accum_bar);          // accumulator complete
         }
     } else {
-        // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ------------------------------------
+        // ---- epilogue: 8 warps; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32), the two warps of a lane quarter
+        // take the even / odd 32-column chunks.
         // tcgen05.ld hands every thread ONE ROW of 32 accumulator columns; written out like that, a warp store touches
-        // 32 different lines (measured: 4x write amplification, the epilogue cost 10x the mainloop at K = 256).  Each
-        // 32x32 chunk is therefore transposed through a private shared-memory tile: afterwards 8 lanes cover the 32
-        // columns of a row with float4s, so every global load / store instruction moves whole 128-byte rows.
+        // 32 different lines (measured: 4x write amplification).  Each 32x32 chunk is therefore transposed through a
+        // private shared-memory tile (the pipeline stages are idle by now and are reused): afterwards 8 lanes cover the
+        // 32 columns of a row with float4s, so every global load / store instruction moves whole 128-byte rows.
         const int q = warp & 3;
-        float* stg = reinterpret_cast<float*>(smem + S::STAGING_OFFSET) + (warp - 2) * (32 * STG_LD);
+        const int half = (warp - 2) >> 2;
+        float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * STG_LD);
+        const long long clk_setup = ep.dbg ? clock64() : 0;
         mbar_wait(accum_bar, 0);
         tcgen05_fence_after();
+        const long long clk_accum = ep.dbg ? clock64() : 0;
         const bool tile_valid = z < Z;
         const int len = (ep.lens && tile_valid) ? (int)ep.lens[z / ad.lens_div] : T;
         const size_t tilebase = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner;
         const int c4 = (lane & 7) * 4;          // my 4 columns inside the chunk
         const int rsub = lane >> 3;             // my row inside each group of 4 rows
 #pragma unroll 1
-        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        for (int chunk = half; chunk < BLOCK_N / 32; chunk += 2) {
+            if (n0 + chunk * 32 >= N) break;   // warp-uniform: the remaining chunks lie beyond N
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
             if (NP == 3) {  // add the small-term accumulator and the other (used) main accumulators
@@ -327,7 +393,6 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                 }
             }
             const int n = n0 + chunk * 32 + c4;
-            if (n0 + chunk * 32 >= N) break;   // warp-uniform: the remaining chunks lie beyond N
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -336,48 +401,18 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                                 __uint_as_float(r[4 * j + 3]));
             __syncwarp();
             if (!tile_valid || n >= N) continue;
-            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bb;
-            if (ep.bias) bb = *reinterpret_cast<const float4*>(ep.bias + n);
-            if (ep.col_scale) {
-                sc = *reinterpret_cast<const float4*>(ep.col_scale + n);
-                sh = *reinterpret_cast<const float4*>(ep.col_shift + n);
+            const int trow0 = t0 + q * 32 + rsub;
+            switch (ep.act) {   // hoisted: one dispatch per chunk instead of one indirect branch per element
+                case CTTS_ACT_RELU: store_chunk<NP, CTTS_ACT_RELU>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
+                case CTTS_ACT_GELU: store_chunk<NP, CTTS_ACT_GELU>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
+                case CTTS_ACT_TANH: store_chunk<NP, CTTS_ACT_TANH>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
+                case CTTS_ACT_SWISH: store_chunk<NP, CTTS_ACT_SWISH>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
+                default: store_chunk<NP, CTTS_ACT_NONE>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rr = rsub + 4 * i;
-                const int t = t0 + q * 32 + rr;
-                if (t >= T) continue;
-                const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + c4);
-                float v[4] = {a4.x, a4.y, a4.z, a4.w};
-                v[0] = (v[0] + bb.x) * ep.alpha; v[1] = (v[1] + bb.y) * ep.alpha;
-                v[2] = (v[2] + bb.z) * ep.alpha; v[3] = (v[3] + bb.w) * ep.alpha;
-                if (ep.col_scale) {
-                    v[0] = v[0] * sc.x + sh.x; v[1] = v[1] * sc.y + sh.y;
-                    v[2] = v[2] * sc.z + sh.z; v[3] = v[3] * sc.w + sh.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], ep.act);
-                const size_t off = tilebase + (size_t)t * (size_t)ad.ldy + (size_t)n;
-                if (ep.residual) {
-                    const float4 rs = *reinterpret_cast<const float4*>(ep.residual + off);
-                    v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
-                }
-                if (t >= len) { v[0] = v[1] = v[2] = v[3] = 0.f; }
-                if (ep.y) *reinterpret_cast<float4*>(ep.y + off) = make_float4(v[0], v[1], v[2], v[3]);
-                if (ep.yp[0]) {
-                    float rem[4] = {v[0], v[1], v[2], v[3]};
-#pragma unroll
-                    for (int p = 0; p < NP; ++p) {
-                        __nv_bfloat16 h[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            h[j] = __float2bfloat16_rn(rem[j]);
-                            rem[j] -= __bfloat162float(h[j]);
-                        }
-                        *reinterpret_cast<uint2*>(ep.yp[p] + off) = *reinterpret_cast<uint2*>(h);
-                    }
-                }
-            }
+        }
+        if (ep.dbg && warp == 2 && lane == 0) {
+            long long* d = ep.dbg + 4 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+            d[0] = clk_start; d[1] = clk_setup; d[2] = clk_accum; d[3] = clock64();
         }
         tcgen05_fence_before();
     }
@@ -458,7 +493,7 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
     const int gx = ((Z * tiles_per_utt + CM - 1) / CM) * CM;   // an odd grid gets one padding CTA (it computes, never stores)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(gx, (N + BLOCK_N - 1) / BLOCK_N, 1);
-    cfg.blockDim = dim3(192, 1, 1);
+    cfg.blockDim = dim3(320, 1, 1);
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -561,6 +596,8 @@ __global__ void transpose_v_kernel(const __nv_bfloat16* __restrict__ q_hi, const
 
 using namespace ctts;
 
+static long long* g_dbg_ptr = nullptr;   // set by ctts_debug_set_timing_buffer (development aid; NULL in production)
+
 static int gemm_split_impl(int np, const void* const* x_planes, const void* const* w_planes, const float* bias, float alpha,
                            const float* col_scale, const float* col_shift, int act, const float* residual,
                            const int64_t* lens, int B, int T, int Cin, int N, int taps, float* y, void* const* y_planes,
@@ -572,7 +609,7 @@ static int gemm_split_impl(int np, const void* const* x_planes, const void* cons
     CTTS_REQUIRE(N % 4 == 0, "gemm_split: N=%d must be a multiple of 4", N);
     CTTS_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), "gemm_split: col_scale/col_shift must come together");
     CTTS_REQUIRE(y || (y_planes && y_planes[0]), "gemm_split: no output requested");
-    Epilogue ep{bias, col_scale, col_shift, residual, lens, y, {nullptr, nullptr, nullptr}, alpha, act};
+    Epilogue ep{bias, col_scale, col_shift, residual, lens, y, {nullptr, nullptr, nullptr}, alpha, act, nullptr};
     const cuuint64_t K = (cuuint64_t)taps * Cin;
     Operand A{{nullptr, nullptr, nullptr}, (cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)Cin,
               (cuuint64_t)T * Cin};
@@ -588,6 +625,7 @@ static int gemm_split_impl(int np, const void* const* x_planes, const void* cons
             ep.yp[p] = (__nv_bfloat16*)y_planes[p];
         }
     }
+    ep.dbg = g_dbg_ptr;
     Addr ad{1, 1, 0, 0, 0x7fffffff, 0, 0, 1, N, (long long)T * N, 0};
     return launch_auto(np, A, W, ep, ad, B, T, Cin, N, taps, (cudaStream_t)stream);
 }
@@ -628,7 +666,7 @@ extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, con
     {
         Operand A{{qkv_hi, qkv_lo, nullptr}, C3, (cuuint64_t)T, (cuuint64_t)B, C3, (cuuint64_t)T * C3};
         Operand W = A;
-        Epilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, scores, {nullptr, nullptr, nullptr}, scale, CTTS_ACT_NONE};
+        Epilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, scores, {nullptr, nullptr, nullptr}, scale, CTTS_ACT_NONE, nullptr};
         Addr ad{H, H, 0, DH, H, C, DH, 1, Tp, (long long)H * T * Tp, (long long)T * Tp};
         if (int e = launch_auto(2, A, W, ep, ad, Z, T, DH, Tp, 1, st)) return e;
     }
@@ -652,9 +690,15 @@ extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, con
         Operand W{{vt_hi, vt_lo, nullptr}, (cuuint64_t)Tp, (cuuint64_t)DH, (cuuint64_t)Z, (cuuint64_t)Tp,
                   (cuuint64_t)DH * Tp};
         Epilogue ep{nullptr, nullptr, nullptr, nullptr, lens, out_f32,
-                    {(__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, nullptr}, 1.f, CTTS_ACT_NONE};
+                    {(__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, nullptr}, 1.f, CTTS_ACT_NONE, nullptr};
         Addr ad{H, 1, 0, 0, 1, 0, 0, H, C, (long long)T * C, (long long)DH};
         if (int e = launch_auto(2, A, W, ep, ad, Z, T, Tp, DH, 1, st)) return e;
     }
+    return 0;
+}
+
+/* development aid: per-CTA cycle stamps of the next ctts_gemm_split launches (4 x int64 per CTA); NULL disables */
+extern "C" int ctts_debug_set_timing_buffer(long long* device_buffer) {
+    g_dbg_ptr = device_buffer;
     return 0;
 }

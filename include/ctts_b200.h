@@ -272,6 +272,10 @@ int ctts_split_planes(const float* x, size_t n, int n_planes, void* const* plane
 int ctts_layernorm_planes(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B, int T,
                           int C, float* y, int n_planes, void* const* planes, void* stream);
 
+/* development aid: when non-NULL, every CTA of the following ctts_gemm_split launches stores four clock64() stamps
+ * {start, setup done, accumulator ready, epilogue done} at device_buffer[4 * cta]; used by profiles/ scripts only. */
+int ctts_debug_set_timing_buffer(long long* device_buffer);
+
 /* fp32 -> (bf16 hi, bf16 lo) with hi = rn(x), lo = rn(x - hi) */
 int ctts_split_bf16(const float* x, size_t n, void* hi, void* lo, void* stream);
 
