@@ -176,10 +176,34 @@ __device__ __forceinline__ float act_fn(float v) {
     return v;
 }
 
+// Where row r of a tile lives: (valid, keep, element offset of column 0).
+struct RowMap {
+    bool packed;
+    int g0, rows_total, T, len, t0;
+    const int64_t* lens;
+    size_t y_outer, tilebase;
+    int ldy;
+    __device__ __forceinline__ bool locate(int r, bool& keep, size_t& off) const {
+        if (packed) {
+            const int g = g0 + r;
+            if (g >= rows_total) return false;
+            const int b = g / T, t = g - b * T;
+            keep = lens ? (t < (int)lens[b]) : true;
+            off = (size_t)b * y_outer + (size_t)t * (size_t)ldy;
+            return true;
+        }
+        const int t = t0 + r;
+        if (t >= T) return false;
+        keep = t < len;
+        off = tilebase + (size_t)t * (size_t)ldy;
+        return true;
+    }
+};
+
 // Second half of the epilogue for one transposed 32x32 chunk: this lane owns 4 columns (n .. n+3) of 8 rows.
 template <int NP, int ACT>
-__device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg, int c4, int rsub, int trow0, int T, int len,
-                                            int n, size_t tilebase, int ldy) {
+__device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg, int c4, int rsub, int row0,
+                                            const RowMap& rm, int n) {
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bb;
     if (ep.bias) bb = *reinterpret_cast<const float4*>(ep.bias + n);
     const bool affine = ep.col_scale != nullptr;
@@ -190,8 +214,10 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg
     const float alpha = ep.alpha;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int t = trow0 + 4 * i;
-        if (t >= T) break;
+        bool keep;
+        size_t off;
+        if (!rm.locate(row0 + 4 * i, keep, off)) break;
+        off += (size_t)n;
         const float4 a4 = *reinterpret_cast<const float4*>(stg + (rsub + 4 * i) * STG_LD + c4);
         float v[4] = {(a4.x + bb.x) * alpha, (a4.y + bb.y) * alpha, (a4.z + bb.z) * alpha, (a4.w + bb.w) * alpha};
         if (affine) {
@@ -200,12 +226,11 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = act_fn<ACT>(v[j]);
-        const size_t off = tilebase + (size_t)t * (size_t)ldy + (size_t)n;
         if (ep.residual) {
             const float4 rs = *reinterpret_cast<const float4*>(ep.residual + off);
             v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
         }
-        if (t >= len) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+        if (!keep) { v[0] = v[1] = v[2] = v[3] = 0.f; }
         if (ep.y) *reinterpret_cast<float4*>(ep.y + off) = make_float4(v[0], v[1], v[2], v[3]);
         if (ep.yp[0]) {
             float rem[4] = {v[0], v[1], v[2], v[3]};
@@ -237,7 +262,7 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg
 template <int BLOCK_N, int STAGES, int NP, int CM>
 __global__ void __launch_bounds__(320, 1)
 gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
-                  int tiles_per_utt, int Z) {
+                  int tiles_per_utt, int Z, int seg_rows) {
     using S = Smem<BLOCK_N, STAGES, NP>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must be 1024-byte aligned in the shared address space
@@ -251,8 +276,14 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     const long long clk_start = ep.dbg ? clock64() : 0;
     const uint32_t cta_rank = (CM > 1) ? cluster_ctarank() : 0u;
     constexpr uint16_t kMask = (uint16_t)((1u << CM) - 1u);
-    const int z = blockIdx.x / tiles_per_utt;   // may be >= Z for the padding CTA of an odd grid (CM = 2)
-    const int t0 = (blockIdx.x - z * tiles_per_utt) * BLOCK_M;
+    // Two tilings of the row space.  Per utterance (seg_rows == 0): tile = (z, t0), rows beyond T are TMA zero fill --
+    // at T = 800 that is 7 tiles per utterance, 12 % of them padding.  PACKED (seg_rows = 32 / 64 / 128 dividing T; plain
+    // conv / linear only): the B*T rows are tiled as one sequence, a tile is fetched as 128/seg_rows row segments, each
+    // with the (utterance, t) coordinates of its own rows so the conv halo still sees zeros at utterance boundaries.
+    const bool packed = seg_rows > 0;
+    const int g0 = blockIdx.x * BLOCK_M;        // first global row of a packed tile
+    const int z = packed ? 0 : blockIdx.x / tiles_per_utt;   // may be >= Z for the padding CTA of an odd grid (CM = 2)
+    const int t0 = packed ? 0 : (blockIdx.x - z * tiles_per_utt) * BLOCK_M;
     const int zh = z % ad.mod;
     const int n0 = blockIdx.y * BLOCK_N;
     const int kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
@@ -306,7 +337,15 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                 const int cw = ad.w_c0 + zh * ad.w_step + tap * Cin + c0, zw = z / ad.w_div;
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
-                    tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES, ca, t0 + tap - pad, za);
+                    if (!packed) {
+                        tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES, ca, t0 + tap - pad, za);
+                    } else {
+                        for (int r = 0; r < BLOCK_M; r += seg_rows) {
+                            const int g = g0 + r, bz = g / T;
+                            tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES + r * (BLOCK_K * 2), ca,
+                                        g - bz * T + tap - pad, bz);
+                        }
+                    }
                     uint8_t* wdst = st + NP * A_TILE_BYTES + p * S::B_TILE_BYTES;
                     if (CM == 1) {
                         tma_load_3d(&tm.w[p], &full_bar[s], wdst, cw, n0, zw);
@@ -371,9 +410,10 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
         mbar_wait(accum_bar, 0);
         tcgen05_fence_after();
         const long long clk_accum = ep.dbg ? clock64() : 0;
-        const bool tile_valid = z < Z;
-        const int len = (ep.lens && tile_valid) ? (int)ep.lens[z / ad.lens_div] : T;
+        const bool tile_valid = packed ? (g0 < Z * T) : (z < Z);
+        const int len = (ep.lens && tile_valid && !packed) ? (int)ep.lens[z / ad.lens_div] : T;
         const size_t tilebase = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner;
+        const RowMap rm{packed, g0, Z * T, T, len, t0, ep.lens, (size_t)ad.y_outer, tilebase, ad.ldy};
         const int c4 = (lane & 7) * 4;          // my 4 columns inside the chunk
         const int rsub = lane >> 3;             // my row inside each group of 4 rows
 #pragma unroll 1
@@ -401,13 +441,13 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                                 __uint_as_float(r[4 * j + 3]));
             __syncwarp();
             if (!tile_valid || n >= N) continue;
-            const int trow0 = t0 + q * 32 + rsub;
+            const int row0 = q * 32 + rsub;     // my first row inside the tile
             switch (ep.act) {   // hoisted: one dispatch per chunk instead of one indirect branch per element
-                case CTTS_ACT_RELU: store_chunk<NP, CTTS_ACT_RELU>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
-                case CTTS_ACT_GELU: store_chunk<NP, CTTS_ACT_GELU>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
-                case CTTS_ACT_TANH: store_chunk<NP, CTTS_ACT_TANH>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
-                case CTTS_ACT_SWISH: store_chunk<NP, CTTS_ACT_SWISH>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
-                default: store_chunk<NP, CTTS_ACT_NONE>(ep, stg, c4, rsub, trow0, T, len, n, tilebase, ad.ldy); break;
+                case CTTS_ACT_RELU: store_chunk<NP, CTTS_ACT_RELU>(ep, stg, c4, rsub, row0, rm, n); break;
+                case CTTS_ACT_GELU: store_chunk<NP, CTTS_ACT_GELU>(ep, stg, c4, rsub, row0, rm, n); break;
+                case CTTS_ACT_TANH: store_chunk<NP, CTTS_ACT_TANH>(ep, stg, c4, rsub, row0, rm, n); break;
+                case CTTS_ACT_SWISH: store_chunk<NP, CTTS_ACT_SWISH>(ep, stg, c4, rsub, row0, rm, n); break;
+                default: store_chunk<NP, CTTS_ACT_NONE>(ep, stg, c4, rsub, row0, rm, n); break;
             }
         }
         if (ep.dbg && warp == 2 && lane == 0) {
@@ -461,13 +501,13 @@ struct Operand {          // NP bf16 planes viewed as a 3-D tensor [d2][d1][d0] 
 
 template <int BLOCK_N, int STAGES, int NP, int CM>
 static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin, int N,
-                  int taps, cudaStream_t st) {
+                  int taps, cudaStream_t st, int seg_rows) {
     using S = Smem<BLOCK_N, STAGES, NP>;
     Maps maps;
     {
         cuuint64_t dims[3] = {A.d0, A.d1, A.d2};
         cuuint64_t str[2] = {A.s1 * 2, A.s2 * 2};
-        cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)(seg_rows > 0 ? seg_rows : BLOCK_M), 1};
         for (int p = 0; p < NP; ++p)
             if (int e = make_map(&maps.a[p], A.p[p], 3, dims, str, box, "activation plane")) return e;
         for (int p = NP; p < 3; ++p) maps.a[p] = maps.a[0];
@@ -490,7 +530,8 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
         configured = true;
     }
     const int tiles_per_utt = (T + BLOCK_M - 1) / BLOCK_M;
-    const int gx = ((Z * tiles_per_utt + CM - 1) / CM) * CM;   // an odd grid gets one padding CTA (it computes, never stores)
+    const int m_tiles = seg_rows > 0 ? (int)(((long long)Z * T + BLOCK_M - 1) / BLOCK_M) : Z * tiles_per_utt;
+    const int gx = ((m_tiles + CM - 1) / CM) * CM;   // an odd grid gets one padding CTA (it computes, never stores)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(gx, (N + BLOCK_N - 1) / BLOCK_N, 1);
     cfg.blockDim = dim3(320, 1, 1);
@@ -503,7 +544,7 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t err = cudaLaunchKernelEx(&cfg, kern, maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kern, maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z, seg_rows);
     if (err != cudaSuccess) {
         set_error("gemm_split launch: %s", cudaGetErrorString(err));
         return 1;
@@ -515,17 +556,23 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
                        int N, int taps, cudaStream_t st) {
     // weights shared by all utterances (conv / linear: w_div huge) can be multicast across a 2-CTA cluster along M
     static const bool use_cluster = getenv("CTTS_NO_CLUSTER") == nullptr;
-    const bool shared_w = use_cluster && ad.w_div == 0x7fffffff && (long long)Z * ((T + BLOCK_M - 1) / BLOCK_M) >= 2;
+    static const bool use_packed = getenv("CTTS_NO_PACKED") == nullptr;
+    const bool plain = ad.w_div == 0x7fffffff && ad.mod == 1;
+    // packed row tiling needs row segments that never straddle an utterance: the largest of 128 / 64 / 32 dividing T
+    int seg = 0;
+    if (plain && use_packed && Z > 1 && T % BLOCK_M != 0) seg = (T % 64 == 0) ? 64 : ((T % 32 == 0) ? 32 : 0);
+    const long long m_tiles = seg ? ((long long)Z * T + BLOCK_M - 1) / BLOCK_M : (long long)Z * ((T + BLOCK_M - 1) / BLOCK_M);
+    const bool shared_w = use_cluster && plain && m_tiles >= 2;
     if (np == 3) {
-        if (shared_w) return launch<128, 2, 3, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
-        return launch<128, 2, 3, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st);   // 2 x 96 KiB stages
+        if (shared_w) return launch<128, 2, 3, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
+        return launch<128, 2, 3, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);   // 2 x 96 KiB stages
     }
     if (N >= 512 && N % 256 == 0) {
-        if (shared_w) return launch<256, 2, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
-        return launch<256, 2, 2, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+        if (shared_w) return launch<256, 2, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
+        return launch<256, 2, 2, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
     }
-    if (shared_w) return launch<128, 3, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st);
-    return launch<128, 3, 2, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st);
+    if (shared_w) return launch<128, 3, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
+    return launch<128, 3, 2, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
 }
 
 // ---- attention helpers: masked softmax over materialised scores, V transpose ----------------------------------------

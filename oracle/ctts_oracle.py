@@ -20,9 +20,10 @@ this oracle, and commits the reference's outputs under `tests/golden/*.npz`;
 needed), and `tests/test_oracle_vs_reference.py` re-checks against the live reference whenever
 `/root/reference` exists.
 
-Scope: block types transformer_fs2 / transformer / fastformer / conformer; prosody "none";
-inference (free-running), supervised teacher-forced, and unsupervised (aligner + MAS) branches
-of the VarianceAdaptor.  Dropout is identity (eval mode); BatchNorm uses running statistics.
+Scope: block types transformer_fs2 / transformer / fastformer / conformer (the latter three in
+ctts_oracle_blocks.py); prosody "none" and "liu2021" (eval mode: predictors); inference
+(free-running), supervised teacher-forced, and unsupervised (aligner + MAS) branches of the
+VarianceAdaptor.  Dropout is identity (eval mode); BatchNorm uses running statistics.
 """
 import math
 

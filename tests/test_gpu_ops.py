@@ -243,6 +243,10 @@ def test_split_bf16_planes():
     (2, 129, 512, 80, 5, "none"),       # PostNet last conv: N < BLOCK_N
     (1, 70, 256, 80, 1, "none"),        # mel_linear
     (2, 257, 512, 512, 5, "tanh"),
+    (3, 96, 256, 256, 3, "relu"),       # packed row tiling, 32-row segments: tiles straddle utterance boundaries
+    (3, 192, 256, 1024, 9, "gelu"),     # packed, 64-row segments, conv halo across the boundary must stay zero
+    (5, 160, 512, 512, 5, "tanh"),      # packed, odd tile count (cluster padding CTA), last tile partial
+    (16, 800, 256, 256, 1, "none"),     # the bench row count (100 packed tiles instead of 112)
 ])
 def test_gemm_bf16x3_matches_fp32(B, T, Cin, N, taps, act):
     x = torch.randn(B, T, Cin, generator=g(41))
