@@ -43,8 +43,9 @@ struct Epilogue {
 };
 
 struct Maps {               // TMA descriptors of the operand planes (NP of each are used)
-    CUtensorMap a[3];
+    CUtensorMap a[3];       // activation planes, box = 128 rows
     CUtensorMap w[3];
+    CUtensorMap a_seg[3];   // activation planes, box = seg_rows rows (packed tiling: tiles that straddle two utterances)
 };
 
 // Operand / output addressing.  z = blockIdx.x / tiles_per_utt is the "utterance" index of a plain conv (z = b) or the
@@ -280,10 +281,13 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     // at T = 800 that is 7 tiles per utterance, 12 % of them padding.  PACKED (seg_rows = 32 / 64 / 128 dividing T; plain
     // conv / linear only): the B*T rows are tiled as one sequence, a tile is fetched as 128/seg_rows row segments, each
     // with the (utterance, t) coordinates of its own rows so the conv halo still sees zeros at utterance boundaries.
+    // Only the tiles that actually straddle an utterance boundary (15 of 100 at T = 800) pay for segmented loads and
+    // per-row output coordinates; the others behave exactly like a per-utterance tile.
     const bool packed = seg_rows > 0;
     const int g0 = blockIdx.x * BLOCK_M;        // first global row of a packed tile
-    const int z = packed ? 0 : blockIdx.x / tiles_per_utt;   // may be >= Z for the padding CTA of an odd grid (CM = 2)
-    const int t0 = packed ? 0 : (blockIdx.x - z * tiles_per_utt) * BLOCK_M;
+    const int z = packed ? g0 / T : blockIdx.x / tiles_per_utt;   // may be >= Z for the padding CTA of an odd grid
+    const int t0 = packed ? g0 - z * T : (blockIdx.x - z * tiles_per_utt) * BLOCK_M;
+    const bool straddle = packed && (t0 + BLOCK_M > T);
     const int zh = z % ad.mod;
     const int n0 = blockIdx.y * BLOCK_N;
     const int kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
@@ -295,6 +299,7 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
         for (int p = 0; p < NP; ++p) {
             tma_prefetch_desc(&tm.a[p]);
             tma_prefetch_desc(&tm.w[p]);
+            if (straddle) tma_prefetch_desc(&tm.a_seg[p]);
         }
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
@@ -337,13 +342,16 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                 const int cw = ad.w_c0 + zh * ad.w_step + tap * Cin + c0, zw = z / ad.w_div;
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
-                    if (!packed) {
+                    if (!straddle) {
                         tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES, ca, t0 + tap - pad, za);
                     } else {
+                        // rows [t0, T) belong to utterance z, the rest to z + 1 (T >= 128 is not required: loop)
+                        int bz = z, tz = t0;
                         for (int r = 0; r < BLOCK_M; r += seg_rows) {
-                            const int g = g0 + r, bz = g / T;
-                            tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES + r * (BLOCK_K * 2), ca,
-                                        g - bz * T + tap - pad, bz);
+                            tma_load_3d(&tm.a_seg[p], &full_bar[s], st + p * A_TILE_BYTES + r * (BLOCK_K * 2), ca,
+                                        tz + tap - pad, bz);
+                            tz += seg_rows;
+                            if (tz >= T) { tz -= T; ++bz; }
                         }
                     }
                     uint8_t* wdst = st + NP * A_TILE_BYTES + p * S::B_TILE_BYTES;
@@ -410,10 +418,10 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
         mbar_wait(accum_bar, 0);
         tcgen05_fence_after();
         const long long clk_accum = ep.dbg ? clock64() : 0;
-        const bool tile_valid = packed ? (g0 < Z * T) : (z < Z);
-        const int len = (ep.lens && tile_valid && !packed) ? (int)ep.lens[z / ad.lens_div] : T;
+        const bool tile_valid = z < Z;
+        const int len = (ep.lens && tile_valid) ? (int)ep.lens[z / ad.lens_div] : T;
         const size_t tilebase = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner;
-        const RowMap rm{packed, g0, Z * T, T, len, t0, ep.lens, (size_t)ad.y_outer, tilebase, ad.ldy};
+        const RowMap rm{straddle, g0, Z * T, T, len, t0, ep.lens, (size_t)ad.y_outer, tilebase, ad.ldy};
         const int c4 = (lane & 7) * 4;          // my 4 columns inside the chunk
         const int rsub = lane >> 3;             // my row inside each group of 4 rows
 #pragma unroll 1
@@ -507,10 +515,17 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
     {
         cuuint64_t dims[3] = {A.d0, A.d1, A.d2};
         cuuint64_t str[2] = {A.s1 * 2, A.s2 * 2};
-        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)(seg_rows > 0 ? seg_rows : BLOCK_M), 1};
-        for (int p = 0; p < NP; ++p)
+        cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+        cuuint32_t box_seg[3] = {BLOCK_K, (cuuint32_t)(seg_rows > 0 ? seg_rows : BLOCK_M), 1};
+        for (int p = 0; p < NP; ++p) {
             if (int e = make_map(&maps.a[p], A.p[p], 3, dims, str, box, "activation plane")) return e;
-        for (int p = NP; p < 3; ++p) maps.a[p] = maps.a[0];
+            if (seg_rows > 0) {
+                if (int e = make_map(&maps.a_seg[p], A.p[p], 3, dims, str, box_seg, "activation plane (segments)")) return e;
+            } else {
+                maps.a_seg[p] = maps.a[p];
+            }
+        }
+        for (int p = NP; p < 3; ++p) { maps.a[p] = maps.a[0]; maps.a_seg[p] = maps.a_seg[0]; }
     }
     {
         cuuint64_t dims[3] = {W.d0, W.d1, W.d2};
@@ -567,7 +582,17 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
         if (shared_w) return launch<128, 2, 3, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
         return launch<128, 2, 3, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);   // 2 x 96 KiB stages
     }
-    if (N >= 512 && N % 256 == 0) {
+    // 128x256 or 128x128 tiles?  Whole waves cost the same whether they are full or not, so pick the shape with the
+    // smaller (waves x per-tile cycles) estimate; per-tile cycles from the measured breakdown in profiles/README.md.
+    bool wide = N >= 512 && N % 256 == 0;
+    if (wide) {
+        const long long nkb = (long long)taps * ((Cin + BLOCK_K - 1) / BLOCK_K);
+        const long long sms = 148;
+        const long long w256 = (m_tiles * ((N + 255) / 256) + sms - 1) / sms, w128 = (m_tiles * ((N + 127) / 128) + sms - 1) / sms;
+        const long long c256 = w256 * (9000 + nkb * 1700), c128 = w128 * (6000 + nkb * 1000);
+        wide = c256 <= c128;
+    }
+    if (wide) {
         if (shared_w) return launch<256, 2, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
         return launch<256, 2, 2, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
     }
