@@ -264,6 +264,11 @@ def main():
         value = world * frames * args.steps / (ms_total / 1e3)
         e2e = world * frames * args.steps / (ms_e2e / 1e3)
         ffn_avg = sum(ffn_ms) / max(len(ffn_ms), 1)
+        traffic = tensor_pct = None
+        summ = os.path.join(ROOT, "profiles", "ncu_ffn1_summary.json")
+        if os.path.exists(summ) and net.decoder_math == "bf16x3":   # one ncu --set full capture of this kernel (committed)
+            nc = json.load(open(summ))
+            traffic, tensor_pct = nc["dram_bytes_total"], nc["tensor_pipe_active_pct_of_peak_sustained_active"]
         ffn_tflops = frames * FFN_FLOP_PER_FRAME / (ffn_avg * 1e-3) / 1e12 if ffn_ms else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -283,7 +288,9 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "decoder FFN Conv1d(256->1024,k9)+GELU implicit GEMM: " + ffn_kernel,
                          "bound": "tensor", "achieved": ffn_tflops, "peak": pk["tensor"], "unit": "TFLOP/s",
-                         "frac": (ffn_tflops / pk["tensor"]) if ffn_tflops else None, "traffic": None,
+                         "frac": (ffn_tflops / pk["tensor"]) if ffn_tflops else None, "traffic": traffic,
+                         "traffic_source": "profiles/ncu_ffn1_summary.json (dram read + write bytes per launch)",
+                         "tensor_pipe_active_pct": tensor_pct, "mma_per_algorithmic_product": 3,
                          "peak_source": pk["src"], "launch_ms": ffn_avg, "launches_timed": len(ffn_ms),
                          "launch_timing": "CUDA events around each launch, eager re-run of the timed steps",
                          "flops_per_launch": frames * FFN_FLOP_PER_FRAME},

@@ -153,6 +153,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int BLOCK_N>
 __host__ __device__ constexpr uint32_t instr_desc() {
     // c_format F32 (1) @4, a_format BF16 (1) @7, b_format BF16 (1) @10, a/b K-major, N>>3 @17, M>>4 @24
@@ -201,10 +214,12 @@ struct RowMap {
     }
 };
 
-// Second half of the epilogue for one transposed 32x32 chunk: this lane owns 4 columns (n .. n+3) of 8 rows.
-template <int NP, int ACT>
+// Second half of the epilogue for one transposed chunk of 32 rows x (4*LPR) columns: LPR lanes cover a row with float4s,
+// so this lane owns 4 columns (n .. n+3) of LPR rows (32/LPR rows apart).  LD = row stride of the staging tile.
+template <int NP, int ACT, int LPR = 8, int LD = STG_LD>
 __device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg, int c4, int rsub, int row0,
                                             const RowMap& rm, int n) {
+    constexpr int RPI = 32 / LPR;   // rows per iteration
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bb;
     if (ep.bias) bb = *reinterpret_cast<const float4*>(ep.bias + n);
     const bool affine = ep.col_scale != nullptr;
@@ -214,12 +229,12 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg
     }
     const float alpha = ep.alpha;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < LPR; ++i) {
         bool keep;
         size_t off;
-        if (!rm.locate(row0 + 4 * i, keep, off)) break;
+        if (!rm.locate(row0 + RPI * i, keep, off)) break;
         off += (size_t)n;
-        const float4 a4 = *reinterpret_cast<const float4*>(stg + (rsub + 4 * i) * STG_LD + c4);
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + (rsub + RPI * i) * LD + c4);
         float v[4] = {(a4.x + bb.x) * alpha, (a4.y + bb.y) * alpha, (a4.z + bb.z) * alpha, (a4.w + bb.w) * alpha};
         if (affine) {
             v[0] = v[0] * sc.x + sh.x; v[1] = v[1] * sc.y + sh.y;
@@ -472,6 +487,215 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     }
 }
 
+// ---- persistent variant (2 operand planes, bf16x3) ---------------------------------------------------------------
+// One CTA per SM loops over output tiles (tile = blockIdx.x + i * gridDim.x).  The TMA ring simply continues across
+// tiles and the accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the epilogue of tile i (8 warps)
+// overlaps the mainloop of tile i + 1 and set-up is paid once per SM instead of once per tile; with one wave of CTAs
+// there is no wave quantisation beyond the tile granularity itself.
+constexpr int PSTG_LD = 20;   // floats per row of the 32 x 16 transpose tile of the persistent epilogue
+
+template <int BLOCK_N, int STAGES>
+struct PSmem {
+    static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = 2 * (A_TILE_BYTES + B_TILE_BYTES);
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int STAGING_OFFSET = BAR_OFFSET + 128;
+    static constexpr int TOTAL = STAGING_OFFSET + 8 * 32 * PSTG_LD * 4 + 1024;
+    static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(320, 1)
+gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
+                       int tiles_per_utt, int Z, int seg_rows, int m_tiles, int n_tiles) {
+    using S = PSmem<BLOCK_N, STAGES>;
+    constexpr int NP = 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;     // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
+    const int num_kb = taps * kb_per_tap;
+    const int pad = taps >> 1;
+    const int total_tiles = m_tiles * n_tiles;
+    const bool packed = seg_rows > 0;
+
+    if (warp == 0 && lane == 0) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            tma_prefetch_desc(&tm.a[p]);
+            tma_prefetch_desc(&tm.w[p]);
+            tma_prefetch_desc(&tm.a_seg[p]);
+        }
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
+        mbar_init(&acc_empty[0], 8);   // one arrival per epilogue warp
+        mbar_init(&acc_empty[1], 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> coordinates (n fastest: CTAs that run together share the activation rows)
+    auto tile_coords = [&](int tile, int& z, int& t0, int& n0, bool& straddle) {
+        const int mt = tile / n_tiles;
+        n0 = (tile - mt * n_tiles) * BLOCK_N;
+        if (packed) {
+            const int g0 = mt * BLOCK_M;
+            z = g0 / T;
+            t0 = g0 - z * T;
+            straddle = t0 + BLOCK_M > T;
+        } else {
+            z = mt / tiles_per_utt;
+            t0 = (mt - z * tiles_per_utt) * BLOCK_M;
+            straddle = false;
+        }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int z, t0, n0; bool straddle;
+                tile_coords(tile, z, t0, n0, straddle);
+                const int zh = z % ad.mod;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_expect_tx(&full_bar[s], (uint32_t)S::STAGE_BYTES);
+                    const int tap = kb / kb_per_tap;
+                    const int c0 = (kb - tap * kb_per_tap) * BLOCK_K;
+                    uint8_t* st = smem + s * S::STAGE_BYTES;
+                    const int ca = ad.a_c0 + zh * ad.a_step + c0, za = z / ad.a_div;
+                    const int cw = ad.w_c0 + zh * ad.w_step + tap * Cin + c0, zw = z / ad.w_div;
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        if (!straddle) {
+                            tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES, ca, t0 + tap - pad, za);
+                        } else {
+                            int bz = z, tz = t0;
+                            for (int r = 0; r < BLOCK_M; r += seg_rows) {
+                                tma_load_3d(&tm.a_seg[p], &full_bar[s], st + p * A_TILE_BYTES + r * (BLOCK_K * 2), ca,
+                                            tz + tap - pad, bz);
+                                tz += seg_rows;
+                                if (tz >= T) { tz -= T; ++bz; }
+                            }
+                        }
+                        tma_load_3d(&tm.w[p], &full_bar[s], st + NP * A_TILE_BYTES + p * S::B_TILE_BYTES, cw, n0, zw);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc<BLOCK_N>();
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+                const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+                mbar_wait(&acc_empty[acc], aph ^ 1u);     // the epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t a0 = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t b0 = a0 + NP * A_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint32_t off = k * UMMA_K * 2;
+                        const uint64_t dah = umma_desc_sw128(a0 + off), dal = umma_desc_sw128(a0 + A_TILE_BYTES + off);
+                        const uint64_t dbh = umma_desc_sw128(b0 + off), dbl = umma_desc_sw128(b0 + S::B_TILE_BYTES + off);
+                        umma_bf16(d_tmem, dal, dbh, idesc, (kb | k) ? 1u : 0u);  // small terms first
+                        umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+                        umma_bf16(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        float* stg = reinterpret_cast<float*>(smem + S::STAGING_OFFSET) + (warp - 2) * (32 * PSTG_LD);
+        const int c4 = (lane & 3) * 4;     // 4 lanes cover the 16 columns of a row
+        const int rsub = lane >> 2;        // 8 rows per iteration
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            int z, t0, n0; bool straddle;
+            tile_coords(tile, z, t0, n0, straddle);
+            const int zh = z % ad.mod;
+            const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+            mbar_wait(&acc_full[acc], aph);
+            tcgen05_fence_after();
+            const bool tile_valid = z < Z;
+            const int len = (ep.lens && tile_valid) ? (int)ep.lens[z / ad.lens_div] : T;
+            const size_t tilebase = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner;
+            const int g0 = packed ? (tile / n_tiles) * BLOCK_M : 0;
+            const RowMap rm{straddle, g0, Z * T, T, len, t0, ep.lens, (size_t)ad.y_outer, tilebase, ad.ldy};
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int u = half; u < BLOCK_N / 16; u += 2) {
+                const bool beyond = n0 + u * 16 >= N;     // warp-uniform
+                uint32_t r[16];
+                if (!beyond) tmem_ld_32x16(d_tmem + (uint32_t)(u * 16), r);
+                const bool last = u + 2 >= BLOCK_N / 16;
+                if (last) {   // all TMEM reads of this warp for the tile are done: hand the accumulator back early
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                }
+                if (beyond) continue;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * PSTG_LD + 4 * j) =
+                        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                    __uint_as_float(r[4 * j + 3]));
+                __syncwarp();
+                const int n = n0 + u * 16 + c4;
+                if (!tile_valid || n >= N) continue;
+                const int row0 = q * 32 + rsub;
+                switch (ep.act) {
+                    case CTTS_ACT_RELU: store_chunk<NP, CTTS_ACT_RELU, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                    case CTTS_ACT_GELU: store_chunk<NP, CTTS_ACT_GELU, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                    case CTTS_ACT_TANH: store_chunk<NP, CTTS_ACT_TANH, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                    case CTTS_ACT_SWISH: store_chunk<NP, CTTS_ACT_SWISH, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                    default: store_chunk<NP, CTTS_ACT_NONE, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -567,6 +791,61 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
     return check_launch("gemm_split");
 }
 
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_persistent(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin,
+                             int N, int taps, cudaStream_t st, int seg_rows) {
+    using S = PSmem<BLOCK_N, STAGES>;
+    constexpr int NP = 2;
+    Maps maps;
+    {
+        cuuint64_t dims[3] = {A.d0, A.d1, A.d2};
+        cuuint64_t str[2] = {A.s1 * 2, A.s2 * 2};
+        cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+        cuuint32_t box_seg[3] = {BLOCK_K, (cuuint32_t)(seg_rows > 0 ? seg_rows : BLOCK_M), 1};
+        for (int p = 0; p < NP; ++p) {
+            if (int e = make_map(&maps.a[p], A.p[p], 3, dims, str, box, "activation plane")) return e;
+            if (int e = make_map(&maps.a_seg[p], A.p[p], 3, dims, str, box_seg, "activation plane (segments)")) return e;
+        }
+        maps.a[2] = maps.a[0];
+        maps.a_seg[2] = maps.a_seg[0];
+    }
+    {
+        cuuint64_t dims[3] = {W.d0, W.d1, W.d2};
+        cuuint64_t str[2] = {W.s1 * 2, W.s2 * 2};
+        cuuint32_t box[3] = {BLOCK_K, BLOCK_N, 1};
+        for (int p = 0; p < NP; ++p)
+            if (int e = make_map(&maps.w[p], W.p[p], 3, dims, str, box, "weight plane")) return e;
+        maps.w[2] = maps.w[0];
+    }
+    auto kern = gemm_persistent_kernel<BLOCK_N, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+            set_error("gemm_persistent: cannot reserve %d bytes of shared memory", S::TOTAL);
+            return 4;
+        }
+        configured = true;
+    }
+    const int tiles_per_utt = (T + BLOCK_M - 1) / BLOCK_M;
+    const int m_tiles = seg_rows > 0 ? (int)(((long long)Z * T + BLOCK_M - 1) / BLOCK_M) : Z * tiles_per_utt;
+    const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+    const long long total = (long long)m_tiles * n_tiles;
+    const int grid = (int)(total < num_sms() ? total : num_sms());
+    kern<<<grid, 320, S::TOTAL, st>>>(maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z, seg_rows, m_tiles, n_tiles);
+    return check_launch("gemm_persistent");
+}
+
 static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin,
                        int N, int taps, cudaStream_t st) {
     // weights shared by all utterances (conv / linear: w_div huge) can be multicast across a 2-CTA cluster along M
@@ -591,6 +870,11 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
         const long long w256 = (m_tiles * ((N + 255) / 256) + sms - 1) / sms, w128 = (m_tiles * ((N + 127) / 128) + sms - 1) / sms;
         const long long c256 = w256 * (9000 + nkb * 1700), c128 = w128 * (6000 + nkb * 1000);
         wide = c256 <= c128;
+    }
+    static const bool use_persistent = getenv("CTTS_NO_PERSISTENT") == nullptr;
+    if (use_persistent) {
+        if (wide) return launch_persistent<256, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
+        return launch_persistent<128, 3>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
     }
     if (wide) {
         if (shared_w) return launch<256, 2, 2, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
