@@ -885,9 +885,17 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
 }
 
 // ---- attention helpers: masked softmax over materialised scores, V transpose ----------------------------------------
+struct Planes3 {
+    __nv_bfloat16* p[3];
+};
+struct CPlanes3 {
+    const __nv_bfloat16* p[3];
+};
+
 // S: [Z, T, Tp] fp32 (already scaled).  P planes: softmax over keys < len, zeros elsewhere (incl. the Tp padding).
+template <int NP>
 __global__ void softmax_planes_kernel(const float* __restrict__ S, const int64_t* __restrict__ lens, int H, int T, int Tp,
-                                      int rows, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
+                                      int rows, const Planes3 out) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // over Z*T
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -895,13 +903,11 @@ __global__ void softmax_planes_kernel(const float* __restrict__ S, const int64_t
     const int t = row - z * T;
     const int len = min((int)lens[z / H], T);
     const float* s = S + (size_t)row * Tp;
-    __nv_bfloat16* oh = p_hi + (size_t)row * Tp;
-    __nv_bfloat16* ol = p_lo + (size_t)row * Tp;
+    const size_t base = (size_t)row * Tp;
     if (t >= len) {
-        for (int j = lane * 4; j < Tp; j += 128) {
-            *reinterpret_cast<uint2*>(oh + j) = make_uint2(0u, 0u);
-            *reinterpret_cast<uint2*>(ol + j) = make_uint2(0u, 0u);
-        }
+        for (int j = lane * 4; j < Tp; j += 128)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) *reinterpret_cast<uint2*>(out.p[p] + base + j) = make_uint2(0u, 0u);
         return;
     }
     float mx = -INFINITY;
@@ -911,39 +917,42 @@ __global__ void softmax_planes_kernel(const float* __restrict__ S, const int64_t
     for (int j = lane; j < len; j += 32) sum += expf(s[j] - mx);
     const float inv = 1.f / warp_sum(sum);
     for (int j = lane * 4; j < Tp; j += 128) {
-        __nv_bfloat16 h[4], l[4];
+        float rem[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float p = (j + e < len) ? expf(s[j + e] - mx) * inv : 0.f;
-            h[e] = __float2bfloat16_rn(p);
-            l[e] = __float2bfloat16_rn(p - __bfloat162float(h[e]));
+        for (int e = 0; e < 4; ++e) rem[e] = (j + e < len) ? expf(s[j + e] - mx) * inv : 0.f;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            __nv_bfloat16 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                h[e] = __float2bfloat16_rn(rem[e]);
+                rem[e] -= __bfloat162float(h[e]);
+            }
+            *reinterpret_cast<uint2*>(out.p[p] + base + j) = *reinterpret_cast<uint2*>(h);
         }
-        *reinterpret_cast<uint2*>(oh + j) = *reinterpret_cast<uint2*>(h);
-        *reinterpret_cast<uint2*>(ol + j) = *reinterpret_cast<uint2*>(l);
     }
 }
 
 // qkv planes [B, T, 3C] -> Vt planes [B*H, DH, Tp] (keys contiguous, zero padded): the K-major B operand of P.V
-__global__ void transpose_v_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restrict__ q_lo, int T,
-                                   int Tp, int C, int H, int DH, __nv_bfloat16* __restrict__ vt_hi,
-                                   __nv_bfloat16* __restrict__ vt_lo) {
-    __shared__ __nv_bfloat16 th[32][34], tl[32][34];
+template <int NP>
+__global__ void transpose_v_kernel(const CPlanes3 q, int T, int Tp, int C, int H, int DH, const Planes3 vt) {
+    __shared__ __nv_bfloat16 tile[NP][32][34];
     const int z = blockIdx.z, b = z / H, h = z % H;
     const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     for (int i = ty; i < 32; i += 8) {
         const int t = t0 + i;
         const size_t src = ((size_t)b * T + t) * (size_t)(3 * C) + 2 * C + h * DH + d0 + tx;
-        th[i][tx] = (t < T) ? q_hi[src] : __float2bfloat16(0.f);
-        tl[i][tx] = (t < T) ? q_lo[src] : __float2bfloat16(0.f);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) tile[p][i][tx] = (t < T) ? q.p[p][src] : __float2bfloat16(0.f);
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int d = d0 + i, t = t0 + tx;
         if (t < Tp) {
             const size_t dst = ((size_t)z * DH + d) * (size_t)Tp + t;
-            vt_hi[dst] = th[tx][i];
-            vt_lo[dst] = tl[tx][i];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) vt.p[p][dst] = tile[p][tx][i];
         }
     }
 }
@@ -1006,51 +1015,80 @@ extern "C" int ctts_gemm_bf16x3(const void* x_hi, const void* x_lo, const void* 
     return gemm_split_impl(2, xp, wp, bias, alpha, col_scale, col_shift, act, residual, lens, B, T, Cin, N, taps, y, yp, stream);
 }
 
-extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, const int64_t* lens, int B, int T, int C,
-                                     int H, float scale, float* scores, void* p_hi, void* p_lo, void* vt_hi, void* vt_lo,
-                                     void* out_hi, void* out_lo, float* out_f32, void* stream) {
-    CTTS_REQUIRE(B > 0 && T > 0 && H > 0 && C % H == 0, "attention_bf16x3: bad shape B=%d T=%d C=%d H=%d", B, T, C, H);
+static int attention_split_impl(int np, const void* const* qkv, const int64_t* lens, int B, int T, int C, int H, float scale,
+                                float* scores, void* const* pp, void* const* vt, void* const* outp, float* out_f32,
+                                cudaStream_t st) {
+    CTTS_REQUIRE(np == 2 || np == 3, "attention_split: n_planes must be 2 or 3");
+    CTTS_REQUIRE(B > 0 && T > 0 && H > 0 && C % H == 0, "attention_split: bad shape B=%d T=%d C=%d H=%d", B, T, C, H);
     const int DH = C / H;
-    CTTS_REQUIRE(DH % 64 == 0, "attention_bf16x3: head_dim %d must be a multiple of 64", DH);
-    CTTS_REQUIRE(lens && scores && p_hi && p_lo && vt_hi && vt_lo, "attention_bf16x3: NULL workspace");
-    CTTS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr) && (out_hi || out_f32), "attention_bf16x3: bad outputs");
-    cudaStream_t st = (cudaStream_t)stream;
+    CTTS_REQUIRE(DH % 64 == 0, "attention_split: head_dim %d must be a multiple of 64", DH);
+    CTTS_REQUIRE(lens && scores && qkv && pp && vt, "attention_split: NULL workspace");
+    CTTS_REQUIRE((outp && outp[0]) || out_f32, "attention_split: no output requested");
     const int Tp = (T + 7) & ~7;
     const int Z = B * H;
     const cuuint64_t C3 = (cuuint64_t)3 * C;
+    Operand Aq{{nullptr, nullptr, nullptr}, C3, (cuuint64_t)T, (cuuint64_t)B, C3, (cuuint64_t)T * C3};
+    Operand Ap{{nullptr, nullptr, nullptr}, (cuuint64_t)Tp, (cuuint64_t)T, (cuuint64_t)Z, (cuuint64_t)Tp, (cuuint64_t)T * Tp};
+    Operand Wv{{nullptr, nullptr, nullptr}, (cuuint64_t)Tp, (cuuint64_t)DH, (cuuint64_t)Z, (cuuint64_t)Tp, (cuuint64_t)DH * Tp};
+    CPlanes3 qc{{nullptr, nullptr, nullptr}};
+    Planes3 pw{{nullptr, nullptr, nullptr}}, vw{{nullptr, nullptr, nullptr}};
+    Epilogue ep_o{nullptr, nullptr, nullptr, nullptr, lens, out_f32, {nullptr, nullptr, nullptr}, 1.f, CTTS_ACT_NONE, nullptr};
+    for (int p = 0; p < np; ++p) {
+        CTTS_REQUIRE(qkv[p] && pp[p] && vt[p], "attention_split: NULL plane %d", p);
+        Aq.p[p] = qkv[p]; Ap.p[p] = pp[p]; Wv.p[p] = vt[p];
+        qc.p[p] = (const __nv_bfloat16*)qkv[p];
+        pw.p[p] = (__nv_bfloat16*)pp[p];
+        vw.p[p] = (__nv_bfloat16*)vt[p];
+        if (outp && outp[0]) {
+            CTTS_REQUIRE(outp[p], "attention_split: NULL output plane %d", p);
+            ep_o.yp[p] = (__nv_bfloat16*)outp[p];
+        }
+    }
     // 1. S[z, t, s] = scale * q[z,t,:] . k[z,s,:]      (A = q columns, W = k columns of the same qkv planes)
     {
-        Operand A{{qkv_hi, qkv_lo, nullptr}, C3, (cuuint64_t)T, (cuuint64_t)B, C3, (cuuint64_t)T * C3};
-        Operand W = A;
-        Epilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, scores, {nullptr, nullptr, nullptr}, scale, CTTS_ACT_NONE, nullptr};
+        Epilogue ep{nullptr, nullptr, nullptr, nullptr, nullptr, scores, {nullptr, nullptr, nullptr}, scale, CTTS_ACT_NONE,
+                    nullptr};
         Addr ad{H, H, 0, DH, H, C, DH, 1, Tp, (long long)H * T * Tp, (long long)T * Tp};
-        if (int e = launch_auto(2, A, W, ep, ad, Z, T, DH, Tp, 1, st)) return e;
+        if (int e = launch_auto(np, Aq, Aq, ep, ad, Z, T, DH, Tp, 1, st)) return e;
     }
     // 2. Vt planes
     {
         dim3 grid((Tp + 31) / 32, DH / 32, Z);
-        transpose_v_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)qkv_hi, (const __nv_bfloat16*)qkv_lo, T, Tp, C, H, DH,
-                                                 (__nv_bfloat16*)vt_hi, (__nv_bfloat16*)vt_lo);
+        if (np == 3) transpose_v_kernel<3><<<grid, 256, 0, st>>>(qc, T, Tp, C, H, DH, vw);
+        else transpose_v_kernel<2><<<grid, 256, 0, st>>>(qc, T, Tp, C, H, DH, vw);
         if (int e = check_launch("transpose_v")) return e;
     }
-    // 3. P = softmax over keys < len of S, written as bf16 hi/lo planes
+    // 3. P = softmax over keys < len of S, written as bf16 planes
     {
         const int rows = Z * T;
-        softmax_planes_kernel<<<(rows + 7) / 8, 256, 0, st>>>(scores, lens, H, T, Tp, rows, (__nv_bfloat16*)p_hi,
-                                                             (__nv_bfloat16*)p_lo);
+        if (np == 3) softmax_planes_kernel<3><<<(rows + 7) / 8, 256, 0, st>>>(scores, lens, H, T, Tp, rows, pw);
+        else softmax_planes_kernel<2><<<(rows + 7) / 8, 256, 0, st>>>(scores, lens, H, T, Tp, rows, pw);
         if (int e = check_launch("softmax_planes")) return e;
     }
     // 4. out[b, t, h*DH + d] = sum_s P[z,t,s] * Vt[z,d,s]; rows t >= len are zeroed
     {
-        Operand A{{p_hi, p_lo, nullptr}, (cuuint64_t)Tp, (cuuint64_t)T, (cuuint64_t)Z, (cuuint64_t)Tp, (cuuint64_t)T * Tp};
-        Operand W{{vt_hi, vt_lo, nullptr}, (cuuint64_t)Tp, (cuuint64_t)DH, (cuuint64_t)Z, (cuuint64_t)Tp,
-                  (cuuint64_t)DH * Tp};
-        Epilogue ep{nullptr, nullptr, nullptr, nullptr, lens, out_f32,
-                    {(__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, nullptr}, 1.f, CTTS_ACT_NONE, nullptr};
         Addr ad{H, 1, 0, 0, 1, 0, 0, H, C, (long long)T * C, (long long)DH};
-        if (int e = launch_auto(2, A, W, ep, ad, Z, T, Tp, DH, 1, st)) return e;
+        if (int e = launch_auto(np, Ap, Wv, ep_o, ad, Z, T, Tp, DH, 1, st)) return e;
     }
     return 0;
+}
+
+extern "C" int ctts_attention_split(int n_planes, const void* const* qkv_planes, const int64_t* lens, int B, int T, int C, int H,
+                                    float scale, float* scores, void* const* p_planes, void* const* vt_planes,
+                                    void* const* out_planes, float* out_f32, void* stream) {
+    return attention_split_impl(n_planes, qkv_planes, lens, B, T, C, H, scale, scores, p_planes, vt_planes, out_planes, out_f32,
+                                (cudaStream_t)stream);
+}
+
+extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, const int64_t* lens, int B, int T, int C,
+                                     int H, float scale, float* scores, void* p_hi, void* p_lo, void* vt_hi, void* vt_lo,
+                                     void* out_hi, void* out_lo, float* out_f32, void* stream) {
+    CTTS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "attention_bf16x3: out_hi/out_lo must come together");
+    const void* q[3] = {qkv_hi, qkv_lo, nullptr};
+    void* pp[3] = {p_hi, p_lo, nullptr};
+    void* vt[3] = {vt_hi, vt_lo, nullptr};
+    void* op[3] = {out_hi, out_lo, nullptr};
+    return attention_split_impl(2, q, lens, B, T, C, H, scale, scores, pp, vt, op, out_f32, (cudaStream_t)stream);
 }
 
 /* development aid: per-CTA cycle stamps of the next ctts_gemm_split launches (4 x int64 per CTA); NULL disables */

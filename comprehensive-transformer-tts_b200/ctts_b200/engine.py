@@ -124,21 +124,20 @@ def attention(qkv, lens, n_head):
 
 
 def attention_tc(qkv_planes, lens, n_head):
-    """Tensor-core masked self-attention on bf16 hi/lo planes (ctts_attention_bf16x3); returns output planes."""
+    """Tensor-core masked self-attention on bf16 planes (ctts_attention_split: 2 planes = bf16x3, 3 planes = bf16x6);
+    returns the output planes."""
     B, T, C3 = qkv_planes.shape
     C = C3 // 3
-    dev = qkv_planes.hi.device
+    n = qkv_planes.n
+    dev = qkv_planes.p[0].device
     Tp = (T + 7) // 8 * 8
     Z = B * n_head
     scores = torch.empty(Z * T * Tp, device=dev, dtype=torch.float32)
-    p_hi = torch.empty(Z * T * Tp, device=dev, dtype=torch.bfloat16)
-    p_lo = torch.empty_like(p_hi)
-    vt_hi = torch.empty(B * C * Tp, device=dev, dtype=torch.bfloat16)
-    vt_lo = torch.empty_like(vt_hi)
-    assert qkv_planes.n == 2
-    out = Planes.empty((B, T, C), dev, 2)
-    capi.call("ctts_attention_bf16x3", qkv_planes.hi, qkv_planes.lo, lens, B, T, C, n_head,
-              1.0 / math.sqrt(C // n_head), scores, p_hi, p_lo, vt_hi, vt_lo, out.hi, out.lo, None, _stream())
+    pp = [torch.empty(Z * T * Tp, device=dev, dtype=torch.bfloat16) for _ in range(n)]
+    vt = [torch.empty(B * C * Tp, device=dev, dtype=torch.bfloat16) for _ in range(n)]
+    out = Planes.empty((B, T, C), dev, n)
+    capi.call("ctts_attention_split", n, capi.ptr_array(qkv_planes.p), lens, B, T, C, n_head, 1.0 / math.sqrt(C // n_head),
+              scores, capi.ptr_array(pp), capi.ptr_array(vt), capi.ptr_array(out.p), None, _stream())
     return out
 
 
@@ -274,20 +273,16 @@ def encoder_fs2(prep, P, cfg, tokens, src_lens, math_mode="fp32"):
 
 
 def _fft_layers_fs2_tc(prep, P, pre, x, lens, n_layers, n_head, kernel, act, n=2):
-    """Same block as _fft_layers_fs2 with the four dense contractions on tcgen05.  n = 2: bf16x3 operands and
-    tensor-core attention (decoder); n = 3: bf16x6 operands (FP32-equivalent) with the FP32 attention kernel (encoder).
+    """Same block as _fft_layers_fs2 with the dense contractions and the attention on tcgen05.  n = 2: bf16x3 operands
+    (decoder); n = 3: bf16x6 operands (FP32-equivalent, encoder).
     LayerNorm, softmax and the residual stream stay FP32.  Returns (final LN fp32, final LN planes)."""
     W = prep.w
     tag = "#planes" if n == 2 else "#planes3"
     for i in range(n_layers):
         lp = "%slayers.%d.op." % (pre, i)
         _, hp = layernorm_planes(x, P[lp + "layer_norm1.weight"], P[lp + "layer_norm1.bias"], 1e-12, n=n)
-        if n == 2:
-            _, qkvp = gemm_tc(hp, W[lp + "self_attn.in_proj_weight" + tag], want_fp32=False, want_planes=True)
-            ap = attention_tc(qkvp, lens, n_head)
-        else:
-            qkv, _ = gemm_tc(hp, W[lp + "self_attn.in_proj_weight" + tag])
-            ap = split_planes(attention(qkv, lens, n_head), n)
+        _, qkvp = gemm_tc(hp, W[lp + "self_attn.in_proj_weight" + tag], want_fp32=False, want_planes=True)
+        ap = attention_tc(qkvp, lens, n_head)
         gemm_tc(ap, W[lp + "self_attn.out_proj.weight" + tag], residual=x, lens=lens, out=x)
         _, hp = layernorm_planes(x, P[lp + "layer_norm2.weight"], P[lp + "layer_norm2.bias"], 1e-12, n=n)
         _, fp = gemm_tc(hp, W[lp + "ffn.ffn_1.weight" + tag], P[lp + "ffn.ffn_1.bias"], alpha=kernel ** -0.5, act=act,

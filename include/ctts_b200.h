@@ -272,6 +272,12 @@ int ctts_split_planes(const float* x, size_t n, int n_planes, void* const* plane
 int ctts_layernorm_planes(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B, int T,
                           int C, float* y, int n_planes, void* const* planes, void* stream);
 
+/* n-plane generalisation of ctts_attention_bf16x3 (n_planes 3 = FP32-equivalent, used by the encoder).  Plane arguments are
+ * HOST arrays of n_planes device pointers; workspaces as above, per plane. */
+int ctts_attention_split(int n_planes, const void* const* qkv_planes, const int64_t* lens, int B, int T, int C, int H,
+                         float scale, float* scores, void* const* p_planes, void* const* vt_planes, void* const* out_planes,
+                         float* out_f32, void* stream);
+
 /* development aid: when non-NULL, every CTA of the following ctts_gemm_split launches stores four clock64() stamps
  * {start, setup done, accumulator ready, epilogue done} at device_buffer[4 * cta]; used by profiles/ scripts only. */
 int ctts_debug_set_timing_buffer(long long* device_buffer);
