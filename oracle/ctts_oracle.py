@@ -110,10 +110,8 @@ def length_regulate(x, duration, max_len=None):
     for b in range(B):
         idx = torch.repeat_interleave(torch.arange(S), reps[b])
         n = idx.numel()
-        if n > out_len:
-            raise RuntimeError("length_regulate: expanded length %d exceeds max_len %d (the reference's "
-                               "F.pad with a negative amount would crop; not exercised)" % (n, out_len))
-        out[b, :n] = x[b, idx]
+        n = min(n, out_len)   # F.pad with a negative amount crops (utils/tools.py:586-592); mel_len keeps the full length
+        out[b, :n] = x[b, idx[:n]]
     return out, lens
 
 
