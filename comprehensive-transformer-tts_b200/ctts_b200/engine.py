@@ -6,6 +6,7 @@ reached through `capi.call` with raw device pointers.  Function names mirror the
 modules; file:line citations point at the reference code each function stands in for.
 """
 import math
+import os
 
 import torch
 
@@ -123,12 +124,31 @@ def attention(qkv, lens, n_head):
     return out
 
 
+FLASH = os.environ.get("CTTS_FLASH_ATTENTION", "1") != "0"
+
+
+def attention_flash(qkv_planes, lens, n_head):
+    """Fused tensor-core attention (ctts_flash_attention_bf16x3): head_dim 128, 2 planes; scores never reach HBM."""
+    B, T, C3 = qkv_planes.shape
+    C = C3 // 3
+    dev = qkv_planes.p[0].device
+    Tp = (T + 7) // 8 * 8
+    vt = [torch.empty(B * C * Tp, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    capi.call("ctts_transpose_v_planes", 2, capi.ptr_array(qkv_planes.p), B, T, C, n_head, capi.ptr_array(vt), _stream())
+    out = Planes.empty((B, T, C), dev, 2)
+    capi.call("ctts_flash_attention_bf16x3", qkv_planes.p[0], qkv_planes.p[1], vt[0], vt[1], lens, B, T, C, n_head,
+              1.0 / math.sqrt(C // n_head), out.p[0], out.p[1], _stream())
+    return out
+
+
 def attention_tc(qkv_planes, lens, n_head):
     """Tensor-core masked self-attention on bf16 planes (ctts_attention_split: 2 planes = bf16x3, 3 planes = bf16x6);
     returns the output planes."""
     B, T, C3 = qkv_planes.shape
     C = C3 // 3
     n = qkv_planes.n
+    if FLASH and n == 2 and C // n_head == 128:
+        return attention_flash(qkv_planes, lens, n_head)
     dev = qkv_planes.p[0].device
     Tp = (T + 7) // 8 * 8
     Z = B * n_head

@@ -278,6 +278,19 @@ int ctts_attention_split(int n_planes, const void* const* qkv_planes, const int6
                          float scale, float* scores, void* const* p_planes, void* const* vt_planes, void* const* out_planes,
                          float* out_f32, void* stream);
 
+/* ---- fused ("flash") tensor-core self-attention, head_dim 128, 2 planes ------------------------------------
+ * One CTA per (batch*head, 128 queries): S = Q K^T in TMEM, softmax in registers, probability planes in shared memory,
+ * O = P V in TMEM; the keys are swept twice (row statistics, then P V) so nothing is rescaled and no score ever reaches
+ * HBM.  vt_* are the V^T planes [B*H, 128, Tp] from ctts_transpose_v_planes.  Output planes [B, T, C]; rows t >= lens[b]
+ * are zero.  Same function as ctts_attention_bf16x3 (transformer_fs2.py:385-394, transformer.py:233-252).
+ */
+int ctts_flash_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, const void* vt_hi, const void* vt_lo,
+                                const int64_t* lens, int B, int T, int C, int H, float scale, void* out_hi, void* out_lo,
+                                void* stream);
+/* qkv planes [B, T, 3C] -> V^T planes [B*H, C/H, Tp] (Tp = T rounded up to 8, zero padded) */
+int ctts_transpose_v_planes(int n_planes, const void* const* qkv_planes, int B, int T, int C, int H, void* const* vt_planes,
+                            void* stream);
+
 /* development aid: when non-NULL, every CTA of the following ctts_gemm_split launches stores four clock64() stamps
  * {start, setup done, accumulator ready, epilogue done} at device_buffer[4 * cta]; used by profiles/ scripts only. */
 int ctts_debug_set_timing_buffer(long long* device_buffer);

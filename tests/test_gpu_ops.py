@@ -336,3 +336,26 @@ def test_gemm_bf16x6_is_fp32_equivalent(B, T, Cin, N, taps, act):
     assert err6 <= max(3 * err32, 8e-6), (err6, err32)
     assert (yp.value() - y).abs().max().item() < 1e-6
     assert yp.n == 3
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 128, 2), (3, 300, 2), (2, 273, 2), (2, 64, 2), (2, 801, 2), (16, 800, 2), (1, 1000, 4)])
+def test_flash_attention_bf16x3(B, T, H):
+    """Fused tensor-core attention (S in TMEM, P planes in shared memory) against fp64 and against the materialised
+    tensor-core path."""
+    C = 128 * H
+    qkv = torch.randn(B, T, 3 * C, generator=g(70)) * 1.5
+    lens = torch.tensor([max(T - 37 * b, 1) for b in range(B)])
+    dh = C // H
+    q, k, v = qkv.double().split(C, -1)
+    q = q.view(B, T, H, dh).transpose(1, 2) / math.sqrt(dh)
+    k = k.view(B, T, H, dh).transpose(1, 2)
+    v = v.view(B, T, H, dh).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    pad = torch.arange(T)[None, :] >= lens[:, None]
+    s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, C)
+    ref = (ref * (~pad).double()[:, :, None]).float()
+    planes = engine.split_planes(qkv.to(DEV), 2)
+    out = engine.attention_flash(planes, lens.to(DEV), H)
+    torch.cuda.synchronize()
+    close(out.value(), ref, atol=1e-4, rtol=1e-4)
