@@ -2,13 +2,13 @@
 //
 // One CTA per (batch*head, 128-query tile).  Scores never leave the SM: S = Q K^T lands in TMEM, the softmax warps turn
 // it into probability planes in shared memory, and P V accumulates into a second TMEM region.  No online rescaling of
-// the output: the keys are swept TWICE -- pass A computes the row maxima and normalisers (only scalars are rescaled),
-// pass B recomputes S, forms p = exp(s - m) / l and accumulates O += P V.  Recomputing Q K^T costs one third more MMA
+// the output: the keys are swept TWICE -- pass A computes the row maxima (no exponentials), pass B recomputes S, forms
+// p = exp(s - m), accumulates the row sums and O += P V; the epilogue divides by the row sum.  Recomputing Q K^T costs one third more MMA
 // work than the minimum and saves the 3 x 82 MB round trips (scores, probability planes) of the materialised version.
 //
 //   warp 0      TMA producer: Q once, K tiles (2 passes), V^T tiles; SWIZZLE_128B; 2-stage rings
 //   warp 1      tcgen05.mma issuer: S (M128 x N64 x K128, 3 plane products) and P V (M128 x N128 x K64)
-//   warps 2-5   softmax / epilogue, one query row per thread (TMEM lane = row)
+//   warps 2-9   softmax / epilogue: TMEM lane = query row, two warps per lane quarter split the columns
 //
 // Replaces transformer_fs2.py:385-394 (F.multi_head_attention_forward) / transformer.py:233-252 on the decoder.
 #include "ctts_common.cuh"
@@ -39,7 +39,7 @@ constexpr int OFF_K = OFF_Q + Q_BYTES;            // 2 stages
 constexpr int OFF_V = OFF_K + 2 * K_STAGE;        // 2 stages
 constexpr int OFF_P = OFF_V + 2 * V_STAGE;
 constexpr int OFF_BAR = OFF_P + P_BYTES;
-constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
+constexpr int SMEM_TOTAL = OFF_BAR + 192 + 1024 + 1024;   // barriers, [2][128] float exchange area, alignment slack
 static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
 struct Maps {
@@ -54,7 +54,7 @@ __host__ __device__ constexpr uint32_t idesc(int n) {
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restrict__ lens, int T, int C, int H, float scale_log2e,
                        __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
     extern __shared__ uint8_t smem_raw[];
@@ -92,9 +92,9 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_empty[i], 4);
+            mbar_init(&s_empty[i], 8);      // one arrival per softmax warp
         }
-        mbar_init(p_full, 4);
+        mbar_init(p_full, 8);
         mbar_init(p_empty, 1);
         mbar_init(o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -196,55 +196,50 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
             umma_commit(o_full);
         }
     } else {
+        // 8 softmax warps: TMEM lane quarter qq = warp % 4 (32 query rows), column half ch = (warp - 2) / 4 (32 of the 64
+        // keys of a tile, 64 of the 128 output dims).  The two warps of a quarter meet twice through shared memory:
+        // after pass A (row maximum) and before the epilogue (row sum).
         const int qq = warp & 3;
+        const int ch = (warp - 2) >> 2;
         const int row = qq * 32 + lane;                  // query row inside the tile == TMEM lane
         const uint32_t lane_base = tmem_base + ((uint32_t)(qq * 32) << 16);
-        float m = -INFINITY, l = 0.f;
-        // ---- pass A: row maximum and normaliser (scores in units of log2: s * scale * log2 e) ----
+        float* xch = reinterpret_cast<float*>(smem + OFF_BAR + 192);     // [2][128] exchange area (1 KiB, see SMEM_TOTAL)
+        // ---- pass A: row maximum only (scores in units of log2: s * scale * log2 e) ----
+        float m = -INFINITY;
         for (int i = 0; i < nkv; ++i) {
             const int s = i & 1;
             mbar_wait(&s_full[s], (i >> 1) & 1);
             tcgen05_fence_after();
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32(lane_base + (uint32_t)(s * BKV), r0);
-            tmem_ld_32x32(lane_base + (uint32_t)(s * BKV + 32), r1);
+            uint32_t r[32];
+            tmem_ld_32x32(lane_base + (uint32_t)(s * BKV + ch * 32), r);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);
-            const int k0 = i * BKV;
-            float mx = m;
+            const int k0 = i * BKV + ch * 32;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const float a = (k0 + c < len) ? __uint_as_float(r0[c]) * scale_log2e : -INFINITY;
-                const float bb = (k0 + 32 + c < len) ? __uint_as_float(r1[c]) * scale_log2e : -INFINITY;
-                r0[c] = __float_as_uint(a);
-                r1[c] = __float_as_uint(bb);
-                mx = fmaxf(mx, fmaxf(a, bb));
-            }
-            float sum = 0.f;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) sum += exp2f(__uint_as_float(r0[c]) - mx) + exp2f(__uint_as_float(r1[c]) - mx);
-            l = l * exp2f(m - mx) + sum;
-            m = mx;
+            for (int c = 0; c < 32; ++c)
+                if (k0 + c < len) m = fmaxf(m, __uint_as_float(r[c]));
         }
-        const float inv_l = 1.f / l;
-        // ---- pass B: probabilities -> bf16 planes in shared memory (SWIZZLE_128B K-major A operand of P V) ----
+        xch[ch * 128 + row] = m;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qq) : "memory");       // the two warps of this lane quarter
+        m = fmaxf(xch[row], xch[128 + row]) * scale_log2e;                  // scale > 0: max commutes with the scaling
+        // ---- pass B: unnormalised probabilities -> bf16 planes in shared memory (SWIZZLE_128B A operand of P V) ----
+        float l = 0.f;
         uint8_t* p_hi = smem + OFF_P + row * 128;
         uint8_t* p_lo = p_hi + P_TILE;
         for (int j = 0; j < nkv; ++j) {
             const int i = nkv + j, s = i & 1;
             mbar_wait(&s_full[s], (i >> 1) & 1);
             tcgen05_fence_after();
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32(lane_base + (uint32_t)(s * BKV), r0);
-            tmem_ld_32x32(lane_base + (uint32_t)(s * BKV + 32), r1);
+            uint32_t r[32];
+            tmem_ld_32x32(lane_base + (uint32_t)(s * BKV + ch * 32), r);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);
-            const int k0 = j * BKV;
+            const int k0 = j * BKV + ch * 32;
             mbar_wait(p_empty, (j & 1) ^ 1);          // the previous P V has finished reading the P planes
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {           // 8 chunks of 8 keys = 16 bytes per plane
+            for (int c8 = 0; c8 < 4; ++c8) {           // my 4 chunks of 8 keys = 16 bytes per plane
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -252,15 +247,15 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int c = c8 * 8 + e * 2 + u;
-                        const float sv = __uint_as_float(c < 32 ? r0[c] : r1[c - 32]) * scale_log2e;
-                        p2[u] = (k0 + c < len) ? exp2f(sv - m) * inv_l : 0.f;
+                        p2[u] = (k0 + c < len) ? exp2f(fmaf(__uint_as_float(r[c]), scale_log2e, -m)) : 0.f;
                     }
+                    l += p2[0] + p2[1];
                     const __nv_bfloat162 hh = __floats2bfloat162_rn(p2[0], p2[1]);
                     const __nv_bfloat162 ll = __floats2bfloat162_rn(p2[0] - __low2float(hh), p2[1] - __high2float(hh));
                     hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
                     lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
-                const int phys = (c8 ^ (row & 7)) * 16;    // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+                const int phys = (((ch * 4 + c8) ^ (row & 7))) * 16;   // 128-byte swizzle: chunk index XOR (row mod 8)
                 *reinterpret_cast<uint4*>(p_hi + phys) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(p_lo + phys) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
@@ -268,26 +263,30 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
         }
-        // ---- epilogue: O (TMEM columns 128..255) -> output planes; padded query rows are zero ----
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qq) : "memory");       // everyone has read the maxima: reuse the area
+        xch[ch * 128 + row] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qq) : "memory");
+        const float inv_l = 1.f / (xch[row] + xch[128 + row]);
+        // ---- epilogue: O (TMEM columns 128..255) / l -> output planes; padded query rows are zero ----
         mbar_wait(o_full, 0);
         tcgen05_fence_after();
         const int t = q0 + row;
         const bool store = t < T;
-        const bool keep = t < len;
-        __nv_bfloat16* oh = out_hi + ((size_t)b * T + (store ? t : 0)) * C + (size_t)h * DH;
-        __nv_bfloat16* ol = out_lo + ((size_t)b * T + (store ? t : 0)) * C + (size_t)h * DH;
+        const float w = (t < len) ? inv_l : 0.f;
+        __nv_bfloat16* oh = out_hi + ((size_t)b * T + (store ? t : 0)) * C + (size_t)h * DH + ch * 64;
+        __nv_bfloat16* ol = out_lo + ((size_t)b * T + (store ? t : 0)) * C + (size_t)h * DH + ch * 64;
 #pragma unroll 1
-        for (int chunk = 0; chunk < DH / 32; ++chunk) {
+        for (int chunk = 0; chunk < 2; ++chunk) {
             uint32_t r[32];
-            tmem_ld_32x32(lane_base + 128u + (uint32_t)(chunk * 32), r);
+            tmem_ld_32x32(lane_base + 128u + (uint32_t)(ch * 64 + chunk * 32), r);
             if (!store) continue;
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float a = keep ? __uint_as_float(r[c8 * 8 + e * 2]) : 0.f;
-                    const float bb = keep ? __uint_as_float(r[c8 * 8 + e * 2 + 1]) : 0.f;
+                    const float a = __uint_as_float(r[c8 * 8 + e * 2]) * w;
+                    const float bb = __uint_as_float(r[c8 * 8 + e * 2 + 1]) * w;
                     const __nv_bfloat162 hh = __floats2bfloat162_rn(a, bb);
                     const __nv_bfloat162 ll = __floats2bfloat162_rn(a - __low2float(hh), bb - __high2float(hh));
                     hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
@@ -364,7 +363,7 @@ extern "C" int ctts_flash_attention_bf16x3(const void* qkv_hi, const void* qkv_l
         configured = true;
     }
     dim3 grid((T + fa::BQ - 1) / fa::BQ, Z);
-    fa::flash_attention_kernel<<<grid, 192, fa::SMEM_TOTAL, (cudaStream_t)stream>>>(
+    fa::flash_attention_kernel<<<grid, 320, fa::SMEM_TOTAL, (cudaStream_t)stream>>>(
         maps, lens, T, C, H, scale * 1.4426950408889634f, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
     return check_launch("flash_attention");
 }
