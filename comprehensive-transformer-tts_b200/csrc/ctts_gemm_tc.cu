@@ -19,6 +19,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "ctts_tc_ptx.cuh"
@@ -591,6 +592,230 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
     }
 }
 
+// ---- CTA-pair persistent variant (cta_group::2, 2 operand planes) ---------------------------------------------------
+// The single-CTA mainloop above is bound by shared-memory bandwidth, not by tensor-core issue: every 128x256x16 MMA
+// reads 4 KiB of A and 8 KiB of B (96 B/clk) while TMA writes the next stage (62 B/clk) -- measured 1.70 k cycles per
+// k-block against the 1.54 k issue floor, tensor pipe 77 % active.  A CTA pair computes a 256 x 256 tile with ONE
+// tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 activation rows and only HALF of the weight tile
+// (128 of the 256 output channels), so the per-SM shared-memory traffic drops by a third and the stage by a third
+// (64 KiB -> 3 stages).  Rank 0 (leader) issues all MMAs; both CTAs' TMA loads complete on the leader's full barrier;
+// tcgen05.commit is multicast to both CTAs' empty / accumulator-full barriers; the epilogue warps of both CTAs hand the
+// accumulator back with a (remote) arrive on the leader's accumulator-empty barrier.
+template <int STAGES>
+struct PairSmem {
+    static constexpr int BLOCK_N = 256;
+    static constexpr int B_HALF_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;              // 16 KiB
+    static constexpr int STAGE_BYTES = 2 * (A_TILE_BYTES + B_HALF_BYTES);         // per CTA: 64 KiB
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int STAGING_OFFSET = BAR_OFFSET + 128;
+    static constexpr int TOTAL = STAGING_OFFSET + 8 * 32 * PSTG_LD * 4 + 1024;
+    static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(320, 1)
+gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
+                 int tiles_per_utt, int Z, int seg_rows, int m_tiles, int n_tiles, int swap_b) {
+    using S = PairSmem<STAGES>;
+    constexpr int NP = 2;
+    constexpr int BLOCK_N = 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);   // used on the leader only
+    uint64_t* empty_bar = full_bar + STAGES;                                  // one set per CTA
+    uint64_t* acc_full = empty_bar + STAGES;                                  // [2], one set per CTA
+    uint64_t* acc_empty = acc_full + 2;                                       // [2], used on the leader only
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
+    const int num_kb = taps * kb_per_tap;
+    const int pad = taps >> 1;
+    const int pair_tiles = ((m_tiles + 1) >> 1) * n_tiles;
+    const bool packed = seg_rows > 0;
+
+    if (warp == 0 && lane == 0) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            tma_prefetch_desc(&tm.a[p]);
+            tma_prefetch_desc(&tm.w[p]);
+            tma_prefetch_desc(&tm.a_seg[p]);
+        }
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
+        mbar_init(&acc_empty[0], 16);   // one arrival per epilogue warp of BOTH CTAs
+        mbar_init(&acc_empty[1], 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;   // all 512 columns: two 128-lane x 256-column accumulators per CTA
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // both CTAs' barriers are initialised and both TMEM allocations exist
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // pair tile -> this CTA's 128 rows (m-tile 2*(pt / n_tiles) + rank) and the pair's 256 output channels
+    auto tile_coords = [&](int pt, int& mt, int& z, int& t0, int& n0, bool& straddle) {
+        const int pm = pt / n_tiles;
+        mt = 2 * pm + (int)rank;
+        n0 = (pt - pm * n_tiles) * BLOCK_N;
+        if (packed) {
+            const int g0 = mt * BLOCK_M;
+            z = g0 / T;
+            t0 = g0 - z * T;
+            straddle = t0 + BLOCK_M > T;
+        } else {
+            z = mt / tiles_per_utt;
+            t0 = (mt - z * tiles_per_utt) * BLOCK_M;
+            straddle = false;
+        }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int b_rows0 = (int)(swap_b ? (rank ^ 1u) : rank) * (BLOCK_N / 2);
+            uint32_t it = 0;
+            for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
+                int mt, z, t0, n0; bool straddle;
+                tile_coords(pt, mt, z, t0, n0, straddle);
+                const int zh = z % ad.mod;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)S::STAGE_BYTES);
+                    const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
+                    const int tap = kb / kb_per_tap;
+                    const int c0 = (kb - tap * kb_per_tap) * BLOCK_K;
+                    uint8_t* st = smem + s * S::STAGE_BYTES;
+                    const int ca = ad.a_c0 + zh * ad.a_step + c0, za = z / ad.a_div;
+                    const int cw = ad.w_c0 + zh * ad.w_step + tap * Cin + c0, zw = z / ad.w_div;
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        if (!straddle) {
+                            tma_load_3d_pair(&tm.a[p], fb, st + p * A_TILE_BYTES, ca, t0 + tap - pad, za);
+                        } else {
+                            int bz = z, tz = t0;
+                            for (int r = 0; r < BLOCK_M; r += seg_rows) {
+                                tma_load_3d_pair(&tm.a_seg[p], fb, st + p * A_TILE_BYTES + r * (BLOCK_K * 2), ca,
+                                                 tz + tap - pad, bz);
+                                tz += seg_rows;
+                                if (tz >= T) { tz -= T; ++bz; }
+                            }
+                        }
+                        tma_load_3d_pair(&tm.w[p], fb, st + NP * A_TILE_BYTES + p * S::B_HALF_BYTES, cw, n0 + b_rows0, zw);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // M = 256 (both CTAs' 128 rows), N = 256 (both CTAs' 128 weight rows)
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                       ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+            uint32_t it = 0, lt = 0;
+            for (int pt = pair; pt < pair_tiles; pt += n_pairs, ++lt) {
+                const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+                mbar_wait_cluster(&acc_empty[acc], aph ^ 1u);   // both CTAs' epilogues have drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t a0 = smem_u32(smem + s * S::STAGE_BYTES);
+                    const uint32_t b0 = a0 + NP * A_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint32_t off = k * UMMA_K * 2;
+                        const uint64_t dah = umma_desc_sw128(a0 + off), dal = umma_desc_sw128(a0 + A_TILE_BYTES + off);
+                        const uint64_t dbh = umma_desc_sw128(b0 + off), dbl = umma_desc_sw128(b0 + S::B_HALF_BYTES + off);
+                        umma_bf16_pair(d_tmem, dal, dbh, idesc, (kb | k) ? 1u : 0u);  // small terms first
+                        umma_bf16_pair(d_tmem, dah, dbl, idesc, 1u);
+                        umma_bf16_pair(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit_pair(&empty_bar[s]);
+                }
+                umma_commit_pair(&acc_full[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        float* stg = reinterpret_cast<float*>(smem + S::STAGING_OFFSET) + (warp - 2) * (32 * PSTG_LD);
+        const int c4 = (lane & 3) * 4;     // 4 lanes cover the 16 columns of a row
+        const int rsub = lane >> 2;        // 8 rows per iteration
+        const uint32_t acc_empty_leader[2] = {mapa_shared(smem_u32(&acc_empty[0]), 0),
+                                              mapa_shared(smem_u32(&acc_empty[1]), 0)};
+        uint32_t lt = 0;
+        for (int pt = pair; pt < pair_tiles; pt += n_pairs, ++lt) {
+            int mt, z, t0, n0; bool straddle;
+            tile_coords(pt, mt, z, t0, n0, straddle);
+            const int zh = z % ad.mod;
+            const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+            mbar_wait(&acc_full[acc], aph);
+            tcgen05_fence_after();
+            const bool tile_valid = z < Z && mt < m_tiles;
+            const int len = (ep.lens && tile_valid) ? (int)ep.lens[z / ad.lens_div] : T;
+            const size_t tilebase = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner;
+            const int g0 = packed ? mt * BLOCK_M : 0;
+            const RowMap rm{straddle, g0, Z * T, T, len, t0, ep.lens, (size_t)ad.y_outer, tilebase, ad.ldy};
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int u = half; u < BLOCK_N / 16; u += 2) {
+                const bool beyond = n0 + u * 16 >= N;     // warp-uniform
+                uint32_t r[16];
+                if (!beyond) tmem_ld_32x16(d_tmem + (uint32_t)(u * 16), r);
+                const bool last = u + 2 >= BLOCK_N / 16;
+                if (last) {   // all TMEM reads of this warp for the tile are done: hand the accumulator back early
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc_empty_leader[acc]);
+                }
+                if (beyond) continue;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * PSTG_LD + 4 * j) =
+                        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                    __uint_as_float(r[4 * j + 3]));
+                __syncwarp();
+                const int n = n0 + u * 16 + c4;
+                if (!tile_valid || n >= N) continue;
+                const int row0 = q * 32 + rsub;
+                switch (ep.act) {
+                    case CTTS_ACT_RELU: store_chunk<NP, CTTS_ACT_RELU, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                    case CTTS_ACT_GELU: store_chunk<NP, CTTS_ACT_GELU, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                    case CTTS_ACT_TANH: store_chunk<NP, CTTS_ACT_TANH, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                    case CTTS_ACT_SWISH: store_chunk<NP, CTTS_ACT_SWISH, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                    default: store_chunk<NP, CTTS_ACT_NONE, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    cluster_sync_all();   // neither CTA may exit (or free TMEM) while its peer can still read its smem / signal its barriers
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -741,6 +966,82 @@ static int launch_persistent(const Operand& A, const Operand& W, const Epilogue&
     return check_launch("gemm_persistent");
 }
 
+template <int STAGES>
+static int launch_pair(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin, int N,
+                       int taps, cudaStream_t st, int seg_rows) {
+    using S = PairSmem<STAGES>;
+    constexpr int NP = 2;
+    Maps maps;
+    {
+        cuuint64_t dims[3] = {A.d0, A.d1, A.d2};
+        cuuint64_t str[2] = {A.s1 * 2, A.s2 * 2};
+        cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+        cuuint32_t box_seg[3] = {BLOCK_K, (cuuint32_t)(seg_rows > 0 ? seg_rows : BLOCK_M), 1};
+        for (int p = 0; p < NP; ++p) {
+            if (int e = make_map(&maps.a[p], A.p[p], 3, dims, str, box, "activation plane")) return e;
+            if (int e = make_map(&maps.a_seg[p], A.p[p], 3, dims, str, box_seg, "activation plane (segments)")) return e;
+        }
+        maps.a[2] = maps.a[0];
+        maps.a_seg[2] = maps.a_seg[0];
+    }
+    {
+        cuuint64_t dims[3] = {W.d0, W.d1, W.d2};
+        cuuint64_t str[2] = {W.s1 * 2, W.s2 * 2};
+        cuuint32_t box[3] = {BLOCK_K, 128, 1};   // each CTA of the pair stages half of the 256 output channels
+        for (int p = 0; p < NP; ++p)
+            if (int e = make_map(&maps.w[p], W.p[p], 3, dims, str, box, "weight plane")) return e;
+        maps.w[2] = maps.w[0];
+    }
+    auto kern = gemm_pair_kernel<STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+            set_error("gemm_pair: cannot reserve %d bytes of shared memory", S::TOTAL);
+            return 4;
+        }
+        configured = true;
+    }
+    const char* sw = getenv("CTTS_PAIR_SWAP_B");
+    const int swap_b = sw != nullptr && atoi(sw) != 0;
+    const int tiles_per_utt = (T + BLOCK_M - 1) / BLOCK_M;
+    const int m_tiles = seg_rows > 0 ? (int)(((long long)Z * T + BLOCK_M - 1) / BLOCK_M) : Z * tiles_per_utt;
+    const int n_tiles = (N + 255) / 256;
+    const long long pair_tiles = (long long)((m_tiles + 1) / 2) * n_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (num_sms() / 2), 1, 1);
+    cfg.blockDim = dim3(320, 1, 1);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // a persistent grid must be co-resident: never launch more pairs than the device can hold at once (a GPC with an
+    // odd number of free SMs cannot host a pair)
+    static int max_pairs = 0;
+    if (!max_pairs) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = num_sms() / 2;
+        }
+        max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+        if (getenv("CTTS_PAIR_VERBOSE")) fprintf(stderr, "[ctts] gemm_pair: %d co-resident CTA pairs (occupancy query: %d)\n", max_pairs, n);
+    }
+    const int pairs = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cudaError_t err = cudaLaunchKernelEx(&cfg, kern, maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z, seg_rows, m_tiles,
+                                         n_tiles, swap_b);
+    if (err != cudaSuccess) {
+        set_error("gemm_pair launch: %s", cudaGetErrorString(err));
+        return 1;
+    }
+    return check_launch("gemm_pair");
+}
+
 static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin,
                        int N, int taps, cudaStream_t st) {
     // weights shared by all utterances (conv / linear: w_div huge) can be multicast across a 2-CTA cluster along M
@@ -753,6 +1054,14 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
     const long long m_tiles = seg ? ((long long)Z * T + BLOCK_M - 1) / BLOCK_M : (long long)Z * ((T + BLOCK_M - 1) / BLOCK_M);
     const bool shared_w = use_cluster && plain && m_tiles >= 2;
     if (np == 3) {
+        // Small grids (the encoder at S ~ 100: 16 row tiles x 2 for a 256-wide output) are bound by per-stage load
+        // latency, not by MMA issue: 128 x 64 tiles double the CTA count and allow a third stage (72 KiB each).
+        const char* nt = getenv("CTTS_NARROW_TILES");
+        const bool narrow = (nt == nullptr || atoi(nt) != 0) && N >= 128 && m_tiles * ((N + 127) / 128) <= 74;
+        if (narrow) {
+            if (shared_w) return launch<64, 3, 3, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
+            return launch<64, 3, 3, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
+        }
         if (shared_w) return launch<128, 2, 3, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
         return launch<128, 2, 3, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);   // 2 x 96 KiB stages
     }
@@ -767,7 +1076,16 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
         wide = c256 <= c128;
     }
     static const bool use_persistent = getenv("CTTS_NO_PERSISTENT") == nullptr;
+    // CTA pairs need ONE weight tile for both CTAs' rows: plain conv / linear only.  1 = where 256-wide tiles are chosen
+    // anyway, 2 = every plain GEMM (tests: N tails, a pair whose second CTA has no rows, straddling tiles)
+    // Default (1): long-K wide GEMMs only (decoder FFN conv, PostNet convs: measured 129 -> 125 us and 93 -> 91 us per
+    // launch; the K = 256 QKV projection is 8 % slower as a pair).  0 = never.
+    const char* pg = getenv("CTTS_PAIR_GEMM");
+    const int pair_mode = pg ? atoi(pg) : 1;
+    const long long num_kb = (long long)taps * ((Cin + BLOCK_K - 1) / BLOCK_K);
     if (use_persistent) {
+        if (plain && ((pair_mode == 1 && wide && m_tiles >= 2 && num_kb >= 16) || pair_mode == 2))
+            return launch_pair<3>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
         if (wide) return launch_persistent<256, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
         return launch_persistent<128, 3>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
     }
@@ -849,6 +1167,52 @@ __global__ void transpose_v_kernel(const CPlanes3 q, int T, int Tp, int C, int H
 #pragma unroll
             for (int p = 0; p < NP; ++p) vt.p[p][dst] = tile[p][tx][i];
         }
+    }
+}
+
+// 64 x 64 tiles, bf16x2 accesses on both sides (the 32 x 32 / 2-byte version above moved 64 B per warp instruction and
+// took 13 us for 26 MB).  DH % 64 == 0, Tp even.
+template <int NP>
+__global__ void __launch_bounds__(256)
+transpose_v_wide_kernel(const CPlanes3 q, int T, int Tp, int C, int H, int DH, const Planes3 vt) {
+    __shared__ __align__(4) __nv_bfloat16 tile[NP][64][66];
+    const int z = blockIdx.z, b = z / H, h = z % H;
+    const int t0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 64; i += 8) {
+        const int t = t0 + i;
+        const size_t src = ((size_t)b * T + t) * (size_t)(3 * C) + 2 * C + h * DH + d0 + 2 * tx;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            uint32_t v = 0u;
+            if (t < T) v = *reinterpret_cast<const uint32_t*>(q.p[p] + src);
+            *reinterpret_cast<uint32_t*>(&tile[p][i][2 * tx]) = v;
+        }
+    }
+    __syncthreads();
+    const int t = t0 + 2 * tx;
+    if (t >= Tp) return;
+    for (int i = ty; i < 64; i += 8) {
+        const size_t dst = ((size_t)z * DH + d0 + i) * (size_t)Tp + t;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            __nv_bfloat162 v;
+            v.x = tile[p][2 * tx][i];
+            v.y = tile[p][2 * tx + 1][i];
+            *reinterpret_cast<__nv_bfloat162*>(vt.p[p] + dst) = v;
+        }
+    }
+}
+
+template <int NP>
+static void launch_transpose_v(const CPlanes3& qc, int T, int Tp, int C, int H, int DH, int Z, const Planes3& vw,
+                               cudaStream_t st) {
+    if (DH % 64 == 0 && Tp % 2 == 0 && C % 2 == 0) {
+        dim3 grid((Tp + 63) / 64, DH / 64, Z);
+        transpose_v_wide_kernel<NP><<<grid, 256, 0, st>>>(qc, T, Tp, C, H, DH, vw);
+    } else {
+        dim3 grid((Tp + 31) / 32, DH / 32, Z);
+        transpose_v_kernel<NP><<<grid, 256, 0, st>>>(qc, T, Tp, C, H, DH, vw);
     }
 }
 
@@ -948,9 +1312,8 @@ static int attention_split_impl(int np, const void* const* qkv, const int64_t* l
     }
     // 2. Vt planes
     {
-        dim3 grid((Tp + 31) / 32, DH / 32, Z);
-        if (np == 3) transpose_v_kernel<3><<<grid, 256, 0, st>>>(qc, T, Tp, C, H, DH, vw);
-        else transpose_v_kernel<2><<<grid, 256, 0, st>>>(qc, T, Tp, C, H, DH, vw);
+        if (np == 3) launch_transpose_v<3>(qc, T, Tp, C, H, DH, Z, vw, st);
+        else launch_transpose_v<2>(qc, T, Tp, C, H, DH, Z, vw, st);
         if (int e = check_launch("transpose_v")) return e;
     }
     // 3. P = softmax over keys < len of S, written as bf16 planes
@@ -998,9 +1361,8 @@ extern "C" int ctts_transpose_v_planes(int n_planes, const void* const* qkv_plan
         qc.p[p] = (const __nv_bfloat16*)qkv_planes[p];
         vw.p[p] = (__nv_bfloat16*)vt_planes[p];
     }
-    dim3 grid((Tp + 31) / 32, DH / 32, B * H);
-    if (n_planes == 3) transpose_v_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(qc, T, Tp, C, H, DH, vw);
-    else transpose_v_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(qc, T, Tp, C, H, DH, vw);
+    if (n_planes == 3) launch_transpose_v<3>(qc, T, Tp, C, H, DH, B * H, vw, (cudaStream_t)stream);
+    else launch_transpose_v<2>(qc, T, Tp, C, H, DH, B * H, vw, (cudaStream_t)stream);
     return check_launch("transpose_v_planes");
 }
 

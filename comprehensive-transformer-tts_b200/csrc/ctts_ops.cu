@@ -33,43 +33,59 @@ void set_error(const char* fmt, ...) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Running count of flagged entries along T, one warp, written to shared memory.
-// pos[t] = flag[t] ? (# flags in [0..t]) : 0        (utils/tools.py:640-652 with padding_idx 0)
-template <typename FlagFn>
-__device__ __forceinline__ void warp_positions(int T, int* pos, FlagFn flag) {
-    const int lane = threadIdx.x & 31;
-    int running = 0;
-    for (int base = 0; base < T; base += 32) {
-        const int t = base + lane;
-        const bool f = (t < T) && flag(t);
+// Positions of rows [r0, r1) of one utterance, by the whole CTA: pos[t] = flag(t) ? #flags in [0, t] : 0
+// (make_positions, utils/tools.py:640-652, with padding_idx 0).  Every warp ballots 32-row chunks of [0, r1) into s_mask; each row then sums the
+// popcounts of the chunks before its own.  r1 <= 32 * POS_MAXCH.
+constexpr int POS_MAXCH = 512;
+template <class F>
+__device__ __forceinline__ void block_positions(int r0, int r1, int* s_pos, unsigned* s_mask, F flag) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int nch = (r1 + 31) >> 5;
+    for (int ch = warp; ch < nch; ch += nw) {
+        const int t = ch * 32 + lane;
+        const bool f = (t < r1) && flag(t);
         const unsigned m = __ballot_sync(0xffffffffu, f);
-        const int incl = __popc(m & (0xffffffffu >> (31 - lane)));
-        if (t < T) pos[t] = f ? running + incl : 0;
-        running += __popc(m);
+        if (lane == 0) s_mask[ch] = m;
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < r1 - r0; i += blockDim.x) {
+        const int t = r0 + i, ch = t >> 5, l = t & 31;
+        const unsigned m = s_mask[ch];
+        int p = 0;
+        if ((m >> l) & 1u) {
+            p = __popc(m & (0xffffffffu >> (31 - l)));
+            for (int c = 0; c < ch; ++c) p += __popc(s_mask[c]);
+        }
+        s_pos[i] = p;
+    }
+    __syncthreads();
 }
 
+// grid (B, ceil(S / EMB_ROWS))
+constexpr int EMB_ROWS = 32;
 __global__ void embed_tokens_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ table,
                                     const float* __restrict__ pe, float scale, int S, int C, int vocab,
                                     float* __restrict__ x, float* __restrict__ word,
                                     const int64_t* __restrict__ lens, int pos_mode) {
-    extern __shared__ int s_pos[];
+    __shared__ int s_pos[EMB_ROWS];
+    __shared__ unsigned s_mask[POS_MAXCH];
     const int b = blockIdx.x;
+    const int r0 = blockIdx.y * EMB_ROWS, r1 = min(r0 + EMB_ROWS, S);
     const int64_t* tok = tokens + (size_t)b * S;
     if (pos_mode == 0) {
-        if (threadIdx.x < 32) warp_positions(S, s_pos, [&](int t) { return tok[t] != 0; });
+        block_positions(r0, r1, s_pos, s_mask, [&](int t) { return tok[t] != 0; });
     } else {
-        for (int t = threadIdx.x; t < S; t += blockDim.x) s_pos[t] = t;  // absolute positions (transformer.py:72-74)
+        for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) s_pos[t - r0] = t;  // absolute positions (transformer.py:72-74)
+        __syncthreads();
     }
-    __syncthreads();
     const int c4 = C >> 2;
     const int len = lens ? (int)lens[b] : S;
-    for (int i = threadIdx.x; i < S * c4; i += blockDim.x) {
-        const int s = i / c4, c = (i - s * c4) << 2;
+    for (int i = threadIdx.x; i < (r1 - r0) * c4; i += blockDim.x) {
+        const int sl = i / c4, s = r0 + sl, c = (i - sl * c4) << 2;
         int64_t id = tok[s];
         id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
         float4 e = *reinterpret_cast<const float4*>(table + (size_t)id * C + c);
-        const float4 p = *reinterpret_cast<const float4*>(pe + (size_t)s_pos[s] * C + c);
+        const float4 p = *reinterpret_cast<const float4*>(pe + (size_t)s_pos[sl] * C + c);
         e.x *= scale; e.y *= scale; e.z *= scale; e.w *= scale;
         const size_t o = ((size_t)b * S + s) * C + c;
         *reinterpret_cast<float4*>(word + o) = e;
@@ -78,35 +94,26 @@ __global__ void embed_tokens_kernel(const int64_t* __restrict__ tokens, const fl
     }
 }
 
-// grid (B, ceil(T / 64)): every CTA re-derives the running position count up to its own 64-row chunk with warp
-// ballots (T strided loads of x[b,t,0], cheap) and then updates its rows -- one CTA per utterance left 132 SMs idle.
-constexpr int POS_ROWS = 64;
+// grid (B, ceil(T / POS_ROWS)): every CTA re-derives the position count up to its own chunk (T strided loads of
+// x[b,t,0] spread over 8 warps) and then updates its rows -- one CTA per utterance left 132 SMs idle, and one warp
+// scanning 800 rows serially cost 15 us.
+constexpr int POS_ROWS = 32;
 __global__ void add_positions_kernel(const float* __restrict__ x, const float* __restrict__ pe,
                                      const float* __restrict__ alpha, const int64_t* __restrict__ lens, int T, int C,
                                      int pos_mode, float* __restrict__ y) {
     __shared__ int s_pos[POS_ROWS];
+    __shared__ unsigned s_mask[POS_MAXCH];
     const int b = blockIdx.x;
     const int r0 = blockIdx.y * POS_ROWS;
     const int r1 = min(r0 + POS_ROWS, T);
     const float* xb = x + (size_t)b * T * C;
     float* yb = y + (size_t)b * T * C;
     if (pos_mode == 0) {
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
-            int running = 0;
-            for (int base = 0; base < r1; base += 32) {
-                const int t = base + lane;
-                const bool f = (t < r1) && xb[(size_t)t * C] != 0.f;
-                const unsigned m = __ballot_sync(0xffffffffu, f);
-                const int incl = __popc(m & (0xffffffffu >> (31 - lane)));
-                if (t >= r0 && t < r1) s_pos[t - r0] = f ? running + incl : 0;
-                running += __popc(m);
-            }
-        }
+        block_positions(r0, r1, s_pos, s_mask, [&](int t) { return xb[(size_t)t * C] != 0.f; });
     } else {
         for (int t = r0 + threadIdx.x; t < r1; t += blockDim.x) s_pos[t - r0] = t;
+        __syncthreads();
     }
-    __syncthreads();
     const float a = alpha ? alpha[0] : 1.f;
     const int len = lens ? (int)lens[b] : T;
     const int c4 = C >> 2;
@@ -311,6 +318,57 @@ conv1d_gemm_fp32_kernel(const float* __restrict__ x, const float* __restrict__ w
             y[row + n] = (t < len) ? v : 0.f;
         }
     }
+}
+
+// Skinny linear layers (a handful of outputs per row, or a handful of rows): the 128 x 64 tile kernel above would run
+// 1-16 CTAs with a serial k-loop (20-30 us of pure latency).  One warp per (row, 8 outputs): the row of x stays in
+// registers, weight rows stream through coalesced float4 loads, one butterfly reduction per output.
+constexpr int SK_NCH = 8;
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float alpha,
+                     const float* __restrict__ col_scale, const float* __restrict__ col_shift, int act,
+                     const float* __restrict__ residual, const int64_t* __restrict__ lens, long long rows, int T, int K,
+                     int N, int chunks, float* __restrict__ y) {
+    const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (gw >= rows * chunks) return;
+    const int lane = threadIdx.x & 31;
+    const long long row = gw / chunks;
+    const int n0 = (int)(gw - row * chunks) * SK_NCH;
+    const float* xr = x + (size_t)row * K;
+    float acc[SK_NCH];
+#pragma unroll
+    for (int j = 0; j < SK_NCH; ++j) acc[j] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + k);
+#pragma unroll
+        for (int j = 0; j < SK_NCH; ++j) {
+            if (n0 + j < N) {
+                const float4 wv = *reinterpret_cast<const float4*>(w + (size_t)(n0 + j) * K + k);
+                acc[j] = fmaf(xv.x, wv.x, acc[j]);
+                acc[j] = fmaf(xv.y, wv.y, acc[j]);
+                acc[j] = fmaf(xv.z, wv.z, acc[j]);
+                acc[j] = fmaf(xv.w, wv.w, acc[j]);
+            }
+        }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < SK_NCH; ++j) {
+        const float sum = warp_sum(acc[j]);
+        if (lane == j) mine = sum;
+    }
+    const int n = n0 + lane;
+    if (lane >= SK_NCH || n >= N) return;
+    const long long b = row / T;
+    const int t = (int)(row - b * T);
+    float v = mine;
+    if (bias) v += bias[n];
+    v *= alpha;
+    if (col_scale) v = v * col_scale[n] + col_shift[n];
+    v = apply_act(v, act);
+    const size_t o = (size_t)row * N + n;
+    if (residual) v += residual[o];
+    y[o] = (!lens || t < (int)lens[b]) ? v : 0.f;
 }
 
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int N, int Cin, int taps, float* __restrict__ p) {
@@ -1027,10 +1085,9 @@ int ctts_embed_tokens(const int64_t* tokens, const float* table, const float* pe
                       void* stream) {
     CTTS_REQUIRE(B > 0 && S > 0 && C % 4 == 0, "embed_tokens: bad shape B=%d S=%d C=%d", B, S, C);
     CTTS_REQUIRE(pe_rows > S - (pos_mode ? 1 : 0), "embed_tokens: positional table has %d rows, need > %d", pe_rows, S);
-    CTTS_REQUIRE((size_t)S * 4 <= 200 * 1024, "embed_tokens: S=%d too long", S);
-    const size_t sm = (size_t)S * sizeof(int);
-    ensure_smem(embed_tokens_kernel, sm);
-    embed_tokens_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(tokens, table, pe, embed_scale, S, C, vocab, x, word, lens,
+    CTTS_REQUIRE(S <= 32 * POS_MAXCH, "embed_tokens: S=%d too long (max %d)", S, 32 * POS_MAXCH);
+    dim3 grid(B, (S + EMB_ROWS - 1) / EMB_ROWS);
+    embed_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tokens, table, pe, embed_scale, S, C, vocab, x, word, lens,
                                                               pos_mode);
     return check_launch("embed_tokens");
 }
@@ -1040,6 +1097,7 @@ int ctts_add_positions(const float* x, const float* pe, int pe_rows, const float
     CTTS_REQUIRE(y != nullptr && y != x, "add_positions: y must be a separate buffer (CTAs re-read x[..., 0] of earlier rows)");
     CTTS_REQUIRE(B > 0 && T > 0 && C % 4 == 0, "add_positions: bad shape B=%d T=%d C=%d", B, T, C);
     CTTS_REQUIRE(pe_rows > T - (pos_mode ? 1 : 0), "add_positions: positional table has %d rows, need > %d", pe_rows, T);
+    CTTS_REQUIRE(T <= 32 * POS_MAXCH, "add_positions: T=%d too long (max %d)", T, 32 * POS_MAXCH);
     dim3 grid(B, (T + POS_ROWS - 1) / POS_ROWS);
     add_positions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, pe, alpha, lens, T, C, pos_mode, y);
     return check_launch("add_positions");
@@ -1089,6 +1147,13 @@ int ctts_conv1d_gemm(const float* x, const float* w, const float* bias, float al
                  T, N, taps);
     CTTS_REQUIRE(Cin % 16 == 0, "conv1d_gemm: Cin=%d must be a multiple of 16", Cin);
     CTTS_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), "conv1d_gemm: col_scale/col_shift must come together");
+    if (taps == 1 && (N <= 16 || (long long)B * T <= 32)) {
+        const int chunks = (N + SK_NCH - 1) / SK_NCH;
+        const long long warps = (long long)B * T * chunks;
+        skinny_linear_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+            x, w, bias, alpha, col_scale, col_shift, act, residual, lens, (long long)B * T, T, Cin, N, chunks, y);
+        return check_launch("conv1d_gemm (skinny)");
+    }
     dim3 grid((T + GM - 1) / GM, (N + GN - 1) / GN, B);
     const GAddr ga{1, (long long)T * Cin, 0, Cin, 0, 0, taps * Cin, (long long)T * N, 0, N, 1};
     conv1d_gemm_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, alpha, col_scale, col_shift, act,

@@ -38,6 +38,7 @@ def stream():
     (2, 37, 256, 768, 1, "none"), (3, 100, 256, 1024, 9, "gelu"), (2, 130, 1024, 256, 1, "none"),
     (2, 300, 80, 512, 5, "tanh"), (2, 129, 512, 80, 5, "none"), (4, 64, 256, 1, 1, "none"),
     (2, 50, 128, 256, 5, "relu"), (1, 16, 256, 11, 1, "none"), (2, 257, 256, 256, 3, "relu"),
+    (1, 16, 256, 256, 1, "relu"), (16, 100, 256, 1, 1, "none"), (2, 800, 256, 11, 1, "none"),   # skinny-linear path
 ])
 def test_conv1d_gemm_fp32(B, T, Cin, N, taps, act):
     x = torch.randn(B, T, Cin, generator=g(1))
@@ -269,6 +270,54 @@ def test_gemm_bf16x3_matches_fp32(B, T, Cin, N, taps, act):
     close(y, ref, atol=2e-4, rtol=2e-4, msg="fp32 output")
     back = yp.value()
     close(back, y, atol=1e-4, rtol=2e-5, msg="hi/lo planes of the output")
+
+
+@pytest.mark.parametrize("B,T,Cin,N,taps,act", [
+    (1, 70, 256, 80, 1, "none"),        # one m-tile: the pair's second CTA has no rows; N tail by TMA zero fill
+    (2, 129, 512, 80, 5, "none"),       # 4 m-tiles per-utterance tiling, conv halo
+    (3, 192, 256, 1024, 9, "gelu"),     # packed 64-row segments, tiles straddle utterances
+    (5, 160, 512, 512, 5, "tanh"),      # packed, odd m-tile count
+    (16, 800, 256, 1024, 9, "gelu"),    # the bench's decoder FFN conv: 200 pair tiles on 74 pairs
+])
+def test_gemm_cta_pair_is_bit_identical(B, T, Cin, N, taps, act, monkeypatch):
+    """The cta_group::2 kernel (256 x 256 tile per CTA pair) issues the same MMAs in the same order per accumulator
+    element as the single-CTA persistent kernel: outputs must be bit-identical."""
+    x = torch.randn(B, T, Cin, generator=g(141))
+    w = torch.randn(N, taps * Cin, generator=g(142)) / math.sqrt(Cin * taps)
+    bias = torch.randn(N, generator=g(143)).to(DEV)
+    res = torch.randn(B, T, N, generator=g(144)).to(DEV)
+    lens = torch.tensor([max(T - 9 * b, 1) for b in range(B)]).to(DEV)
+    xp, wp = engine.split_planes(x.to(DEV)), engine.split_planes(w.to(DEV))
+    out = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("CTTS_PAIR_GEMM", mode)
+        y, yp = engine.gemm_tc(xp, wp, bias, act=engine._ACTS[act], residual=res, lens=lens, taps=taps, want_planes=True)
+        torch.cuda.synchronize()
+        out[mode] = (y, yp)
+    assert torch.equal(out["0"][0], out["2"][0])
+    for a, b in zip(out["0"][1].p, out["2"][1].p):
+        assert torch.equal(a, b)
+    ref = engine.conv_gemm(x.to(DEV), w.to(DEV), bias, act=engine._ACTS[act], residual=res, lens=lens, taps=taps)
+    close(out["2"][0], ref, atol=2e-4, rtol=2e-4)
+
+
+@pytest.mark.parametrize("B,T,Cin,N,taps", [(16, 100, 1024, 256, 1), (4, 100, 256, 256, 3), (2, 70, 256, 384, 1)])
+def test_gemm_bf16x6_narrow_tiles_bit_identical(B, T, Cin, N, taps, monkeypatch):
+    """128 x 64 tiles (small grids) vs 128 x 128: same MMA order per accumulator element."""
+    x = torch.randn(B, T, Cin, generator=g(151))
+    w = torch.randn(N, taps * Cin, generator=g(152)) / math.sqrt(Cin * taps)
+    bias = torch.randn(N, generator=g(153)).to(DEV)
+    lens = torch.tensor([max(T - 9 * b, 1) for b in range(B)]).to(DEV)
+    xp, wp = engine.split_planes(x.to(DEV), 3), engine.split_planes(w.to(DEV), 3)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CTTS_NARROW_TILES", mode)
+        y, yp = engine.gemm_tc(xp, wp, bias, act=engine._ACTS["relu"], lens=lens, taps=taps, want_planes=True)
+        torch.cuda.synchronize()
+        out[mode] = (y, yp)
+    assert torch.equal(out["0"][0], out["1"][0])
+    for a, b in zip(out["0"][1].p, out["1"][1].p):
+        assert torch.equal(a, b)
 
 
 def test_gemm_bf16x3_full_size_linearity():
