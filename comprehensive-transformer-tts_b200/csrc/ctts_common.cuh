@@ -29,6 +29,38 @@ inline void ensure_smem(K kernel, size_t bytes) {
     ensure_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// Every kernel of the library is launched with programmaticStreamSerialization: the grid may be scheduled (and run its
+// set-up: barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream is still draining.
+// CTTS_PDL_SYNC() is the first thing a kernel does that touches global memory: it lets the NEXT kernel start launching
+// (griddepcontrol.launch_dependents) and then waits until the PREVIOUS grid has completed and its writes are visible
+// (griddepcontrol.wait).  Every kernel must execute it, also one that needs nothing from its predecessor: completion
+// then chains through the stream exactly as without the attribute.  Opt-in (CTTS_PDL=1): measured with the benchmark
+// under CUDA-graph replay it changes nothing (3.59 vs 3.58 ms per step) -- the graph already pre-stages the launches --
+// so the default launches without the attribute (the two instructions are no-ops then).
+#define CTTS_PDL_SYNC()                                                      \
+    do {                                                                     \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                   \
+    } while (0)
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in check_launch()
+}
+
 #define CTTS_REQUIRE(cond, ...)            \
     do {                                   \
         if (!(cond)) {                     \

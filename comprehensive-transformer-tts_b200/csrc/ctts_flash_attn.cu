@@ -72,6 +72,7 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
     uint64_t* o_full = bars + 15;       // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
+    CTTS_PDL_SYNC();   // lens[] below may come from the previous kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int z = blockIdx.y, b = z / H, h = z - b * H;
     const int q0 = blockIdx.x * BQ;
@@ -363,7 +364,7 @@ extern "C" int ctts_flash_attention_bf16x3(const void* qkv_hi, const void* qkv_l
         configured = true;
     }
     dim3 grid((T + fa::BQ - 1) / fa::BQ, Z);
-    fa::flash_attention_kernel<<<grid, 320, fa::SMEM_TOTAL, (cudaStream_t)stream>>>(
+    launch_k(fa::flash_attention_kernel, grid, 320, fa::SMEM_TOTAL, (cudaStream_t)stream, 
         maps, lens, T, C, H, scale * 1.4426950408889634f, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
     return check_launch("flash_attention");
 }

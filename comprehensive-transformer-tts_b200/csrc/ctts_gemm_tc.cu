@@ -238,6 +238,7 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     if (CM > 1) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast into them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    CTTS_PDL_SYNC();   // set-up above overlapped the previous kernel's tail; nothing before this line touches its outputs
 
     if (warp == 0) {
         if (lane == 0) {
@@ -450,6 +451,7 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    CTTS_PDL_SYNC();   // set-up above overlapped the previous kernel's tail; nothing before this line touches its outputs
 
     // tile -> coordinates (n fastest: CTAs that run together share the activation rows)
     auto tile_coords = [&](int tile, int& z, int& t0, int& n0, bool& straddle) {
@@ -666,6 +668,7 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
     cluster_sync_all();      // both CTAs' barriers are initialised and both TMEM allocations exist
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    CTTS_PDL_SYNC();   // set-up above overlapped the previous kernel's tail; nothing before this line touches its outputs
 
     // pair tile -> this CTA's 128 rows (m-tile 2*(pt / n_tiles) + rank) and the pair's 256 output channels
     auto tile_coords = [&](int pt, int& mt, int& z, int& t0, int& n0, bool& straddle) {
@@ -896,13 +899,15 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
     cfg.blockDim = dim3(320, 1, 1);
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CM;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t err = cudaLaunchKernelEx(&cfg, kern, maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z, seg_rows);
     if (err != cudaSuccess) {
         set_error("gemm_split launch: %s", cudaGetErrorString(err));
@@ -962,7 +967,7 @@ static int launch_persistent(const Operand& A, const Operand& W, const Epilogue&
     const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
     const long long total = (long long)m_tiles * n_tiles;
     const int grid = (int)(total < num_sms() ? total : num_sms());
-    kern<<<grid, 320, S::TOTAL, st>>>(maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z, seg_rows, m_tiles, n_tiles);
+    launch_k(kern, grid, 320, S::TOTAL, st, maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z, seg_rows, m_tiles, n_tiles);
     return check_launch("gemm_persistent");
 }
 
@@ -1012,13 +1017,15 @@ static int launch_pair(const Operand& A, const Operand& W, const Epilogue& ep, c
     cfg.blockDim = dim3(320, 1, 1);
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1;   // the occupancy query below takes the cluster attribute only
     // a persistent grid must be co-resident: never launch more pairs than the device can hold at once (a GPC with an
     // odd number of free SMs cannot host a pair)
     static int max_pairs = 0;
@@ -1033,6 +1040,7 @@ static int launch_pair(const Operand& A, const Operand& W, const Epilogue& ep, c
     }
     const int pairs = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
     cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t err = cudaLaunchKernelEx(&cfg, kern, maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z, seg_rows, m_tiles,
                                          n_tiles, swap_b);
     if (err != cudaSuccess) {
@@ -1076,15 +1084,19 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
         wide = c256 <= c128;
     }
     static const bool use_persistent = getenv("CTTS_NO_PERSISTENT") == nullptr;
-    // CTA pairs need ONE weight tile for both CTAs' rows: plain conv / linear only.  1 = where 256-wide tiles are chosen
-    // anyway, 2 = every plain GEMM (tests: N tails, a pair whose second CTA has no rows, straddling tiles)
-    // Default (1): long-K wide GEMMs only (decoder FFN conv, PostNet convs: measured 129 -> 125 us and 93 -> 91 us per
-    // launch; the K = 256 QKV projection is 8 % slower as a pair).  0 = never.
+    // CTA pairs need ONE weight tile for both CTAs' rows: plain conv / linear only.  Measured with the benchmark (A/B on
+    // one box, ms per step): pair only where a 256-wide single-CTA tile would be chosen anyway (decoder FFN conv: 145 ->
+    // 137 us per launch) 3.56; also for the 256/512-wide outputs (FFN second GEMM, PostNet convs: 50 / 100 pair tiles on
+    // 74 pairs) 3.62 = no better than no pairs at all; every plain GEMM 3.71.
+    //   CTTS_PAIR_GEMM = 0 never, 1 (default) the first rule, 2 every plain GEMM (tests: N tails, a pair whose second CTA
+    //   has no rows, straddling tiles);  CTTS_PAIR_MIN_KB = minimum number of 64-wide k-blocks (default 16).
     const char* pg = getenv("CTTS_PAIR_GEMM");
     const int pair_mode = pg ? atoi(pg) : 1;
+    const char* pk = getenv("CTTS_PAIR_MIN_KB");
+    const long long pair_min_kb = pk ? atoll(pk) : 16;
     const long long num_kb = (long long)taps * ((Cin + BLOCK_K - 1) / BLOCK_K);
     if (use_persistent) {
-        if (plain && ((pair_mode == 1 && wide && m_tiles >= 2 && num_kb >= 16) || pair_mode == 2))
+        if (plain && ((pair_mode == 1 && wide && m_tiles >= 2 && num_kb >= pair_min_kb) || pair_mode == 2))
             return launch_pair<3>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
         if (wide) return launch_persistent<256, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
         return launch_persistent<128, 3>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
@@ -1109,6 +1121,7 @@ struct CPlanes3 {
 template <int NP>
 __global__ void softmax_planes_kernel(const float* __restrict__ S, const int64_t* __restrict__ lens, int H, int T, int Tp,
                                       int rows, const Planes3 out) {
+    CTTS_PDL_SYNC();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // over Z*T
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -1149,6 +1162,7 @@ __global__ void softmax_planes_kernel(const float* __restrict__ S, const int64_t
 // qkv planes [B, T, 3C] -> Vt planes [B*H, DH, Tp] (keys contiguous, zero padded): the K-major B operand of P.V
 template <int NP>
 __global__ void transpose_v_kernel(const CPlanes3 q, int T, int Tp, int C, int H, int DH, const Planes3 vt) {
+    CTTS_PDL_SYNC();
     __shared__ __nv_bfloat16 tile[NP][32][34];
     const int z = blockIdx.z, b = z / H, h = z % H;
     const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -1175,6 +1189,7 @@ __global__ void transpose_v_kernel(const CPlanes3 q, int T, int Tp, int C, int H
 template <int NP>
 __global__ void __launch_bounds__(256)
 transpose_v_wide_kernel(const CPlanes3 q, int T, int Tp, int C, int H, int DH, const Planes3 vt) {
+    CTTS_PDL_SYNC();
     __shared__ __align__(4) __nv_bfloat16 tile[NP][64][66];
     const int z = blockIdx.z, b = z / H, h = z % H;
     const int t0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
@@ -1209,10 +1224,10 @@ static void launch_transpose_v(const CPlanes3& qc, int T, int Tp, int C, int H, 
                                cudaStream_t st) {
     if (DH % 64 == 0 && Tp % 2 == 0 && C % 2 == 0) {
         dim3 grid((Tp + 63) / 64, DH / 64, Z);
-        transpose_v_wide_kernel<NP><<<grid, 256, 0, st>>>(qc, T, Tp, C, H, DH, vw);
+        launch_k(transpose_v_wide_kernel<NP>, grid, 256, 0, st, qc, T, Tp, C, H, DH, vw);
     } else {
         dim3 grid((Tp + 31) / 32, DH / 32, Z);
-        transpose_v_kernel<NP><<<grid, 256, 0, st>>>(qc, T, Tp, C, H, DH, vw);
+        launch_k(transpose_v_kernel<NP>, grid, 256, 0, st, qc, T, Tp, C, H, DH, vw);
     }
 }
 
@@ -1319,8 +1334,8 @@ static int attention_split_impl(int np, const void* const* qkv, const int64_t* l
     // 3. P = softmax over keys < len of S, written as bf16 planes
     {
         const int rows = Z * T;
-        if (np == 3) softmax_planes_kernel<3><<<(rows + 7) / 8, 256, 0, st>>>(scores, lens, H, T, Tp, rows, pw);
-        else softmax_planes_kernel<2><<<(rows + 7) / 8, 256, 0, st>>>(scores, lens, H, T, Tp, rows, pw);
+        if (np == 3) launch_k(softmax_planes_kernel<3>, (rows + 7) / 8, 256, 0, st, scores, lens, H, T, Tp, rows, pw);
+        else launch_k(softmax_planes_kernel<2>, (rows + 7) / 8, 256, 0, st, scores, lens, H, T, Tp, rows, pw);
         if (int e = check_launch("softmax_planes")) return e;
     }
     // 4. out[b, t, h*DH + d] = sum_s P[z,t,s] * Vt[z,d,s]; rows t >= len are zeroed

@@ -6,6 +6,8 @@
 // ctts_gemm_tc.cu.  Reference call sites are cited in include/ctts_b200.h.
 #include "ctts_common.cuh"
 
+#include <stdlib.h>
+
 #include <math.h>
 #include <string.h>
 
@@ -23,6 +25,14 @@ void ensure_smem_impl(const void* kernel, size_t bytes) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         g = bytes;
     }
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("CTTS_PDL");
+        return e != nullptr && atoi(e) != 0;
+    }();
+    return on;
 }
 
 void set_error(const char* fmt, ...) {
@@ -67,6 +77,7 @@ __global__ void embed_tokens_kernel(const int64_t* __restrict__ tokens, const fl
                                     const float* __restrict__ pe, float scale, int S, int C, int vocab,
                                     float* __restrict__ x, float* __restrict__ word,
                                     const int64_t* __restrict__ lens, int pos_mode) {
+    CTTS_PDL_SYNC();
     __shared__ int s_pos[EMB_ROWS];
     __shared__ unsigned s_mask[POS_MAXCH];
     const int b = blockIdx.x;
@@ -101,6 +112,7 @@ constexpr int POS_ROWS = 32;
 __global__ void add_positions_kernel(const float* __restrict__ x, const float* __restrict__ pe,
                                      const float* __restrict__ alpha, const int64_t* __restrict__ lens, int T, int C,
                                      int pos_mode, float* __restrict__ y) {
+    CTTS_PDL_SYNC();
     __shared__ int s_pos[POS_ROWS];
     __shared__ unsigned s_mask[POS_MAXCH];
     const int b = blockIdx.x;
@@ -140,6 +152,7 @@ template <int NP>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, const int64_t* __restrict__ lens, int rows,
                                  int T, int C, float* __restrict__ y, const PlanePtrs yp) {
+    CTTS_PDL_SYNC();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -220,6 +233,7 @@ conv1d_gemm_fp32_kernel(const float* __restrict__ x, const float* __restrict__ w
                         float alpha, const float* __restrict__ col_scale, const float* __restrict__ col_shift, int act,
                         const float* __restrict__ residual, const int64_t* __restrict__ lens, int T, int Cin, int N,
                         int taps, float* __restrict__ y, const GAddr ga) {
+    CTTS_PDL_SYNC();
     __shared__ __align__(16) float As[2][GK][GM + GPAD];
     __shared__ __align__(16) float Bs[2][GK][GN + GPAD];
     const int b = blockIdx.z;
@@ -329,6 +343,7 @@ skinny_linear_kernel(const float* __restrict__ x, const float* __restrict__ w, c
                      const float* __restrict__ col_scale, const float* __restrict__ col_shift, int act,
                      const float* __restrict__ residual, const int64_t* __restrict__ lens, long long rows, int T, int K,
                      int N, int chunks, float* __restrict__ y) {
+    CTTS_PDL_SYNC();
     const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (gw >= rows * chunks) return;
     const int lane = threadIdx.x & 31;
@@ -372,6 +387,7 @@ skinny_linear_kernel(const float* __restrict__ x, const float* __restrict__ w, c
 }
 
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int N, int Cin, int taps, float* __restrict__ p) {
+    CTTS_PDL_SYNC();
     const size_t total = (size_t)N * Cin * taps;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % Cin);
@@ -388,6 +404,7 @@ template <int DH>
 __global__ void __launch_bounds__(128)
 attention_fp32_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ lens, int T, int C, float scale,
                       float* __restrict__ out) {
+    CTTS_PDL_SYNC();
     constexpr int LD = DH + 4;
     constexpr int DPT = DH / 4;
     extern __shared__ __align__(16) float smem[];
@@ -496,6 +513,7 @@ attention_fp32_kernel(const float* __restrict__ qkv, const int64_t* __restrict__
 
 // ---------------------------------------------------------------------------------------------
 __global__ void decode_durations_kernel(const float* __restrict__ log_d, float d_control, int n, float* __restrict__ dur) {
+    CTTS_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dur[i] = fmaxf(rintf(expf(log_d[i]) - 1.f) * d_control, 0.f);
 }
@@ -505,6 +523,7 @@ __global__ void length_scan_kernel(const float* __restrict__ dur_f, const int64_
                                    const int64_t* __restrict__ src_lens, int S, int32_t* __restrict__ cum_lr,
                                    int32_t* __restrict__ cum_m2p, int64_t* __restrict__ mel_len,
                                    int64_t* __restrict__ m2p_len) {
+    CTTS_PDL_SYNC();
     const int b = blockIdx.x, lane = threadIdx.x;
     const int slen = src_lens ? (int)src_lens[b] : S;
     int run_a = 0, run_b = 0;
@@ -556,6 +575,7 @@ __global__ void length_expand_kernel(const float* __restrict__ src, const float*
                                      const int64_t* __restrict__ row_index, const int32_t* __restrict__ cum_lr, int S,
                                      int C, int M, int accumulate, float* __restrict__ out,
                                      const int32_t* __restrict__ cum_m2p, int64_t* __restrict__ mel2ph, int M2) {
+    CTTS_PDL_SYNC();
     const int b = blockIdx.y;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -607,6 +627,7 @@ cwt_to_pitch_kernel(const float* __restrict__ cwt, int cwt_stride, const float* 
                     const float* __restrict__ mean, const float* __restrict__ stdv, int stat_stride, float std_scale,
                     float eps, const float* __restrict__ uv_src, int use_uv, int T, float* __restrict__ f0_norm,
                     float* __restrict__ f0_denorm, int64_t* __restrict__ pitch_idx) {
+    CTTS_PDL_SYNC();
     extern __shared__ float rec[];
     __shared__ float red[8];
     const int b = blockIdx.x;
@@ -648,6 +669,7 @@ cwt_to_pitch_kernel(const float* __restrict__ cwt, int cwt_stride, const float* 
 
 __global__ void f0_to_pitch_kernel(const float* __restrict__ f0n, const float* __restrict__ uv, int n,
                                    float* __restrict__ f0_denorm, int64_t* __restrict__ pitch_idx) {
+    CTTS_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float fd = (uv && uv[i] > 0.f) ? 0.f : exp2f(f0n[i]);
@@ -657,6 +679,7 @@ __global__ void f0_to_pitch_kernel(const float* __restrict__ f0n, const float* _
 
 __global__ void gather_add_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, int rows, int C,
                                   int table_rows, float* __restrict__ x) {
+    CTTS_PDL_SYNC();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -674,6 +697,7 @@ __global__ void gather_add_kernel(const float* __restrict__ table, const int64_t
 
 __global__ void bucketize_kernel(const float* __restrict__ v, float v_scale, const float* __restrict__ bins, int n_bins,
                                  int n, int64_t* __restrict__ idx) {
+    CTTS_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float x = v[i] * v_scale;
@@ -687,6 +711,7 @@ __global__ void bucketize_kernel(const float* __restrict__ v, float v_scale, con
 
 __global__ void add_row_broadcast_kernel(const float* __restrict__ x, const float* __restrict__ row, int T, int C,
                                          size_t total4, float* __restrict__ y) {
+    CTTS_PDL_SYNC();
     const int c4 = C >> 2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
         const size_t tok = i / c4;
@@ -701,6 +726,7 @@ __global__ void add_row_broadcast_kernel(const float* __restrict__ x, const floa
 
 template <int NP>
 __global__ void split_bf16_kernel(const float* __restrict__ x, size_t n, const PlanePtrs out) {
+    CTTS_PDL_SYNC();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float rem = x[i];
 #pragma unroll
@@ -721,6 +747,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, size_t n, const P
 __global__ void __launch_bounds__(256)
 fastformer_pool_kernel(const float* __restrict__ logits, const float* __restrict__ values, const int64_t* __restrict__ lens,
                        int T, int Hh, int hs, float div, float* __restrict__ pooled) {
+    CTTS_PDL_SYNC();
     __shared__ float red[8][32];
     __shared__ float red2[8][32][4];
     const int b = blockIdx.x;
@@ -761,6 +788,7 @@ fastformer_pool_kernel(const float* __restrict__ logits, const float* __restrict
 // y = op(a, b) [masked]: op 0: a + b, op 1: a * b ; b is either full-size or one row per batch element (b_rowwise)
 __global__ void binary_kernel(const float* __restrict__ a, const float* __restrict__ bb, int op, int b_rowwise,
                               const int64_t* __restrict__ lens, int T, int C, size_t total4, float* __restrict__ y) {
+    CTTS_PDL_SYNC();
     const int c4 = C >> 2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
         const size_t tok = i / c4;
@@ -781,6 +809,7 @@ __global__ void binary_kernel(const float* __restrict__ a, const float* __restri
 //   glu:   g[b,t,c] = h[b,t,c] * sigmoid(h[b,t,C+c])                         (GLU over the channel dim, blocks.py:123-134)
 //   dwconv: y[b,t,c] = swish( BN( sum_j g[b,t+j-K/2,c] * w[c,j] ) )          (depthwise k=31 'same', eval BatchNorm folded)
 __global__ void glu_kernel(const float* __restrict__ h, int C, size_t rows, float* __restrict__ g) {
+    CTTS_PDL_SYNC();
     const size_t total = rows * (size_t)C;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / C;
@@ -793,6 +822,7 @@ __global__ void glu_kernel(const float* __restrict__ h, int C, size_t rows, floa
 __global__ void dwconv_bn_swish_kernel(const float* __restrict__ g, const float* __restrict__ w, int K,
                                        const float* __restrict__ scale, const float* __restrict__ shift, int T, int C,
                                        float* __restrict__ y) {
+    CTTS_PDL_SYNC();
     const int b = blockIdx.z, t = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -814,6 +844,7 @@ __global__ void dwconv_bn_swish_kernel(const float* __restrict__ g, const float*
 // One warp per (z, i) row; P is written with row stride ldp (>= T, zero padded) so that it can feed the P.V GEMM.
 __global__ void relshift_softmax_kernel(const float* __restrict__ content, const float* __restrict__ pos, int T, int ldp,
                                         float sqrt_dim, size_t rows, float* __restrict__ P) {
+    CTTS_PDL_SYNC();
     const size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -841,6 +872,7 @@ __global__ void relshift_softmax_kernel(const float* __restrict__ content, const
 // x [B, T, ld_in] (channel offset c0, heads of DH) -> xt [B*H, DH, ldt] (time contiguous, zero padded)
 __global__ void transpose_heads_kernel(const float* __restrict__ x, int T, int ld_in, int c0, int H, int DH, int ldt,
                                        float* __restrict__ xt) {
+    CTTS_PDL_SYNC();
     __shared__ float tile[32][33];
     const int z = blockIdx.z, b = z / H, h = z % H;
     const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -867,6 +899,7 @@ __global__ void __launch_bounds__(256)
 aligner_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ prior,
                          const int64_t* __restrict__ src_lens, float temperature, int M, int S, int C,
                          float* __restrict__ soft, float* __restrict__ logprob) {
+    CTTS_PDL_SYNC();
     extern __shared__ float sm[];
     float* ks = sm;                 // [C][S+1] transposed keys
     float* qs = sm + (size_t)C * (S + 1);   // [8][C]
@@ -922,6 +955,7 @@ aligner_attention_kernel(const float* __restrict__ q, const float* __restrict__ 
 __global__ void __launch_bounds__(1024)
 mas_kernel(const float* __restrict__ attn, const int64_t* __restrict__ src_lens, const int64_t* __restrict__ mel_lens, int M,
            int S, uint8_t* __restrict__ prev, float* __restrict__ hard, float* __restrict__ dur) {
+    CTTS_PDL_SYNC();
     extern __shared__ float rowbuf[];  // 2 x S
     const int b = blockIdx.x;
     const int Sb = min((int)src_lens[b], S), Mb = min((int)mel_lens[b], M);
@@ -964,6 +998,7 @@ mas_kernel(const float* __restrict__ attn, const int64_t* __restrict__ src_lens,
 __global__ void phoneme_energy_kernel(const float* __restrict__ dur, const int64_t* __restrict__ src_lens,
                                       const float* __restrict__ energy, int B, int S, int M, float* __restrict__ work,
                                       float* __restrict__ out) {
+    CTTS_PDL_SYNC();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float* e = work + (size_t)b * M;
@@ -995,6 +1030,7 @@ __global__ void gru_bidir_kernel(const float* __restrict__ gi_f, const float* __
                                  const float* __restrict__ whh_f, const float* __restrict__ bhh_f,
                                  const float* __restrict__ whh_b, const float* __restrict__ bhh_b, int T, int H,
                                  float* __restrict__ out, float* __restrict__ h_final) {
+    CTTS_PDL_SYNC();
     extern __shared__ float sm[];
     const int G = 3 * H;
     float* wt = sm;              // [H][G]
@@ -1038,6 +1074,7 @@ __global__ void gru_bidir_kernel(const float* __restrict__ gi_f, const float* __
 // y[r, n] = sum_{k<K} x[r,k] w[n,k] + bias[n] (+ residual[r,n]); tiny K (the 4-d phoneme prosody code, modules.py:861)
 __global__ void linear_smallk_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                      const float* __restrict__ residual, size_t rows, int K, int N, float* __restrict__ y) {
+    CTTS_PDL_SYNC();
     const size_t total = rows * (size_t)N;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / N;
@@ -1063,7 +1100,7 @@ static int launch_attention(const float* qkv, const int64_t* lens, int B, int T,
     const size_t sm = (size_t)(3 * 32 * (DH + 4) + 32 * 33) * sizeof(float);
     ensure_smem(attention_fp32_kernel<DH>, sm);
     dim3 grid((T + 31) / 32, H, B);
-    attention_fp32_kernel<DH><<<grid, 128, sm, st>>>(qkv, lens, T, C, scale, out);
+    launch_k(attention_fp32_kernel<DH>, grid, 128, sm, st, qkv, lens, T, C, scale, out);
     return check_launch("attention");
 }
 
@@ -1087,7 +1124,7 @@ int ctts_embed_tokens(const int64_t* tokens, const float* table, const float* pe
     CTTS_REQUIRE(pe_rows > S - (pos_mode ? 1 : 0), "embed_tokens: positional table has %d rows, need > %d", pe_rows, S);
     CTTS_REQUIRE(S <= 32 * POS_MAXCH, "embed_tokens: S=%d too long (max %d)", S, 32 * POS_MAXCH);
     dim3 grid(B, (S + EMB_ROWS - 1) / EMB_ROWS);
-    embed_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tokens, table, pe, embed_scale, S, C, vocab, x, word, lens,
+    launch_k(embed_tokens_kernel, grid, 256, 0, (cudaStream_t)stream, tokens, table, pe, embed_scale, S, C, vocab, x, word, lens,
                                                               pos_mode);
     return check_launch("embed_tokens");
 }
@@ -1099,7 +1136,7 @@ int ctts_add_positions(const float* x, const float* pe, int pe_rows, const float
     CTTS_REQUIRE(pe_rows > T - (pos_mode ? 1 : 0), "add_positions: positional table has %d rows, need > %d", pe_rows, T);
     CTTS_REQUIRE(T <= 32 * POS_MAXCH, "add_positions: T=%d too long (max %d)", T, 32 * POS_MAXCH);
     dim3 grid(B, (T + POS_ROWS - 1) / POS_ROWS);
-    add_positions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, pe, alpha, lens, T, C, pos_mode, y);
+    launch_k(add_positions_kernel, grid, 256, 0, (cudaStream_t)stream, x, pe, alpha, lens, T, C, pos_mode, y);
     return check_launch("add_positions");
 }
 
@@ -1116,9 +1153,9 @@ static int layernorm_impl(const float* x, const float* gamma, const float* beta,
         pp.p[p] = (__nv_bfloat16*)planes[p];
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (np == 3) layernorm_kernel<3><<<grid, 256, 0, st>>>(x, gamma, beta, eps, lens, rows, T, C, y, pp);
-    else if (np == 2) layernorm_kernel<2><<<grid, 256, 0, st>>>(x, gamma, beta, eps, lens, rows, T, C, y, pp);
-    else layernorm_kernel<0><<<grid, 256, 0, st>>>(x, gamma, beta, eps, lens, rows, T, C, y, pp);
+    if (np == 3) launch_k(layernorm_kernel<3>, grid, 256, 0, st, x, gamma, beta, eps, lens, rows, T, C, y, pp);
+    else if (np == 2) launch_k(layernorm_kernel<2>, grid, 256, 0, st, x, gamma, beta, eps, lens, rows, T, C, y, pp);
+    else launch_k(layernorm_kernel<0>, grid, 256, 0, st, x, gamma, beta, eps, lens, rows, T, C, y, pp);
     return check_launch("layernorm");
 }
 
@@ -1150,13 +1187,13 @@ int ctts_conv1d_gemm(const float* x, const float* w, const float* bias, float al
     if (taps == 1 && (N <= 16 || (long long)B * T <= 32)) {
         const int chunks = (N + SK_NCH - 1) / SK_NCH;
         const long long warps = (long long)B * T * chunks;
-        skinny_linear_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        launch_k(skinny_linear_kernel, (unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream, 
             x, w, bias, alpha, col_scale, col_shift, act, residual, lens, (long long)B * T, T, Cin, N, chunks, y);
         return check_launch("conv1d_gemm (skinny)");
     }
     dim3 grid((T + GM - 1) / GM, (N + GN - 1) / GN, B);
     const GAddr ga{1, (long long)T * Cin, 0, Cin, 0, 0, taps * Cin, (long long)T * N, 0, N, 1};
-    conv1d_gemm_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, alpha, col_scale, col_shift, act,
+    launch_k(conv1d_gemm_fp32_kernel, grid, 256, 0, (cudaStream_t)stream, x, w, bias, alpha, col_scale, col_shift, act,
                                                                     residual, lens, T, Cin, N, taps, y, ga);
     return check_launch("conv1d_gemm");
 }
@@ -1170,7 +1207,7 @@ int ctts_batched_gemm_fp32(const float* x, const float* w, float alpha, const in
                  "batched_gemm_fp32: operand strides must be multiples of 4 floats");
     dim3 grid((T + GM - 1) / GM, (N + GN - 1) / GN, Z);
     const GAddr ga{mod, x_so, x_sh, x_ld, w_so, w_sh, w_ld, y_so, y_sh, y_ld, lens_div > 0 ? lens_div : 1};
-    conv1d_gemm_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, nullptr, alpha, nullptr, nullptr, CTTS_ACT_NONE,
+    launch_k(conv1d_gemm_fp32_kernel, grid, 256, 0, (cudaStream_t)stream, x, w, nullptr, alpha, nullptr, nullptr, CTTS_ACT_NONE,
                                                                     nullptr, lens, T, K, N, 1, y, ga);
     return check_launch("batched_gemm_fp32");
 }
@@ -1179,7 +1216,7 @@ int ctts_pack_conv_weight(const float* w, int N, int Cin, int taps, float* packe
     const size_t total = (size_t)N * Cin * taps;
     CTTS_REQUIRE(total > 0, "pack_conv_weight: empty");
     const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-    pack_conv_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, N, Cin, taps, packed);
+    launch_k(pack_conv_weight_kernel, grid, 256, 0, (cudaStream_t)stream, w, N, Cin, taps, packed);
     return check_launch("pack_conv_weight");
 }
 
@@ -1198,7 +1235,7 @@ int ctts_attention(const float* qkv, const int64_t* lens, int B, int T, int C, i
 
 int ctts_decode_durations(const float* log_d, float d_control, int n, float* dur, void* stream) {
     CTTS_REQUIRE(n > 0, "decode_durations: empty");
-    decode_durations_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(log_d, d_control, n, dur);
+    launch_k(decode_durations_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, log_d, d_control, n, dur);
     return check_launch("decode_durations");
 }
 
@@ -1207,7 +1244,7 @@ int ctts_length_scan(const float* dur_f32, const int64_t* dur_i64, const int64_t
     CTTS_REQUIRE((dur_f32 != nullptr) != (dur_i64 != nullptr), "length_scan: exactly one of dur_f32 / dur_i64");
     CTTS_REQUIRE(B > 0 && S > 0, "length_scan: bad shape");
     // mel_len has room for 2*B entries: [0,B) = LR lengths, [B,2B) = mel2ph lengths
-    length_scan_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(dur_f32, dur_i64, src_lens, S, cum_lr, cum_m2p, mel_len,
+    launch_k(length_scan_kernel, B, 32, 0, (cudaStream_t)stream, dur_f32, dur_i64, src_lens, S, cum_lr, cum_m2p, mel_len,
                                                            mel_len + B);
     return check_launch("length_scan");
 }
@@ -1220,7 +1257,7 @@ int ctts_length_expand(const float* src, const float* table, const int64_t* row_
     CTTS_REQUIRE(C % 4 == 0 && M > 0, "length_expand: bad shape C=%d M=%d", C, M);
     const int rows = M > M2 ? M : (mel2ph ? M2 : M);
     dim3 grid((rows + 7) / 8, B);
-    length_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, table, row_index, cum_lr, S, C, M, accumulate, out,
+    launch_k(length_expand_kernel, grid, 256, 0, (cudaStream_t)stream, src, table, row_index, cum_lr, S, C, M, accumulate, out,
                                                                  cum_m2p, mel2ph, M2);
     return check_launch("length_expand");
 }
@@ -1233,7 +1270,7 @@ int ctts_cwt_to_pitch(const float* cwt, int cwt_stride, const float* scale_w, co
     const size_t sm = (size_t)T * sizeof(float);
     CTTS_REQUIRE(sm <= 200 * 1024, "cwt_to_pitch: T=%d too long", T);
     ensure_smem(cwt_to_pitch_kernel, sm);
-    cwt_to_pitch_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(cwt, cwt_stride, scale_w, mean, std, stat_stride, std_scale,
+    launch_k(cwt_to_pitch_kernel, B, 256, sm, (cudaStream_t)stream, cwt, cwt_stride, scale_w, mean, std, stat_stride, std_scale,
                                                               eps, uv_src, use_uv, T, f0_norm, f0_denorm, pitch_idx);
     return check_launch("cwt_to_pitch");
 }
@@ -1241,19 +1278,19 @@ int ctts_cwt_to_pitch(const float* cwt, int cwt_stride, const float* scale_w, co
 int ctts_f0_to_pitch(const float* f0_norm, const float* uv_src, int n, float* f0_denorm, int64_t* pitch_idx,
                      void* stream) {
     CTTS_REQUIRE(n > 0, "f0_to_pitch: empty");
-    f0_to_pitch_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(f0_norm, uv_src, n, f0_denorm, pitch_idx);
+    launch_k(f0_to_pitch_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, f0_norm, uv_src, n, f0_denorm, pitch_idx);
     return check_launch("f0_to_pitch");
 }
 
 int ctts_gather_add(const float* table, const int64_t* idx, int rows, int C, int table_rows, float* x, void* stream) {
     CTTS_REQUIRE(rows > 0 && C % 4 == 0, "gather_add: bad shape");
-    gather_add_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(table, idx, rows, C, table_rows, x);
+    launch_k(gather_add_kernel, (rows + 7) / 8, 256, 0, (cudaStream_t)stream, table, idx, rows, C, table_rows, x);
     return check_launch("gather_add");
 }
 
 int ctts_bucketize(const float* v, float v_scale, const float* bins, int n_bins, int n, int64_t* idx, void* stream) {
     CTTS_REQUIRE(n > 0 && n_bins > 0, "bucketize: bad shape");
-    bucketize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(v, v_scale, bins, n_bins, n, idx);
+    launch_k(bucketize_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, v, v_scale, bins, n_bins, n, idx);
     return check_launch("bucketize");
 }
 
@@ -1261,7 +1298,7 @@ int ctts_add_row_broadcast(const float* x, const float* row, int B, int T, int C
     CTTS_REQUIRE(C % 4 == 0, "add_row_broadcast: C %% 4 != 0");
     const size_t total4 = (size_t)B * T * (C / 4);
     const int grid = (int)((total4 + 255) / 256 < 8192 ? (total4 + 255) / 256 : 8192);
-    add_row_broadcast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, row, T, C, total4, y);
+    launch_k(add_row_broadcast_kernel, grid, 256, 0, (cudaStream_t)stream, x, row, T, C, total4, y);
     return check_launch("add_row_broadcast");
 }
 
@@ -1273,8 +1310,8 @@ int ctts_split_planes(const float* x, size_t n, int n_planes, void* const* plane
         CTTS_REQUIRE(planes[p], "split_planes: NULL plane %d", p);
         pp.p[p] = (__nv_bfloat16*)planes[p];
     }
-    if (n_planes == 3) split_bf16_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, pp);
-    else split_bf16_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, pp);
+    if (n_planes == 3) launch_k(split_bf16_kernel<3>, grid, 256, 0, (cudaStream_t)stream, x, n, pp);
+    else launch_k(split_bf16_kernel<2>, grid, 256, 0, (cudaStream_t)stream, x, n, pp);
     return check_launch("split_planes");
 }
 
@@ -1290,7 +1327,7 @@ int ctts_fastformer_pool(const float* logits, const float* values, const int64_t
     CTTS_REQUIRE(lens != nullptr, "fastformer_pool: lens is NULL");
     dim3 grid(B, (heads + 31) / 32);
     // the reference divides by python's attention_head_size ** 0.5 (fastformer.py:310,328)
-    fastformer_pool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, values, lens, T, heads, head_size,
+    launch_k(fastformer_pool_kernel, grid, 256, 0, (cudaStream_t)stream, logits, values, lens, T, heads, head_size,
                                                                    (float)sqrt((double)head_size), pooled);
     return check_launch("fastformer_pool");
 }
@@ -1300,7 +1337,7 @@ int ctts_binary(const float* a, const float* b, int op, int b_rowwise, const int
     CTTS_REQUIRE(C % 4 == 0 && B > 0 && T > 0 && (op == 0 || op == 1), "binary: bad arguments");
     const size_t total4 = (size_t)B * T * (C / 4);
     const int grid = (int)((total4 + 255) / 256 < 8192 ? (total4 + 255) / 256 : 8192);
-    binary_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, op, b_rowwise, lens, T, C, total4, y);
+    launch_k(binary_kernel, grid, 256, 0, (cudaStream_t)stream, a, b, op, b_rowwise, lens, T, C, total4, y);
     return check_launch("binary");
 }
 
@@ -1308,7 +1345,7 @@ int ctts_glu(const float* h, int rows, int C, float* g, void* stream) {
     CTTS_REQUIRE(rows > 0 && C > 0, "glu: bad shape");
     const size_t total = (size_t)rows * C;
     const int grid = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
-    glu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, C, (size_t)rows, g);
+    launch_k(glu_kernel, grid, 256, 0, (cudaStream_t)stream, h, C, (size_t)rows, g);
     return check_launch("glu");
 }
 
@@ -1316,7 +1353,7 @@ int ctts_dwconv_bn_swish(const float* g, const float* w, int K, const float* sca
                          float* y, void* stream) {
     CTTS_REQUIRE(B > 0 && T > 0 && C > 0 && (K & 1), "dwconv_bn_swish: bad shape");
     dim3 grid((C + 127) / 128, T, B);
-    dwconv_bn_swish_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(g, w, K, scale, shift, T, C, y);
+    launch_k(dwconv_bn_swish_kernel, grid, 128, 0, (cudaStream_t)stream, g, w, K, scale, shift, T, C, y);
     return check_launch("dwconv_bn_swish");
 }
 
@@ -1324,7 +1361,7 @@ int ctts_relshift_softmax(const float* content, const float* pos, int Z, int T, 
                           void* stream) {
     CTTS_REQUIRE(Z > 0 && T > 0 && ldp >= T, "relshift_softmax: bad shape");
     const size_t rows = (size_t)Z * T;
-    relshift_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(content, pos, T, ldp, sqrt_dim, rows,
+    launch_k(relshift_softmax_kernel, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, content, pos, T, ldp, sqrt_dim, rows,
                                                                                         P);
     return check_launch("relshift_softmax");
 }
@@ -1332,7 +1369,7 @@ int ctts_relshift_softmax(const float* content, const float* pos, int Z, int T, 
 int ctts_transpose_heads(const float* x, int B, int T, int ld_in, int c0, int H, int DH, int ldt, float* xt, void* stream) {
     CTTS_REQUIRE(B > 0 && T > 0 && H > 0 && DH > 0 && ldt >= T, "transpose_heads: bad shape");
     dim3 grid((ldt + 31) / 32, (DH + 31) / 32, B * H);
-    transpose_heads_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, T, ld_in, c0, H, DH, ldt, xt);
+    launch_k(transpose_heads_kernel, grid, 256, 0, (cudaStream_t)stream, x, T, ld_in, c0, H, DH, ldt, xt);
     return check_launch("transpose_heads");
 }
 
@@ -1343,7 +1380,7 @@ int ctts_aligner_attention(const float* q, const float* k, const float* prior, c
     CTTS_REQUIRE(sm <= 200 * 1024, "aligner_attention: S=%d too long for the shared-memory key tile", S);
     ensure_smem(aligner_attention_kernel, sm);
     dim3 grid((M + 7) / 8, B);
-    aligner_attention_kernel<<<grid, 256, sm, (cudaStream_t)stream>>>(q, k, prior, src_lens, temperature, M, S, C, soft,
+    launch_k(aligner_attention_kernel, grid, 256, sm, (cudaStream_t)stream, q, k, prior, src_lens, temperature, M, S, C, soft,
                                                                       logprob);
     return check_launch("aligner_attention");
 }
@@ -1354,14 +1391,14 @@ int ctts_mas(const float* attn, const int64_t* src_lens, const int64_t* mel_lens
     const size_t sm = 2 * (size_t)S * sizeof(float);
     CTTS_REQUIRE(sm <= 48 * 1024, "mas: S=%d too long", S);
     const int threads = S >= 1024 ? 1024 : ((S + 31) / 32) * 32;
-    mas_kernel<<<B, threads, sm, (cudaStream_t)stream>>>(attn, src_lens, mel_lens, M, S, prev_workspace, hard, dur);
+    launch_k(mas_kernel, B, threads, sm, (cudaStream_t)stream, attn, src_lens, mel_lens, M, S, prev_workspace, hard, dur);
     return check_launch("mas");
 }
 
 int ctts_phoneme_energy(const float* dur, const int64_t* src_lens, const float* energy, int B, int S, int M, float* workspace,
                         float* out, void* stream) {
     CTTS_REQUIRE(B > 0 && S > 0 && M > 0 && workspace, "phoneme_energy: bad arguments");
-    phoneme_energy_kernel<<<(B + 31) / 32, 32, 0, (cudaStream_t)stream>>>(dur, src_lens, energy, B, S, M, workspace, out);
+    launch_k(phoneme_energy_kernel, (B + 31) / 32, 32, 0, (cudaStream_t)stream, dur, src_lens, energy, B, S, M, workspace, out);
     return check_launch("phoneme_energy");
 }
 
@@ -1372,7 +1409,7 @@ int ctts_gru_bidir(const float* gi_fwd, const float* gi_bwd, const float* w_hh_f
     const size_t sm = ((size_t)H * 3 * H + H + 3 * H) * sizeof(float);
     CTTS_REQUIRE(sm <= 227 * 1024, "gru_bidir: hidden size %d does not fit the shared-memory weight tile", H);
     ensure_smem(gru_bidir_kernel, sm);
-    gru_bidir_kernel<<<dim3(B, 2), 3 * H, sm, (cudaStream_t)stream>>>(gi_fwd, gi_bwd, w_hh_fwd, b_hh_fwd, w_hh_bwd, b_hh_bwd,
+    launch_k(gru_bidir_kernel, dim3(B, 2), 3 * H, sm, (cudaStream_t)stream, gi_fwd, gi_bwd, w_hh_fwd, b_hh_fwd, w_hh_bwd, b_hh_bwd,
                                                                       T, H, out, h_final);
     return check_launch("gru_bidir");
 }
@@ -1382,7 +1419,7 @@ int ctts_linear_smallk(const float* x, const float* w, const float* bias, const 
     CTTS_REQUIRE(rows > 0 && K > 0 && K <= 64 && N > 0, "linear_smallk: bad shape");
     const size_t total = (size_t)rows * N;
     const int grid = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
-    linear_smallk_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, residual, (size_t)rows, K, N, y);
+    launch_k(linear_smallk_kernel, grid, 256, 0, (cudaStream_t)stream, x, w, bias, residual, (size_t)rows, K, N, y);
     return check_launch("linear_smallk");
 }
 
