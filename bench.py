@@ -206,7 +206,8 @@ def main():
             return fn(x, w, *a, **k)
         return wrapper
 
-    ffn_kernel = ("ctts_gemm_bf16x3 (tcgen05, bf16 hi/lo x3)" if net.decoder_math == "bf16x3"
+    ffn_kernel = ("ctts_gemm_split -> gemm_pair_kernel (tcgen05 cta_group::2, TMA, TMEM; bf16 hi/lo planes x3 MMAs)"
+                  if net.decoder_math == "bf16x3"
                   else "ctts_conv1d_gemm (FP32 CUDA cores)")
 
     def step_device():

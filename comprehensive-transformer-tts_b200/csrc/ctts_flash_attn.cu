@@ -2,11 +2,15 @@
 //
 // One CTA per (batch*head, 128-query tile).  Scores never leave the SM: S = Q K^T lands in TMEM, the softmax warps turn
 // it into probability planes in shared memory, and P V accumulates into a second TMEM region.  No online rescaling of
-// the output: the keys are swept TWICE -- pass A computes the row maxima (no exponentials), pass B recomputes S, forms
-// p = exp(s - m), accumulates the row sums and O += P V; the epilogue divides by the row sum.  Recomputing Q K^T costs one third more MMA
-// work than the minimum and saves the 3 x 82 MB round trips (scores, probability planes) of the materialised version.
+// the output: the keys are swept TWICE -- pass A computes row maxima (no exponentials), pass B recomputes S, forms
+// p = exp(s - m), accumulates the row sums and O += P V; the epilogue divides by the row sum.  Softmax is invariant to
+// the shift m, so pass A does not need the exact maximum: it multiplies the HI planes only (one MMA per k-slice instead
+// of three, half the K bytes), which bounds p by 2^(a few 1e-2) instead of 1 and changes nothing else.  Pass A is
+// latency-bound (one 16 KiB tile per 256 MMA cycles), so its K tiles go through a 4-slot ring laid over the K region.
+// The extra sweep costs 1/9 more MMA work than the minimum and saves the 3 x 82 MB round trips (scores, probability
+// planes) of the materialised version.
 //
-//   warp 0      TMA producer: Q once, K tiles (2 passes), V^T tiles; SWIZZLE_128B; 2-stage rings
+//   warp 0      TMA producer: Q once, K hi tiles (pass A, 4 slots), K + V^T tiles (pass B, 2-stage rings); SWIZZLE_128B
 //   warp 1      tcgen05.mma issuer: S (M128 x N64 x K128, 3 plane products) and P V (M128 x N128 x K64)
 //   warps 2-9   softmax / epilogue: TMEM lane = query row, two warps per lane quarter split the columns
 //
@@ -34,12 +38,15 @@ constexpr int Q_BYTES = 4 * Q_TILE;       // 2 planes x 2 k-blocks = 64 KiB
 constexpr int K_STAGE = 4 * K_TILE;       // 32 KiB
 constexpr int V_STAGE = 2 * V_TILE;       // 32 KiB
 constexpr int P_BYTES = 2 * P_TILE;       // 32 KiB
+constexpr int KA_SLOT = 2 * K_TILE;       // pass A: hi plane of one key tile (2 k-blocks) = 16 KiB
+constexpr int KA_SLOTS = 4;               // ... 4 slots over the 64 KiB K region
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + Q_BYTES;            // 2 stages
 constexpr int OFF_V = OFF_K + 2 * K_STAGE;        // 2 stages
 constexpr int OFF_P = OFF_V + 2 * V_STAGE;
 constexpr int OFF_BAR = OFF_P + P_BYTES;
-constexpr int SMEM_TOTAL = OFF_BAR + 192 + 1024 + 1024;   // barriers, [2][128] float exchange area, alignment slack
+constexpr int OFF_XCH = OFF_BAR + 256;            // [2][128] float exchange area
+constexpr int SMEM_TOTAL = OFF_XCH + 1024 + 1024; // + alignment slack
 static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
 struct Maps {
@@ -53,6 +60,11 @@ __host__ __device__ constexpr uint32_t idesc(int n) {
 }
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {   // one MUFU op; arguments are <= ~0, huge negatives flush to 0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __global__ void __launch_bounds__(320, 1)
 flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restrict__ lens, int T, int C, int H, float scale_log2e,
@@ -71,6 +83,8 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
     uint64_t* p_empty = bars + 14;      // 1
     uint64_t* o_full = bars + 15;       // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* ka_full = bars + 17;      // [4]  pass A ring over the K region
+    uint64_t* ka_empty = bars + 21;     // [4]
 
     CTTS_PDL_SYNC();   // lens[] below may come from the previous kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,6 +108,10 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
             mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 8);      // one arrival per softmax warp
+        }
+        for (int i = 0; i < KA_SLOTS; ++i) {
+            mbar_init(&ka_full[i], 1);
+            mbar_init(&ka_empty[i], 1);
         }
         mbar_init(p_full, 8);
         mbar_init(p_empty, 1);
@@ -121,11 +139,25 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_3d(&tm.q[p], q_full, smem + OFF_Q + (p * 2 + kb) * Q_TILE, h * DH + kb * 64, q0, b);
-            // K tiles: pass A then pass B (same order); V^T tiles during pass B
-            for (int i = 0; i < 2 * nkv; ++i) {
-                const int j = i < nkv ? i : i - nkv;
-                const int s = i & 1;
-                mbar_wait(&k_empty[s], ((i >> 1) & 1) ^ 1);
+            // pass A: hi planes of the key tiles, 4-slot ring over the K region
+            for (int i = 0; i < nkv; ++i) {
+                const int a = i & (KA_SLOTS - 1);
+                mbar_wait(&ka_empty[a], ((i >> 2) & 1) ^ 1);
+                mbar_expect_tx(&ka_full[a], KA_SLOT);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+                    tma_load_3d(&tm.k[0], &ka_full[a], smem + OFF_K + a * KA_SLOT + kb * K_TILE, C + h * DH + kb * 64,
+                                i * BKV, b);
+            }
+            // the pass-B stages reuse the same bytes: every slot's last pass-A MMA must have completed
+            for (int a = 0; a < KA_SLOTS && a < nkv; ++a) {
+                const int uses = (nkv - a + KA_SLOTS - 1) / KA_SLOTS;
+                mbar_wait(&ka_empty[a], (uses - 1) & 1);
+            }
+            // pass B: both planes of the key tiles and the V^T tiles, 2-stage rings
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&k_full[s], K_STAGE);
 #pragma unroll
                 for (int p = 0; p < 2; ++p)
@@ -133,26 +165,41 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
                     for (int kb = 0; kb < 2; ++kb)
                         tma_load_3d(&tm.k[p], &k_full[s], smem + OFF_K + s * K_STAGE + (p * 2 + kb) * K_TILE,
                                     C + h * DH + kb * 64, j * BKV, b);
-                if (i >= nkv) {
-                    const int vs = j & 1;
-                    mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&v_full[vs], V_STAGE);
+                mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&v_full[s], V_STAGE);
 #pragma unroll
-                    for (int p = 0; p < 2; ++p)
-                        tma_load_3d(&tm.vt[p], &v_full[vs], smem + OFF_V + vs * V_STAGE + p * V_TILE, j * BKV, 0, z);
-                }
+                for (int p = 0; p < 2; ++p)
+                    tma_load_3d(&tm.vt[p], &v_full[s], smem + OFF_V + s * V_STAGE + p * V_TILE, j * BKV, 0, z);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = idesc(BKV), idesc_o = idesc(DH);
             const uint32_t q_addr = smem_u32(smem + OFF_Q);
-            auto issue_s = [&](int i) {   // S[i & 1] = Q K_j^T   (i runs over both passes)
-                const int s = i & 1;
-                mbar_wait(&k_full[s], (i >> 1) & 1);
+            auto issue_a = [&](int i) {   // pass A: S[i & 1] ~ Q_hi K_hi,j^T  (row maxima only)
+                const int s = i & 1, a = i & (KA_SLOTS - 1);
+                mbar_wait(&ka_full[a], (i >> 2) & 1);
                 mbar_wait(&s_empty[s], ((i >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
-                const uint32_t k_addr = smem_u32(smem + OFF_K + s * K_STAGE);
+                const uint32_t k_addr = smem_u32(smem + OFF_K + a * KA_SLOT);
+                const uint32_t d = tmem_base + (uint32_t)(s * BKV);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t off = k * 32;
+                        umma_bf16(d, umma_desc_sw128(q_addr + kb * Q_TILE + off), umma_desc_sw128(k_addr + kb * K_TILE + off),
+                                  idesc_s, (kb | k) ? 1u : 0u);
+                    }
+                umma_commit(&ka_empty[a]);
+                umma_commit(&s_full[s]);
+            };
+            auto issue_s = [&](int j) {   // pass B: S[(nkv + j) & 1] = Q K_j^T, all three plane products
+                const int i = nkv + j, s = i & 1, ks = j & 1;
+                mbar_wait(&k_full[ks], (j >> 1) & 1);
+                mbar_wait(&s_empty[s], ((i >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t k_addr = smem_u32(smem + OFF_K + ks * K_STAGE);
                 const uint32_t d = tmem_base + (uint32_t)(s * BKV);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
@@ -167,14 +214,14 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
                         umma_bf16(d, qh, kl, idesc_s, 1u);
                         umma_bf16(d, qh, kh, idesc_s, 1u);
                     }
-                umma_commit(&k_empty[s]);
+                umma_commit(&k_empty[ks]);
                 umma_commit(&s_full[s]);
             };
             mbar_wait(q_full, 0);
-            for (int i = 0; i < nkv; ++i) issue_s(i);                  // pass A
-            issue_s(nkv);                                              // pass B, software pipelined by one tile
+            for (int i = 0; i < nkv; ++i) issue_a(i);                  // pass A
+            issue_s(0);                                                // pass B, software pipelined by one tile
             for (int j = 0; j < nkv; ++j) {
-                if (j + 1 < nkv) issue_s(nkv + j + 1);
+                if (j + 1 < nkv) issue_s(j + 1);
                 const int vs = j & 1;
                 mbar_wait(p_full, j & 1);
                 mbar_wait(&v_full[vs], (j >> 1) & 1);
@@ -204,7 +251,7 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
         const int ch = (warp - 2) >> 2;
         const int row = qq * 32 + lane;                  // query row inside the tile == TMEM lane
         const uint32_t lane_base = tmem_base + ((uint32_t)(qq * 32) << 16);
-        float* xch = reinterpret_cast<float*>(smem + OFF_BAR + 192);     // [2][128] exchange area (1 KiB, see SMEM_TOTAL)
+        float* xch = reinterpret_cast<float*>(smem + OFF_XCH);           // [2][128] exchange area (1 KiB)
         // ---- pass A: row maximum only (scores in units of log2: s * scale * log2 e) ----
         float m = -INFINITY;
         for (int i = 0; i < nkv; ++i) {
@@ -217,9 +264,14 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);
             const int k0 = i * BKV + ch * 32;
+            if (k0 + 32 <= len) {                       // warp-uniform: only the last tile is partial
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-                if (k0 + c < len) m = fmaxf(m, __uint_as_float(r[c]));
+                for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(r[c]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (k0 + c < len) m = fmaxf(m, __uint_as_float(r[c]));
+            }
         }
         xch[ch * 128 + row] = m;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + qq) : "memory");       // the two warps of this lane quarter
@@ -238,27 +290,30 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);
             const int k0 = j * BKV + ch * 32;
+            // exponentials and the hi/lo split go to registers first: they overlap the previous tile's P V, and only
+            // the shared-memory stores wait for it
+            const bool full = k0 + 32 <= len;           // warp-uniform: only the last tile is partial
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * e]), scale_log2e, -m));
+                float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * e + 1]), scale_log2e, -m));
+                if (!full) {
+                    if (k0 + 2 * e >= len) p0 = 0.f;
+                    if (k0 + 2 * e + 1 >= len) p1 = 0.f;
+                }
+                l += p0 + p1;
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(p0 - __low2float(hh), p1 - __high2float(hh));
+                hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
             mbar_wait(p_empty, (j & 1) ^ 1);          // the previous P V has finished reading the P planes
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {           // my 4 chunks of 8 keys = 16 bytes per plane
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float p2[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int c = c8 * 8 + e * 2 + u;
-                        p2[u] = (k0 + c < len) ? exp2f(fmaf(__uint_as_float(r[c]), scale_log2e, -m)) : 0.f;
-                    }
-                    l += p2[0] + p2[1];
-                    const __nv_bfloat162 hh = __floats2bfloat162_rn(p2[0], p2[1]);
-                    const __nv_bfloat162 ll = __floats2bfloat162_rn(p2[0] - __low2float(hh), p2[1] - __high2float(hh));
-                    hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
-                    lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
-                }
                 const int phys = (((ch * 4 + c8) ^ (row & 7))) * 16;   // 128-byte swizzle: chunk index XOR (row mod 8)
-                *reinterpret_cast<uint4*>(p_hi + phys) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(p_lo + phys) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(p_hi + phys) = make_uint4(hi[4 * c8], hi[4 * c8 + 1], hi[4 * c8 + 2], hi[4 * c8 + 3]);
+                *reinterpret_cast<uint4*>(p_lo + phys) = make_uint4(lo[4 * c8], lo[4 * c8 + 1], lo[4 * c8 + 2], lo[4 * c8 + 3]);
             }
             fence_async_smem();       // make the generic-proxy stores visible to the tensor core (async proxy)
             __syncwarp();
