@@ -280,7 +280,10 @@ def main():
         pk = peaks()
         value = world * frames * args.steps / (ms_total / 1e3)
         e2e = world * frames * args.steps / (ms_e2e / 1e3)
-        ffn_avg = sum(ffn_ms) / max(len(ffn_ms), 1)
+        ffn_mean = sum(ffn_ms) / max(len(ffn_ms), 1)
+        # median: in the eager re-run the host occasionally falls behind the GPU (descriptor encoding, allocator), and a
+        # start event that completes on an idle GPU then also counts the host's delay before the launch
+        ffn_avg = sorted(ffn_ms)[len(ffn_ms) // 2] if ffn_ms else 0.0
         traffic = tensor_pct = None
         summ = os.path.join(ROOT, "profiles", "ncu_ffn1_summary.json")
         if os.path.exists(summ) and net.decoder_math == "bf16x3":   # one ncu --set full capture of this kernel (committed)
@@ -308,9 +311,9 @@ def main():
                          "frac": (ffn_tflops / pk["tensor"]) if ffn_tflops else None, "traffic": traffic,
                          "traffic_source": "profiles/ncu_ffn1_summary.json (dram read + write bytes per launch)",
                          "tensor_pipe_active_pct": tensor_pct, "mma_per_algorithmic_product": 3,
-                         "peak_source": pk["src"], "launch_ms": ffn_avg, "launches_timed": len(ffn_ms),
-                         "launch_timing": "CUDA events around each launch in an eager re-run of the timed steps (host kept ahead of the "
-                                          "GPU by a device-side spin at the start of each stage)",
+                         "peak_source": pk["src"], "launch_ms": ffn_avg, "launch_ms_mean": ffn_mean, "launches_timed": len(ffn_ms),
+                         "launch_timing": "median over CUDA-event pairs around each launch in an eager re-run of the timed steps "
+                                          "(host kept ahead of the GPU by a device-side spin at the start of each stage)",
                          "flops_per_launch": frames * FFN_FLOP_PER_FRAME},
         }
         if world == 1 and not args.no_cpu_baseline:
