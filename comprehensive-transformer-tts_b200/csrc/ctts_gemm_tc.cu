@@ -1064,8 +1064,9 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
     if (np == 3) {
         // Small grids (the encoder at S ~ 100: 16 row tiles x 2 for a 256-wide output) are bound by per-stage load
         // latency, not by MMA issue: 128 x 64 tiles double the CTA count and allow a third stage (72 KiB each).
-        const char* nt = getenv("CTTS_NARROW_TILES");
-        const bool narrow = (nt == nullptr || atoi(nt) != 0) && N >= 128 && m_tiles * ((N + 127) / 128) <= 74;
+        const char* nt = getenv("CTTS_NARROW_TILES");   // 0 = never, otherwise the largest 128-wide grid that is narrowed
+        const long long narrow_max = nt ? atoll(nt) : 74;
+        const bool narrow = N >= 128 && m_tiles * ((N + 127) / 128) <= narrow_max;
         if (narrow) {
             if (shared_w) return launch<64, 3, 3, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
             return launch<64, 3, 3, 1>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);

@@ -44,8 +44,8 @@ void set_error(const char* fmt, ...) {
 
 // ---------------------------------------------------------------------------------------------
 // Positions of rows [r0, r1) of one utterance, by the whole CTA: pos[t] = flag(t) ? #flags in [0, t] : 0
-// (make_positions, utils/tools.py:640-652, with padding_idx 0).  Every warp ballots 32-row chunks of [0, r1) into s_mask; each row then sums the
-// popcounts of the chunks before its own.  r1 <= 32 * POS_MAXCH.
+// (make_positions, utils/tools.py:640-652, with padding_idx 0).  Every warp ballots 32-row chunks of [0, r1) into
+// s_mask; each row then sums the popcounts of the chunks before its own.  r1 <= 32 * POS_MAXCH.
 constexpr int POS_MAXCH = 512;
 template <class F>
 __device__ __forceinline__ void block_positions(int r0, int r1, int* s_pos, unsigned* s_mask, F flag) {
