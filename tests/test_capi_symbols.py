@@ -54,3 +54,41 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(d, f)).read()
                 for line in txt.splitlines():
                     assert not re.match(r"\s*(from|import)\s+oracle", line), "%s imports the oracle" % f
+
+
+def _prototypes():
+    """name -> list of parameter type strings, parsed from the header (comments stripped)."""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for m in re.finditer(r"\b(?:int|const char\s*\*)\s*(ctts_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = m.group(2).strip()
+        if params in ("", "void"):
+            out[m.group(1)] = []
+            continue
+        out[m.group(1)] = [" ".join(p.split()) for p in params.split(",")]
+    return out
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every parameter of every prototype in include/ctts_b200.h has the matching ctypes kind in capi.SIGNATURES:
+    pointer -> c_void_p, float -> c_float, long long -> c_longlong, size_t -> c_size_t, int -> c_int.  Catches ABI drift without a GPU."""
+    from ctts_b200 import capi
+    protos = _prototypes()
+    assert sorted(protos) == sorted(capi.SIGNATURES)
+    for name, params in protos.items():
+        sig = capi.SIGNATURES[name]
+        assert len(sig) == len(params), "%s: header has %d parameters, binding %d" % (name, len(params), len(sig))
+        for i, (p, c) in enumerate(zip(params, sig)):
+            if "*" in p:
+                want = ctypes.c_void_p
+            elif re.match(r"(const )?float\b", p):
+                want = ctypes.c_float
+            elif re.match(r"(const )?long long\b", p):
+                want = ctypes.c_longlong
+            elif re.match(r"(const )?size_t\b", p):
+                want = ctypes.c_size_t
+            else:
+                assert re.match(r"(const )?int\b", p), "%s: unexpected parameter type %r" % (name, p)
+                want = ctypes.c_int
+            assert c is want, "%s parameter %d (%s): binding uses %s" % (name, i, p, c.__name__)
