@@ -271,6 +271,8 @@ def pitch_embedding_cwt(P, cfg, pcfg, decoder_inp, f0, uv, mel2ph, control, x_or
     """get_pitch_embedding, pitch_type == 'cwt' branch, modules.py:890-948."""
     pitch_cfg = pcfg["preprocessing"]["pitch"]
     pre = "variance_adaptor."
+    g = cfg["variance_predictor"]["predictor_grad"]          # modules.py:904: gradient scaling, values unchanged
+    decoder_inp = decoder_inp.detach() + g * (decoder_inp - decoder_inp.detach())
     h = F.linear(decoder_inp, P[pre + "cwt_predictor.0.weight"], P[pre + "cwt_predictor.0.bias"])
     cwt = pitch_style_predictor(P, cfg, pre + "cwt_predictor.1.", h) * control
     s = F.relu(F.linear(x_org[:, 0, :], P[pre + "cwt_stats_layers.0.weight"], P[pre + "cwt_stats_layers.0.bias"]))
@@ -337,6 +339,95 @@ def parallel_prosody_predictor(P, cfg, pre, x, phoneme_level):
                              P[pre + "gru.bias_ih_l0_reverse"], P[pre + "gru.bias_hh_l0_reverse"], True)
     vec = torch.cat([fw, bw], -1) if phoneme_level else torch.cat([h_f, h_b], -1).unsqueeze(1)
     return F.linear(vec, P[pre + "predictor_bottleneck.weight"], P[pre + "predictor_bottleneck.bias"])
+
+
+def _batch_norm_train(h, P, pre, stats_out=None, momentum=0.1, eps=1e-5):
+    """nn.BatchNorm{1,2}d in training mode: normalise with the batch mean / biased variance over every dim but the
+    channel one; if `stats_out` is a dict it receives the buffers the module would hold afterwards
+    (running = (1 - momentum) * running + momentum * batch statistic, the variance one unbiased; num_batches_tracked + 1)."""
+    y = F.batch_norm(h, None, None, P[pre + "weight"], P[pre + "bias"], True, momentum, eps)
+    if stats_out is not None:
+        with torch.no_grad():
+            dims = [d for d in range(h.dim()) if d != 1]
+            n = h.numel() // h.shape[1]
+            mean = h.mean(dims)
+            var = h.var(dims, unbiased=False) * (n / max(n - 1, 1))
+            stats_out[pre + "running_mean"] = (1 - momentum) * P[pre + "running_mean"] + momentum * mean
+            stats_out[pre + "running_var"] = (1 - momentum) * P[pre + "running_var"] + momentum * var
+            stats_out[pre + "num_batches_tracked"] = P[pre + "num_batches_tracked"] + 1
+    return y
+
+
+# --- liu2021 reference encoders: mel -> prosody, training mode only (modules.py:332-569) -----------
+def _add_coords_2d(x):
+    """AddCoords(rank=2, with_r=True), coordconv.py:36-71: channels [x, row coordinate, column coordinate, radius],
+    coordinates scaled to [-1, 1], radius measured from (0.5, 0.5) as the reference does."""
+    N, _, H, W = x.shape
+    rows = torch.arange(H, dtype=torch.int32)[None, None, :, None].expand(1, 1, H, W)
+    cols = torch.arange(W, dtype=torch.int32)[None, None, None, :].expand(1, 1, H, W)
+    xx = (rows.float() / (H - 1)) * 2 - 1
+    yy = (cols.float() / (W - 1)) * 2 - 1
+    xx, yy = xx.repeat(N, 1, 1, 1), yy.repeat(N, 1, 1, 1)
+    rr = torch.sqrt(torch.pow(xx - 0.5, 2) + torch.pow(yy - 0.5, 2))
+    return torch.cat([x, xx, yy, rr], dim=1)
+
+
+def reference_encoder(P, pre, pcfg, cfg, mel, mask, stats_out=None):
+    """ReferenceEncoder.forward, modules.py:370-392: CoordConv2d + 5 Conv2d (stride (1, 2): time is kept), each followed
+    by BatchNorm2d with BATCH statistics (the module only ever runs in training mode) and ReLU, then a GRU over time.
+    Returns (memory [N, Ty, g], last hidden state [N, g])."""
+    c = cfg["prosody_modeling"]["liu2021"]
+    n_mel = pcfg["preprocessing"]["mel"]["n_mel_channels"]
+    stride, pad = tuple(c["ref_enc_strides"]), tuple(c["ref_enc_pad"])
+    N = mel.shape[0]
+    out = mel.reshape(N, 1, -1, n_mel)
+    for i in range(len(c["ref_enc_filters"])):
+        if i == 0:
+            out = F.conv2d(_add_coords_2d(out), P[pre + "convs.0.conv.weight"], P[pre + "convs.0.conv.bias"], stride, pad)
+        else:
+            out = F.conv2d(out, P[pre + "convs.%d.weight" % i], P[pre + "convs.%d.bias" % i], stride, pad)
+        out = _batch_norm_train(out, P, pre + "bns.%d." % i, stats_out)
+        out = F.relu(out)
+    out = out.transpose(1, 2)
+    out = out.contiguous().view(N, out.shape[1], -1)
+    if mask is not None:
+        out = out.masked_fill(mask.unsqueeze(-1), 0)
+    return _gru_direction(out, P[pre + "gru.weight_ih_l0"], P[pre + "gru.weight_hh_l0"], P[pre + "gru.bias_ih_l0"],
+                          P[pre + "gru.bias_hh_l0"], False)
+
+
+def utterance_prosody_encoder(P, pcfg, cfg, mel, mel_mask, stats_out=None):
+    """UtteranceLevelProsodyEncoder.forward, modules.py:555-569 (+ STL / StyleEmbedAttention with one head,
+    modules.py:471-533; ref_attention_dropout is dropout: identity at p = 0)."""
+    pre = "variance_adaptor.utterance_prosody_encoder."
+    E = cfg["transformer"]["encoder_hidden"]
+    _, h = reference_encoder(P, pre + "encoder.", pcfg, cfg, mel, mel_mask, stats_out)
+    query = F.linear(h, P[pre + "encoder_prj.weight"], P[pre + "encoder_prj.bias"]).unsqueeze(1)       # [N, 1, E/2]
+    tokens = torch.tanh(P[pre + "stl.embed"]).unsqueeze(0).expand(mel.shape[0], -1, -1)                # [N, tokens, E]
+    values = F.linear(tokens, P[pre + "stl.attention.W_value.weight"])
+    querys = F.linear(query, P[pre + "stl.attention.W_query.weight"])
+    keys = F.linear(tokens, P[pre + "stl.attention.W_key.weight"])
+    scores = F.softmax(torch.matmul(querys, keys.transpose(1, 2)) / (E ** 0.5), dim=2)
+    style = torch.matmul(scores, values)                                                                # [N, 1, E]
+    return F.linear(style, P[pre + "encoder_bottleneck.weight"], P[pre + "encoder_bottleneck.bias"])
+
+
+def phoneme_prosody_encoder(P, pcfg, cfg, x, src_mask, mel, mel_mask, stats_out=None):
+    """PhonemeLevelProsodyEncoder.forward, modules.py:421-450: text queries attend over the reference-encoder memory."""
+    pre = "variance_adaptor.phoneme_prosody_encoder."
+    E = cfg["transformer"]["encoder_hidden"]
+    memory, _ = reference_encoder(P, pre + "encoder.", pcfg, cfg, mel, mel_mask, stats_out)
+    emb = F.linear(memory, P[pre + "encoder_prj.weight"], P[pre + "encoder_prj.bias"])
+    k, v = torch.split(emb, E, dim=-1)
+    S, M = x.shape[1], mel.shape[1]
+    q = F.linear(x, P[pre + "linears.0.linear.weight"])
+    k = F.linear(k, P[pre + "linears.1.linear.weight"])
+    attn = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(E)
+    attn = attn.masked_fill(mel_mask.unsqueeze(1).expand(-1, S, -1), -float("inf"))
+    attn = F.softmax(attn, dim=-1)
+    attn = attn.masked_fill(src_mask.unsqueeze(-1).expand(-1, -1, M), 0.0)
+    out = F.linear(torch.bmm(attn, v), P[pre + "encoder_bottleneck.weight"], P[pre + "encoder_bottleneck.bias"])
+    return out.masked_fill(src_mask.unsqueeze(-1), 0.0), attn
 
 
 # --- unsupervised duration modelling: AlignmentEncoder + MAS -----------------------------------
@@ -417,8 +508,11 @@ def phoneme_level_energy(duration, src_len, energy_frame):
 
 def variance_adaptor(P, pcfg, cfg, tcfg, speaker_embedding, text, text_embedding, src_len, src_mask, mel, mel_len,
                      mel_mask, max_len, pitch_target, energy_target, duration_target, attn_prior,
-                     p_control, e_control, d_control, step):
-    """VarianceAdaptor.forward (prosody model 'none' or 'liu2021' in eval mode), modules.py:962-1114."""
+                     p_control, e_control, d_control, step, training=False, stats_out=None):
+    """VarianceAdaptor.forward (prosody model 'none' or 'liu2021'), modules.py:962-1114.  `training` selects the
+    reference encoders of liu2021 (modules.py:1005-1016); every dropout is the identity (parity is defined at p = 0).
+    The predictor inputs carry the reference's gradient scaling x.detach() + predictor_grad * (x - x.detach())
+    (values unchanged), so autograd through this function reproduces the reference's gradients."""
     assert cfg["prosody_modeling"]["model_type"] in ("none", "liu2021")
     assert pcfg["preprocessing"]["pitch"]["pitch_type"] == "cwt"
     learn_alignment = cfg["duration_modeling"]["learn_alignment"]
@@ -428,14 +522,19 @@ def variance_adaptor(P, pcfg, cfg, tcfg, speaker_embedding, text, text_embedding
     prosody_info = None
     if cfg["prosody_modeling"]["model_type"] == "liu2021":
         # eval mode: the predictors stand in for the reference encoders (modules.py:1002-1023)
+        u_emb = p_emb_ref = p_attn = None
+        if training:
+            u_emb = utterance_prosody_encoder(P, pcfg, cfg, mel, mel_mask, stats_out)
+            p_emb_ref, p_attn = phoneme_prosody_encoder(P, pcfg, cfg, x, src_mask, mel, mel_mask, stats_out)
         u_vec = parallel_prosody_predictor(P, cfg, "variance_adaptor.utterance_prosody_predictor.", x, False)
-        x = x + F.linear(u_vec, P["variance_adaptor.utterance_prosody_prj.weight"],
+        x = x + F.linear(u_emb if training else u_vec, P["variance_adaptor.utterance_prosody_prj.weight"],
                          P["variance_adaptor.utterance_prosody_prj.bias"])
         p_vec = parallel_prosody_predictor(P, cfg, "variance_adaptor.phoneme_prosody_predictor.", x, True)
-        x = x + F.linear(p_vec, P["variance_adaptor.phoneme_prosody_prj.weight"],
+        x = x + F.linear(p_emb_ref if training else p_vec, P["variance_adaptor.phoneme_prosody_prj.weight"],
                          P["variance_adaptor.phoneme_prosody_prj.bias"])
-        prosody_info = (None, None, u_vec, p_vec, None)
-    log_d = duration_predictor(P, cfg, x, src_mask)
+        prosody_info = (u_emb, p_emb_ref, u_vec, p_vec, p_attn)
+    g = cfg["variance_predictor"]["predictor_grad"]
+    log_d = duration_predictor(P, cfg, x.detach() + g * (x - x.detach()), src_mask)
 
     attn_soft = attn_hard = attn_hard_dur = attn_logprob = None
     if attn_prior is not None:
@@ -496,14 +595,19 @@ def variance_adaptor(P, pcfg, cfg, tcfg, speaker_embedding, text, text_embedding
 # ----------------------------------------------------------------------------------------------
 # mel head (model/CompTransTTS.py:133-135, model/modules.py:78-148)
 # ----------------------------------------------------------------------------------------------
-def postnet(P, x):
-    """PostNet.forward in eval mode (BatchNorm1d running stats, dropout off), modules.py:140-148."""
+def postnet(P, x, training=False, stats_out=None):
+    """PostNet.forward, modules.py:140-148.  Eval: BatchNorm1d running statistics.  Training: batch statistics over all
+    B x T frames, padded ones included, as the reference computes them (`stats_out` receives the updated buffers); the
+    hard-coded dropout(0.5) is the identity (parity is defined at p = 0)."""
     h = x.transpose(1, 2)
     for i in range(5):
         pre = "postnet.convolutions.%d." % i
         h = F.conv1d(h, P[pre + "0.conv.weight"], P[pre + "0.conv.bias"], padding=2)
-        h = F.batch_norm(h, P[pre + "1.running_mean"], P[pre + "1.running_var"], P[pre + "1.weight"],
-                         P[pre + "1.bias"], False, 0.1, 1e-5)
+        if training:
+            h = _batch_norm_train(h, P, pre + "1.", stats_out)
+        else:
+            h = F.batch_norm(h, P[pre + "1.running_mean"], P[pre + "1.running_var"], P[pre + "1.weight"],
+                             P[pre + "1.bias"], False, 0.1, 1e-5)
         if i < 4:
             h = torch.tanh(h)
     return h.transpose(1, 2)
@@ -514,9 +618,14 @@ def postnet(P, x):
 # ----------------------------------------------------------------------------------------------
 def comp_trans_tts_forward(P, pcfg, cfg, tcfg, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None,
                            max_mel_len=None, p_targets=None, e_targets=None, d_targets=None, attn_priors=None,
-                           spker_embeds=None, p_control=1.0, e_control=1.0, d_control=1.0, step=None, taps=None):
-    """Returns the reference's 14-tuple.  `taps`, if a dict, receives intermediate activations."""
+                           spker_embeds=None, p_control=1.0, e_control=1.0, d_control=1.0, step=None, taps=None,
+                           training=False, stats_out=None):
+    """Returns the reference's 14-tuple.  `taps`, if a dict, receives intermediate activations.
+    training=True restates model.train() with every dropout probability 0 (transformer_fs2 blocks only): PostNet
+    BatchNorm on batch statistics (`stats_out`, a dict, receives the updated running buffers), liu2021 reference
+    encoders; differentiable, so torch.autograd through it is the oracle for the backward pass."""
     block = cfg["block_type"]
+    assert not training or block == "transformer_fs2", "training-mode oracle: transformer_fs2 blocks only"
     src_masks = pad_mask_from_lengths(src_lens, max_src_len)
     mel_masks = pad_mask_from_lengths(mel_lens, max_mel_len) if mel_lens is not None else None
     if block == "transformer_fs2":
@@ -536,7 +645,7 @@ def comp_trans_tts_forward(P, pcfg, cfg, tcfg, speakers, texts, src_lens, max_sr
     (x, p_targets, p_pred, e_targets, e_pred, log_d, d_rounded, mel_lens, mel_masks, attn_outs, prosody) = \
         variance_adaptor(P, pcfg, cfg, tcfg, spk, enc, word, src_lens, src_masks, mels, mel_lens, mel_masks,
                          max_mel_len, p_targets, e_targets, d_targets, attn_priors, p_control, e_control, d_control,
-                         step)
+                         step, training, stats_out)
     if taps is not None:
         taps["decoder_in"] = x
     if block == "transformer_fs2":
@@ -547,6 +656,6 @@ def comp_trans_tts_forward(P, pcfg, cfg, tcfg, speakers, texts, src_lens, max_sr
     if taps is not None:
         taps["decoder_out"] = dec
     mel = F.linear(dec, P["mel_linear.weight"], P["mel_linear.bias"])
-    post = postnet(P, mel) + mel
+    post = postnet(P, mel, training, stats_out) + mel
     return (mel, post, p_pred, e_pred, log_d, d_rounded, src_masks, mel_masks, src_lens, mel_lens, attn_outs, prosody,
             p_targets, e_targets)

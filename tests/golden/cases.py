@@ -38,6 +38,18 @@ CASES = {
                               batch=2, s_max=40, s_step=9, pin=4, seed=9, prosody="liu2021"),
 }
 
+# Training-step cases (make_golden_train.py / test_oracle_train.py): model.train() with every dropout probability 0,
+# teacher-forced targets, a fixed scalar objective (train_objective below) and its gradients w.r.t. every parameter.
+TRAIN_CASES = {
+    "fs2_train": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="teacher",
+                      batch=3, s_max=24, s_step=5, pin=None, seed=11),
+    # liu2021: the two reference encoders (CoordConv2d stack + BatchNorm2d + GRU, STL / cross attention) only run here
+    "fs2_liu2021_train": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="teacher",
+                              batch=2, s_max=20, s_step=6, pin=None, seed=12, prosody="liu2021"),
+}
+CASES_ALL = dict(CASES, **TRAIN_CASES)
+GRAD_SAMPLES = 512   # gradient entries stored per parameter tensor (evenly strided)
+
 TAP_STRIDE = 4  # intermediate activations are stored for every 4th row only
 
 # names of the arrays stored per case (prefix "ref.")
@@ -48,7 +60,7 @@ TUPLE_NAMES = ["mel", "postnet_mel", "p_predictions", "e_predictions", "log_d_pr
 def build_case(name):
     """(configs, state_dict, batch) for a case -- importable without the reference."""
     from ctts_b200 import configs, spec, synth
-    c = CASES[name]
+    c = CASES_ALL[name]
     p, m, t = configs.builtin_configs(c["dataset"], block_type=c["block_type"], learn_alignment=c["learn_alignment"],
                                       prosody=c.get("prosody"))
     entries, _, _ = spec.parameter_spec(p, m)
@@ -93,3 +105,38 @@ def call_kwargs(batch):
     if "attn_priors" in kw:
         kw["step"] = 120000
     return args, kw
+
+
+def train_objective(out):
+    """A fixed scalar function of the differentiable outputs of the 14-tuple: every output is contracted with a
+    deterministic pseudo-random tensor (cos of an index ramp), so all parameter gradients are exercised with O(1) weights."""
+    import torch
+    flat = []
+
+    def put(v):
+        if v is None:
+            return
+        if isinstance(v, dict):
+            for k in sorted(v):
+                put(v[k])
+        elif isinstance(v, (tuple, list)):
+            for x in v:
+                put(x)
+        elif isinstance(v, torch.Tensor) and v.is_floating_point() and v.requires_grad:
+            flat.append(v)
+
+    for i in (0, 1, 2, 3, 4, 11):        # mel, postnet mel, pitch / energy / log-duration predictions, prosody info
+        put(out[i])
+    total = 0.0
+    for j, v in enumerate(flat):
+        w = torch.cos(torch.arange(v.numel(), dtype=torch.float32) * (0.37 + 0.11 * j)).reshape(v.shape)
+        total = total + (v * w).sum() / (v.numel() ** 0.5)
+    return total
+
+
+def grad_sample_index(numel):
+    """Indices (into the flattened gradient) stored in the fixtures."""
+    import numpy as np
+    if numel <= GRAD_SAMPLES:
+        return np.arange(numel)
+    return np.linspace(0, numel - 1, GRAD_SAMPLES).astype(np.int64)
