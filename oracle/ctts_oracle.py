@@ -621,18 +621,17 @@ def comp_trans_tts_forward(P, pcfg, cfg, tcfg, speakers, texts, src_lens, max_sr
                            spker_embeds=None, p_control=1.0, e_control=1.0, d_control=1.0, step=None, taps=None,
                            training=False, stats_out=None):
     """Returns the reference's 14-tuple.  `taps`, if a dict, receives intermediate activations.
-    training=True restates model.train() with every dropout probability 0 (transformer_fs2 blocks only): PostNet
+    training=True restates model.train() with every dropout probability 0: PostNet / conformer / reference-encoder
     BatchNorm on batch statistics (`stats_out`, a dict, receives the updated running buffers), liu2021 reference
     encoders; differentiable, so torch.autograd through it is the oracle for the backward pass."""
     block = cfg["block_type"]
-    assert not training or block == "transformer_fs2", "training-mode oracle: transformer_fs2 blocks only"
     src_masks = pad_mask_from_lengths(src_lens, max_src_len)
     mel_masks = pad_mask_from_lengths(mel_lens, max_mel_len) if mel_lens is not None else None
     if block == "transformer_fs2":
         enc, word = encoder_fs2(P, cfg, texts, src_masks, taps)
     else:
         from . import ctts_oracle_blocks as OB
-        enc, word = OB.ENCODERS[block](P, cfg, texts, src_masks, taps)
+        enc, word = OB.ENCODERS[block](P, cfg, texts, src_masks, taps, training=training, stats_out=stats_out)
     if taps is not None:
         taps["encoder_out"] = enc
     spk = None
@@ -652,7 +651,7 @@ def comp_trans_tts_forward(P, pcfg, cfg, tcfg, speakers, texts, src_lens, max_sr
         dec, mel_masks = decoder_fs2(P, cfg, x, mel_masks, taps)
     else:
         from . import ctts_oracle_blocks as OB
-        dec, mel_masks = OB.DECODERS[block](P, cfg, x, mel_masks, taps)
+        dec, mel_masks = OB.DECODERS[block](P, cfg, x, mel_masks, taps, training=training, stats_out=stats_out)
     if taps is not None:
         taps["decoder_out"] = dec
     mel = F.linear(dec, P["mel_linear.weight"], P["mel_linear.bias"])

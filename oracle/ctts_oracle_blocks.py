@@ -1,14 +1,23 @@
 """CPU oracle, block types other than transformer_fs2.  TEST INFRASTRUCTURE -- NOT PRODUCT (see ctts_oracle.py).
 
-Functional fp32 PyTorch restatements of model/transformers/{transformer,fastformer,conformer}.py in eval mode
-(dropout = identity, BatchNorm running statistics), over the reference's state_dict key names.
+Functional fp32 PyTorch restatements of model/transformers/{transformer,fastformer,conformer}.py (dropout = identity;
+BatchNorm on running statistics in eval mode, on batch statistics with training=True), over the reference's state_dict
+key names.
 """
 import math
 
 import torch
 import torch.nn.functional as F
 
-from .ctts_oracle import sinusoid_table_interleaved
+from .ctts_oracle import _batch_norm_train, sinusoid_table_interleaved
+
+
+def _no_truncation(training, T, cfg):
+    """In training mode the reference truncates sequences longer than max_seq_len (transformer.py:128-143 and the same
+    branch in fastformer.py / conformer.py); the training oracle restates the un-truncated case only."""
+    if training and T > cfg["max_seq_len"]:
+        raise NotImplementedError("training-mode oracle: sequence length %d > max_seq_len %d (the reference truncates)"
+                                  % (T, cfg["max_seq_len"]))
 
 
 def _abs_positions(P, key, T, d_model, max_seq_len):
@@ -55,19 +64,22 @@ def _stack_transformer(P, pre, x, pad_mask, n_layers, n_head, kernel, taps=None)
     return x
 
 
-def encoder_transformer(P, cfg, tokens, pad_mask, taps=None):
+def encoder_transformer(P, cfg, tokens, pad_mask, taps=None, training=False, stats_out=None):
     """TextEncoder.forward, transformer.py:56-83."""
     c = cfg["transformer"]
+    _no_truncation(training, tokens.shape[1], cfg)
     word = F.embedding(tokens, P["encoder.src_word_emb.weight"], padding_idx=0)
     x = word + _abs_positions(P, "encoder.position_enc", tokens.shape[1], c["encoder_hidden"], cfg["max_seq_len"])[None]
     x = _stack_transformer(P, "encoder.", x, pad_mask, c["encoder_layer"], c["encoder_head"], c["conv_kernel_size"], taps)
     return x, word
 
 
-def decoder_transformer(P, cfg, x, pad_mask, taps=None):
-    """Decoder.forward in eval mode, transformer.py:121-154 (no truncation when eval and T > max_seq_len)."""
+def decoder_transformer(P, cfg, x, pad_mask, taps=None, training=False, stats_out=None):
+    """Decoder.forward, transformer.py:121-154 (eval: no truncation when T > max_seq_len; training: see
+    _no_truncation)."""
     c = cfg["transformer"]
     T = x.shape[1]
+    _no_truncation(training, T, cfg)
     if T <= cfg["max_seq_len"]:
         x = x + P["decoder.position_enc"][0, :T][None]
     else:
@@ -122,17 +134,19 @@ def _stack_fastformer(P, pre, x, pad_mask, n_layers, d_head, kernel, taps=None):
     return x
 
 
-def encoder_fastformer(P, cfg, tokens, pad_mask, taps=None):
+def encoder_fastformer(P, cfg, tokens, pad_mask, taps=None, training=False, stats_out=None):
     c = cfg["transformer"]  # fastformer reads the `transformer` section, fastformer.py:24-34
+    _no_truncation(training, tokens.shape[1], cfg)
     word = F.embedding(tokens, P["encoder.src_word_emb.weight"], padding_idx=0)
     x = word + _abs_positions(P, "encoder.position_enc", tokens.shape[1], c["encoder_hidden"], cfg["max_seq_len"])[None]
     d_head = c["encoder_hidden"] // c["encoder_head"]
     return _stack_fastformer(P, "encoder.", x, pad_mask, c["encoder_layer"], d_head, c["conv_kernel_size"], taps), word
 
 
-def decoder_fastformer(P, cfg, x, pad_mask, taps=None):
+def decoder_fastformer(P, cfg, x, pad_mask, taps=None, training=False, stats_out=None):
     c = cfg["transformer"]
     T = x.shape[1]
+    _no_truncation(training, T, cfg)
     x = x + _abs_positions(P, "decoder.position_enc", T, c["decoder_hidden"], cfg["max_seq_len"])[None]
     d_head = c["decoder_hidden"] // c["decoder_head"]
     return _stack_fastformer(P, "decoder.", x, pad_mask, c["decoder_layer"], d_head, c["conv_kernel_size"], taps), pad_mask
@@ -149,8 +163,9 @@ def _rel_shift(s):
     return p[:, :, 1:].reshape(B, H, T1, T2)
 
 
-def _conformer_block(P, pre, x, pos, n_head, kernel):
-    """ConformerBlock.sequential, conformer.py:205-246 (no attention mask is passed: :242-246)."""
+def _conformer_block(P, pre, x, pos, n_head, kernel, training=False, stats_out=None):
+    """ConformerBlock.sequential, conformer.py:205-246 (no attention mask is passed: :242-246).  training: the conv
+    module's BatchNorm1d uses batch statistics over all B x T positions (padded ones included); dropout = identity."""
     B, T, C = x.shape
     dh = C // n_head
 
@@ -178,8 +193,11 @@ def _conformer_block(P, pre, x, pos, n_head, kernel):
     o, g = h.chunk(2, dim=1)
     h = o * torch.sigmoid(g)
     h = F.conv1d(h, P[c + "4.conv.weight"], None, padding=(kernel - 1) // 2, groups=C)
-    h = F.batch_norm(h, P[c + "5.running_mean"], P[c + "5.running_var"], P[c + "5.weight"], P[c + "5.bias"], False, 0.1,
-                     1e-5)
+    if training:
+        h = _batch_norm_train(h, P, c + "5.", stats_out)
+    else:
+        h = F.batch_norm(h, P[c + "5.running_mean"], P[c + "5.running_var"], P[c + "5.weight"], P[c + "5.bias"], False,
+                         0.1, 1e-5)
     h = h * torch.sigmoid(h)
     h = F.conv1d(h, P[c + "7.conv.weight"], P[c + "7.conv.bias"]).transpose(1, 2)
     x = h + x
@@ -187,33 +205,36 @@ def _conformer_block(P, pre, x, pos, n_head, kernel):
     return F.layer_norm(x, (C,), P[pre + "sequential.4.weight"], P[pre + "sequential.4.bias"], 1e-5)
 
 
-def _stack_conformer(P, pre, x, pad_mask, n_layers, n_head, kernel, d_model, max_seq_len, taps=None):
+def _stack_conformer(P, pre, x, pad_mask, n_layers, n_head, kernel, d_model, max_seq_len, taps=None, training=False,
+                     stats_out=None):
     keep = (~pad_mask)[:, :, None]
     T = x.shape[1]
     for i in range(n_layers):
         lp = "%slayer_stack.%d." % (pre, i)
         pos = _abs_positions(P, lp + "sequential.1.module.positional_encoding", T, d_model, max_seq_len)[None]
-        x = _conformer_block(P, lp, x, pos, n_head, kernel) * keep
+        x = _conformer_block(P, lp, x, pos, n_head, kernel, training, stats_out) * keep
         if taps is not None:
             taps["%slayer_stack.%d" % (pre, i)] = x
     return x
 
 
-def encoder_conformer(P, cfg, tokens, pad_mask, taps=None):
+def encoder_conformer(P, cfg, tokens, pad_mask, taps=None, training=False, stats_out=None):
     c = cfg["conformer"]
+    _no_truncation(training, tokens.shape[1], cfg)
     word = F.embedding(tokens, P["encoder.src_word_emb.weight"], padding_idx=0)
     x = word + _abs_positions(P, "encoder.position_enc", tokens.shape[1], c["encoder_hidden"], cfg["max_seq_len"])[None]
     x = _stack_conformer(P, "encoder.", x, pad_mask, c["encoder_layer"], c["encoder_head"], c["conv_kernel_size"],
-                         c["encoder_hidden"], cfg["max_seq_len"], taps)
+                         c["encoder_hidden"], cfg["max_seq_len"], taps, training, stats_out)
     return x, word
 
 
-def decoder_conformer(P, cfg, x, pad_mask, taps=None):
+def decoder_conformer(P, cfg, x, pad_mask, taps=None, training=False, stats_out=None):
     c = cfg["conformer"]
     T = x.shape[1]
+    _no_truncation(training, T, cfg)
     x = x + _abs_positions(P, "decoder.position_enc", T, c["decoder_hidden"], cfg["max_seq_len"])[None]
     x = _stack_conformer(P, "decoder.", x, pad_mask, c["decoder_layer"], c["decoder_head"], c["conv_kernel_size"],
-                         c["decoder_hidden"], cfg["max_seq_len"], taps)
+                         c["decoder_hidden"], cfg["max_seq_len"], taps, training, stats_out)
     return x, pad_mask
 
 

@@ -46,6 +46,13 @@ TRAIN_CASES = {
     # liu2021: the two reference encoders (CoordConv2d stack + BatchNorm2d + GRU, STL / cross attention) only run here
     "fs2_liu2021_train": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="teacher",
                               batch=2, s_max=20, s_step=6, pin=None, seed=12, prosody="liu2021"),
+    # the other block types: dropout aside, training differs from eval in PostNet's (and conformer's) BatchNorm only
+    "transformer_train": dict(dataset="LJSpeech", block_type="transformer", learn_alignment=False, mode="teacher",
+                              batch=2, s_max=20, s_step=6, pin=None, seed=13),
+    "fastformer_train": dict(dataset="LJSpeech", block_type="fastformer", learn_alignment=False, mode="teacher",
+                             batch=2, s_max=20, s_step=6, pin=None, seed=14),
+    "conformer_train": dict(dataset="LJSpeech", block_type="conformer", learn_alignment=False, mode="teacher",
+                            batch=2, s_max=20, s_step=6, pin=None, seed=15),
 }
 CASES_ALL = dict(CASES, **TRAIN_CASES)
 GRAD_SAMPLES = 512   # gradient entries stored per parameter tensor (evenly strided)

@@ -10,7 +10,8 @@ deterministic / runnable here (neither touches its arithmetic):
   * torch.Tensor.cuda -> identity: coordconv.py:28,63 tests `torch.cuda.is_available` (the function object, always
     true) and moves tensors to the GPU unconditionally, which cannot work in a CPU-only container.
 Stored per case: the 14-tuple of the forward, the value of cases.train_objective, GRAD_SAMPLES strided entries of its
-gradient w.r.t. every parameter (plus each gradient's L2 norm), and the BatchNorm buffers after the step.
+gradient w.r.t. every parameter (plus each gradient's L2 norm and which parameters are frozen), and the BatchNorm
+buffers after the step.
 """
 import os
 import sys
@@ -60,6 +61,8 @@ def run_reference(name):
         gf = g.detach().reshape(-1)
         flat["grad." + k] = gf[torch.from_numpy(cases.grad_sample_index(gf.numel()))].numpy()
         flat["gnorm." + k] = np.float64(gf.double().norm().item())
+        if not prm.requires_grad:
+            flat["frozen." + k] = np.int8(1)      # nn.Parameter(requires_grad=False): sinusoid tables, bucket edges
     for k, buf in net.named_buffers():
         if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
             flat["buf." + k] = buf.detach().numpy().copy()

@@ -14,10 +14,14 @@ import cases  # noqa: E402
 from oracle import ctts_oracle as O  # noqa: E402
 
 
-def run_oracle_train(name):
+def run_oracle_train(name, frozen=()):
     (p, m, t), sd, batch = cases.build_case(name)
-    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
-         for k, v in sd.items()}
+    P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k and k not in frozen
+             else v.clone()) for k, v in sd.items()}
+    from ctts_b200 import spec
+    for k, _, _, init in spec.parameter_spec(p, m)[0]:     # tied entries are ONE tensor under several names, as in the
+        if init.startswith("tie:"):                        # reference, so its gradient accumulates over all uses
+            P[k] = P[init[4:]]
     args, kw = cases.call_kwargs(batch)
     stats = {}
     out = O.comp_trans_tts_forward(P, p, m, t, *args, training=True, stats_out=stats, **kw)
@@ -29,7 +33,8 @@ def run_oracle_train(name):
 @pytest.mark.parametrize("name", sorted(cases.TRAIN_CASES))
 def test_training_oracle_matches_reference(name, golden_dir):
     gold = np.load(os.path.join(golden_dir, name + ".npz"))
-    P, out, loss, stats = run_oracle_train(name)
+    frozen = {k[7:] for k in gold.files if k.startswith("frozen.")}
+    P, out, loss, stats = run_oracle_train(name, frozen)
     flat = cases.flatten_outputs(out)
     n_out = 0
     for key in gold.files:
@@ -63,7 +68,7 @@ def test_training_oracle_matches_reference(name, golden_dir):
         assert abs(float(gf.double().norm()) - norm) <= 1e-3 * norm + 1e-6, "gradient norm of " + k
         n_grad += 1
         n_nonzero += int(norm > 0)
-    assert n_grad >= 150 and n_nonzero >= n_grad - 8
+    assert n_grad >= 150 and n_nonzero >= n_grad - len(frozen) - 6   # frozen tables, unused CoordConv parent tensors
 
     # BatchNorm buffers after the step
     n_buf = 0
@@ -86,3 +91,16 @@ def test_training_oracle_is_the_eval_oracle_apart_from_batchnorm():
         b = O.comp_trans_tts_forward(sd, p, m, t, *cases.call_kwargs(batch)[0], training=True, **cases.call_kwargs(batch)[1])
     assert torch.equal(a[0], b[0]) and torch.equal(a[4], b[4])
     assert (a[1] - b[1]).abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize("name", sorted(cases.TRAIN_CASES))
+def test_drop_in_module_freezes_what_the_reference_freezes(name, golden_dir):
+    """requires_grad flags of the drop-in module's parameters == the reference's (sinusoid tables and bucket edges are
+    nn.Parameter(requires_grad=False) there): an optimizer built over model.parameters() must see the same set."""
+    import ctts_b200
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    frozen = {k[7:] for k in gold.files if k.startswith("frozen.")}
+    (p, m, t), _, _ = cases.build_case(name)
+    net = ctts_b200.CompTransTTS(p, m, t)
+    mine = {k for k, prm in net.named_parameters(remove_duplicate=False) if not prm.requires_grad}
+    assert mine == frozen
