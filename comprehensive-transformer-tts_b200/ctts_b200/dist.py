@@ -39,3 +39,77 @@ def sum_over_ranks(value, device, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Training step: the one real exchange of the path is the gradient all-reduce of data-parallel
+# training (the reference wraps the model in nn.DataParallel, train.py:38; one process per GPU replaces it).  Host logic
+# only -- it runs on whatever backend the process group has (NCCL over NVLink on GPUs, gloo in tests/test_dist_gloo.py).
+class GradientBuckets:
+    """Flat fp32 buckets over the trainable parameters, filled in REVERSE registration order (the order in which backward
+    produces gradients, so the first bucket is complete first and its all-reduce can overlap the rest of backward).
+
+    * a Parameter registered under several names (tied: fastformer logits, conformer positional encodings) enters once;
+    * frozen parameters (requires_grad False: sinusoid tables, bucket edges) are skipped;
+    * a parameter whose .grad is None on this rank contributes zeros, so every rank issues identical collectives.
+    """
+
+    def __init__(self, parameters, bucket_bytes=25 << 20):
+        seen, params = set(), []
+        for prm in parameters:
+            if prm.requires_grad and id(prm) not in seen:
+                seen.add(id(prm))
+                params.append(prm)
+        params.reverse()
+        self.buckets, cur, size = [], [], 0
+        for prm in params:
+            n = prm.numel() * 4
+            if cur and size + n > bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(prm)
+            size += n
+        if cur:
+            self.buckets.append(cur)
+        self._flat = [None] * len(self.buckets)
+        self._work = [None] * len(self.buckets)
+
+    def launch(self, index, world):
+        """Pack bucket `index` and start its (asynchronous) SUM all-reduce."""
+        bucket = self.buckets[index]
+        dev = bucket[0].device
+        flat = torch.zeros(sum(p.numel() for p in bucket), device=dev, dtype=torch.float32)
+        off = 0
+        for p in bucket:
+            if p.grad is not None:
+                flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+            off += p.numel()
+        self._flat[index] = flat
+        self._work[index] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
+
+    def finish(self, world):
+        """Wait for every launched bucket, divide by the world size and write the averaged gradients back."""
+        for i, bucket in enumerate(self.buckets):
+            if self._flat[i] is None:
+                self.launch(i, world)
+            if self._work[i] is not None:
+                self._work[i].wait()
+            flat = self._flat[i] / world
+            off = 0
+            for p in bucket:
+                g = flat[off:off + p.numel()].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += p.numel()
+            self._flat[i] = self._work[i] = None
+
+
+def allreduce_gradients(parameters, world, bucket_bytes=25 << 20):
+    """Average .grad over the ranks (call after backward): the non-overlapped form of GradientBuckets."""
+    gb = GradientBuckets(parameters, bucket_bytes)
+    for i in range(len(gb.buckets)):
+        gb.launch(i, world)
+    gb.finish(world)
+    return len(gb.buckets)
