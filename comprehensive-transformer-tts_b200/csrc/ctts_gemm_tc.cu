@@ -7,14 +7,22 @@
 // operands are stored as two bf16 planes (x = hi + lo, hi = rn(x), lo = rn(x - hi); 16 mantissa bits) and each
 // k-slice issues three kind::f16 MMAs into the same FP32 TMEM accumulator:  hi*hi + hi*lo + lo*hi.
 //
-// Structure (one 128 x BLOCK_N output tile per CTA, 192 threads):
+// "bf16x6" (encoder, predictors: everything upstream of a quantiser) uses three planes per operand, six MMAs per k-slice
+// and four TMEM accumulators (see gemm_split_kernel).
+//
+// Structure of every kernel in this file (128-row tiles, 320 threads):
 //   warp 0      TMA producer: A tiles from a 3-D tensor map over [B, T, Cin] -- the conv halo (t < 0, t >= T) and
-//               the channel tail are produced by TMA out-of-bounds zero fill -- and W tiles from a 2-D map over
+//               the channel tail are produced by TMA out-of-bounds zero fill -- and W tiles from a map over
 //               [N, taps*Cin]; SWIZZLE_128B; STAGES-deep mbarrier ring.
-//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BLOCK_N, K=16), tcgen05.commit to free
-//               smem stages and to publish the accumulator.
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / scale / folded-BN / activation /
-//               residual / pad-mask, stores fp32 and (optionally) the bf16 hi/lo planes the next GEMM consumes.
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (M=128 or 256 for a CTA pair, N=BLOCK_N, K=16),
+//               tcgen05.commit to free smem stages and to publish the accumulator.
+//   warps 2-9   epilogue: tcgen05.ld, transpose through shared memory so that global accesses are whole rows, bias /
+//               scale / folded-BN / activation / residual / pad-mask, stores fp32 and (optionally) the bf16 planes the
+//               next GEMM consumes.
+// Variants: gemm_split_kernel (one tile per CTA; 2 or 3 planes; optional weight multicast over a 2-CTA cluster),
+// gemm_persistent_kernel (one CTA per SM loops over tiles, double-buffered TMEM accumulator), gemm_pair_kernel (the same
+// with tcgen05.mma.cta_group::2: a 256 x 256 tile per CTA pair).  launch_auto() picks by shape; profiles/README.md has
+// the measurements behind its rules.
 #include "ctts_common.cuh"
 
 #include <cuda.h>
