@@ -53,6 +53,13 @@ TRAIN_CASES = {
                              batch=2, s_max=20, s_step=6, pin=None, seed=14),
     "conformer_train": dict(dataset="LJSpeech", block_type="conformer", learn_alignment=False, mode="teacher",
                             batch=2, s_max=20, s_step=6, pin=None, seed=15),
+    # unsupervised duration modelling in training (BASELINE configs[2] family: learn_alignment True): before
+    # binarization_start_steps the decoder input is the SOFT alignment bmm(attn_soft, x) and gradients flow through the
+    # aligner; afterwards MAS durations (no gradient through the hard path) drive the length regulator
+    "fs2_unsup_train_soft": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=True, mode="unsup",
+                                 batch=2, s_max=16, s_step=5, pin=None, seed=16, step=100),
+    "conformer_unsup_train": dict(dataset="LJSpeech", block_type="conformer", learn_alignment=True, mode="unsup",
+                                  batch=2, s_max=16, s_step=5, pin=None, seed=17, step=120000),
 }
 CASES_ALL = dict(CASES, **TRAIN_CASES)
 GRAD_SAMPLES = 512   # gradient entries stored per parameter tensor (evenly strided)
@@ -102,7 +109,7 @@ def flatten_outputs(out):
     return flat
 
 
-def call_kwargs(batch):
+def call_kwargs(batch, step=None):
     """Positional / keyword arguments of CompTransTTS.forward from a synth batch (deep-copied targets)."""
     import copy
     b = copy.deepcopy(batch)
@@ -110,7 +117,7 @@ def call_kwargs(batch):
     kw = {k: b[k] for k in ("mels", "mel_lens", "max_mel_len", "p_targets", "e_targets", "d_targets", "attn_priors",
                             "spker_embeds") if k in b}
     if "attn_priors" in kw:
-        kw["step"] = 120000
+        kw["step"] = 120000 if step is None else step
     return args, kw
 
 
@@ -132,7 +139,8 @@ def train_objective(out):
         elif isinstance(v, torch.Tensor) and v.is_floating_point() and v.requires_grad:
             flat.append(v)
 
-    for i in (0, 1, 2, 3, 4, 11):        # mel, postnet mel, pitch / energy / log-duration predictions, prosody info
+    for i in (0, 1, 2, 3, 4, 10, 11):    # mel, postnet mel, pitch / energy / log-duration predictions, aligner
+        # outputs (attn_soft, attn_logprob: what the reference's CTC / binarisation losses read), prosody info
         put(out[i])
     total = 0.0
     for j, v in enumerate(flat):

@@ -42,7 +42,7 @@ def run_reference(name):
     net = ref_model.CompTransTTS(rp, rm, rt)
     net.load_state_dict(sd, strict=True)
     net.train()
-    args, kw = cases.call_kwargs(batch)
+    args, kw = cases.call_kwargs(batch, c.get("step"))
     orig_dropout, orig_cuda = F.dropout, torch.Tensor.cuda
     F.dropout = lambda input, p=0.5, training=True, inplace=False: input
     torch.Tensor.cuda = lambda self, *a, **k: self

@@ -22,7 +22,7 @@ def run_oracle_train(name, frozen=()):
     for k, _, _, init in spec.parameter_spec(p, m)[0]:     # tied entries are ONE tensor under several names, as in the
         if init.startswith("tie:"):                        # reference, so its gradient accumulates over all uses
             P[k] = P[init[4:]]
-    args, kw = cases.call_kwargs(batch)
+    args, kw = cases.call_kwargs(batch, cases.TRAIN_CASES[name].get("step"))
     stats = {}
     out = O.comp_trans_tts_forward(P, p, m, t, *args, training=True, stats_out=stats, **kw)
     loss = cases.train_objective(out)
