@@ -60,6 +60,9 @@ TRAIN_CASES = {
                                  batch=2, s_max=16, s_step=5, pin=None, seed=16, step=100),
     "conformer_unsup_train": dict(dataset="LJSpeech", block_type="conformer", learn_alignment=True, mode="unsup",
                                   batch=2, s_max=16, s_step=5, pin=None, seed=17, step=120000),
+    # BASELINE configs[3] family: fastformer, VCTK (DeepSpeaker embeddings -> Linear, speaker-conditioned aligner)
+    "fastformer_vctk_unsup_train": dict(dataset="VCTK", block_type="fastformer", learn_alignment=True, mode="unsup",
+                                        batch=2, s_max=14, s_step=4, pin=None, seed=18, step=120000),
 }
 CASES_ALL = dict(CASES, **TRAIN_CASES)
 GRAD_SAMPLES = 512   # gradient entries stored per parameter tensor (evenly strided)
