@@ -21,9 +21,14 @@ needed), and `tests/test_oracle_vs_reference.py` re-checks against the live refe
 `/root/reference` exists.
 
 Scope: block types transformer_fs2 / transformer / fastformer / conformer (the latter three in
-ctts_oracle_blocks.py); prosody "none" and "liu2021" (eval mode: predictors); inference
-(free-running), supervised teacher-forced, and unsupervised (aligner + MAS) branches of the
-VarianceAdaptor.  Dropout is identity (eval mode); BatchNorm uses running statistics.
+ctts_oracle_blocks.py); prosody "none" and "liu2021" (eval mode: predictors; training mode: the
+reference encoders); inference (free-running), supervised teacher-forced, and unsupervised
+(aligner + MAS) branches of the VarianceAdaptor.  Eval mode: dropout is identity, BatchNorm uses
+running statistics.  `training=True` restates model.train() with every dropout probability 0
+(BatchNorm on batch statistics); it is differentiable, and torch.autograd through it is the oracle
+for the backward pass -- pinned the same way by tests/golden/make_golden_train.py /
+tests/test_oracle_train.py (outputs, gradients of a fixed objective w.r.t. every parameter,
+BatchNorm buffers after the step).
 """
 import math
 
