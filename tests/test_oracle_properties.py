@@ -73,3 +73,39 @@ def test_mas_finds_the_best_monotonic_path(M, S, seed):
     score = np.log(a)[np.arange(M), cols].sum()
     best = max(np.log(a)[np.arange(M), p].sum() for p in _all_monotonic_paths(M, S))
     assert score >= best - 1e-4
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(min_value=2, max_value=5), st.integers(min_value=1, max_value=6), st.integers(min_value=2, max_value=9),
+       st.booleans(), st.integers(min_value=0, max_value=10**6))
+def test_batch_norm_train_is_torch_batchnorm_in_training_mode(n, c, t, two_d, seed):
+    """_batch_norm_train (training-mode oracle): output AND the buffers left behind equal nn.BatchNorm1d / 2d .train()."""
+    g = torch.Generator().manual_seed(seed)
+    shape = (n, c, t, 3) if two_d else (n, c, t)
+    x = torch.randn(*shape, generator=g) * 2 + 0.5
+    bn = (torch.nn.BatchNorm2d if two_d else torch.nn.BatchNorm1d)(c)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(c, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(c, generator=g))
+        bn.running_mean.copy_(torch.randn(c, generator=g))
+        bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+    P = {"bn." + k: v.clone() for k, v in bn.state_dict().items()}
+    stats = {}
+    got = O._batch_norm_train(x, P, "bn.", stats)
+    want = bn.train()(x)
+    assert torch.allclose(got, want, atol=1e-6, rtol=1e-5)
+    after = bn.state_dict()
+    for k in ("running_mean", "running_var"):
+        assert torch.allclose(stats["bn." + k], after[k], atol=1e-6, rtol=1e-5), k
+    assert int(stats["bn.num_batches_tracked"]) == int(after["num_batches_tracked"]) == 1
+
+
+def test_coord_channels_follow_the_reference_convention():
+    """coordconv.py:36-71 with with_r: [input, row coordinate, column coordinate, radius from (0.5, 0.5)], coordinates in
+    [-1, 1] (first / last row and column exactly -1 / +1)."""
+    x = torch.zeros(2, 1, 5, 4)
+    y = O._add_coords_2d(x)
+    assert y.shape == (2, 4, 5, 4)
+    assert torch.equal(y[:, 1, 0], torch.full((2, 4), -1.0)) and torch.equal(y[:, 1, -1], torch.full((2, 4), 1.0))
+    assert torch.equal(y[:, 2, :, 0], torch.full((2, 5), -1.0)) and torch.equal(y[:, 2, :, -1], torch.full((2, 5), 1.0))
+    assert torch.allclose(y[0, 3, 0, 0], torch.tensor((1.5 ** 2 * 2) ** 0.5))
