@@ -91,4 +91,33 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Positions of rows [r0, r1) of one utterance, by the whole CTA: pos[t] = flag(t) ? #flags in [0, t] : 0
+// (make_positions, utils/tools.py:640-652, with padding_idx 0).  Every warp ballots 32-row chunks of [0, r1) into
+// s_mask; each row then sums the popcounts of the chunks before its own.  r1 <= 32 * POS_MAXCH.
+constexpr int POS_MAXCH = 512;
+template <class F>
+__device__ __forceinline__ void block_positions(int r0, int r1, int* s_pos, unsigned* s_mask, F flag) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int nch = (r1 + 31) >> 5;
+    for (int ch = warp; ch < nch; ch += nw) {
+        const int t = ch * 32 + lane;
+        const bool f = (t < r1) && flag(t);
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_mask[ch] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < r1 - r0; i += blockDim.x) {
+        const int t = r0 + i, ch = t >> 5, l = t & 31;
+        const unsigned m = s_mask[ch];
+        int p = 0;
+        if ((m >> l) & 1u) {
+            p = __popc(m & (0xffffffffu >> (31 - l)));
+            for (int c = 0; c < ch; ++c) p += __popc(s_mask[c]);
+        }
+        s_pos[i] = p;
+    }
+    __syncthreads();
+}
+
 }  // namespace ctts

@@ -68,6 +68,10 @@ struct Addr {
     int lens_div;             // pad-mask length = lens[z / lens_div]
     int ldy;                  // output row stride (elements)
     long long y_outer, y_inner;  // output offset = (z / mod)*y_outer + (z % mod)*y_inner + t*ldy + n
+    // K-batched mode (kz > 0; gemm_split_kernel only): the reduction runs over kz operand batches of `Cin` elements each
+    // (a weight gradient: k = (utterance, time)); A tile coords (k + a_ks0 + z*a_kstep, t, kbatch), W tile coords
+    // (k, n, kbatch).  z then only selects the K shift (the conv tap) and the output offset.
+    int kz, a_ks0, a_kstep;
 };
 
 template <int BLOCK_N>
@@ -210,7 +214,7 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     const int zh = z % ad.mod;
     const int n0 = blockIdx.y * BLOCK_N;
     const int kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
-    const int num_kb = taps * kb_per_tap;
+    const int num_kb = (ad.kz > 0 ? ad.kz : taps) * kb_per_tap;
     const int pad = taps >> 1;
 
     if (warp == 0 && lane == 0) {
@@ -258,6 +262,15 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                 const int tap = kb / kb_per_tap;
                 const int c0 = (kb - tap * kb_per_tap) * BLOCK_K;
                 uint8_t* st = smem + s * S::STAGE_BYTES;
+                if (ad.kz > 0) {   // K-batched: `tap` is the operand batch, the K shift comes from z
+                    const int ka = c0 + ad.a_ks0 + z * ad.a_kstep;
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES, ka, t0, tap);
+                        tma_load_3d(&tm.w[p], &full_bar[s], st + NP * A_TILE_BYTES + p * S::B_TILE_BYTES, c0, n0, tap);
+                    }
+                    continue;
+                }
                 const int ca = ad.a_c0 + zh * ad.a_step + c0, za = z / ad.a_div;
                 const int cw = ad.w_c0 + zh * ad.w_step + tap * Cin + c0, zw = z / ad.w_div;
 #pragma unroll
@@ -1388,6 +1401,71 @@ extern "C" int ctts_transpose_v_planes(int n_planes, const void* const* qkv_plan
     if (n_planes == 3) launch_transpose_v<3>(qc, T, Tp, C, H, DH, B * H, vw, (cudaStream_t)stream);
     else launch_transpose_v<2>(qc, T, Tp, C, H, DH, B * H, vw, (cudaStream_t)stream);
     return check_launch("transpose_v_planes");
+}
+
+// ---- weight gradient on the tensor cores ------------------------------------------------------------------------
+//   dw[n, tap*Cin + c] (+)= alpha * sum_{b,t} dz[b, t, n] * x[b, t + tap - taps/2, c]
+// Both operands come TRANSPOSED (time contiguous: ctts_split_transpose) so that the reduction index is the K-major one:
+//   dzT planes [B, N, Tp], xT planes [B, Cin, Tp] (Tp = T rounded up to 8; only t < T is read, the rest is TMA zero fill).
+// One 128 x 128 tile of dw per CTA; the K loop runs over all B utterances x ceil(T/64) blocks; the tap offset is a shift of
+// the dzT K coordinate (out-of-range columns are zero fill, which is exactly the conv's zero padding).
+extern "C" int ctts_gemm_wgrad(int n_planes, const void* const* dzT_planes, const void* const* xT_planes, int B, int T, int Tp,
+                               int Cin, int N, int taps, float alpha, int accumulate, float* dw_packed, void* stream) {
+    CTTS_REQUIRE(n_planes == 2 || n_planes == 3, "gemm_wgrad: n_planes must be 2 or 3");
+    CTTS_REQUIRE(dzT_planes && xT_planes && dw_packed, "gemm_wgrad: NULL argument");
+    CTTS_REQUIRE(B > 0 && T > 0 && Tp >= T && Tp % 8 == 0 && N > 0 && Cin > 0 && Cin % 4 == 0 && taps >= 1 && (taps & 1),
+                 "gemm_wgrad: bad shape B=%d T=%d Tp=%d Cin=%d N=%d taps=%d", B, T, Tp, Cin, N, taps);
+    Operand A{{nullptr, nullptr, nullptr}, (cuuint64_t)T, (cuuint64_t)N, (cuuint64_t)B, (cuuint64_t)Tp, (cuuint64_t)N * Tp};
+    Operand W{{nullptr, nullptr, nullptr}, (cuuint64_t)T, (cuuint64_t)Cin, (cuuint64_t)B, (cuuint64_t)Tp, (cuuint64_t)Cin * Tp};
+    for (int p = 0; p < n_planes; ++p) {
+        CTTS_REQUIRE(dzT_planes[p] && xT_planes[p], "gemm_wgrad: NULL operand plane %d", p);
+        CTTS_REQUIRE((((uintptr_t)dzT_planes[p] | (uintptr_t)xT_planes[p]) & 15) == 0, "gemm_wgrad: planes must be 16-byte aligned");
+        A.p[p] = dzT_planes[p];
+        W.p[p] = xT_planes[p];
+    }
+    Epilogue ep{nullptr, nullptr, nullptr, accumulate ? dw_packed : nullptr, nullptr, dw_packed, {nullptr, nullptr, nullptr},
+                alpha, CTTS_ACT_NONE, nullptr};
+    // z = tap: K shift of the dzT operand = -(tap - taps/2); output columns start at tap*Cin
+    Addr ad{1, 1, 0, 0, 1, 0, 0, 1, taps * Cin, (long long)Cin, 0, B, taps / 2, -1};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_planes == 3) return launch<128, 2, 3, 1>(A, W, ep, ad, taps, N, T, Cin, 1, st, 0);
+    return launch<128, 3, 2, 1>(A, W, ep, ad, taps, N, T, Cin, 1, st, 0);
+}
+
+// ---- batched plane GEMM with explicit operand views (the products of the attention backward) ---------------------------
+//   y[z][t, n] = alpha * sum_k A[z][t, k] * W[z][n, k]        z = zo*mod + zh in [0, Z)
+// Operands are 3-D views [d2][d1][d0] of bf16 planes (d0 = k contiguous); a_view / w_view = {d0, d1, d2, s1, s2} in elements.
+// addr = {mod, a_div, a_c0, a_step, w_div, w_c0, w_step, lens_div, ldy}: tile coordinates as in `Addr` above;
+// output offset = (z / mod) * y_outer + (z % mod) * y_inner + t * ldy + n.  residual (nullable) is added (same addressing
+// as y: pass y itself to accumulate).
+extern "C" int ctts_gemm_batched_planes(int n_planes, const void* const* a_planes, const long long* a_view,
+                                        const void* const* w_planes, const long long* w_view, const int* addr,
+                                        long long y_outer, long long y_inner, float alpha, const float* residual,
+                                        const int64_t* lens, int Z, int T, int K, int N, float* y, void* const* y_planes,
+                                        void* stream) {
+    CTTS_REQUIRE(n_planes == 2 || n_planes == 3, "gemm_batched_planes: n_planes must be 2 or 3");
+    CTTS_REQUIRE(a_planes && w_planes && a_view && w_view && addr, "gemm_batched_planes: NULL argument");
+    CTTS_REQUIRE(Z > 0 && T > 0 && K > 0 && N > 0 && N % 4 == 0, "gemm_batched_planes: bad shape Z=%d T=%d K=%d N=%d", Z, T, K, N);
+    CTTS_REQUIRE(a_view[3] % 8 == 0 && a_view[4] % 8 == 0 && w_view[3] % 8 == 0 && w_view[4] % 8 == 0,
+                 "gemm_batched_planes: strides must be multiples of 8 elements (16 bytes)");
+    CTTS_REQUIRE(y || (y_planes && y_planes[0]), "gemm_batched_planes: no output requested");
+    Operand A{{nullptr, nullptr, nullptr}, (cuuint64_t)a_view[0], (cuuint64_t)a_view[1], (cuuint64_t)a_view[2],
+              (cuuint64_t)a_view[3], (cuuint64_t)a_view[4]};
+    Operand W{{nullptr, nullptr, nullptr}, (cuuint64_t)w_view[0], (cuuint64_t)w_view[1], (cuuint64_t)w_view[2],
+              (cuuint64_t)w_view[3], (cuuint64_t)w_view[4]};
+    Epilogue ep{nullptr, nullptr, nullptr, residual, lens, y, {nullptr, nullptr, nullptr}, alpha, CTTS_ACT_NONE, nullptr};
+    for (int p = 0; p < n_planes; ++p) {
+        CTTS_REQUIRE(a_planes[p] && w_planes[p], "gemm_batched_planes: NULL operand plane %d", p);
+        A.p[p] = a_planes[p];
+        W.p[p] = w_planes[p];
+        if (y_planes && y_planes[0]) {
+            CTTS_REQUIRE(y_planes[p], "gemm_batched_planes: NULL output plane %d", p);
+            ep.yp[p] = (__nv_bfloat16*)y_planes[p];
+        }
+    }
+    Addr ad{addr[0], addr[1], addr[2], addr[3], addr[4], addr[5], addr[6], addr[7], addr[8], y_outer, y_inner, 0, 0, 0};
+    CTTS_REQUIRE(ad.mod > 0 && ad.a_div > 0 && ad.w_div > 0 && ad.lens_div > 0, "gemm_batched_planes: bad addressing");
+    return launch_auto(n_planes, A, W, ep, ad, Z, T, K, N, 1, (cudaStream_t)stream);
 }
 
 /* development aid: per-CTA cycle stamps of the next ctts_gemm_split launches (4 x int64 per CTA); NULL disables */

@@ -56,6 +56,36 @@ SIGNATURES = {
     "ctts_debug_set_timing_buffer": [_P],
     "ctts_split_bf16": [_P, _Z, _P, _P, _P],
     "ctts_layernorm_split": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _P, _P, _P],
+    # ---- training step (include/ctts_b200.h, "TRAINING STEP") ----
+    "ctts_gemm_generic": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    "ctts_act_bwd": [_P, _P, _I, _F, _P, _I, _I, _I, _I, _P, _P, _P],
+    "ctts_layernorm_bwd": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _I, _P, _P, _P],
+    "ctts_mask_rows": [_P, _P, _I, _I, _I, _P],
+    "ctts_axpy": [_P, _F, _Z, _I, _P, _P],
+    "ctts_rowscale_axpy": [_P, _P, _F, _I, _I, _I, _P, _P],
+    "ctts_scatter_add_rows": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P],
+    "ctts_length_expand_bwd": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "ctts_add_positions_bwd": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "ctts_masked_softmax": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "ctts_softmax_bwd": [_P, _P, _I, _I, _I, _I, _F, _P, _P],
+    "ctts_bn_stats": [_P, _I, _I, _P, _P, _P],
+    "ctts_bn_act_fwd": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _I, _P, _P],
+    "ctts_bn_update_running": [_P, _P, _I, _F, _I, _P, _P, _P, _P],
+    "ctts_bn_bwd": [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ctts_dropout": [_P, _Z, _F, ctypes.c_ulonglong, ctypes.c_ulonglong, _P, _P],
+    "ctts_pack_conv_weight_dgrad": [_P, _I, _I, _I, _P, _P],
+    "ctts_unpack_conv_wgrad": [_P, _I, _I, _I, _I, _P, _P],
+    "ctts_split_transpose": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "ctts_gemm_wgrad": [_I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P],
+    "ctts_gemm_batched_planes": [_I, _P, _P, _P, _P, _P, _L, _L, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "ctts_aligner_attention_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
+    "ctts_glu_bwd": [_P, _P, _I, _I, _P, _P],
+    "ctts_dwconv": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "ctts_dwconv_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "ctts_relshift_bwd": [_P, _I, _I, _I, _F, _P, _P, _P],
+    "ctts_fastformer_pool_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "ctts_mul_bwd": [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P],
+    "ctts_gru_bwd": [_P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
 }
 
 _lib = None

@@ -302,6 +302,122 @@ int ctts_split_bf16(const float* x, size_t n, void* hi, void* lo, void* stream);
 int ctts_layernorm_split(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B,
                          int T, int C, float* y, void* y_hi, void* y_lo, void* stream);
 
+
+/* =====================================================================================================================
+ * TRAINING STEP (reference: train.py:104-123 -- forward in model.train(), loss.backward()).
+ * The reference's backward is torch.autograd over ATen ops; here every backward step is an explicit entry point.  The
+ * host side (ctts_b200/train_engine.py) records the forward on a tape and replays it in reverse.  All gradient outputs
+ * that belong to PARAMETERS accumulate (+=) into the caller's flat gradient arena; activation gradients take an explicit
+ * `accumulate` flag.  Dense contractions: dgrad = ctts_gemm_split on weights re-packed by ctts_pack_conv_weight_dgrad,
+ * wgrad = ctts_gemm_wgrad; ctts_gemm_generic is the FP32 CUDA-core GEMM for the odd shapes (1/2/4/11-wide heads,
+ * aligner products) and the implementation the tensor-core wgrad is tested against.
+ * ===================================================================================================================== */
+
+/* y[z][m,n] = alpha * sum_k A[z][m,k] * B[z][n,k'] (+ y[z][m,n] if accumulate),  z = zo*zmod + zi.
+ * Fully strided: a_str = {zo, zi, m, k, kb}, b_str = {zo, zi, n, k, kb}, y_str = {zo, zi, m, n} (element strides).
+ * The reduction index splits as k = kb*Kin + kt (Kin <= 0: Kin = K); B is read at kt + shift0 + z*shift_z and is zero
+ * outside [0, Kin): the tap shift of a Conv1d weight gradient (reduction over (utterance, time)). */
+int ctts_gemm_generic(const float* a, const float* b, float* y, int Z, int zmod, int M, int N, int K, const long long* a_str,
+                      const long long* b_str, const long long* y_str, int Kin, int shift0, int shift_z, float alpha,
+                      int accumulate, void* stream);
+
+/* Backward of the GEMM epilogue  v = (acc + bias) * alpha; y = act(v) [* keep]:
+ *   dz[r,n] = dy[r,n] * keep(r) * act'(.) * alpha;  dbias[z, n] += sum_r dz[r,n]
+ * `ref` = pre-activation v for GELU / SWISH, the OUTPUT y for RELU / TANH, unused for NONE.  dy/ref/dz: [Z, rows, N];
+ * keep(r): global row z*rows + r = (b, t) with t < lens[b] (lens nullable).  dz may alias dy; dz or dbias may be NULL.
+ * With Z = B, rows = T, dz = NULL it is the backward of a row broadcast (modules.py:985-988): dbias[b, n] += sum_t dy. */
+int ctts_act_bwd(const float* dy, const float* ref, int act, float alpha, const int64_t* lens, int Z, int T, int rows, int N,
+                 float* dz, float* dbias, void* stream);
+
+/* LayerNorm backward (blocks.py:137-156, nn.LayerNorm): dx (+)= ..., dgamma += , dbeta += ; statistics recomputed from x */
+int ctts_layernorm_bwd(const float* x, const float* gamma, const float* dy, float eps, const int64_t* lens, int B, int T,
+                       int C, float* dx, int accumulate, float* dgamma, float* dbeta, void* stream);
+
+/* x[b,t,:] = 0 for t >= lens[b]  (backward of the `* nonpadding` masks, transformer_fs2.py:60,192,199) */
+int ctts_mask_rows(float* x, const int64_t* lens, int B, int T, int C, void* stream);
+/* y = (accumulate ? y : 0) + a * x      (gradient fan-in; predictor_grad scaling modules.py:1026,893) */
+int ctts_axpy(const float* x, float a, size_t n, int accumulate, float* y, void* stream);
+/* y[r,c] = (accumulate ? y : 0) + a * x[r,c] * s[r] */
+int ctts_rowscale_axpy(const float* x, const float* s, float a, int rows, int C, int accumulate, float* y, void* stream);
+
+/* nn.Embedding backward: dtable[idx[r]] += scale * dy[r] (rows t >= lens[b] and idx == skip_idx (padding_idx) skipped) */
+int ctts_scatter_add_rows(const float* dy, const int64_t* idx, const int64_t* lens, int T, int rows, int C, int table_rows,
+                          int skip_idx, float scale, float* dtable, void* stream);
+
+/* LengthRegulator backward (modules.py:1222-1249): dsrc[b,j] (+)= sum of dy over the frames phoneme j was copied to */
+int ctts_length_expand_bwd(const float* dy, const int32_t* cum_lr, int B, int S, int C, int M, int accumulate, float* dsrc,
+                           void* stream);
+
+/* gradient of the learnable positional scale: dalpha += sum dy * pe[pos]  (transformer_fs2.py:54-58, modules.py:1349) */
+int ctts_add_positions_bwd(const float* dy, const float* x, const float* pe, int pe_rows, const int64_t* lens, int B, int T,
+                           int C, int pos_mode, float* dalpha, void* stream);
+
+/* softmax over materialised scores [Z, T, ld] (keys >= lens[z/H] excluded; rows t >= lens zero if mask_rows) and its
+ * backward dS = P * (dP - sum P dP) * scale.  FP32 attention backward path (transformer_fs2.py:385-394). */
+int ctts_masked_softmax(const float* S, const int64_t* lens, int H, int Z, int T, int Tk, int ld, int mask_rows, float* P,
+                        void* stream);
+int ctts_softmax_bwd(const float* P, const float* dP, int Z, int T, int Tk, int ld, float scale, float* dS, void* stream);
+
+/* BatchNorm1d in training mode (PostNet modules.py:140-148; conformer.py:465): batch mean / biased variance over all rows
+ * (padded frames included, as in the reference), normalise + activation, running-buffer update, backward. */
+int ctts_bn_stats(const float* x, int rows, int C, float* mean, float* var, void* stream);
+int ctts_bn_act_fwd(const float* x, const float* mean, const float* var, const float* gamma, const float* beta, float eps,
+                    int act, int rows, int C, float* y, int n_planes, void* const* planes, void* stream);
+int ctts_bn_update_running(const float* mean, const float* var, int rows, float momentum, int C, float* running_mean,
+                           float* running_var, int64_t* num_batches_tracked, void* stream);
+/* dx = d/dx of act(BN(x)); dgamma += ; dbeta += ; workspace: 2*C floats */
+int ctts_bn_bwd(const float* dy, const float* x, const float* mean, const float* var, const float* gamma, const float* beta,
+                float eps, int act, int rows, int C, float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);
+
+/* Dropout with a counter-based Philox4x32-10 stream: y = x * keep / (1 - p); the mask is a pure function of
+ * (seed, offset, element index), so the backward pass calls the same entry on dy.  Replaces F.dropout / nn.Dropout
+ * (transformer_fs2.py:58,118,190,197,237; modules.py:144-145,1287,1337). */
+int ctts_dropout(const float* x, size_t n, float p, unsigned long long seed, unsigned long long offset, float* y, void* stream);
+
+/* weight layouts of the backward GEMMs: wd[c, j*N + n] = w[n, c, taps-1-j] (dgrad operand);
+ * dw[n, c, j] (+)= dw_packed[n, j*Cin + c] (wgrad result -> torch Conv1d layout) */
+int ctts_pack_conv_weight_dgrad(const float* w, int N, int Cin, int taps, float* wd, void* stream);
+int ctts_unpack_conv_wgrad(const float* dw_packed, int N, int Cin, int taps, int accumulate, float* dw, void* stream);
+
+/* x fp32 [Z, R, ld_in] columns [c0, c0+C) -> bf16 planes [Z, C, Rp] (rows contiguous, zero padded): wgrad operands */
+int ctts_split_transpose(const float* x, int Z, int R, int C, int ld_in, int c0, int Rp, int n_planes, void* const* planes,
+                         void* stream);
+
+/* tcgen05 weight gradient: dw_packed[n, tap*Cin + c] (+)= alpha * sum_{b,t} dz[b,t,n] * x[b, t+tap-taps/2, c] from the
+ * transposed planes dzT [B, N, Tp] and xT [B, Cin, Tp] */
+int ctts_gemm_wgrad(int n_planes, const void* const* dzT_planes, const void* const* xT_planes, int B, int T, int Tp,
+                    int Cin, int N, int taps, float alpha, int accumulate, float* dw_packed, void* stream);
+
+/* batched plane GEMM with explicit operand views (attention backward products); see ctts_gemm_tc.cu */
+int ctts_gemm_batched_planes(int n_planes, const void* const* a_planes, const long long* a_view,
+                             const void* const* w_planes, const long long* w_view, const int* addr, long long y_outer,
+                             long long y_inner, float alpha, const float* residual, const int64_t* lens, int Z, int T, int K,
+                             int N, float* y, void* const* y_planes, void* stream);
+
+/* AlignmentEncoder backward, score part (modules.py:1198-1212): da [B,M,S] = gradient w.r.t. -temp*|q-k|^2 from the
+ * gradients of attn_soft / attn_logprob (either may be NULL) */
+int ctts_aligner_attention_bwd(const float* soft, const float* logprob, const float* prior, const float* dsoft,
+                               const float* dlogprob, const int64_t* src_lens, int B, int M, int S, float* da, void* stream);
+
+/* block-specific pieces: GLU backward (blocks.py:123-134); depthwise Conv1d forward / backward (conformer.py:522-560; the
+ * training path needs the un-fused conv because BatchNorm uses batch statistics); relative-shift backward
+ * (conformer.py:423-431); fastformer pooling backward (fastformer.py:308-336); elementwise product backward */
+int ctts_glu_bwd(const float* h, const float* dg, int rows, int C, float* dh, void* stream);
+int ctts_dwconv(const float* x, const float* w, int K, int B, int T, int C, float* y, void* stream);
+int ctts_dwconv_bwd(const float* dy, const float* x, const float* w, int K, int B, int T, int C, float* dx, float* dw,
+                    void* stream);
+int ctts_relshift_bwd(const float* dscore, int Z, int T, int ld, float sqrt_dim, float* dcontent, float* dpos, void* stream);
+int ctts_fastformer_pool_bwd(const float* logits, const float* values, const int64_t* lens, const float* dpooled, int B, int T,
+                             int heads, int head_size, float* dlogits, float* dvalues, void* stream);
+int ctts_mul_bwd(const float* dy, const float* a, const float* b, int b_rowwise, const int64_t* lens, int B, int T, int C,
+                 float* da, float* db, void* stream);
+
+/* single-direction GRU backward through time (liu2021, modules.py:620-640 / :356-392): dgi, dgh [B,T,3H]; dW_hh and db_hh
+ * follow by ctts_gemm_generic / ctts_act_bwd on dgh */
+int ctts_gru_bwd(const float* gi, const float* w_hh, const float* b_hh, const float* out, int out_ld, int out_off,
+                 const float* dout, const float* dh_final, int dhf_ld, int B, int T, int H, int reverse, float* dgi, float* dgh,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,8 @@ def test_ctypes_signatures_match_the_header():
                 want = ctypes.c_void_p
             elif re.match(r"(const )?float\b", p):
                 want = ctypes.c_float
+            elif re.match(r"(const )?unsigned long long\b", p):
+                want = ctypes.c_ulonglong
             elif re.match(r"(const )?long long\b", p):
                 want = ctypes.c_longlong
             elif re.match(r"(const )?size_t\b", p):
