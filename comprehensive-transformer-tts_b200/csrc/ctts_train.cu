@@ -489,6 +489,54 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ x, const float* __re
     }
 }
 
+// y = act(x) -> fp32 and / or planes (training keeps the pre-activation for GELU / Swish, so the activation is its own pass)
+template <int NP>
+__global__ void act_fwd_kernel(const float* __restrict__ x, size_t n, int act, float* __restrict__ y, const TPlanes yp) {
+    CTTS_PDL_SYNC();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = apply_act(x[i], act);
+        if (y) y[i] = v;
+        if (NP > 0) {
+            float rem = v;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+                yp.p[p][i] = h;
+                rem -= __bfloat162float(h);
+            }
+        }
+    }
+}
+
+struct CTPlanes {
+    const __nv_bfloat16* p[3];
+};
+// y = sum of the bf16 planes (the fp32 value a tensor-core kernel emitted as planes only)
+template <int NP>
+__global__ void merge_planes_kernel(const CTPlanes in, size_t n, float* __restrict__ y) {
+    CTTS_PDL_SYNC();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int p = NP - 1; p >= 0; --p) v += __bfloat162float(in.p[p][i]);
+        y[i] = v;
+    }
+}
+
+// dst[r, 0:C] = (accumulate ? dst : 0) + src[r, 0:C] with independent row strides (first-row gather / scatter, re-striding)
+__global__ void copy_rows_kernel(const float* __restrict__ src, long long src_stride, size_t rows, int C, float* __restrict__ dst,
+                                 long long dst_stride, int accumulate) {
+    CTTS_PDL_SYNC();
+    const size_t total = rows * (size_t)C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / C;
+        const int c = (int)(i - r * C);
+        float* d = dst + r * dst_stride + c;
+        const float v = src[r * src_stride + c];
+        *d = accumulate ? *d + v : v;
+    }
+}
+
 // running = (1 - momentum) * running + momentum * batch statistic (the variance one unbiased), num_batches_tracked += 1
 __global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ var, int rows, float momentum,
                                          int C, float* __restrict__ rmean, float* __restrict__ rvar, int64_t* __restrict__ count) {
@@ -1099,6 +1147,42 @@ int ctts_bn_act_fwd(const float* x, const float* mean, const float* var, const f
     else if (n_planes == 2) launch_k(bn_act_fwd_kernel<2>, grid, 256, 0, st, x, mean, var, gamma, beta, eps, act, (size_t)rows, C, y, tp);
     else launch_k(bn_act_fwd_kernel<0>, grid, 256, 0, st, x, mean, var, gamma, beta, eps, act, (size_t)rows, C, y, tp);
     return check_launch("bn_act_fwd");
+}
+
+int ctts_act_fwd(const float* x, size_t n, int act, float* y, int n_planes, void* const* planes, void* stream) {
+    CTTS_REQUIRE(x && n > 0 && (y || n_planes), "act_fwd: bad arguments");
+    CTTS_REQUIRE(n_planes == 0 || n_planes == 2 || n_planes == 3, "act_fwd: n_planes");
+    TPlanes tp{{nullptr, nullptr, nullptr}};
+    for (int p = 0; p < n_planes; ++p) {
+        CTTS_REQUIRE(planes && planes[p], "act_fwd: NULL plane");
+        tp.p[p] = (__nv_bfloat16*)planes[p];
+    }
+    const int grid = grid_for(n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_planes == 3) launch_k(act_fwd_kernel<3>, grid, 256, 0, st, x, n, act, y, tp);
+    else if (n_planes == 2) launch_k(act_fwd_kernel<2>, grid, 256, 0, st, x, n, act, y, tp);
+    else launch_k(act_fwd_kernel<0>, grid, 256, 0, st, x, n, act, y, tp);
+    return check_launch("act_fwd");
+}
+
+int ctts_merge_planes(int n_planes, const void* const* planes, size_t n, float* y, void* stream) {
+    CTTS_REQUIRE((n_planes == 2 || n_planes == 3) && planes && y && n > 0, "merge_planes: bad arguments");
+    CTPlanes cp{{nullptr, nullptr, nullptr}};
+    for (int p = 0; p < n_planes; ++p) {
+        CTTS_REQUIRE(planes[p], "merge_planes: NULL plane");
+        cp.p[p] = (const __nv_bfloat16*)planes[p];
+    }
+    if (n_planes == 3) launch_k(merge_planes_kernel<3>, grid_for(n), 256, 0, (cudaStream_t)stream, cp, n, y);
+    else launch_k(merge_planes_kernel<2>, grid_for(n), 256, 0, (cudaStream_t)stream, cp, n, y);
+    return check_launch("merge_planes");
+}
+
+int ctts_copy_rows(const float* src, long long src_stride, int rows, int C, float* dst, long long dst_stride, int accumulate,
+                   void* stream) {
+    CTTS_REQUIRE(src && dst && rows > 0 && C > 0, "copy_rows: bad arguments");
+    launch_k(copy_rows_kernel, grid_for((size_t)rows * C), 256, 0, (cudaStream_t)stream, src, src_stride, (size_t)rows, C, dst,
+             dst_stride, accumulate);
+    return check_launch("copy_rows");
 }
 
 int ctts_bn_update_running(const float* mean, const float* var, int rows, float momentum, int C, float* running_mean,

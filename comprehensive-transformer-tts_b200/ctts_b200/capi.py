@@ -85,6 +85,9 @@ SIGNATURES = {
     "ctts_relshift_bwd": [_P, _I, _I, _I, _F, _P, _P, _P],
     "ctts_fastformer_pool_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "ctts_mul_bwd": [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P],
+    "ctts_act_fwd": [_P, _Z, _I, _P, _I, _P, _P],
+    "ctts_merge_planes": [_I, _P, _Z, _P, _P],
+    "ctts_copy_rows": [_P, _L, _I, _I, _P, _L, _I, _P],
     "ctts_gru_bwd": [_P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
 }
 
@@ -145,6 +148,12 @@ def call(name, *args):
     rc = getattr(lib, name)(*conv)
     if rc != 0:
         raise CttsError("%s failed (%d): %s" % (name, rc, lib.ctts_last_error().decode()))
+
+
+def require_cuda_tensor(t):
+    """The product path has no CPU implementation: refuse host tensors instead of computing somewhere else."""
+    if not t.is_cuda:
+        raise CttsError("CompTransTTS (B200) runs on CUDA tensors only; got %s -- there is no CPU path" % t.device)
 
 
 _arch_checked = False

@@ -747,9 +747,7 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
             d_control=1.0, step=None):
     """CompTransTTS.forward, model/CompTransTTS.py:64-152.  Returns the reference's 14-tuple."""
     capi.require_device()
-    if not texts.is_cuda:
-        raise capi.CttsError("CompTransTTS (B200) runs on CUDA tensors only; got %s -- there is no CPU path"
-                             % texts.device)
+    capi.require_cuda_tensor(texts)
     pcfg, cfg, tcfg = module.preprocess_config, module.model_config, module.train_config
     prep = module._prepared
     sig_before = prep.sig

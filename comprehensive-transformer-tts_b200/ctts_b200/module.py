@@ -116,14 +116,35 @@ class CompTransTTS(nn.Module):
         self.use_cuda_graphs = os.environ.get("CTTS_CUDA_GRAPHS", "1") != "0"
         self._graphs = engine.GraphCache()
         self._prepared = engine.Prepared(self)
+        # training step (train_engine.py): flat gradient arena, dropout stream, optional data-parallel reducer
+        self._arena = None
+        self._anchor = None
+        self._reducer = None
+        self._dropout_seed = int(os.environ.get("CTTS_DROPOUT_SEED", train_config.get("seed", 1234)
+                                                if isinstance(train_config, dict) else 1234))
+        self._dropout_offset = 0
+
+    def grad_arena(self):
+        """The flat fp32 buffer all parameter gradients live in (param.grad are views of it); rebuilt when the parameters
+        move (`.to(device)`) or are replaced."""
+        from . import train_engine
+        if self._arena is None or self._arena.sig != train_engine.GradArena.signature(self):
+            self._arena = train_engine.GradArena(self)
+        return self._arena
+
+    def autograd_anchor(self, device):
+        if self._anchor is None or self._anchor.device != device:
+            self._anchor = torch.zeros(1, device=device, requires_grad=True)
+        return self._anchor
 
     def forward(self, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
                 p_targets=None, e_targets=None, d_targets=None, attn_priors=None, spker_embeds=None, p_control=1.0,
                 e_control=1.0, d_control=1.0, step=None):
         if self.training:
-            raise NotImplementedError(
-                "training-mode forward (dropout, batch-statistics BatchNorm, backward kernels) is not built yet; "
-                "call .eval() -- SURVEY.md section 7 step 7")
+            from . import train_engine
+            return train_engine.forward(self, speakers, texts, src_lens, max_src_len, mels, mel_lens, max_mel_len,
+                                        p_targets, e_targets, d_targets, attn_priors, spker_embeds, p_control, e_control,
+                                        d_control, step)
         with torch.no_grad():
             return engine.forward(self, speakers, texts, src_lens, max_src_len, mels, mel_lens, max_mel_len,
                                   p_targets, e_targets, d_targets, attn_priors, spker_embeds, p_control, e_control,

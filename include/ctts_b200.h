@@ -369,6 +369,16 @@ int ctts_bn_update_running(const float* mean, const float* var, int rows, float 
 int ctts_bn_bwd(const float* dy, const float* x, const float* mean, const float* var, const float* gamma, const float* beta,
                 float eps, int act, int rows, int C, float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);
 
+/* y = act(x) as fp32 and / or bf16 planes: training keeps the pre-activation of GELU / Swish layers for the backward pass
+ * (transformer_fs2.py:231-232), so the activation is its own pass there */
+int ctts_act_fwd(const float* x, size_t n, int act, float* y, int n_planes, void* const* planes, void* stream);
+/* y = sum of n_planes bf16 planes (fp32 value of a tensor the tensor-core kernels emitted as planes only) */
+int ctts_merge_planes(int n_planes, const void* const* planes, size_t n, float* y, void* stream);
+/* dst[r, 0:C] = (accumulate ? dst : 0) + src[r, 0:C], independent row strides: x_org[:, 0] gather for the CWT statistics
+ * MLP (modules.py:909-912) and its scatter in the backward pass; re-striding of attn_soft for the soft upsampling */
+int ctts_copy_rows(const float* src, long long src_stride, int rows, int C, float* dst, long long dst_stride, int accumulate,
+                   void* stream);
+
 /* Dropout with a counter-based Philox4x32-10 stream: y = x * keep / (1 - p); the mask is a pure function of
  * (seed, offset, element index), so the backward pass calls the same entry on dy.  Replaces F.dropout / nn.Dropout
  * (transformer_fs2.py:58,118,190,197,237; modules.py:144-145,1287,1337). */

@@ -1,0 +1,41 @@
+"""CPU: the HOST logic of the training step (ctts_b200/train_engine.py: tape, gradient routing, shapes, strides) with every
+C-ABI call answered by the torch restatement in oracle/capi_emulator.py, against the reference's training fixtures
+(tests/golden/*_train.npz: outputs, gradient samples + norms of every parameter, BatchNorm buffers).  The kernels
+themselves are checked on the GPU (tests/test_gpu_train.py); this test is what can run without one."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import cases  # noqa: E402
+from oracle import capi_emulator as emu  # noqa: E402
+
+import train_checks  # noqa: E402
+
+BUILT = ["fs2_train", "fs2_unsup_train_soft"]
+
+
+@pytest.mark.parametrize("math_mode", ["tc", "fp32"])
+@pytest.mark.parametrize("name", BUILT)
+def test_training_step_host_logic(name, math_mode, golden_dir, monkeypatch):
+    emu.install(monkeypatch)
+    if math_mode == "fp32":
+        monkeypatch.setenv("CTTS_DECODER_MATH", "fp32")
+        monkeypatch.setenv("CTTS_ENCODER_MATH", "fp32")
+        monkeypatch.setenv("CTTS_TRAIN_BWD_MATH", "fp32")
+    monkeypatch.setenv("CTTS_DROPOUT", "0")
+    net, out, loss = train_checks.run_training_case(name, torch.device("cpu"))
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    # fp32 arithmetic: the oracle's own tolerances (tests/test_oracle_train.py); tensor-core planes: north_star's output
+    # tolerance (1e-3 abs / 1e-2 rel) and 3x the gradient allowance
+    if math_mode == "fp32":
+        train_checks.check_against_fixture(net, out, loss, gold)
+    else:
+        train_checks.check_against_fixture(net, out, loss, gold, out_atol=1e-3, out_rtol=1e-2, grad_scale=3.0, loss_rtol=1e-3)
+    used = set(emu.CALLS)
+    assert "ctts_layernorm_bwd" in used and "ctts_act_bwd" in used
+    if math_mode == "tc":
+        assert "ctts_gemm_wgrad" in used and "ctts_gemm_split" in used
