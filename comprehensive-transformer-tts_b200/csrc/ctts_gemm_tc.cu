@@ -1406,17 +1406,20 @@ extern "C" int ctts_transpose_v_planes(int n_planes, const void* const* qkv_plan
 // ---- weight gradient on the tensor cores ------------------------------------------------------------------------
 //   dw[n, tap*Cin + c] (+)= alpha * sum_{b,t} dz[b, t, n] * x[b, t + tap - taps/2, c]
 // Both operands come TRANSPOSED (time contiguous: ctts_split_transpose) so that the reduction index is the K-major one:
-//   dzT planes [B, N, Tp], xT planes [B, Cin, Tp] (Tp = T rounded up to 8; only t < T is read, the rest is TMA zero fill).
-// One 128 x 128 tile of dw per CTA; the K loop runs over all B utterances x ceil(T/64) blocks; the tap offset is a shift of
-// the dzT K coordinate (out-of-range columns are zero fill, which is exactly the conv's zero padding).
+//   dzT planes [B, N, Tp];  xT planes [B, taps, Cin, Tp] with the tap shift already applied (TMA box origins must be
+//   16-byte aligned in the innermost dimension, so the shift cannot be a load coordinate).  Tp = T rounded up to 8; only
+//   t < T is read, the rest is TMA zero fill.
+// It is then ONE GEMM [N x taps*Cin] with K = (utterance, time): one 128 x 128 tile of dw per CTA, the K loop runs over
+// all B utterances x ceil(T/64) blocks (Addr::kz).
 extern "C" int ctts_gemm_wgrad(int n_planes, const void* const* dzT_planes, const void* const* xT_planes, int B, int T, int Tp,
                                int Cin, int N, int taps, float alpha, int accumulate, float* dw_packed, void* stream) {
     CTTS_REQUIRE(n_planes == 2 || n_planes == 3, "gemm_wgrad: n_planes must be 2 or 3");
     CTTS_REQUIRE(dzT_planes && xT_planes && dw_packed, "gemm_wgrad: NULL argument");
     CTTS_REQUIRE(B > 0 && T > 0 && Tp >= T && Tp % 8 == 0 && N > 0 && Cin > 0 && Cin % 4 == 0 && taps >= 1 && (taps & 1),
                  "gemm_wgrad: bad shape B=%d T=%d Tp=%d Cin=%d N=%d taps=%d", B, T, Tp, Cin, N, taps);
+    const cuuint64_t KC = (cuuint64_t)taps * Cin;
     Operand A{{nullptr, nullptr, nullptr}, (cuuint64_t)T, (cuuint64_t)N, (cuuint64_t)B, (cuuint64_t)Tp, (cuuint64_t)N * Tp};
-    Operand W{{nullptr, nullptr, nullptr}, (cuuint64_t)T, (cuuint64_t)Cin, (cuuint64_t)B, (cuuint64_t)Tp, (cuuint64_t)Cin * Tp};
+    Operand W{{nullptr, nullptr, nullptr}, (cuuint64_t)T, KC, (cuuint64_t)B, (cuuint64_t)Tp, KC * Tp};
     for (int p = 0; p < n_planes; ++p) {
         CTTS_REQUIRE(dzT_planes[p] && xT_planes[p], "gemm_wgrad: NULL operand plane %d", p);
         CTTS_REQUIRE((((uintptr_t)dzT_planes[p] | (uintptr_t)xT_planes[p]) & 15) == 0, "gemm_wgrad: planes must be 16-byte aligned");
@@ -1425,11 +1428,10 @@ extern "C" int ctts_gemm_wgrad(int n_planes, const void* const* dzT_planes, cons
     }
     Epilogue ep{nullptr, nullptr, nullptr, accumulate ? dw_packed : nullptr, nullptr, dw_packed, {nullptr, nullptr, nullptr},
                 alpha, CTTS_ACT_NONE, nullptr};
-    // z = tap: K shift of the dzT operand = -(tap - taps/2); output columns start at tap*Cin
-    Addr ad{1, 1, 0, 0, 1, 0, 0, 1, taps * Cin, (long long)Cin, 0, B, taps / 2, -1};
+    Addr ad{1, 1, 0, 0, 1, 0, 0, 1, (int)KC, 0, 0, B, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_planes == 3) return launch<128, 2, 3, 1>(A, W, ep, ad, taps, N, T, Cin, 1, st, 0);
-    return launch<128, 3, 2, 1>(A, W, ep, ad, taps, N, T, Cin, 1, st, 0);
+    if (n_planes == 3) return launch<128, 2, 3, 1>(A, W, ep, ad, 1, N, T, (int)KC, 1, st, 0);
+    return launch<128, 3, 2, 1>(A, W, ep, ad, 1, N, T, (int)KC, 1, st, 0);
 }
 
 // ---- batched plane GEMM with explicit operand views (the products of the attention backward) ---------------------------

@@ -678,26 +678,30 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int N, int Ci
     }
 }
 
-// x fp32 [Z, R, C] (row stride ld_in, column offset c0) -> NP bf16 planes [Z, C, Rp] (rows contiguous, zero padded): the
-// K-major operands of the wgrad GEMM, whose reduction runs over the rows.
+// x fp32 [Z, R, C] (row stride ld_in, column offset c0) -> NP bf16 planes [Z, taps, C, Rp] with
+//   out[z, tap, c, r] = x[z, r + tap - taps/2, c]   (zero outside [0, R), and for r >= R)
+// i.e. the transposed (rows contiguous) and, for a Conv1d, per-tap pre-shifted operand of the wgrad GEMM, whose reduction
+// runs over the rows.  (TMA box origins must be 16-byte aligned in the innermost dimension, so the tap shift cannot be a
+// coordinate offset of the load: it is applied here.)
 template <int NP>
 __global__ void __launch_bounds__(256)
-split_transpose_kernel(const float* __restrict__ x, int R, int C, int ld_in, int c0, int Rp, const TPlanes out) {
+split_transpose_kernel(const float* __restrict__ x, int R, int C, int ld_in, int c0, int Rp, int taps, const TPlanes out) {
     CTTS_PDL_SYNC();
     __shared__ float tile[32][33];
-    const int z = blockIdx.z;
+    const int z = blockIdx.z / taps, tap = blockIdx.z - z * taps;
+    const int shift = tap - (taps >> 1);
     const int r0 = blockIdx.x * 32, cc0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int i = ty; i < 32; i += 8) {
-        const int r = r0 + i, c = cc0 + tx;
-        tile[i][tx] = (r < R && c < C) ? x[((size_t)z * R + r) * ld_in + c0 + c] : 0.f;
+        const int r = r0 + i, rs = r + shift, c = cc0 + tx;
+        tile[i][tx] = (r < R && rs >= 0 && rs < R && c < C) ? x[((size_t)z * R + rs) * ld_in + c0 + c] : 0.f;
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int c = cc0 + i, r = r0 + tx;
         if (c < C && r < Rp) {
             float rem = tile[tx][i];
-            const size_t o = ((size_t)z * C + c) * Rp + r;
+            const size_t o = (((size_t)z * taps + tap) * C + c) * Rp + r;
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 const __nv_bfloat16 h = __float2bfloat16_rn(rem);
@@ -1229,17 +1233,18 @@ int ctts_unpack_conv_wgrad(const float* dw_packed, int N, int Cin, int taps, int
     return check_launch("unpack_conv_wgrad");
 }
 
-int ctts_split_transpose(const float* x, int Z, int R, int C, int ld_in, int c0, int Rp, int n_planes, void* const* planes,
-                         void* stream) {
-    CTTS_REQUIRE(x && planes && Z > 0 && R > 0 && C > 0 && Rp >= R && (n_planes == 2 || n_planes == 3), "split_transpose: bad arguments");
+int ctts_split_transpose(const float* x, int Z, int R, int C, int ld_in, int c0, int Rp, int taps, int n_planes,
+                         void* const* planes, void* stream) {
+    CTTS_REQUIRE(x && planes && Z > 0 && R > 0 && C > 0 && Rp >= R && taps >= 1 && (taps & 1) && (n_planes == 2 || n_planes == 3),
+                 "split_transpose: bad arguments");
     TPlanes tp{{nullptr, nullptr, nullptr}};
     for (int p = 0; p < n_planes; ++p) {
         CTTS_REQUIRE(planes[p], "split_transpose: NULL plane");
         tp.p[p] = (__nv_bfloat16*)planes[p];
     }
-    dim3 grid((Rp + 31) / 32, (C + 31) / 32, Z);
-    if (n_planes == 3) launch_k(split_transpose_kernel<3>, grid, 256, 0, (cudaStream_t)stream, x, R, C, ld_in, c0, Rp, tp);
-    else launch_k(split_transpose_kernel<2>, grid, 256, 0, (cudaStream_t)stream, x, R, C, ld_in, c0, Rp, tp);
+    dim3 grid((Rp + 31) / 32, (C + 31) / 32, Z * taps);
+    if (n_planes == 3) launch_k(split_transpose_kernel<3>, grid, 256, 0, (cudaStream_t)stream, x, R, C, ld_in, c0, Rp, taps, tp);
+    else launch_k(split_transpose_kernel<2>, grid, 256, 0, (cudaStream_t)stream, x, R, C, ld_in, c0, Rp, taps, tp);
     return check_launch("split_transpose");
 }
 

@@ -75,7 +75,7 @@ SIGNATURES = {
     "ctts_dropout": [_P, _Z, _F, ctypes.c_ulonglong, ctypes.c_ulonglong, _P, _P],
     "ctts_pack_conv_weight_dgrad": [_P, _I, _I, _I, _P, _P],
     "ctts_unpack_conv_wgrad": [_P, _I, _I, _I, _I, _P, _P],
-    "ctts_split_transpose": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "ctts_split_transpose": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "ctts_gemm_wgrad": [_I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P],
     "ctts_gemm_batched_planes": [_I, _P, _P, _P, _P, _P, _L, _L, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "ctts_aligner_attention_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],

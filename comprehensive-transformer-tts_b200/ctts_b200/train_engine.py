@@ -245,12 +245,12 @@ def _dgrad(ctx, dz, wname, taps, x):
         _generic(dz, w, out, 1, 1, B * T, Cin, N, (0, 0, N, 1, 0), (0, 0, 1, Cin, 0), (0, 0, Cin, 1), accumulate=acc)
 
 
-def transposed_planes(t, n=2):
-    """fp32 [B, T, C] -> Planes [B, C, Tp] (time contiguous, Tp = T rounded up to 8)."""
+def transposed_planes(t, taps=1, n=2):
+    """fp32 [B, T, C] -> Planes [B, taps, C, Tp] (time contiguous, Tp = T rounded up to 8, tap shifts applied)."""
     B, T, C = t.shape
     Tp = (T + 7) // 8 * 8
-    p = Planes.empty((B, C, Tp), t.device, n)
-    capi.call("ctts_split_transpose", t, B, T, C, C, 0, Tp, n, capi.ptr_array(p.p), _st())
+    p = Planes.empty((B, taps, C, Tp), t.device, n)
+    capi.call("ctts_split_transpose", t, B, T, C, C, 0, Tp, taps, n, capi.ptr_array(p.p), _st())
     return p
 
 
@@ -266,14 +266,16 @@ def _wgrad(ctx, dz, x, wname, taps):
         Tp = (T + 7) // 8 * 8
         dzT = transposed_planes(dz)
         if x._tplanes is None:
-            x._tplanes = transposed_planes(x.v)
+            x._tplanes = {}
+        xT = x._tplanes.get(taps)
+        if xT is None:
+            xT = x._tplanes[taps] = transposed_planes(x.v, taps)
         if taps == 1:
-            capi.call("ctts_gemm_wgrad", 2, capi.ptr_array(dzT.p), capi.ptr_array(x._tplanes.p), B, T, Tp, Cin, N, 1, 1.0, 1,
-                      G, st)
+            capi.call("ctts_gemm_wgrad", 2, capi.ptr_array(dzT.p), capi.ptr_array(xT.p), B, T, Tp, Cin, N, 1, 1.0, 1, G, st)
         else:
             tmp = torch.empty(N, taps * Cin, device=dz.device, dtype=torch.float32)
-            capi.call("ctts_gemm_wgrad", 2, capi.ptr_array(dzT.p), capi.ptr_array(x._tplanes.p), B, T, Tp, Cin, N, taps, 1.0,
-                      0, tmp, st)
+            capi.call("ctts_gemm_wgrad", 2, capi.ptr_array(dzT.p), capi.ptr_array(xT.p), B, T, Tp, Cin, N, taps, 1.0, 0, tmp,
+                      st)
             capi.call("ctts_unpack_conv_wgrad", tmp, N, Cin, taps, 1, G, st)
         return
     if taps == 1:

@@ -389,12 +389,13 @@ int ctts_dropout(const float* x, size_t n, float p, unsigned long long seed, uns
 int ctts_pack_conv_weight_dgrad(const float* w, int N, int Cin, int taps, float* wd, void* stream);
 int ctts_unpack_conv_wgrad(const float* dw_packed, int N, int Cin, int taps, int accumulate, float* dw, void* stream);
 
-/* x fp32 [Z, R, ld_in] columns [c0, c0+C) -> bf16 planes [Z, C, Rp] (rows contiguous, zero padded): wgrad operands */
-int ctts_split_transpose(const float* x, int Z, int R, int C, int ld_in, int c0, int Rp, int n_planes, void* const* planes,
-                         void* stream);
+/* x fp32 [Z, R, ld_in] columns [c0, c0+C) -> bf16 planes [Z, taps, C, Rp] (rows contiguous, zero padded) with
+ * out[z, tap, c, r] = x[z, r + tap - taps/2, c]: the K-major (and per-tap pre-shifted) operands of ctts_gemm_wgrad */
+int ctts_split_transpose(const float* x, int Z, int R, int C, int ld_in, int c0, int Rp, int taps, int n_planes,
+                         void* const* planes, void* stream);
 
 /* tcgen05 weight gradient: dw_packed[n, tap*Cin + c] (+)= alpha * sum_{b,t} dz[b,t,n] * x[b, t+tap-taps/2, c] from the
- * transposed planes dzT [B, N, Tp] and xT [B, Cin, Tp] */
+ * transposed planes dzT [B, N, Tp] (ctts_split_transpose, taps 1) and xT [B, taps, Cin, Tp] (ctts_split_transpose, taps) */
 int ctts_gemm_wgrad(int n_planes, const void* const* dzT_planes, const void* const* xT_planes, int B, int T, int Tp,
                     int Cin, int N, int taps, float alpha, int accumulate, float* dw_packed, void* stream);
 

@@ -579,25 +579,22 @@ def ctts_unpack_conv_wgrad(dwp, N, Cin, taps, accumulate, dw, stream):
     d.copy_(d + v if accumulate else v)
 
 
-def ctts_split_transpose(x, Z, R, C, ld_in, c0, Rp, n, planes, stream):
-    xv = _v(x, Z, R, ld_in)[:, :, c0:c0 + C].transpose(1, 2)
-    out = torch.zeros(Z, C, Rp)
-    out[:, :, :R] = xv
-    _split_into(out, _planes(planes, n), Z, C, Rp)
+def ctts_split_transpose(x, Z, R, C, ld_in, c0, Rp, taps, n, planes, stream):
+    xv = _v(x, Z, R, ld_in)[:, :, c0:c0 + C].transpose(1, 2)          # [Z, C, R]
+    out = torch.zeros(Z, taps, C, Rp)
+    pad = taps // 2
+    for j in range(taps):
+        sh = j - pad
+        lo, hi = max(0, -sh), min(R, R - sh)
+        if hi > lo:
+            out[:, j, :, lo:hi] = xv[:, :, lo + sh:hi + sh]
+    _split_into(out, _planes(planes, n), Z, taps, C, Rp)
 
 
 def ctts_gemm_wgrad(n, dzT, xT, B, T, Tp, Cin, N, taps, alpha, accumulate, dwp, stream):
     dz = _val(dzT, n, B, N, Tp)[:, :, :T]
-    x = _val(xT, n, B, Cin, Tp)[:, :, :T]
-    out = torch.zeros(N, taps, Cin)
-    pad = taps // 2
-    for j in range(taps):
-        sh = j - pad
-        xs = torch.zeros(B, Cin, T)
-        lo, hi = max(0, -sh), min(T, T - sh)
-        if hi > lo:
-            xs[:, :, lo:hi] = x[:, :, lo + sh:hi + sh]
-        out[:, j, :] = torch.einsum("bnt,bct->nc", dz, xs)
+    xs = _val(xT, n, B, taps, Cin, Tp)[:, :, :, :T]
+    out = torch.einsum("bnt,bjct->njc", dz, xs)
     d = _v(dwp, N, taps, Cin)
     d.copy_((d if accumulate else 0) + alpha * out)
 
