@@ -122,9 +122,9 @@ class Ctx:
     def __init__(self, module, arena):
         self.module = module
         self.prep = module._prepared
-        self.P = self.prep.params()
+        self.P = dict(self.prep.params())     # per-step copies: blocks add virtual (concatenated) weights
         self.W = self.prep.w
-        self.G = arena.views
+        self.G = dict(arena.views)
         self.tape = []
         self.cfg = module.model_config
         self.pcfg = module.preprocess_config
@@ -297,7 +297,7 @@ def linear(ctx, x, wname, bname=None, alpha=1.0, act=ACT_NONE, residual=None, le
     bias = P[bname] if bname else None
     keep_pre = act in (ACT_GELU, ACT_SWISH)
     assert not (keep_pre and (residual is not None or lens is not None))
-    assert residual is None or (act == ACT_NONE and alpha == 1.0)
+    assert residual is None or act == ACT_NONE
     fwd_act = ACT_NONE if keep_pre else act
     res_t = residual.v if residual is not None else None
     use_tc = math in ("tc2", "tc3") and Cin % 8 == 0 and N % 4 == 0 and N >= 16
@@ -327,14 +327,22 @@ def linear(ctx, x, wname, bname=None, alpha=1.0, act=ACT_NONE, residual=None, le
         if y.g is None:
             return
         dz = y.g
-        if lens is not None or act != ACT_NONE or alpha != 1.0 or bias is not None:
+        mask = lens
+        res_done = False
+        if residual is not None and alpha != 1.0:     # y = alpha * (..) + residual: the residual sees the unscaled gradient
+            if mask is not None:
+                capi.call("ctts_mask_rows", dz, mask, B, T, N, _st())
+                mask = None
+            accumulate_copy(residual, dz)
+            res_done = True
+        if mask is not None or act != ACT_NONE or alpha != 1.0 or bias is not None:
             ref = pre if keep_pre else (y.v if act in (ACT_RELU, ACT_TANH) else None)
-            capi.call("ctts_act_bwd", dz, ref, int(act), float(alpha), lens, 1, T, B * T, N, dz,
+            capi.call("ctts_act_bwd", dz, ref, int(act), float(alpha), mask, 1, T, B * T, N, dz,
                       ctx.G.get(bname) if bname else None, _st())
         if x.needs_grad:
             _dgrad(ctx, dz, wname, taps, x)
         _wgrad(ctx, dz, x, wname, taps)
-        if residual is not None:
+        if residual is not None and not res_done:
             accumulate_into(residual, dz)
         y.g = None
 
@@ -405,12 +413,12 @@ def residual_add(ctx, res, y_in, lens):
     return y
 
 
-def sublayer(ctx, x, h, wname, bname, lens, p_drop, math):
-    """x + dropout(linear(h)) masked: fused into the GEMM epilogue when there is no dropout."""
+def sublayer(ctx, x, h, wname, bname, lens, p_drop, math, alpha=1.0, taps=1):
+    """x + dropout(alpha * linear(h)) masked: fused into the GEMM epilogue when there is no dropout."""
     if p_drop > 0.0 and ctx.dropout_on:
-        y = linear(ctx, h, wname, bname, math=math)
+        y = linear(ctx, h, wname, bname, alpha=alpha, taps=taps, math=math)
         return residual_add(ctx, x, dropout(ctx, y, p_drop), lens)
-    return linear(ctx, h, wname, bname, residual=x, lens=lens, math=math)
+    return linear(ctx, h, wname, bname, alpha=alpha, residual=x, lens=lens, taps=taps, math=math)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

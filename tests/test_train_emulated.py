@@ -15,7 +15,8 @@ from oracle import capi_emulator as emu  # noqa: E402
 
 import train_checks  # noqa: E402
 
-BUILT = ["fs2_train", "fs2_unsup_train_soft"]
+BUILT = ["fs2_train", "fs2_unsup_train_soft", "transformer_train", "fastformer_train", "conformer_train",
+         "conformer_unsup_train", "fastformer_vctk_unsup_train"]
 
 
 @pytest.mark.parametrize("math_mode", ["tc", "fp32"])
@@ -34,7 +35,8 @@ def test_training_step_host_logic(name, math_mode, golden_dir, monkeypatch):
     if math_mode == "fp32":
         train_checks.check_against_fixture(net, out, loss, gold)
     else:
-        train_checks.check_against_fixture(net, out, loss, gold, out_atol=1e-3, out_rtol=1e-2, grad_scale=3.0, loss_rtol=1e-3)
+        train_checks.check_against_fixture(net, out, loss, gold, out_atol=1e-3, out_rtol=1e-2, grad_scale=3.0, loss_rtol=1e-3,
+                                           outlier_frac=0.03, outlier_bound=0.3)
     used = set(emu.CALLS)
     assert "ctts_layernorm_bwd" in used and "ctts_act_bwd" in used
     if math_mode == "tc":
