@@ -113,3 +113,95 @@ def allreduce_gradients(parameters, world, bucket_bytes=25 << 20):
         gb.launch(i, world)
     gb.finish(world)
     return len(gb.buckets)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The training step's own reducer: the gradients already live in ONE flat fp32 arena (train_engine.GradArena; param.grad are
+# views of it), laid out in the order the backward pass finishes them.  So there is nothing to pack: each "bucket" is a
+# contiguous slice of the arena, all-reduced IN PLACE (ncclAllReduce over NVLink / NVSwitch through torch.distributed) as
+# soon as the backward pass has left the stage that writes it -- decoder + mel head first, then the variance adaptor,
+# then the encoder -- on NCCL's own stream, overlapping the rest of the backward.  The 1/world of DDP's mean is folded into
+# the seed of the backward pass (train_engine.run_backward), not applied as a separate pass.
+STAGE_OF_PREFIX = (("postnet.", "decoder"), ("mel_linear.", "decoder"), ("decoder.", "decoder"),
+                   ("variance_adaptor.", "variance_adaptor"))
+
+
+def _stage_of(name):
+    for prefix, stage in STAGE_OF_PREFIX:
+        if name.startswith(prefix):
+            return stage
+    return "encoder"      # encoder.*, speaker_emb.*: final only when the whole tape has been replayed
+
+
+class ArenaAllReduce:
+    def __init__(self, process_group=None, max_bucket_bytes=64 << 20):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.max_bucket = max_bucket_bytes // 4
+        self.works = []
+        self.launched = []        # (lo, hi) element ranges, for tests / the benchmark record
+        self.enabled = True
+
+    def _runs(self, arena):
+        """Contiguous slices of the arena whose slots all become final at the same stage."""
+        runs = []
+        for name, off, n in arena.order:
+            stage = _stage_of(name)
+            end = off + (n + 3) // 4 * 4
+            if runs and runs[-1][0] == stage and runs[-1][2] == off:
+                runs[-1][2] = end
+            else:
+                runs.append([stage, off, end])
+        return runs
+
+    def begin(self, ctx, arena):
+        """Register the launch points of this backward pass on the tape."""
+        self.works, self.launched = [], []
+        if self.world == 1 or not self.enabled:
+            return
+        runs = self._runs(arena)
+
+        def launcher(stage):
+            def fire():
+                for st, lo, hi in runs:
+                    if st != stage:
+                        continue
+                    pos = lo
+                    while pos < hi:
+                        nxt = min(hi, pos + self.max_bucket)
+                        self.works.append(dist.all_reduce(arena.flat[pos:nxt], op=dist.ReduceOp.SUM, group=self.group,
+                                                          async_op=True))
+                        self.launched.append((pos, nxt))
+                        pos = nxt
+            return fire
+
+        ctx.hooks.append((ctx.marks.get("decoder", 0), launcher("decoder")))
+        ctx.hooks.append((ctx.marks.get("variance_adaptor", 0), launcher("variance_adaptor")))
+        self._last = launcher("encoder")
+
+    def finish(self):
+        if self.world == 1 or not self.enabled:
+            return
+        self._last()
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+
+class DistributedDataParallel(torch.nn.Module):
+    """Stand-in for torch.nn.parallel.DistributedDataParallel at train.py:58 (`model = DistributedDataParallel(model,
+    device_ids=[rank])`, then `model.module.state_dict()` at train.py:193): broadcasts parameters and buffers from rank 0
+    at construction like DDP does, and attaches the arena reducer so that `loss.backward()` leaves the AVERAGED gradients in
+    param.grad.  One import line changes in the reference's train.py."""
+
+    def __init__(self, module, device_ids=None, output_device=None, process_group=None, bucket_cap_mb=64, **_ignored):
+        super().__init__()
+        self.module = module
+        if dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, src=0, group=process_group)
+        module._reducer = ArenaAllReduce(process_group, int(bucket_cap_mb) << 20)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)

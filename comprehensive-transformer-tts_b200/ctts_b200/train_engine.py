@@ -138,6 +138,7 @@ class Ctx:
         self._dgrad = {}
         self._wplanes = {}
         self.hooks = []          # (tape position, callable): fired when the backward pass reaches that position
+        self.marks = {}          # stage name -> index of its first tape closure
 
     def record(self, fn):
         self.tape.append(fn)
@@ -424,6 +425,92 @@ def sublayer(ctx, x, h, wname, bname, lens, p_drop, math, alpha=1.0, taps=1):
 # ---------------------------------------------------------------------------------------------------------------------
 # attention (fs2 / transformer: softmax(q k^T * scale + key padding mask) v on a packed qkv tensor)
 # ---------------------------------------------------------------------------------------------------------------------
+def _attention_bwd_fp32(qkv, dO, lens, n_head, scale):
+    """Backward of softmax(q k^T * scale + key mask) v with the scores re-materialised in FP32 (CUDA-core GEMMs)."""
+    B, T, C3 = qkv.v.shape
+    C = C3 // 3
+    DH = C // n_head
+    st = _st()
+    dev = qkv.v.device
+    Z = B * n_head
+    q = qkv.v
+    k = q.view(-1)[C:]
+    v = q.view(-1)[2 * C:]
+    qs = (T * C3, DH, C3, 1, 0)                      # strides (zo, zi, row, k, kb) of a head slice of qkv
+    S = torch.empty(Z, T, T, device=dev, dtype=torch.float32)
+    _generic(q, k, S, Z, n_head, T, T, DH, qs, qs, (n_head * T * T, T * T, T, 1), alpha=scale)
+    Pm = torch.empty_like(S)
+    capi.call("ctts_masked_softmax", S, lens, n_head, Z, T, T, T, 1, Pm, st)
+    os_ = (T * C, DH, C, 1, 0)
+    dP = S                                           # reuse
+    _generic(dO, v, dP, Z, n_head, T, T, DH, os_, qs, (n_head * T * T, T * T, T, 1))
+    dqkv = torch.empty_like(q)
+    dq, dk, dv = dqkv, dqkv.view(-1)[C:], dqkv.view(-1)[2 * C:]
+    ys = (T * C3, DH, C3, 1)
+    # dV[s, d] = sum_t P[t, s] dO[t, d]
+    _generic(Pm, dO, dv, Z, n_head, T, DH, T, (n_head * T * T, T * T, 1, T, 0), (T * C, DH, 1, C, 0), ys)
+    capi.call("ctts_softmax_bwd", Pm, dP, Z, T, T, T, 1.0, dP, st)
+    dS = dP
+    # dQ[t, d] = scale * sum_s dS[t, s] K[s, d];  dK[s, d] = scale * sum_t dS[t, s] Q[t, d]
+    _generic(dS, k, dq, Z, n_head, T, DH, T, (n_head * T * T, T * T, T, 1, 0), (T * C3, DH, 1, C3, 0), ys, alpha=scale)
+    _generic(dS, q, dk, Z, n_head, T, DH, T, (n_head * T * T, T * T, 1, T, 0), (T * C3, DH, 1, C3, 0), ys, alpha=scale)
+    return dqkv
+
+
+def _bgemm(a_planes, a_view, w_planes, w_view, addr, y_outer, y_inner, alpha, Z, T, K, N, y):
+    capi.call("ctts_gemm_batched_planes", 2, capi.ptr_array(a_planes.p), _ll(*a_view), capi.ptr_array(w_planes.p), _ll(*w_view),
+              _ints(*addr), int(y_outer), int(y_inner), float(alpha), None, None, Z, T, K, N, y, None, _st())
+
+
+def _attention_bwd_tc(qkv, dO, lens, n_head, scale):
+    """The same backward on tcgen05 (2 bf16 planes per operand, ctts_gemm_batched_planes): five batched GEMMs over the
+    re-materialised probabilities; the operands whose reduction index is time come from ctts_split_transpose."""
+    B, T, C3 = qkv.v.shape
+    C = C3 // 3
+    H = n_head
+    DH = C // H
+    Z = B * H
+    Tp = (T + 7) // 8 * 8
+    st = _st()
+    dev = qkv.v.device
+    qp = planes_of(qkv, 2)                                        # [B, T, 3C]
+    qkv_view = (C3, T, B, C3, T * C3)
+    big = (H * T * Tp, T * Tp)
+    # 1. S = scale * q k^T  -> [Z, T, Tp] fp32
+    S = torch.empty(Z, T, Tp, device=dev, dtype=torch.float32)
+    _bgemm(qp, qkv_view, qp, qkv_view, (H, H, 0, DH, H, C, DH, 1, Tp), big[0], big[1], scale, Z, T, DH, Tp, S)
+    # 2. P (fp32), its planes and transposed planes
+    Pm = torch.empty_like(S)
+    capi.call("ctts_masked_softmax", S, lens, H, Z, T, T, Tp, 1, Pm, st)
+    PT = Planes.empty((Z, 1, T, Tp), dev, 2)
+    capi.call("ctts_split_transpose", Pm, Z, T, T, Tp, 0, Tp, 1, 2, capi.ptr_array(PT.p), st)
+    # 3. dP = dO v^T
+    dOp = engine.split_planes(dO, 2)
+    _bgemm(dOp, (C, T, B, C, T * C), qp, qkv_view, (H, H, 0, DH, H, 2 * C, DH, 1, Tp), big[0], big[1], 1.0, Z, T, DH, Tp, S)
+    # 4. dS = P * (dP - sum P dP)
+    capi.call("ctts_softmax_bwd", Pm, S, Z, T, T, Tp, 1.0, S, st)
+    dSp = engine.split_planes(S, 2)                               # [Z, T, Tp]
+    dST = Planes.empty((Z, 1, T, Tp), dev, 2)
+    capi.call("ctts_split_transpose", S, Z, T, T, Tp, 0, Tp, 1, 2, capi.ptr_array(dST.p), st)
+    # time-major copies of q, k, dO: [B, C, Tp] == [Z, DH, Tp]
+    def tr(src, ld, c0):
+        p = Planes.empty((B, 1, C, Tp), dev, 2)
+        capi.call("ctts_split_transpose", src, B, T, C, ld, c0, Tp, 1, 2, capi.ptr_array(p.p), st)
+        return p
+    qT, kT, dOT = tr(qkv.v, C3, 0), tr(qkv.v, C3, C), tr(dO, C, 0)
+    sq_view = (T, T, Z, Tp, T * Tp)                               # [Z][T rows][T valid of Tp]
+    hT_view = (T, DH, Z, Tp, DH * Tp)
+    dqkv = torch.empty_like(qkv.v)
+    addr = (H, 1, 0, 0, 1, 0, 0, 1, C3)
+    # 5. dV[s, d] = sum_t P^T[s, t] dO^T[d, t]
+    _bgemm(PT, sq_view, dOT, hT_view, addr, T * C3, DH, 1.0, Z, T, T, DH, dqkv.view(-1)[2 * C:])
+    # 6. dQ[t, d] = scale * sum_s dS[t, s] K^T[d, s]
+    _bgemm(dSp, sq_view, kT, hT_view, addr, T * C3, DH, scale, Z, T, T, DH, dqkv)
+    # 7. dK[s, d] = scale * sum_t dS^T[s, t] Q^T[d, t]
+    _bgemm(dST, sq_view, qT, hT_view, addr, T * C3, DH, scale, Z, T, T, DH, dqkv.view(-1)[C:])
+    return dqkv
+
+
 def attention(ctx, qkv, lens, n_head, math):
     B, T, C3 = qkv.v.shape
     C = C3 // 3
@@ -442,31 +529,10 @@ def attention(ctx, qkv, lens, n_head, math):
     def bwd():
         if a.g is None:
             return
-        st = _st()
-        dev = qkv.v.device
-        Z = B * n_head
-        q = qkv.v
-        k = q.view(-1)[C:]
-        v = q.view(-1)[2 * C:]
-        qs = (T * C3, DH, C3, 1, 0)                      # strides (zo, zi, row, k, kb) of a head slice of qkv
-        S = torch.empty(Z, T, T, device=dev, dtype=torch.float32)
-        _generic(q, k, S, Z, n_head, T, T, DH, qs, qs, (n_head * T * T, T * T, T, 1), alpha=scale)
-        Pm = torch.empty_like(S)
-        capi.call("ctts_masked_softmax", S, lens, n_head, Z, T, T, T, 1, Pm, st)
-        dO = a.g
-        os_ = (T * C, DH, C, 1, 0)
-        dP = S                                           # reuse
-        _generic(dO, v, dP, Z, n_head, T, T, DH, os_, qs, (n_head * T * T, T * T, T, 1))
-        dqkv = torch.empty_like(q)
-        dq, dk, dv = dqkv, dqkv.view(-1)[C:], dqkv.view(-1)[2 * C:]
-        ys = (T * C3, DH, C3, 1)
-        # dV[s, d] = sum_t P[t, s] dO[t, d]
-        _generic(Pm, dO, dv, Z, n_head, T, DH, T, (n_head * T * T, T * T, 1, T, 0), (T * C, DH, 1, C, 0), ys)
-        capi.call("ctts_softmax_bwd", Pm, dP, Z, T, T, T, 1.0, dP, st)
-        dS = dP
-        # dQ[t, d] = scale * sum_s dS[t, s] K[s, d];  dK[s, d] = scale * sum_t dS[t, s] Q[t, d]
-        _generic(dS, k, dq, Z, n_head, T, DH, T, (n_head * T * T, T * T, T, 1, 0), (T * C3, DH, 1, C3, 0), ys, alpha=scale)
-        _generic(dS, q, dk, Z, n_head, T, DH, T, (n_head * T * T, T * T, 1, T, 0), (T * C3, DH, 1, C3, 0), ys, alpha=scale)
+        if ctx.bwd_tc and DH % 64 == 0:
+            dqkv = _attention_bwd_tc(qkv, a.g, lens, n_head, scale)
+        else:
+            dqkv = _attention_bwd_fp32(qkv, a.g, lens, n_head, scale)
         accumulate_into(qkv, dqkv)
         a.g = None
 
@@ -988,6 +1054,7 @@ def forward_train(ctx, speakers, texts, src_lens, max_src_len, mels, mel_lens, m
     mel_lens_t = _i64(mel_lens) if mel_lens is not None else None
     B, S = texts.shape
     enc, word = ENCODERS[block](ctx, texts, src_lens)
+    ctx.marks["variance_adaptor"] = len(ctx.tape)     # closures below this index belong to the encoder
     spk = None
     if module.has_speaker_emb:
         if module.embedder_type == "none":
@@ -1008,6 +1075,7 @@ def forward_train(ctx, speakers, texts, src_lens, max_src_len, mels, mel_lens, m
             spk = _reshape(ctx, linear(ctx, e, "speaker_emb.weight", "speaker_emb.bias"), (B, -1))
     va = variance_adaptor(ctx, spk, enc, word, src_lens, mels, mel_lens_t, max_mel_len, p_targets, e_targets, d_targets,
                           attn_priors, p_control, e_control, step)
+    ctx.marks["decoder"] = len(ctx.tape)               # closures from here on: decoder + mel head
     dec = DECODERS[block](ctx, va["x"], va["mel_len"])
     mel, post = mel_head(ctx, dec)
     return va, mel, post

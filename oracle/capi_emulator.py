@@ -707,13 +707,15 @@ def ctts_gemm_batched_planes(n, ap, a_view, wp, w_view, addr, y_outer, y_inner, 
     for z in range(Z):
         zh = z % mod
         za, zw = z // a_div, z // w_div
-        Az = A.as_strided((T, K), (a_view[3], 1), za * a_view[4] + a_c0 + zh * a_step)
-        Wz = W.as_strided((N, K), (w_view[3], 1), zw * w_view[4] + w_c0 + zh * w_step)
         # out-of-range rows / columns of the views are TMA zero fill on the device
         ka = max(0, min(K, a_view[0] - (a_c0 + zh * a_step)))
         kw = max(0, min(K, w_view[0] - (w_c0 + zh * w_step)))
         kk = min(ka, kw)
-        out = alpha * (Az[:, :kk] @ Wz[:, :kk].t())
+        ra, rw = min(T, a_view[1]), min(N, w_view[1])
+        Az = A.as_strided((ra, kk), (a_view[3], 1), za * a_view[4] + a_c0 + zh * a_step)
+        Wz = W.as_strided((rw, kk), (w_view[3], 1), zw * w_view[4] + w_c0 + zh * w_step)
+        out = torch.zeros(T, N)
+        out[:ra, :rw] = alpha * (Az @ Wz.t())
         off = (z // mod) * y_outer + zh * y_inner
         if residual is not None:
             rf = _flat(residual)

@@ -104,3 +104,80 @@ def test_two_ranks_gloo_gradient_buckets():
     assert int(n_buckets) == 2          # [c (4000 B) + b (44 B)] | [a (8400 B > bucket size: alone)]
     assert int(c_first) == 1
     assert int(n_params) == 3           # a once, b, c; frozen skipped
+
+
+def test_two_ranks_data_parallel_training_step_arena_allreduce():
+    """world_size 2, gloo, kernels answered by the C-ABI emulator: the DistributedDataParallel stand-in leaves in
+    param.grad the MEAN over ranks of the per-rank gradients (train.py:58 semantics), reduced in place on slices of the
+    flat arena that are launched stage by stage during the backward pass."""
+    code = textwrap.dedent("""
+        import os, sys
+        for p in %r:
+            sys.path.insert(0, p)
+        os.environ["CTTS_DROPOUT"] = "0"
+        import torch, torch.distributed as dist
+        import cases, train_checks
+        from oracle import capi_emulator as emu
+        from ctts_b200 import dist as cd, synth
+        import ctts_b200
+
+        class MP:
+            def setattr(self, o, n, v): setattr(o, n, v)
+        emu.install(MP())
+        rank, world, _ = cd.env_rank_world()
+        dist.init_process_group("gloo")
+
+        def grads_for(seed, ddp):
+            (p, m, t), sd, _ = cases.build_case("fs2_train")
+            m["transformer_fs2"]["encoder_layer"] = 1
+            m["transformer_fs2"]["decoder_layer"] = 1
+            from ctts_b200 import spec
+            entries, _, _ = spec.parameter_spec(p, m)
+            sd = synth.synthetic_state_dict(entries, pin_frames_per_phoneme=None)
+            if ddp and rank == 1:                       # DDP broadcasts rank 0's parameters at construction
+                sd = {k: v + 1.0 if v.is_floating_point() and "running" not in k else v for k, v in sd.items()}
+            net = ctts_b200.CompTransTTS(p, m, t)
+            net.load_state_dict(sd, strict=True)
+            net.train()
+            model = cd.DistributedDataParallel(net) if ddp else net
+            batch = synth.ljspeech_batch(batch=2, s_max=12, s_step=3, mode="teacher", seed=seed)
+            args, kw = cases.call_kwargs(batch)
+            out = model(*args, **kw)
+            cases.train_objective(out).backward()
+            return net, net.grad_arena().flat.clone()
+
+        net, mine = grads_for(100 + rank, True)
+        launched = list(net._reducer.launched)
+        other = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(other, mine)
+        same = all(torch.equal(o, mine) for o in other)
+        if rank == 0:
+            _, g0 = grads_for(100, False)
+            _, g1 = grads_for(101, False)
+            ref = (g0 + g1) / 2
+            err = (mine - ref).abs().max().item() / ref.abs().max().item()
+            arena = net.grad_arena()
+            covered = sorted(launched)
+            contiguous = covered[0][0] == 0 and all(a[1] == b[0] for a, b in zip(covered, covered[1:])) \\
+                and covered[-1][1] == arena.flat.numel()
+            views = all(p.grad.data_ptr() == v.data_ptr() for p, v in arena.params)
+            print("RESULT", same, err, len(launched), contiguous, views)
+        dist.destroy_process_group()
+    """) % ([ROOT, os.path.join(ROOT, "comprehensive-transformer-tts_b200"), os.path.join(ROOT, "tests", "golden")],)
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(code)
+        path = f.name
+    try:
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29633", path], capture_output=True,
+                             text=True, timeout=600)
+    finally:
+        os.unlink(path)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+    assert line, out.stderr[-3000:]
+    _, same, err, n_launch, contiguous, views = line[0].split()
+    assert same == "True"                    # every rank ends up with the same gradients
+    assert float(err) < 1e-5                 # = the mean of the two single-process gradients
+    assert int(n_launch) >= 3                # decoder / variance adaptor / encoder stages were launched separately
+    assert contiguous == "True" and views == "True"
