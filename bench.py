@@ -158,6 +158,144 @@ def run_reference(args, rank, world):
     }))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Training step (BASELINE.json configs[2], [3]; train.py:104-123): forward in model.train() + objective + backward + the
+# data-parallel gradient all-reduce.  Reported as a sub-record of the headline line.
+TRAIN_CONFIGS = [
+    # name, dataset, block, learn_alignment, mode, global batch, s_max, s_step
+    ("transformer_fs2 LJSpeech-shape B16 supervised duration (configs[1] shape, training step)", "LJSpeech",
+     "transformer_fs2", False, "teacher", 16, 100, 2),
+    ("fastformer VCTK-shape B32 multi-speaker, unsupervised alignment (configs[3])", "VCTK", "fastformer", True, "unsup",
+     32, 50, 1),
+    ("conformer LJSpeech-shape B16 unsupervised alignment (configs[2])", "LJSpeech", "conformer", True, "unsup", 16, 100, 2),
+]
+
+
+def _train_objective(out):
+    """A scalar on every differentiable output (stands in for model/loss.py: plain torch on the 14-tuple)."""
+    terms = [out[0], out[1], out[4]]
+    if out[2] is not None:
+        terms += [out[2]["cwt"], out[2]["f0_mean"], out[2]["f0_std"]]
+    if out[3] is not None:
+        terms.append(out[3])
+    if out[10][0] is not None:
+        terms += [out[10][0], out[10][3]]
+    return sum(t.float().pow(2).mean() for t in terms)
+
+
+def train_record(rank, world, dev, steps=5, warmup=2, only=None):
+    import torch.distributed as dist
+    import ctts_b200
+    from ctts_b200 import capi, configs, spec, synth
+    from ctts_b200 import dist as cdist
+    records = []
+    for idx, (name, dataset, block, learn, mode, gbatch, s_max, s_step) in enumerate(TRAIN_CONFIGS):
+        if only is not None and idx not in only:
+            continue
+        if gbatch % world:
+            continue
+        per = gbatch // world
+        p, m, t = configs.builtin_configs(dataset, block_type=block, learn_alignment=learn)
+        sd = synth.synthetic_state_dict(spec.parameter_spec(p, m)[0], pin_frames_per_phoneme=None)
+        net = ctts_b200.CompTransTTS(p, m, t)
+        net.load_state_dict(sd, strict=True)
+        net.to(dev).train()
+        model = cdist.DistributedDataParallel(net) if world > 1 else net
+        # the global batch is synthesised identically on every rank and each rank keeps its contiguous slice (train.py:237)
+        full = synth.ljspeech_batch(batch=gbatch, s_max=s_max, s_step=s_step, mode=mode, seed=7,
+                                    spk_dim=512 if dataset == "VCTK" else None)
+        lo, hi = rank * per, (rank + 1) * per
+
+        def cut(v):
+            if torch.is_tensor(v):
+                return v[lo:hi].contiguous().to(dev) if v.dim() > 0 and v.shape[0] == gbatch else v.to(dev)
+            if isinstance(v, dict):
+                return {k: cut(x) for k, x in v.items()}
+            return v
+
+        b = {k: cut(v) for k, v in full.items()}
+        S = int(b["src_lens"].max())
+        M = int(b["mel_lens"].max())
+        b["texts"] = b["texts"][:, :S].contiguous()
+        b["max_src_len"], b["max_mel_len"] = S, M
+        b["mels"] = b["mels"][:, :M].contiguous()
+        for k in list(b["p_targets"]):
+            v = b["p_targets"][k]
+            if v.dim() >= 2:
+                b["p_targets"][k] = v[:, :M].contiguous()
+        if mode == "teacher":
+            b["e_targets"] = b["e_targets"][:, :S].contiguous()
+            b["d_targets"] = b["d_targets"][:, :S].contiguous()
+        else:
+            b["e_targets"] = b["e_targets"][:, :M].contiguous()
+            b["attn_priors"] = b["attn_priors"][:, :S, :M].contiguous()
+        frames_global = int(full["mel_lens"].sum())
+        kw = {k: b[k] for k in ("mels", "mel_lens", "max_mel_len", "p_targets", "e_targets", "d_targets", "attn_priors",
+                                "spker_embeds") if k in b}
+        if mode == "unsup":
+            kw["step"] = 120000
+
+        def one_step():
+            import copy
+            k2 = dict(kw)
+            k2["p_targets"] = dict(kw["p_targets"])
+            net.zero_grad(set_to_none=True)
+            out = model(b["speakers"], b["texts"], b["src_lens"], b["max_src_len"], **k2)
+            _train_objective(out).backward()
+
+        def timed(n_steps, n_warm):
+            for _ in range(n_warm):
+                one_step()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            l0 = capi.LAUNCHES
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n_steps):
+                one_step()
+            e1.record()
+            e1.synchronize()
+            if world > 1:
+                dist.barrier()
+            return cdist.max_over_ranks(e0.elapsed_time(e1), dev, world) / n_steps, (capi.LAUNCHES - l0) // n_steps
+
+        ms, launches = timed(steps, warmup)
+        rec = {"config": name, "global_batch": gbatch, "per_gpu_batch": per, "scaling": "strong (global batch fixed, "
+               "train.py:237)", "S_max": S, "M_max": M, "valid_mel_frames_global": frames_global, "steps": steps,
+               "ms_per_step": ms, "mel_frames_per_s": frames_global / (ms * 1e-3), "kernel_launches_per_step": launches,
+               "includes": "training-mode forward, objective, backward, gradient all-reduce (N > 1); no optimizer step",
+               "dropout": os.environ.get("CTTS_DROPOUT", "1") != "0"}
+        arena = net.grad_arena()
+        rec["grad_arena_mb"] = arena.flat.numel() * 4 / 1e6
+        if world > 1:
+            net._reducer.enabled = False
+            ms_off, _ = timed(steps, 1)
+            net._reducer.enabled = True
+            # the all-reduce alone: the whole arena in one call, on an otherwise idle GPU
+            torch.cuda.synchronize()
+            dist.barrier()
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dist.all_reduce(arena.flat)
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ar = cdist.max_over_ranks(sorted(ts)[len(ts) // 2], dev, world)
+            nbytes = arena.flat.numel() * 4
+            rec.update({"ms_per_step_without_allreduce": ms_off, "allreduce_exposed_ms": ms - ms_off,
+                        "allreduce_standalone_ms": ar, "allreduce_bus_gbs": 2 * (world - 1) / world * nbytes / (ar * 1e-3) / 1e9,
+                        "allreduce_buckets": len(net._reducer.launched),
+                        "nvlink_peak_gbs_per_direction": 900.0})
+        records.append(rec)
+        del net, model
+        torch.cuda.empty_cache()
+    return records
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +303,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record")
+    ap.add_argument("--train-only", action="store_true", help="print only the training-step record (development)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,6 +321,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     args.warmup = max(args.warmup, 3)
+
+    if args.train_only:
+        recs = train_record(rank, world, dev)
+        if rank == 0:
+            print(json.dumps({"train": recs, "n_gpus": world}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cfgs, sd, batch, frames = build_workload(seed=rank)
     net = ctts_b200.CompTransTTS(*cfgs).eval()
@@ -275,6 +423,14 @@ def main():
     if graphs_were_on:
         launches = eager_launches   # kernels per step are the same; replayed steps do not pass through capi.call
     clocks = sampler.stop() if sampler else None
+    train = None
+    if not args.no_train:
+        del flush
+        torch.cuda.empty_cache()
+        try:
+            train = train_record(rank, world, dev)
+        except Exception as e:      # the headline line must not be lost to a failure of the sub-record
+            train = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     if rank == 0:
         pk = peaks()
@@ -316,6 +472,8 @@ def main():
                                           "(host kept ahead of the GPU by a device-side spin at the start of each stage)",
                          "flops_per_launch": frames * FFN_FLOP_PER_FRAME},
         }
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
             v, iters, threads, med = cpu_forward_timer(cfgs, sd, batch, frames)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

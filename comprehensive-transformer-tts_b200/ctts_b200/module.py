@@ -118,6 +118,7 @@ class CompTransTTS(nn.Module):
         self._prepared = engine.Prepared(self)
         # training step (train_engine.py): flat gradient arena, dropout stream, optional data-parallel reducer
         self._arena = None
+        self._train_weights = None
         self._anchor = None
         self._reducer = None
         self._dropout_seed = int(os.environ.get("CTTS_DROPOUT_SEED", train_config.get("seed", 1234)
@@ -130,6 +131,7 @@ class CompTransTTS(nn.Module):
         from . import train_engine
         if self._arena is None or self._arena.sig != train_engine.GradArena.signature(self):
             self._arena = train_engine.GradArena(self)
+            self._train_weights = train_engine.TrainWeights()
         return self._arena
 
     def autograd_anchor(self, device):

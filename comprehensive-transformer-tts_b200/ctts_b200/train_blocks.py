@@ -34,7 +34,7 @@ def _add_abs(ctx, x):
 def linear_cat(ctx, x, vname, parts, math, out_planes=0):
     """One GEMM over the concatenation of several [C, C] projections (prep.w[vname], built by engine_blocks.PREPARE): the
     weight gradient of the concatenation is distributed to the parts' arena slots afterwards."""
-    ctx.P[vname] = ctx.W[vname]
+    cat = ctx.concat(vname, parts)
     holder = {}
 
     def distribute():
@@ -54,7 +54,7 @@ def linear_cat(ctx, x, vname, parts, math, out_planes=0):
     y = linear(ctx, x, vname, math=math, out_planes=out_planes)
 
     def alloc():
-        holder["g"] = ctx.G[vname] = torch.zeros_like(ctx.W[vname])
+        holder["g"] = ctx.G[vname] = torch.zeros_like(cat)
 
     ctx.record(alloc)
     return y

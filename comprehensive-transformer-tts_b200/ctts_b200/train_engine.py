@@ -116,14 +116,45 @@ class GradArena:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+class TrainWeights:
+    """Kernel-layout copies of the weights the training step uses (tap-major packed Conv1d weights, bf16 operand planes,
+    dgrad re-packs, concatenated projections), built lazily PER WEIGHT and re-built only when that weight's storage or
+    version changed -- i.e. once per optimizer step for the weights a step actually touches."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, key, sources, build):
+        sig = tuple((t.data_ptr(), t._version) for t in sources)
+        e = self.cache.get(key)
+        if e is None or e[0] != sig:
+            e = (sig, build())
+            self.cache[key] = e
+        return e[1]
+
+
+_CONSTANTS = {}
+
+
+def cwt_scale_weights(device):
+    """(i + 1 + 2.5) ** -2.5 for the 10 CWT scales, utils/pitch_tools.py:260."""
+    k = ("cwt_scale_w", str(device))
+    if k not in _CONSTANTS:
+        _CONSTANTS[k] = ((torch.arange(0, 10).float() + 1 + 2.5) ** (-2.5)).to(device)
+    return _CONSTANTS[k]
+
+
 class Ctx:
     """State of one training step: parameters, kernel-layout weights, the tape, dropout stream."""
 
     def __init__(self, module, arena):
         self.module = module
-        self.prep = module._prepared
-        self.P = dict(self.prep.params())     # per-step copies: blocks add virtual (concatenated) weights
-        self.W = self.prep.w
+        self.prep = module._prepared          # positional tables only (they do not depend on the weights)
+        P = {k: v for k, v in module.named_parameters(remove_duplicate=False)}
+        P.update({k: v for k, v in module.named_buffers(remove_duplicate=False)})
+        self.P = P                            # per-step dict: blocks add virtual (concatenated) weights
+        self.src = {}                         # virtual weight name -> the parameters it is built from
+        self.tw = module._train_weights
         self.G = dict(arena.views)
         self.tape = []
         self.cfg = module.model_config
@@ -135,8 +166,6 @@ class Ctx:
         self.dropout_on = os.environ.get("CTTS_DROPOUT", "1") != "0"
         self.seed = module._dropout_seed
         self.offset = module._dropout_offset
-        self._dgrad = {}
-        self._wplanes = {}
         self.hooks = []          # (tape position, callable): fired when the backward pass reaches that position
         self.marks = {}          # stage name -> index of its first tape closure
 
@@ -144,38 +173,46 @@ class Ctx:
         self.tape.append(fn)
 
     # -- kernel-layout weights -------------------------------------------------------------------------------------
+    def _sources(self, name):
+        return self.src.get(name) or [self.P[name]]
+
+    def concat(self, vname, parts):
+        """Virtual weight: rows of several projections stacked (q | k | v)."""
+        srcs = [self.P[n] for n in parts]
+        self.src[vname] = srcs
+        self.P[vname] = self.tw.get(("cat", vname), srcs, lambda: torch.cat([_f32(t.detach()) for t in srcs], 0).contiguous())
+        return self.P[vname]
+
     def packed(self, name):
         """fp32 weight as [N, taps*Cin] (tap-major for Conv1d)."""
         t = self.P[name]
-        return self.W[name] if t.dim() == 3 else t
+        if t.dim() != 3:
+            return t
+
+        def build():
+            n, cin, taps = t.shape
+            out = torch.empty(n, taps * cin, device=t.device, dtype=torch.float32)
+            capi.call("ctts_pack_conv_weight", _f32(t.detach()), n, cin, taps, out, _st())
+            return out
+        return self.tw.get(("packed", name), self._sources(name), build)
 
     def weight_planes(self, name, n):
-        key = name + ("#planes" if n == 2 else "#planes3")
-        wp = self.W.get(key)
-        if wp is None:
-            wp = self._wplanes.get(key)
-            if wp is None:
-                wp = self._wplanes[key] = engine.split_planes(self.packed(name), n)
-        return wp
+        return self.tw.get(("planes", name, n), self._sources(name), lambda: engine.split_planes(self.packed(name), n))
 
     def dgrad_packed(self, name):
         """[Cin, taps*N] with flipped taps: dx = conv(dz, wd)."""
-        d = self._dgrad.get(name)
-        if d is None:
-            t = self.P[name]
+        t = self.P[name]
+
+        def build():
             N, Cin = t.shape[0], t.shape[1]
             taps = t.shape[2] if t.dim() == 3 else 1
             wd = torch.empty(Cin, taps * N, device=t.device, dtype=torch.float32)
             capi.call("ctts_pack_conv_weight_dgrad", _f32(t.detach()), N, Cin, taps, wd, _st())
-            d = self._dgrad[name] = [wd, None]
-        return d[0]
+            return wd
+        return self.tw.get(("dgrad", name), self._sources(name), build)
 
     def dgrad_planes(self, name):
-        self.dgrad_packed(name)
-        d = self._dgrad[name]
-        if d[1] is None:
-            d[1] = engine.split_planes(d[0], 2)
-        return d[1]
+        return self.tw.get(("dgrad_planes", name), self._sources(name), lambda: engine.split_planes(self.dgrad_packed(name), 2))
 
     def next_offset(self):
         self.offset += 1
@@ -909,7 +946,7 @@ def variance_adaptor(ctx, spk, text, text_embedding, src_lens, mel, mel_lens, ma
         f0_denorm = torch.empty(B, M, device=dev, dtype=torch.float32)
         idx = torch.empty(B, M, device=dev, dtype=torch.int64)
         spec = _f32(pitch_target["cwt_spec"])
-        capi.call("ctts_cwt_to_pitch", spec, spec.shape[-1], ctx.W["cwt_scale_w"], _f32(pitch_target["f0_mean"]),
+        capi.call("ctts_cwt_to_pitch", spec, spec.shape[-1], cwt_scale_weights(dev), _f32(pitch_target["f0_mean"]),
                   _f32(pitch_target["f0_std"]), 1, 1.0, float(pitch_cfg["pitch_norm_eps"]), _f32(pitch_target["uv"]),
                   1 if pitch_cfg["use_uv"] else 0, B, M, f0n, f0_denorm, idx, st)
         pitch_target["f0"] = f0n
