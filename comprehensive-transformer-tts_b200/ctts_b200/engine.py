@@ -181,6 +181,7 @@ class Prepared:
         self.sig = None
         self.w = {}
         self.pe = {}
+        self.pe_retired = []
 
     def _signature(self, P):
         return tuple((k, v.data_ptr(), v._version) for k, v in P.items())
@@ -240,6 +241,10 @@ class Prepared:
         key = ("fs2", dim, str(device))
         tab = self.pe.get(key)
         if tab is None or tab.shape[0] < rows:
+            if tab is not None:
+                # captured CUDA graphs hold the old table's address: keep it alive (its rows are a prefix of the new one)
+                self.pe_retired.append(tab)
+                rows = max(rows, 2 * tab.shape[0])     # grow geometrically: regrowth stays rare
             rows = max(rows, 2048)
             half = dim // 2
             step = math.log(10000) / (half - 1)
@@ -714,6 +719,7 @@ class GraphCache:
                 out = fn(static)
             e = table[key] = (g, static, out, {})
         g, static, out, sub = e
+        table[key] = table.pop(key)          # LRU: a hit moves the entry to the young end, eviction takes the oldest
         for k, v in tensor_inputs.items():
             static[k].copy_(v, non_blocking=True)
         g.replay()
@@ -753,8 +759,9 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
     sig_before = prep.sig
     P = prep.params()
     graphs = module._graphs if module.use_cuda_graphs else None
-    if graphs is not None and prep.sig is not sig_before:
-        graphs.clear()   # weights were re-laid-out: captured graphs point at stale buffers
+    if prep.sig is not sig_before:
+        module._graphs.clear()   # weights were re-laid-out: captured graphs point at stale buffers (also when graphs are
+        #                          switched off right now -- they may be switched on again later)
     texts = _i64(texts)
     src_lens = _i64(src_lens)
     B, S = texts.shape

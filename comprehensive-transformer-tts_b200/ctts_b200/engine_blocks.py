@@ -30,6 +30,9 @@ def abs_table(prep, P, key, T, d, max_seq_len, device):
     ck = ("interleaved", d, str(device))
     tab = prep.pe.get(ck)
     if tab is None or tab.shape[0] < T:
+        if tab is not None:
+            prep.pe_retired.append(tab)    # captured CUDA graphs hold its address (rows are a prefix of the new table)
+            T = max(T, 2 * tab.shape[0])
         tab = _interleaved_table(T, d, device)
         prep.pe[ck] = tab
     return tab
