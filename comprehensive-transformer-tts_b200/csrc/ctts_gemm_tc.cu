@@ -51,6 +51,7 @@ struct Epilogue {
     float alpha;
     int act;
     long long* dbg;         // optional per-CTA cycle stamps {start, setup done, accumulator ready, epilogue done}
+    int atomic;             // split-K: y += v with fp32 atomics instead of a store (y only; no planes)
 };
 
 struct Maps {               // TMA descriptors of the operand planes (NP of each are used)
@@ -155,7 +156,10 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg
             v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
         }
         if (!keep) { v[0] = v[1] = v[2] = v[3] = 0.f; }
-        if (ep.y) *reinterpret_cast<float4*>(ep.y + off) = make_float4(v[0], v[1], v[2], v[3]);
+        if (ep.atomic) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(ep.y + off + j, v[j]);
+        } else if (ep.y) *reinterpret_cast<float4*>(ep.y + off) = make_float4(v[0], v[1], v[2], v[3]);
         if (ep.yp[0]) {
             float rem[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
@@ -214,7 +218,16 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
     const int zh = z % ad.mod;
     const int n0 = blockIdx.y * BLOCK_N;
     const int kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
-    const int num_kb = (ad.kz > 0 ? ad.kz : taps) * kb_per_tap;
+    const int num_kb_all = (ad.kz > 0 ? ad.kz : taps) * kb_per_tap;
+    // split-K (K-batched mode only): gridDim.z CTAs share one output tile, each reduces its own range of k-blocks and adds
+    // its partial tile to y with atomics (Epilogue::atomic)
+    int kb0 = 0, num_kb = num_kb_all;
+    if (gridDim.z > 1) {
+        const int chunk = (num_kb_all + (int)gridDim.z - 1) / (int)gridDim.z;
+        kb0 = (int)blockIdx.z * chunk;
+        num_kb = min(num_kb_all - kb0, chunk);
+        if (num_kb <= 0) return;     // whole CTA, before any barrier / TMEM use (CM == 1 in this mode)
+    }
     const int pad = taps >> 1;
 
     if (warp == 0 && lane == 0) {
@@ -254,9 +267,10 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+            for (int it = 0; it < num_kb; ++it) {
+                const int kb = kb0 + it;
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 mbar_expect_tx(&full_bar[s], (uint32_t)S::STAGE_BYTES);
                 const int tap = kb / kb_per_tap;
@@ -875,9 +889,11 @@ struct Operand {          // NP bf16 planes viewed as a 3-D tensor [d2][d1][d0] 
     cuuint64_t s1, s2;       // strides of d1 / d2 in elements
 };
 
+static int num_sms();
+
 template <int BLOCK_N, int STAGES, int NP, int CM>
 static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin, int N,
-                  int taps, cudaStream_t st, int seg_rows) {
+                  int taps, cudaStream_t st, int seg_rows, int grid_z = 1) {
     using S = Smem<BLOCK_N, STAGES, NP>;
     Maps maps;
     {
@@ -916,7 +932,7 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
     const int m_tiles = seg_rows > 0 ? (int)(((long long)Z * T + BLOCK_M - 1) / BLOCK_M) : Z * tiles_per_utt;
     const int gx = ((m_tiles + CM - 1) / CM) * CM;   // an odd grid gets one padding CTA (it computes, never stores)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(gx, (N + BLOCK_N - 1) / BLOCK_N, 1);
+    cfg.gridDim = dim3(gx, (N + BLOCK_N - 1) / BLOCK_N, grid_z);
     cfg.blockDim = dim3(320, 1, 1);
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = st;
@@ -1427,11 +1443,24 @@ extern "C" int ctts_gemm_wgrad(int n_planes, const void* const* dzT_planes, cons
         W.p[p] = xT_planes[p];
     }
     Epilogue ep{nullptr, nullptr, nullptr, accumulate ? dw_packed : nullptr, nullptr, dw_packed, {nullptr, nullptr, nullptr},
-                alpha, CTTS_ACT_NONE, nullptr};
+                alpha, CTTS_ACT_NONE, nullptr, 0};
     Addr ad{1, 1, 0, 0, 1, 0, 0, 1, (int)KC, 0, 0, B, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_planes == 3) return launch<128, 2, 3, 1>(A, W, ep, ad, 1, N, T, (int)KC, 1, st, 0);
-    return launch<128, 3, 2, 1>(A, W, ep, ad, 1, N, T, (int)KC, 1, st, 0);
+    // Split-K: a [256 x 256] weight is only 4 output tiles and its reduction runs over all B*T rows (212 k-blocks at the
+    // benchmark shape: measured 118 us on 4 SMs).  The k-blocks are spread over gridDim.z CTAs per tile (>= 8 k-blocks
+    // each, ~2 CTAs per SM in total); the partial tiles are added with fp32 atomics -- a weight gradient accumulates anyway.
+    const long long tiles = (long long)((N + 127) / 128) * (long long)((KC + 127) / 128);
+    const long long num_kb = (long long)B * ((T + BLOCK_K - 1) / BLOCK_K);
+    long long ksplit = (2LL * num_sms()) / tiles;
+    if (ksplit > num_kb / 8) ksplit = num_kb / 8;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > 1) {
+        if (!accumulate) cudaMemsetAsync(dw_packed, 0, (size_t)N * KC * sizeof(float), st);
+        ep.residual = nullptr;
+        ep.atomic = 1;
+    }
+    if (n_planes == 3) return launch<128, 2, 3, 1>(A, W, ep, ad, 1, N, T, (int)KC, 1, st, 0, (int)ksplit);
+    return launch<128, 3, 2, 1>(A, W, ep, ad, 1, N, T, (int)KC, 1, st, 0, (int)ksplit);
 }
 
 // ---- batched plane GEMM with explicit operand views (the products of the attention backward) ---------------------------

@@ -634,8 +634,9 @@ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr, uint6
 }
 
 __global__ void dropout_kernel(const float* __restrict__ x, size_t n, float p, uint64_t seed, uint64_t offset,
-                               float* __restrict__ y) {
+                               const unsigned long long* __restrict__ offset_dev, float* __restrict__ y) {
     CTTS_PDL_SYNC();
+    if (offset_dev) offset += (uint64_t)offset_dev[0];    // step counter kept on the device: a replayed CUDA graph draws fresh masks
     const float inv = 1.f / (1.f - p);
     const uint32_t thresh = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
     const size_t n4 = (n + 3) >> 2;
@@ -687,27 +688,49 @@ template <int NP>
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ x, int R, int C, int ld_in, int c0, int Rp, int taps, const TPlanes out) {
     CTTS_PDL_SYNC();
-    __shared__ float tile[32][33];
+    // 64 x 64 tiles: float4 row loads (when the row pitch allows), bf16x2 stores of two neighbouring rows -> every warp
+    // store instruction writes one whole 128-byte output row segment per plane
+    __shared__ float tile[64][65];
     const int z = blockIdx.z / taps, tap = blockIdx.z - z * taps;
     const int shift = tap - (taps >> 1);
-    const int r0 = blockIdx.x * 32, cc0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int i = ty; i < 32; i += 8) {
-        const int r = r0 + i, rs = r + shift, c = cc0 + tx;
-        tile[i][tx] = (r < R && rs >= 0 && rs < R && c < C) ? x[((size_t)z * R + rs) * ld_in + c0 + c] : 0.f;
+    const int r0 = blockIdx.x * 64, cc0 = blockIdx.y * 64;
+    const int tid = threadIdx.x;
+    const bool vec = ((ld_in | c0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (C & 3) == 0;
+    {
+        const int cq = (tid & 15) * 4, rr = tid >> 4;      // 16 lanes x float4 cover 64 columns; 16 rows per pass
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rl = rr + 16 * i, r = r0 + rl, rs = r + shift, c = cc0 + cq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < R && rs >= 0 && rs < R) {
+                const float* src = x + ((size_t)z * R + rs) * ld_in + c0 + c;
+                if (vec && c + 3 < C) v = *reinterpret_cast<const float4*>(src);
+                else {
+                    if (c < C) v.x = src[0];
+                    if (c + 1 < C) v.y = src[1];
+                    if (c + 2 < C) v.z = src[2];
+                    if (c + 3 < C) v.w = src[3];
+                }
+            }
+            tile[rl][cq] = v.x; tile[rl][cq + 1] = v.y; tile[rl][cq + 2] = v.z; tile[rl][cq + 3] = v.w;
+        }
     }
     __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        const int c = cc0 + i, r = r0 + tx;
-        if (c < C && r < Rp) {
-            float rem = tile[tx][i];
-            const size_t o = (((size_t)z * taps + tap) * C + c) * Rp + r;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int r = r0 + 2 * lane;
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(rem);
-                out.p[p][o] = h;
-                rem -= __bfloat162float(h);
-            }
+    for (int i = 0; i < 8; ++i) {
+        const int cl = warp + 8 * i, c = cc0 + cl;
+        if (c >= C || r >= Rp) continue;
+        float a = tile[2 * lane][cl], b = tile[2 * lane + 1][cl];
+        const size_t o = (((size_t)z * taps + tap) * C + c) * Rp + r;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            if (r + 1 < Rp) *reinterpret_cast<__nv_bfloat162*>(out.p[p] + o) = h;
+            else out.p[p][o] = __low2bfloat16(h);
+            a -= __low2float(h);
+            b -= __high2float(h);
         }
     }
 }
@@ -1213,9 +1236,11 @@ int ctts_bn_bwd(const float* dy, const float* x, const float* mean, const float*
     return check_launch("bn_bwd");
 }
 
-int ctts_dropout(const float* x, size_t n, float p, unsigned long long seed, unsigned long long offset, float* y, void* stream) {
+int ctts_dropout(const float* x, size_t n, float p, unsigned long long seed, unsigned long long offset,
+                 const unsigned long long* offset_dev, float* y, void* stream) {
     CTTS_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "dropout: bad arguments (p=%f)", (double)p);
-    launch_k(dropout_kernel, grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream, x, n, p, (uint64_t)seed, (uint64_t)offset, y);
+    launch_k(dropout_kernel, grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream, x, n, p, (uint64_t)seed, (uint64_t)offset,
+             offset_dev, y);
     return check_launch("dropout");
 }
 
@@ -1242,7 +1267,8 @@ int ctts_split_transpose(const float* x, int Z, int R, int C, int ld_in, int c0,
         CTTS_REQUIRE(planes[p], "split_transpose: NULL plane");
         tp.p[p] = (__nv_bfloat16*)planes[p];
     }
-    dim3 grid((Rp + 31) / 32, (C + 31) / 32, Z * taps);
+    CTTS_REQUIRE(Rp % 2 == 0, "split_transpose: Rp must be even");
+    dim3 grid((Rp + 63) / 64, (C + 63) / 64, Z * taps);
     if (n_planes == 3) launch_k(split_transpose_kernel<3>, grid, 256, 0, (cudaStream_t)stream, x, R, C, ld_in, c0, Rp, taps, tp);
     else launch_k(split_transpose_kernel<2>, grid, 256, 0, (cudaStream_t)stream, x, R, C, ld_in, c0, Rp, taps, tp);
     return check_launch("split_transpose");

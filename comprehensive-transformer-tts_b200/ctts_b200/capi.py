@@ -72,7 +72,7 @@ SIGNATURES = {
     "ctts_bn_act_fwd": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _I, _P, _P],
     "ctts_bn_update_running": [_P, _P, _I, _F, _I, _P, _P, _P, _P],
     "ctts_bn_bwd": [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P],
-    "ctts_dropout": [_P, _Z, _F, ctypes.c_ulonglong, ctypes.c_ulonglong, _P, _P],
+    "ctts_dropout": [_P, _Z, _F, ctypes.c_ulonglong, ctypes.c_ulonglong, _P, _P, _P],
     "ctts_pack_conv_weight_dgrad": [_P, _I, _I, _I, _P, _P],
     "ctts_unpack_conv_wgrad": [_P, _I, _I, _I, _I, _P, _P],
     "ctts_split_transpose": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],

@@ -157,6 +157,7 @@ class ArenaAllReduce:
     def begin(self, ctx, arena):
         """Register the launch points of this backward pass on the tape."""
         self.works, self.launched = [], []
+        ctx.hooks = []
         if self.world == 1 or not self.enabled:
             return
         runs = self._runs(arena)

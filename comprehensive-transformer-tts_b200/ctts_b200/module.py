@@ -124,6 +124,16 @@ class CompTransTTS(nn.Module):
         self._dropout_seed = int(os.environ.get("CTTS_DROPOUT_SEED", train_config.get("seed", 1234)
                                                 if isinstance(train_config, dict) else 1234))
         self._dropout_offset = 0
+        self._dropout_counter = None
+        from . import train_engine
+        self._train_graphs = train_engine.TrainGraphs()
+        self._train_graphs.sig = None
+
+    def dropout_counter(self, device):
+        """Device-side step counter of the dropout stream (added to every site's offset; CUDA-graph mode)."""
+        if self._dropout_counter is None or self._dropout_counter.device != device:
+            self._dropout_counter = torch.zeros(1, device=device, dtype=torch.int64)
+        return self._dropout_counter
 
     def grad_arena(self):
         """The flat fp32 buffer all parameter gradients live in (param.grad are views of it); rebuilt when the parameters

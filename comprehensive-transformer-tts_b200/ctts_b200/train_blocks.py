@@ -237,7 +237,7 @@ def _relpos_attention(ctx, a, qkv, pos_proj, n_head, p_drop):
     if p_drop > 0.0 and ctx.dropout_on:
         drop_off = ctx.next_offset()
         prob_used = torch.empty_like(prob)
-        capi.call("ctts_dropout", prob, prob.numel(), float(p_drop), ctx.seed, drop_off, prob_used, st)
+        capi.call("ctts_dropout", prob, prob.numel(), float(p_drop), ctx.seed, drop_off, ctx.offset_dev, prob_used, st)
     out = torch.empty(B, T, C, device=dev, dtype=torch.float32)
     # ctx[b, t, h*dh + d] = sum_s P[z][t, s] v[b, s, h*dh + d]
     _generic(prob_used, vv, out, Z, n_head, T, dh, T, (n_head * TT, TT, T, 1, 0), (T * C3, dh, 1, C3, 0), (T * C, dh, C, 1))
@@ -255,7 +255,7 @@ def _relpos_attention(ctx, a, qkv, pos_proj, n_head, p_drop):
         _generic(dO, vv, dP, Z, n_head, T, T, dh, hs_q, hs_kv, sc)
         _generic(prob_used, dO, dv, Z, n_head, T, dh, T, (n_head * TT, TT, 1, T, 0), (T * C, dh, 1, C, 0), (T * C3, dh, C3, 1))
         if drop_off is not None:
-            capi.call("ctts_dropout", dP, dP.numel(), float(p_drop), ctx.seed, drop_off, dP, st2)
+            capi.call("ctts_dropout", dP, dP.numel(), float(p_drop), ctx.seed, drop_off, ctx.offset_dev, dP, st2)
         capi.call("ctts_softmax_bwd", prob, dP, Z, T, T, T, 1.0, dP, st2)
         dcontent = torch.empty(Z, T, T, device=dev, dtype=torch.float32)
         dpos = torch.empty(Z, T, T, device=dev, dtype=torch.float32)

@@ -166,6 +166,7 @@ class Ctx:
         self.dropout_on = os.environ.get("CTTS_DROPOUT", "1") != "0"
         self.seed = module._dropout_seed
         self.offset = module._dropout_offset
+        self.offset_dev = None   # device step counter added to every dropout offset (CUDA-graph mode)
         self.hooks = []          # (tape position, callable): fired when the backward pass reaches that position
         self.marks = {}          # stage name -> index of its first tape closure
 
@@ -300,7 +301,7 @@ def _wgrad(ctx, dz, x, wname, taps):
     B, T, N = dz.shape
     Cin = x.v.shape[-1]
     st = _st()
-    if ctx.bwd_tc and Cin % 4 == 0 and N >= 32:
+    if ctx.bwd_tc and Cin % 4 == 0:
         Tp = (T + 7) // 8 * 8
         dzT = transposed_planes(dz)
         if x._tplanes is None:
@@ -417,13 +418,13 @@ def dropout(ctx, x, p):
         return x
     off = ctx.next_offset()
     out = torch.empty_like(x.v)
-    capi.call("ctts_dropout", x.v, x.v.numel(), float(p), ctx.seed, off, out, _st())
+    capi.call("ctts_dropout", x.v, x.v.numel(), float(p), ctx.seed, off, ctx.offset_dev, out, _st())
     y = Var(out)
 
     def bwd():
         if y.g is None:
             return
-        capi.call("ctts_dropout", y.g, y.g.numel(), float(p), ctx.seed, off, y.g, _st())
+        capi.call("ctts_dropout", y.g, y.g.numel(), float(p), ctx.seed, off, ctx.offset_dev, y.g, _st())
         accumulate_into(x, y.g)
         y.g = None
 
@@ -904,10 +905,13 @@ def variance_adaptor(ctx, spk, text, text_embedding, src_lens, mel, mel_lens, ma
     cum_lr, cum_m2p, lens2 = engine.length_scan(duration_rounded, src_lens, B, S, dev)
     soft = attn_prior is not None and step < tcfg["duration"]["binarization_start_steps"]
     need_m2p = attn_prior is not None
-    if max_len is None or need_m2p:
-        maxes = lens2.view(2, B).max(dim=1).values.tolist()       # the step's single host sync
-        M = int(max_len) if max_len is not None else int(maxes[0])
-        M2 = int(maxes[1])
+    if max_len is None:
+        maxes = lens2.view(2, B).max(dim=1).values.tolist()       # host sync (only when the caller gives no max_mel_len)
+        M, M2 = int(maxes[0]), int(maxes[1])
+    elif need_m2p:
+        # MAS assigns every frame of utterance b to exactly one phoneme, so the durations sum to mel_lens[b] and the length
+        # of mel2ph is max(mel_lens) -- which is what train.py passes as max_mel_len (utils/tools.py:69-147): no host sync
+        M = M2 = int(max_len)
     else:
         M, M2 = int(max_len), 0
     mel2ph = torch.empty(B, M2, device=dev, dtype=torch.int64) if (need_m2p and M2 > 0) else None
@@ -1135,27 +1139,181 @@ class StepFunction(torch.autograd.Function):
         return None, None
 
 
-def run_backward(ctx, arena, out_vars, grads, world=1, reducer=None):
+def _seed_gradients(out_vars, grads, world):
+    """Private copies of the incoming output gradients with DDP's 1/world mean folded in (train.py:58)."""
     st = _st()
-    arena.begin_backward()
     inv = 1.0 / world
     for var, g in zip(out_vars, grads):
         if var is None or g is None:
             continue
         buf = torch.empty(var.v.shape, device=var.v.device, dtype=torch.float32)
         gc = g if (g.is_contiguous() and g.dtype == torch.float32) else g.float().contiguous()
-        capi.call("ctts_axpy", gc, inv, gc.numel(), 0, buf, st)     # private copy, 1/world folded in (train.py:58 DDP mean)
+        capi.call("ctts_axpy", gc, inv, gc.numel(), 0, buf, st)
         var.g = buf
-    hooks = dict(ctx.hooks)
-    for i in range(len(ctx.tape) - 1, -1, -1):
-        ctx.tape[i]()
-        h = hooks.get(i)
-        if h is not None:
+
+
+def _segments(ctx, reducer):
+    """Tape ranges [hi, lo] (replayed downwards) between the points where a slice of the gradient arena becomes final."""
+    n = len(ctx.tape)
+    if reducer is None or reducer.world == 1 or not reducer.enabled:
+        return [(n - 1, 0, None)]
+    cuts = sorted({min(max(i, 0), n) for i, _ in ctx.hooks}, reverse=True)
+    fire = {}
+    for i, fn in ctx.hooks:
+        fire.setdefault(min(max(i, 0), n), []).append(fn)
+    segs, hi = [], n - 1
+    for c in cuts:
+        if c <= 0:
+            continue
+        segs.append((hi, c, fire[c]))
+        hi = c - 1
+    segs.append((hi, 0, fire.get(0)))
+    return segs
+
+
+def run_backward(ctx, arena, out_vars, grads, world=1, reducer=None):
+    """Eager backward: replay the tape in reverse; launch the arena all-reduce of a stage as soon as the stage is done."""
+    arena.begin_backward()
+    _seed_gradients(out_vars, grads, world)
+    for hi, lo, hooks in _segments(ctx, reducer):
+        for i in range(hi, lo - 1, -1):
+            ctx.tape[i]()
+        for h in hooks or ():
             h()
     ctx.tape = []
     if reducer is not None:
         reducer.finish()
     arena.publish()
+
+
+def _leaves_of(va, mel, post):
+    leaves = [("mel", mel), ("post", post), ("log_d", va["log_d"])]
+    if va["pitch_pred"] is not None:
+        leaves += [("cwt", va["pitch_pred"]["cwt"]), ("stats", va["pitch_pred"]["stats"])]
+    if va["energy_pred"] is not None:
+        leaves.append(("e_pred", va["energy_pred"]))
+    if va["attn"] is not None:
+        leaves += [("attn_soft", va["attn"][0]), ("attn_logprob", va["attn"][3])]
+    if va["prosody_info"] is not None:
+        for i, v in enumerate(va["prosody_info"]):
+            if isinstance(v, Var):
+                leaves.append(("prosody.%d" % i, v))
+    return leaves
+
+
+def _side_outputs(va):
+    """The non-differentiable tensors of the 14-tuple that the forward computes (pytree of tensors)."""
+    return dict(f0_denorm=va["pitch_pred"]["f0_denorm"] if va["pitch_pred"] is not None else None,
+                attn_hard=va["attn"][1] if va["attn"] is not None else None,
+                attn_hard_dur=va["attn"][2] if va["attn"] is not None else None,
+                prosody=tuple(None if isinstance(v, Var) else v for v in va["prosody_info"])
+                if va["prosody_info"] is not None else None,
+                duration_rounded=va["duration_rounded"], mel_len=va["mel_len"], pitch_target=va["pitch_target"],
+                energy_target=va["energy_target"])
+
+
+class TrainGraphs:
+    """Shape-keyed cache of training steps captured as CUDA graphs.  A step is run eagerly the first time its key is seen,
+    captured the second time (forward graph; the backward graph(s) at the first backward call) and replayed afterwards:
+    the eager step is bound by ~1000 Python -> ctypes launches, not by the GPU.  With a data-parallel reducer the backward
+    is captured as one graph per stage so that the arena all-reduce of a stage is launched between them."""
+
+    def __init__(self, max_entries=4):
+        self.entries = {}
+        self.max_entries = max_entries
+        self.pool = None
+
+    def clear(self):
+        self.entries.clear()
+
+
+def _unflatten_inputs(t):
+    pt = {k[len("p_targets."):]: v for k, v in t.items() if k.startswith("p_targets.")}
+    return dict(speakers=t.get("speakers"), texts=t["texts"], src_lens=t["src_lens"], mels=t.get("mels"),
+                mel_lens=t.get("mel_lens"), p_targets=pt if pt else None, e_targets=t.get("e_targets"),
+                d_targets=t.get("d_targets"), attn_priors=t.get("attn_priors"), spker_embeds=t.get("spker_embeds"))
+
+
+class _Step:
+    """One training-mode forward on the tape, and its backward."""
+
+    def __init__(self, module, arena, scalars, graph_mode=False):
+        self.module, self.arena, self.scalars = module, arena, scalars
+        self.graph_mode = graph_mode
+        self.ctx = None
+        self.bwd_graphs = None
+        self.bwd_pattern = None
+        self.pending = False
+
+    def record(self, t):
+        """Run forward_train on the tensors `t` (tape recorded in self.ctx)."""
+        module = self.module
+        max_src_len, max_mel_len, p_control, e_control, d_control, step = self.scalars
+        ctx = Ctx(module, self.arena)
+        if self.graph_mode:
+            ctx.tw = TrainWeights()                 # re-layout kernels are captured and re-run with every replay
+            ctx.offset_dev = module.dropout_counter(t["texts"].device)
+            ctx.offset = 0
+        a = _unflatten_inputs(t)
+        with torch.no_grad():
+            va, mel, post = forward_train(ctx, a["speakers"], a["texts"], a["src_lens"], max_src_len, a["mels"], a["mel_lens"],
+                                          max_mel_len, a["p_targets"], a["e_targets"], a["d_targets"], a["attn_priors"],
+                                          a["spker_embeds"], p_control, e_control, d_control, step)
+        if not self.graph_mode:
+            module._dropout_offset = ctx.offset
+        self.ctx = ctx
+        self.n_dropout_sites = ctx.offset
+        leaves = _leaves_of(va, mel, post)
+        self.names = [n for n, _ in leaves]
+        self.vars = [v for _, v in leaves]
+        self.side = _side_outputs(va)
+        return [v.v for v in self.vars]
+
+    # -- backward ------------------------------------------------------------------------------------------------
+    def backward(self, grads):
+        module, arena, ctx = self.module, self.arena, self.ctx
+        reducer = module._reducer
+        world = reducer.world if reducer is not None else 1
+        if reducer is not None:
+            reducer.begin(ctx, arena)
+        if not self.graph_mode:
+            run_backward(ctx, arena, self.vars, grads, world=world, reducer=reducer)
+            return
+        pattern = tuple(g is not None for g in grads)
+        arena.begin_backward()
+        gs = [None if g is None else (g if (g.is_contiguous() and g.dtype == torch.float32) else g.float().contiguous())
+              for g in grads]
+        if self.bwd_graphs is None or self.bwd_pattern != pattern:
+            self.bwd_pattern = pattern
+            self.static_grads = [None if g is None else g.clone() for g in gs]
+            self.bwd_graphs = []
+            segs = _segments(ctx, reducer)
+            cache = module._train_graphs
+            torch.cuda.synchronize()
+            for si, (hi, lo, hooks) in enumerate(segs):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=cache.pool):
+                    if si == 0:
+                        _seed_gradients(self.vars, self.static_grads, world)
+                    for i in range(hi, lo - 1, -1):
+                        ctx.tape[i]()
+                self.bwd_graphs.append((g, hooks))
+            ctx.tape = None        # the closures live on in the graphs
+        for dst, src in zip(self.static_grads, gs):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        for g, hooks in self.bwd_graphs:
+            g.replay()
+            for h in hooks or ():
+                h()
+        if reducer is not None:
+            reducer.finish()
+        arena.publish()
+        self.pending = False
+
+
+def _clone_tree(v):
+    return engine._tree_map(lambda t: t.clone(), v)
 
 
 def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None, p_targets=None,
@@ -1166,59 +1324,86 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
     capi.require_device()
     capi.require_cuda_tensor(texts)
     arena = module.grad_arena()
-    ctx = Ctx(module, arena)
-    state = {}
+    tcfg = module.train_config
+    soft = attn_priors is not None and step is not None and step < tcfg["duration"]["binarization_start_steps"]
+    tin = {}
+    engine._flatten("", dict(speakers=speakers if module.has_speaker_emb and module.embedder_type == "none" else None,
+                             texts=_i64(texts), src_lens=_i64(src_lens), mels=mels if attn_priors is not None or
+                             module.model_config["prosody_modeling"]["model_type"] != "none" else None,
+                             mel_lens=_i64(mel_lens) if mel_lens is not None else None, p_targets=p_targets,
+                             e_targets=e_targets, d_targets=d_targets, attn_priors=attn_priors,
+                             spker_embeds=spker_embeds if module.has_speaker_emb and module.embedder_type != "none" else None),
+                    tin)
+    scalars = (max_src_len, max_mel_len, float(p_control), float(e_control), float(d_control), step)
+    graphs = module._train_graphs if (module.use_cuda_graphs and texts.is_cuda and
+                                      os.environ.get("CTTS_TRAIN_GRAPHS", "1") != "0") else None
+    st = None
+    outs_are_static = False
+    if graphs is not None and max_mel_len is not None:
+        if graphs.sig != arena.sig:
+            graphs.clear()
+            graphs.sig = arena.sig
+        key = (max_src_len, max_mel_len, float(p_control), float(e_control), float(d_control), bool(soft),
+               os.environ.get("CTTS_DROPOUT", "1"), os.environ.get("CTTS_TRAIN_BWD_MATH", "tc"), module._reducer is not None
+               and module._reducer.enabled, tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tin.items())))
+        e = graphs.entries.get(key)
+        if e is None:
+            if len(graphs.entries) >= graphs.max_entries:
+                graphs.entries.pop(next(iter(graphs.entries)))
+            graphs.entries[key] = False
+        elif e is False:
+            st = _Step(module, arena, scalars, graph_mode=True)
+            st.static_in = {k: v.clone() for k, v in tin.items()}
+            torch.cuda.synchronize()
+            if graphs.pool is None:
+                graphs.pool = torch.cuda.graph_pool_handle()
+            st.fwd_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st.fwd_graph, pool=graphs.pool):
+                st.static_out = st.record(st.static_in)
+            graphs.entries[key] = st
+        elif not e.pending:
+            st = e
+            graphs.entries[key] = graphs.entries.pop(key)       # LRU
+        if st is not None:
+            for k, v in tin.items():
+                st.static_in[k].copy_(v, non_blocking=True)
+            if st.n_dropout_sites:
+                module.dropout_counter(texts.device).add_(st.n_dropout_sites)
+            st.fwd_graph.replay()
+            st.pending = True
+            outs_are_static = True
+    if st is None:
+        st = _Step(module, arena, scalars)
 
     def run():
-        with torch.no_grad():
-            va, mel, post = forward_train(ctx, speakers, texts, src_lens, max_src_len, mels, mel_lens, max_mel_len,
-                                          p_targets, e_targets, d_targets, attn_priors, spker_embeds, p_control, e_control,
-                                          d_control, step)
-        module._dropout_offset = ctx.offset
-        state["va"] = va
-        leaves = [("mel", mel), ("post", post), ("log_d", va["log_d"])]
-        if va["pitch_pred"] is not None:
-            leaves += [("cwt", va["pitch_pred"]["cwt"]), ("stats", va["pitch_pred"]["stats"])]
-        if va["energy_pred"] is not None:
-            leaves.append(("e_pred", va["energy_pred"]))
-        if va["attn"] is not None:
-            leaves += [("attn_soft", va["attn"][0]), ("attn_logprob", va["attn"][3])]
-        if va["prosody_info"] is not None:
-            for i, v in enumerate(va["prosody_info"]):
-                if isinstance(v, Var):
-                    leaves.append(("prosody.%d" % i, v))
-        state["names"] = [n for n, _ in leaves]
-        state["vars"] = [v for _, v in leaves]
-        return [v.v for v in state["vars"]]
+        if outs_are_static:
+            return [t.clone() for t in st.static_out]      # the static buffers are overwritten by the next replay
+        return st.record(tin)
 
-    def backward(grads):
-        reducer = module._reducer
-        if reducer is not None:
-            reducer.begin(ctx, arena)
-        run_backward(ctx, arena, state["vars"], grads, world=reducer.world if reducer is not None else 1, reducer=reducer)
-
-    holder = {"run": run, "backward": backward}
-    anchor = module.autograd_anchor(texts.device)
-    outs = StepFunction.apply(anchor, holder)
-    o = dict(zip(state["names"], outs))
-    va = state["va"]
+    holder = {"run": run, "backward": st.backward}
+    outs = StepFunction.apply(module.autograd_anchor(texts.device), holder)
+    o = dict(zip(st.names, outs))
+    side = _clone_tree(st.side) if outs_are_static else st.side
     B = texts.shape[0]
     src_lens = _i64(src_lens)
     src_masks = pad_mask(src_lens, max_src_len)
     mel_masks = pad_mask(_i64(mel_lens), max_mel_len) if mel_lens is not None else None
     p_pred = None
-    if va["pitch_pred"] is not None:
+    if "cwt" in o:
         stats = o["stats"].view(B, 2)
-        p_pred = {"pitch_pred": None, "f0_denorm": va["pitch_pred"]["f0_denorm"], "cwt": o["cwt"], "f0_mean": stats[:, 0],
+        p_pred = {"pitch_pred": None, "f0_denorm": side["f0_denorm"], "cwt": o["cwt"], "f0_mean": stats[:, 0],
                   "f0_std": stats[:, 1]}
     e_pred = o["e_pred"].squeeze(-1) if "e_pred" in o else None
     attn_outs = (None, None, None, None)
-    if va["attn"] is not None:
-        attn_outs = (o["attn_soft"], va["attn"][1], va["attn"][2], o["attn_logprob"])
+    if "attn_soft" in o:
+        attn_outs = (o["attn_soft"], side["attn_hard"], side["attn_hard_dur"], o["attn_logprob"])
     prosody = None
-    if va["prosody_info"] is not None:
-        prosody = tuple(o.get("prosody.%d" % i, v if not isinstance(v, Var) else None)
-                        for i, v in enumerate(va["prosody_info"]))
-    d_rounded = d_targets if (d_targets is not None and attn_priors is None) else va["duration_rounded"]
+    if side["prosody"] is not None:
+        prosody = tuple(o.get("prosody.%d" % i, v) for i, v in enumerate(side["prosody"]))
+    d_rounded = d_targets if (d_targets is not None and attn_priors is None) else side["duration_rounded"]
+    p_out = side["pitch_target"]
+    if p_targets is not None and p_out is not None and p_out is not p_targets:
+        p_targets.update(p_out)        # the reference mutates the caller's dict (modules.py:1053,1078-1083; train.py:107)
+        p_out = p_targets
     return (o["mel"], o["post"], p_pred, e_pred, o["log_d"].squeeze(-1), d_rounded, src_masks, mel_masks, src_lens,
-            va["mel_len"], attn_outs, prosody, va["pitch_target"], va["energy_target"])
+            side["mel_len"], attn_outs, prosody, p_out, side["energy_target"])

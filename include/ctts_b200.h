@@ -380,9 +380,11 @@ int ctts_copy_rows(const float* src, long long src_stride, int rows, int C, floa
                    void* stream);
 
 /* Dropout with a counter-based Philox4x32-10 stream: y = x * keep / (1 - p); the mask is a pure function of
- * (seed, offset, element index), so the backward pass calls the same entry on dy.  Replaces F.dropout / nn.Dropout
- * (transformer_fs2.py:58,118,190,197,237; modules.py:144-145,1287,1337). */
-int ctts_dropout(const float* x, size_t n, float p, unsigned long long seed, unsigned long long offset, float* y, void* stream);
+ * (seed, offset [+ *offset_dev], element index), so the backward pass calls the same entry on dy.  offset_dev (nullable,
+ * device) is a step counter added to `offset`: a training step replayed as a CUDA graph then draws fresh masks.  Replaces
+ * F.dropout / nn.Dropout (transformer_fs2.py:58,118,190,197,237; modules.py:144-145,1287,1337). */
+int ctts_dropout(const float* x, size_t n, float p, unsigned long long seed, unsigned long long offset,
+                 const unsigned long long* offset_dev, float* y, void* stream);
 
 /* weight layouts of the backward GEMMs: wd[c, j*N + n] = w[n, c, taps-1-j] (dgrad operand);
  * dw[n, c, j] (+)= dw_packed[n, j*Cin + c] (wgrad result -> torch Conv1d layout) */

@@ -562,7 +562,9 @@ def dropout_mask(n, p, seed, offset):
     return torch.from_numpy((r >= thresh).astype(np.float32))
 
 
-def ctts_dropout(x, n, p, seed, offset, y, stream):
+def ctts_dropout(x, n, p, seed, offset, offset_dev, y, stream):
+    if offset_dev is not None:
+        offset = int(offset) + int(_v(offset_dev, 1)[0])
     keep = dropout_mask(n, p, seed, offset)
     inv = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
     _v(y, n).copy_(_v(x, n) * keep * float(inv))

@@ -6,13 +6,19 @@ import torch
 import cases
 
 
-def run_training_case(name, device):
+def make_net(name, device):
     import ctts_b200
     (p, m, t), sd, batch = cases.build_case(name)
     net = ctts_b200.CompTransTTS(p, m, t)
     net.load_state_dict(sd, strict=True)
     net.to(device)
     net.train()
+    return net, batch
+
+
+def run_training_case(name, device, net=None, batch=None):
+    if net is None:
+        net, batch = make_net(name, device)
     args, kw = cases.call_kwargs(batch, cases.TRAIN_CASES[name].get("step"))
 
     def mv(v):

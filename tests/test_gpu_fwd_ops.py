@@ -10,7 +10,7 @@ import pytest
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from gpu_harness import g, run_both  # noqa: E402
+from gpu_harness import Scratch, g, run_both  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -88,4 +88,4 @@ def test_phoneme_energy_sequential_in_place_semantics():
     B, S, M = 3, 9, 30
     dur = torch.tensor([[3, 0, 5, 1, 1, 7, 2, 0, 4], [1, 1, 1, 1, 1, 1, 1, 1, 1], [10, 10, 10, 0, 0, 0, 0, 0, 0]]).float()
     lens = torch.tensor([9, 9, 3])
-    run_both("ctts_phoneme_energy", [dur, lens, g(B, M), B, S, M, torch.zeros(B * M), torch.zeros(B, S)], atol=1e-6)
+    run_both("ctts_phoneme_energy", [dur, lens, g(B, M), B, S, M, Scratch(torch.zeros(B * M)), torch.zeros(B, S)], atol=1e-6)

@@ -152,14 +152,15 @@ def test_dropout_is_the_philox_stream_and_keeps_1_minus_p():
     n = 100003
     x = torch.ones(n)
     y = torch.zeros(n)
-    run_both("ctts_dropout", [x, n, 0.3, 1234, 7, y], atol=1e-6)
+    run_both("ctts_dropout", [x, n, 0.3, 1234, 7, None, y], atol=1e-6)
+    run_both("ctts_dropout", [x, n, 0.3, 1234, 2, torch.tensor([5]), y], atol=1e-6)
     yg = torch.zeros(n, device=DEV)
-    capi.call("ctts_dropout", x.to(DEV), n, 0.3, 1234, 7, yg, torch.cuda.current_stream().cuda_stream)
+    capi.call("ctts_dropout", x.to(DEV), n, 0.3, 1234, 7, None, yg, torch.cuda.current_stream().cuda_stream)
     kept = (yg > 0).float().mean().item()
     assert abs(kept - 0.7) < 0.01
     assert abs(yg.mean().item() - 1.0) < 0.02          # scaled by 1 / (1 - p)
     y2 = torch.zeros(n, device=DEV)
-    capi.call("ctts_dropout", x.to(DEV), n, 0.3, 1234, 8, y2, torch.cuda.current_stream().cuda_stream)
+    capi.call("ctts_dropout", x.to(DEV), n, 0.3, 1234, 8, None, y2, torch.cuda.current_stream().cuda_stream)
     assert (yg != y2).float().mean().item() > 0.3      # a different offset draws a different mask
 
 
@@ -185,7 +186,7 @@ def test_split_transpose():
 
 
 @pytest.mark.parametrize("shape", [(2, 40, 64, 128, 1), (3, 100, 256, 1024, 9), (2, 33, 80, 160, 3), (16, 64, 256, 256, 1),
-                                   (2, 50, 512, 80, 5)])
+                                   (2, 50, 512, 80, 5), (16, 100, 256, 1, 1), (4, 50, 256, 11, 1), (16, 800, 256, 256, 1)])
 def test_gemm_wgrad_tensor_core(shape):
     """tcgen05 weight gradient against the fp64 definition (and the emulator)."""
     B, T, Cin, N, taps = shape

@@ -14,5 +14,6 @@ run "batched planes" tests/test_gpu_train_ops.py "batched_planes"
 run "e2e fp32" tests/test_gpu_train.py "matches_reference and fp32 and not tc_fwd"
 run "e2e tc fwd fp32 bwd" tests/test_gpu_train.py "tc_fwd_fp32_bwd"
 run "e2e tc" tests/test_gpu_train.py "matches_reference and tc and not fp32"
-run "arena + dropout" tests/test_gpu_train.py "arena or dropout"
+run "arena + dropout" tests/test_gpu_train.py "arena or dropout_training"
+run "train graphs" tests/test_gpu_train.py "graph"
 cat $out
