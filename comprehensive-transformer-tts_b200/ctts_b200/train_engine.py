@@ -1354,6 +1354,7 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         elif e is False:
             st = _Step(module, arena, scalars, graph_mode=True)
             st.static_in = {k: v.clone() for k, v in tin.items()}
+            module.dropout_counter(texts.device)     # allocate OUTSIDE the capture (a captured zeros() would re-zero it)
             torch.cuda.synchronize()
             if graphs.pool is None:
                 graphs.pool = torch.cuda.graph_pool_handle()
