@@ -34,6 +34,18 @@ UNIT = "mel-frames/s"
 FFN_FLOP_PER_FRAME = 2 * 256 * 9 * 1024  # the dominant kernel: Conv1d(256->1024, k=9) of one decoder FFN
 
 
+def _port_over_reference():
+    """Time of the oracle port / time of the unmodified reference on this workload, measured in the build container where
+    the reference is mounted (profiles/r02_port_vs_reference.json; tools/port_vs_reference.py)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_port_vs_reference.json")))["port_over_reference"]
+    except Exception:
+        return None
+
+
+PORT_OVER_REFERENCE = _port_over_reference()
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -135,9 +147,9 @@ def run_reference(args, rank, world):
     threads = pick_cpu_threads(cfgs, sd)
     a = (batch["speakers"], batch["texts"], batch["src_lens"], batch["max_src_len"])
     with torch.no_grad():
-        for _ in range(max(min(args.warmup, 2), 1)):
+        for _ in range(max(args.warmup, 1)):
             O.comp_trans_tts_forward(sd, p, m, t, *a)
-        steps = min(steps, 10)  # ~2.5 s per step on 8 cores: bounded so the run ends within a few minutes
+        # the same number of steps as the GPU arm (0.5 - 2.5 s per step depending on the host: K = 20 ends within a minute)
         t0 = time.perf_counter()
         for _ in range(steps):
             O.comp_trans_tts_forward(sd, p, m, t, *a)
@@ -153,7 +165,8 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d full forward passes of the batch-16 workload (oracle/ctts_oracle.py); thread count = "
                                    "best of 8/16/32/64/all on a 4-utterance slice; host has %d logical cores"
-                                   % (steps, os.cpu_count() or 1)},
+                                   % (steps, os.cpu_count() or 1),
+                         "port_over_reference_time": PORT_OVER_REFERENCE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -485,6 +498,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, iters, threads, med = cpu_forward_timer(cfgs, sd, batch, frames)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "port_over_reference_time": PORT_OVER_REFERENCE,
                                     "sample": "%d full forward passes of the same batch-16 workload on the host "
                                               "(oracle/ctts_oracle.py, torch fp32, median %.0f ms; thread count = best of "
                                               "8/16/32/64/all on a 4-utterance slice; host has %d logical cores)"
