@@ -54,11 +54,37 @@ def peaks():
     return dict(hbm=6650.0, tensor=1590.0, src="fallback (B200_PROFILING.md)")
 
 
-def build_workload(seed):
+# Workloads.  "fs2" is the headline (BASELINE.json configs[1]); the others are the same batch-16 LJSpeech shape through
+# the other block types, and BASELINE configs[4] (fs2 + liu2021 prosody, every utterance S = M / 8 phonemes long).
+WORKLOADS = {
+    "fs2": dict(block="transformer_fs2", prosody=None, s_max=100, s_step=2,
+                text="transformer_fs2 + supervised duration (learn_alignment False), LJSpeech shape, batch 16 per GPU, "
+                     "S 100..70, 8 frames/phoneme (M 800, 10880 valid frames), free-running inference, random-init weights"),
+    "transformer": dict(block="transformer", prosody=None, s_max=100, s_step=2),
+    "fastformer": dict(block="fastformer", prosody=None, s_max=100, s_step=2),
+    "conformer": dict(block="conformer", prosody=None, s_max=100, s_step=2),
+    "liu2021_m64": dict(block="transformer_fs2", prosody="liu2021", s_max=8, s_step=0),
+    "liu2021_m256": dict(block="transformer_fs2", prosody="liu2021", s_max=32, s_step=0),
+    "liu2021_m1024": dict(block="transformer_fs2", prosody="liu2021", s_max=128, s_step=0),
+}
+
+
+def workload_text(name):
+    w = WORKLOADS[name]
+    if "text" in w:
+        return w["text"]
+    return "%s%s, supervised duration, LJSpeech config, batch 16 per GPU, S %d%s, 8 frames/phoneme (M %d), free-running " \
+           "inference, random-init weights" % (w["block"], " + liu2021 prosody" if w["prosody"] else "", w["s_max"],
+                                               "..%d" % (w["s_max"] - 15 * w["s_step"]) if w["s_step"] else " (all utterances)",
+                                               8 * w["s_max"])
+
+
+def build_workload(seed, name="fs2"):
     from ctts_b200 import configs, spec, synth
-    p, m, t = configs.builtin_configs("LJSpeech", block_type="transformer_fs2", learn_alignment=False)
+    w = WORKLOADS[name]
+    p, m, t = configs.builtin_configs("LJSpeech", block_type=w["block"], learn_alignment=False, prosody=w["prosody"])
     sd = synth.synthetic_state_dict(spec.parameter_spec(p, m)[0], pin_frames_per_phoneme=FRAMES_PER_PHONEME)
-    batch = synth.ljspeech_batch(batch=BATCH, s_max=100, s_step=2, mode="infer", seed=seed)
+    batch = synth.ljspeech_batch(batch=BATCH, s_max=w["s_max"], s_step=w["s_step"], mode="infer", seed=seed)
     frames = int(batch["src_lens"].sum()) * FRAMES_PER_PHONEME
     return (p, m, t), sd, batch, frames
 
@@ -322,6 +348,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step sub-record")
+    ap.add_argument("--workload", default="fs2", choices=sorted(WORKLOADS), help="fs2 = the headline (BASELINE configs[1])")
     ap.add_argument("--train-only", action="store_true", help="print only the training-step record (development)")
     ap.add_argument("--train-config", type=int, default=None, help="restrict the training record to one TRAIN_CONFIGS entry")
     ap.add_argument("--train-steps", type=int, default=5)
@@ -351,7 +378,12 @@ def main():
             dist.destroy_process_group()
         return
 
-    cfgs, sd, batch, frames = build_workload(seed=rank)
+    cfgs, sd, batch, frames = build_workload(seed=rank, name=args.workload)
+    m_max = FRAMES_PER_PHONEME * WORKLOADS[args.workload]["s_max"]
+    conformer = WORKLOADS[args.workload]["block"] == "conformer"
+    flop_per_frame = 2 * 256 * 1024 if conformer else FFN_FLOP_PER_FRAME
+    if args.workload != "fs2":
+        args.no_train = True
     net = ctts_b200.CompTransTTS(*cfgs).eval()
     net.load_state_dict(sd, strict=True)
     net.to(dev)
@@ -365,7 +397,9 @@ def main():
 
     def timed(fn):
         def wrapper(x, w, *a, **k):
-            if k.get("taps", 1) == 9 and x.shape[1] >= 400:
+            # the decoder's widest GEMM: the k = 9 FFN conv (conformer: the first FFN linear 256 -> 1024)
+            hit = (k.get("taps", 1) == 9) if not conformer else (k.get("taps", 1) == 1 and w.shape[0] == 1024)
+            if hit and x.shape[1] == m_max:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 y = fn(x, w, *a, **k)
@@ -438,7 +472,8 @@ def main():
     _, eager_launches = run_timed(step_instrumented, args.steps, 1)
     engine.variance_stage_b = orig_stage_b
     torch.cuda.synchronize()
-    ffn_ms = [a.elapsed_time(b) for a, b in ffn_events[-6 * args.steps:]]
+    per_step = len(ffn_events) // max(args.steps + 1, 1)
+    ffn_ms = [a.elapsed_time(b) for a, b in ffn_events[-max(per_step, 1) * args.steps:]]
     engine.conv_gemm, engine.gemm_tc = orig_conv, orig_tc
     net.use_cuda_graphs = graphs_were_on
     if graphs_were_on:
@@ -463,40 +498,45 @@ def main():
         ffn_avg = sorted(ffn_ms)[len(ffn_ms) // 2] if ffn_ms else 0.0
         traffic = tensor_pct = None
         summ = os.path.join(ROOT, "profiles", "ncu_ffn1_summary.json")
-        if os.path.exists(summ) and net.decoder_math == "bf16x3":   # one ncu --set full capture of this kernel (committed)
+        if os.path.exists(summ) and net.decoder_math == "bf16x3" and args.workload == "fs2":   # one ncu --set full capture of this kernel (committed)
             nc = json.load(open(summ))
             traffic, tensor_pct = nc["dram_bytes_total"], nc["tensor_pipe_active_pct_of_peak_sustained_active"]
-        ffn_tflops = frames * FFN_FLOP_PER_FRAME / (ffn_avg * 1e-3) / 1e12 if ffn_ms else None
+        ffn_tflops = frames * flop_per_frame / (ffn_avg * 1e-3) / 1e12 if ffn_ms else None
+        burst = None
+        try:
+            burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (decoder/PostNet GEMMs: bf16 hi+lo planes x3 MMAs, fp32 accumulate)" if net.decoder_math == "bf16x3"
             else "f32", "data": "synthetic",
-            "config": {"workload": "transformer_fs2 + supervised duration (learn_alignment False), LJSpeech shape, "
-                                   "batch 16 per GPU, S 100..70, 8 frames/phoneme (M 800, 10880 valid frames), "
-                                   "free-running inference, random-init weights",
+            "config": {"workload": workload_text(args.workload), "workload_name": args.workload,
                        "l2_flush": "256 MiB device write between timed steps", "timing": "CUDA events per step, max over ranks",
                        "parallelism": "independent shards x%d" % world,
                        "cuda_graphs": bool(net.use_cuda_graphs)},
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host_in)),
-                    "d2h_bytes_per_step": int(BATCH * 800 * 80 * 4 + BATCH * 8), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(BATCH * m_max * 80 * 4 + BATCH * 8), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": "decoder FFN Conv1d(256->1024,k9)+GELU implicit GEMM: " + ffn_kernel,
                          "bound": "tensor", "achieved": ffn_tflops, "peak": pk["tensor"], "unit": "TFLOP/s",
-                         "frac": (ffn_tflops / pk["tensor"]) if ffn_tflops else None, "traffic": traffic,
+                         "frac": (ffn_tflops / pk["tensor"]) if ffn_tflops else None,
+                         "frac_of_burst_peak": (ffn_tflops / burst) if (ffn_tflops and burst) else None, "burst_peak": burst,
+                         "traffic": traffic,
                          "traffic_source": "profiles/ncu_ffn1_summary.json (dram read + write bytes per launch)",
                          "tensor_pipe_active_pct": tensor_pct, "mma_per_algorithmic_product": 3,
                          "peak_source": pk["src"], "launch_ms": ffn_avg, "launch_ms_mean": ffn_mean, "launches_timed": len(ffn_ms),
                          "launch_timing": "median over CUDA-event pairs around each launch in an eager re-run of the timed steps "
                                           "(host kept ahead of the GPU by a device-side spin at the start of each stage)",
-                         "flops_per_launch": frames * FFN_FLOP_PER_FRAME},
+                         "flops_per_launch": frames * flop_per_frame},
         }
         if train is not None:
             line["train"] = train
         if world == 1 and not args.no_cpu_baseline:
-            v, iters, threads, med = cpu_forward_timer(cfgs, sd, batch, frames)
+            v, iters, threads, med = cpu_forward_timer(cfgs, sd, batch, frames, budget_s=20.0 if args.workload == "fs2" else 8.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "port_over_reference_time": PORT_OVER_REFERENCE,
                                     "sample": "%d full forward passes of the same batch-16 workload on the host "

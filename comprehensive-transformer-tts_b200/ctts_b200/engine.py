@@ -549,7 +549,7 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
         M_in = attn_soft.shape[2]
         Sp = (S + 15) // 16 * 16
         a_pad = torch.zeros(B, M_in, Sp, device=dev, dtype=torch.float32)
-        a_pad[:, :, :S] = attn_soft[:, 0]
+        capi.call("ctts_copy_rows", attn_soft, S, B * M_in, S, a_pad, Sp, 0, st)      # re-stride [.., S] -> [.., Sp]
         xt = torch.empty(B, C, Sp, device=dev, dtype=torch.float32)
         capi.call("ctts_transpose_heads", x, B, S, C, 0, 1, C, Sp, xt, st)
         xe = torch.empty(B, M_in, C, device=dev, dtype=torch.float32)
@@ -782,7 +782,10 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         spk = None
         if module.has_speaker_emb:
             if module.embedder_type == "none":
-                spk = P["speaker_emb.weight"][_i64(t["speakers"])]
+                tab = P["speaker_emb.weight"]
+                idx = _i64(t["speakers"])
+                spk = torch.zeros(idx.shape[0], tab.shape[1], device=idx.device, dtype=torch.float32)
+                capi.call("ctts_gather_add", tab, idx, idx.shape[0], tab.shape[1], tab.shape[0], spk, _stream())
             else:
                 assert "spker_embeds" in t, "Speaker embedding should not be None"
                 Bs = t["spker_embeds"].shape[0]
