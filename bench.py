@@ -453,6 +453,8 @@ def main():
     graphs_were_on = net.use_cuda_graphs
     net.use_cuda_graphs = False
     engine.conv_gemm, engine.gemm_tc = timed(orig_conv), timed(orig_tc)
+    from ctts_b200 import engine_blocks      # the other block types bind the two functions at import time
+    engine_blocks.conv_gemm, engine_blocks.gemm_tc = engine.conv_gemm, engine.gemm_tc
     ffn_events.clear()
     # Without graphs the host is slower than the GPU, and an event pair would then include the wait for the launch.
     # A ~4 ms device-side spin at the start of each stage lets the host queue the whole stage ahead of the GPU, so the
@@ -475,6 +477,7 @@ def main():
     per_step = len(ffn_events) // max(args.steps + 1, 1)
     ffn_ms = [a.elapsed_time(b) for a, b in ffn_events[-max(per_step, 1) * args.steps:]]
     engine.conv_gemm, engine.gemm_tc = orig_conv, orig_tc
+    engine_blocks.conv_gemm, engine_blocks.gemm_tc = orig_conv, orig_tc
     net.use_cuda_graphs = graphs_were_on
     if graphs_were_on:
         launches = eager_launches   # kernels per step are the same; replayed steps do not pass through capi.call

@@ -962,6 +962,78 @@ __global__ void mul_bwd_kernel(const float* __restrict__ dy, const float* __rest
     }
 }
 
+// ---- liu2021 reference encoder (training only; modules.py:332-397, coordconv.py:140-159) --------------------------------
+// Activations are channels-last [N, H, W, C] (H = mel frames, W = mel bins).  The 3x3 / stride (1, 2) / pad (1, 1)
+// convolutions run as im2col + the dense GEMM engine; BatchNorm2d is BatchNorm over the N*H*W rows.
+// AddCoords(rank 2, with_r): channels [x, row coordinate, column coordinate, radius], coordinates scaled to [-1, 1], the
+// radius measured from (0.5, 0.5) as the reference does (coordconv.py:36-71).
+__global__ void add_coords_kernel(const float* __restrict__ x, int H, int W, size_t total, float* __restrict__ y) {
+    CTTS_PDL_SYNC();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        const int h = (int)((i / W) % H);
+        const float xx = ((float)h / (float)(H - 1)) * 2.f - 1.f;
+        const float yy = ((float)w / (float)(W - 1)) * 2.f - 1.f;
+        const float rr = sqrtf((xx - 0.5f) * (xx - 0.5f) + (yy - 0.5f) * (yy - 0.5f));
+        reinterpret_cast<float4*>(y)[i] = make_float4(x[i], xx, yy, rr);
+    }
+}
+
+// col[(n, h, wo), (kh*3 + kw)*C + c] = x[n, h + kh - 1, 2*wo + kw - 1, c]   (zero outside)
+__global__ void im2col_3x3_s12_kernel(const float* __restrict__ x, int H, int W, int C, int Wo, size_t total,
+                                      float* __restrict__ col) {
+    CTTS_PDL_SYNC();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int k = (int)((i / C) % 9);
+        size_t r = i / ((size_t)9 * C);
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int h = (int)(r % H);
+        const size_t n = r / H;
+        const int hh = h + k / 3 - 1, ww = 2 * wo + k % 3 - 1;
+        col[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((n * H + hh) * W + ww) * C + c] : 0.f;
+    }
+}
+
+// dx[n, h, w, c] = sum over the (kh, kw, wo) that read it of dcol[(n, h - kh + 1, wo), (kh*3 + kw)*C + c]   (gather form)
+__global__ void col2im_3x3_s12_kernel(const float* __restrict__ dcol, int H, int W, int C, int Wo, size_t total,
+                                      float* __restrict__ dx) {
+    CTTS_PDL_SYNC();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        size_t r = i / C;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const size_t n = r / H;
+        float acc = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int ho = h - kh + 1;
+            if (ho < 0 || ho >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int t = w - kw + 1;
+                if (t < 0 || (t & 1)) continue;
+                const int wo = t >> 1;
+                if (wo >= Wo) continue;
+                acc += dcol[(((n * H + ho) * Wo + wo) * 9 + (kh * 3 + kw)) * (size_t)C + c];
+            }
+        }
+        dx[i] = acc;
+    }
+}
+
+// y[r, b, a] = x[r, a, b]
+__global__ void permute_last2_kernel(const float* __restrict__ x, int A, int Bd, size_t total, float* __restrict__ y) {
+    CTTS_PDL_SYNC();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int a = (int)(i % A);
+        const int b = (int)((i / A) % Bd);
+        const size_t r = i / ((size_t)A * Bd);
+        y[i] = x[(r * A + a) * Bd + b];
+    }
+}
+
 // GRU backward (single direction, nn.GRU gates r|z|n), one CTA per utterance, BPTT over all T steps.
 //   forward per step: gh = W_hh h + b_hh; r = s(gi_r + gh_r); z = s(gi_z + gh_z); n = tanh(gi_n + r * gh_n); h' = (1-z) n + z h
 // The hidden states are read from `out` (h_t for every t, saved by the forward); gate pre-activations are recomputed
@@ -1334,6 +1406,36 @@ int ctts_mul_bwd(const float* dy, const float* a, const float* b, int b_rowwise,
     const size_t total = (size_t)B * T * C;
     launch_k(mul_bwd_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, dy, a, b, b_rowwise, lens, T, C, total, da, db);
     return check_launch("mul_bwd");
+}
+
+int ctts_add_coords(const float* x, int N, int H, int W, float* y, void* stream) {
+    CTTS_REQUIRE(x && y && N > 0 && H > 1 && W > 1, "add_coords: bad arguments");
+    const size_t total = (size_t)N * H * W;
+    launch_k(add_coords_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, x, H, W, total, y);
+    return check_launch("add_coords");
+}
+
+int ctts_im2col_3x3_s12(const float* x, int N, int H, int W, int C, float* col, void* stream) {
+    CTTS_REQUIRE(x && col && N > 0 && H > 0 && W > 0 && C > 0, "im2col_3x3_s12: bad arguments");
+    const int Wo = (W + 2 - 3) / 2 + 1;
+    const size_t total = (size_t)N * H * Wo * 9 * C;
+    launch_k(im2col_3x3_s12_kernel, grid_for(total, 256, 65535), 256, 0, (cudaStream_t)stream, x, H, W, C, Wo, total, col);
+    return check_launch("im2col_3x3_s12");
+}
+
+int ctts_col2im_3x3_s12(const float* dcol, int N, int H, int W, int C, float* dx, void* stream) {
+    CTTS_REQUIRE(dcol && dx && N > 0 && H > 0 && W > 0 && C > 0, "col2im_3x3_s12: bad arguments");
+    const int Wo = (W + 2 - 3) / 2 + 1;
+    const size_t total = (size_t)N * H * W * C;
+    launch_k(col2im_3x3_s12_kernel, grid_for(total, 256, 65535), 256, 0, (cudaStream_t)stream, dcol, H, W, C, Wo, total, dx);
+    return check_launch("col2im_3x3_s12");
+}
+
+int ctts_permute_last2(const float* x, int rows, int A, int Bd, float* y, void* stream) {
+    CTTS_REQUIRE(x && y && rows > 0 && A > 0 && Bd > 0, "permute_last2: bad arguments");
+    const size_t total = (size_t)rows * A * Bd;
+    launch_k(permute_last2_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, x, A, Bd, total, y);
+    return check_launch("permute_last2");
 }
 
 int ctts_gru_bwd(const float* gi, const float* w_hh, const float* b_hh, const float* out, int out_ld, int out_off,

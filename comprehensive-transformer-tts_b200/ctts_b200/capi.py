@@ -88,6 +88,10 @@ SIGNATURES = {
     "ctts_act_fwd": [_P, _Z, _I, _P, _I, _P, _P],
     "ctts_merge_planes": [_I, _P, _Z, _P, _P],
     "ctts_copy_rows": [_P, _L, _I, _I, _P, _L, _I, _P],
+    "ctts_add_coords": [_P, _I, _I, _I, _P, _P],
+    "ctts_im2col_3x3_s12": [_P, _I, _I, _I, _I, _P, _P],
+    "ctts_col2im_3x3_s12": [_P, _I, _I, _I, _I, _P, _P],
+    "ctts_permute_last2": [_P, _I, _I, _I, _P, _P],
     "ctts_gru_bwd": [_P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
 }
 

@@ -348,9 +348,9 @@ def linear(ctx, x, wname, bname=None, alpha=1.0, act=ACT_NONE, residual=None, le
     elif Cin % 16 == 0:
         out = engine.conv_gemm(x.v, ctx.packed(wname), bias, alpha, act=fwd_act, residual=res_t, lens=lens, taps=taps)
     else:
-        assert taps == 1 and residual is None and lens is None and act == ACT_NONE and alpha == 1.0
+        assert taps == 1 and lens is None and act == ACT_NONE and alpha == 1.0
         out = torch.empty(B, T, N, device=x.v.device, dtype=torch.float32)
-        capi.call("ctts_linear_smallk", x.v, P[wname], bias, None, B * T, Cin, N, out, _st())
+        capi.call("ctts_linear_smallk", x.v, ctx.packed(wname), bias, res_t, B * T, Cin, N, out, _st())
     pre = None
     if keep_pre:
         pre = out

@@ -425,6 +425,14 @@ int ctts_fastformer_pool_bwd(const float* logits, const float* values, const int
 int ctts_mul_bwd(const float* dy, const float* a, const float* b, int b_rowwise, const int64_t* lens, int B, int T, int C,
                  float* da, float* db, void* stream);
 
+/* liu2021 reference encoder, training only (modules.py:332-397 ReferenceEncoder, coordconv.py:36-71,140-159): channels-last
+ * activations [N, H, W, C]; AddCoords(rank 2, with_r) -> [N, H, W, 4]; im2col / col2im of the 3x3, stride (1, 2), pad (1, 1)
+ * convolutions (the contraction itself is the dense GEMM engine; column order (kh*3 + kw)*C + c); [R, A, B] -> [R, B, A] */
+int ctts_add_coords(const float* x, int N, int H, int W, float* y, void* stream);
+int ctts_im2col_3x3_s12(const float* x, int N, int H, int W, int C, float* col, void* stream);
+int ctts_col2im_3x3_s12(const float* dcol, int N, int H, int W, int C, float* dx, void* stream);
+int ctts_permute_last2(const float* x, int rows, int A, int Bd, float* y, void* stream);
+
 /* single-direction GRU backward through time (liu2021, modules.py:620-640 / :356-392): dgi, dgh [B,T,3H]; dW_hh and db_hh
  * follow by ctts_gemm_generic / ctts_act_bwd on dgh */
 int ctts_gru_bwd(const float* gi, const float* w_hh, const float* b_hh, const float* out, int out_ld, int out_off,

@@ -744,6 +744,37 @@ def ctts_act_fwd(x, n, act, y, n_planes, planes, stream):
         _split_into(v, _planes(planes, n_planes), n)
 
 
+def ctts_add_coords(x, N, H, W, y, stream):
+    xv = _v(x, N, H, W)
+    xx = (torch.arange(H).float() / (H - 1) * 2 - 1)[None, :, None].expand(N, H, W)
+    yy = (torch.arange(W).float() / (W - 1) * 2 - 1)[None, None, :].expand(N, H, W)
+    rr = torch.sqrt((xx - 0.5) ** 2 + (yy - 0.5) ** 2)
+    _v(y, N, H, W, 4).copy_(torch.stack([xv, xx, yy, rr], -1))
+
+
+def _unfold(xv, N, H, W, C):
+    """[N,H,W,C] -> [N*H*Wo, 9*C] with column order (kh*3 + kw)*C + c (3x3, stride (1,2), pad (1,1))."""
+    cols = F.unfold(xv.permute(0, 3, 1, 2), (3, 3), padding=(1, 1), stride=(1, 2))       # [N, C*9, H*Wo], rows c*9 + k
+    Wo = (W + 2 - 3) // 2 + 1
+    return cols.view(N, C, 9, H * Wo).permute(0, 3, 2, 1).reshape(N * H * Wo, 9 * C), Wo
+
+
+def ctts_im2col_3x3_s12(x, N, H, W, C, col, stream):
+    c, Wo = _unfold(_v(x, N, H, W, C), N, H, W, C)
+    _v(col, N * H * Wo, 9 * C).copy_(c)
+
+
+def ctts_col2im_3x3_s12(dcol, N, H, W, C, dx, stream):
+    xv = torch.zeros(N, H, W, C, requires_grad=True)
+    c, Wo = _unfold(xv, N, H, W, C)
+    c.backward(_v(dcol, N * H * Wo, 9 * C))
+    _v(dx, N, H, W, C).copy_(xv.grad)
+
+
+def ctts_permute_last2(x, rows, A, Bd, y, stream):
+    _v(y, rows, Bd, A).copy_(_v(x, rows, A, Bd).transpose(1, 2))
+
+
 def ctts_merge_planes(n_planes, planes, n, y, stream):
     _v(y, n).copy_(_val(planes, n_planes, n))
 

@@ -276,3 +276,17 @@ def test_gru_bwd(reverse):
     emu.ctts_gru_bidir(gi, gi, whh, bhh, whh, bhh, B, T, H, out, hf, 0)
     run_both("ctts_gru_bwd", [gi, whh, bhh, out, 2 * H, reverse * H, g(B, T, 2 * H, seed=3), g(B, 2 * H, seed=4).view(-1)[reverse * H:],
                               2 * H, B, T, H, reverse, torch.zeros(B, T, 3 * H), torch.zeros(B, T, 3 * H)], atol=2e-5, rtol=1e-3)
+
+
+def test_reference_encoder_helper_kernels():
+    """AddCoords / im2col / col2im of the 3x3 stride-(1,2) convolutions / last-two-dims permute (liu2021 training)."""
+    N, H, W, C = 2, 13, 10, 8
+    run_both("ctts_add_coords", [g(N, H, W), N, H, W, torch.zeros(N, H, W, 4)], atol=1e-6)
+    Wo = (W + 2 - 3) // 2 + 1
+    run_both("ctts_im2col_3x3_s12", [g(N, H, W, C), N, H, W, C, torch.zeros(N * H * Wo, 9 * C)], atol=0, rtol=0)
+    run_both("ctts_col2im_3x3_s12", [g(N * H * Wo, 9 * C), N, H, W, C, torch.zeros(N, H, W, C)], atol=1e-5)
+    W = 5      # odd width: the last output column reads one real and one padded input column
+    Wo = (W + 2 - 3) // 2 + 1
+    run_both("ctts_im2col_3x3_s12", [g(N, H, W, C), N, H, W, C, torch.zeros(N * H * Wo, 9 * C)], atol=0, rtol=0)
+    run_both("ctts_col2im_3x3_s12", [g(N * H * Wo, 9 * C), N, H, W, C, torch.zeros(N, H, W, C)], atol=1e-5)
+    run_both("ctts_permute_last2", [g(7, 3, 128), 7, 3, 128, torch.zeros(7, 128, 3)], atol=0, rtol=0)
