@@ -288,6 +288,16 @@ __global__ void mask_rows_kernel(float* __restrict__ x, const int64_t* __restric
     }
 }
 
+__global__ void mask_rows_scalar_kernel(float* __restrict__ x, const int64_t* __restrict__ lens, int T, int C, size_t total) {
+    CTTS_PDL_SYNC();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t tok = i / C;
+        const size_t b = tok / T;
+        const int t = (int)(tok - b * T);
+        if (t >= (int)lens[b]) x[i] = 0.f;
+    }
+}
+
 // y = (accumulate ? y : 0) + a * x
 __global__ void axpy_kernel(const float* __restrict__ x, float a, size_t n, int accumulate, float* __restrict__ y) {
     CTTS_PDL_SYNC();
@@ -1160,7 +1170,12 @@ int ctts_layernorm_bwd(const float* x, const float* gamma, const float* dy, floa
 }
 
 int ctts_mask_rows(float* x, const int64_t* lens, int B, int T, int C, void* stream) {
-    CTTS_REQUIRE(x && lens && C % 4 == 0, "mask_rows: bad arguments");
+    CTTS_REQUIRE(x && lens && C > 0, "mask_rows: bad arguments");
+    if (C % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) {
+        const size_t total = (size_t)B * T * C;
+        launch_k(mask_rows_scalar_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, x, lens, T, C, total);
+        return check_launch("mask_rows");
+    }
     const size_t total4 = (size_t)B * T * (C / 4);
     launch_k(mask_rows_kernel, grid_for(total4), 256, 0, (cudaStream_t)stream, x, lens, T, C, total4);
     return check_launch("mask_rows");

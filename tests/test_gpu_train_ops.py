@@ -89,6 +89,7 @@ def test_layernorm_bwd(C, lens):
 def test_mask_axpy_rowscale_copy_rows():
     B, T, C = 3, 19, 32
     run_both("ctts_mask_rows", [g(B, T, C), torch.tensor([19, 4, 0]), B, T, C])
+    run_both("ctts_mask_rows", [g(B, T, 7), torch.tensor([19, 4, 0]), B, T, 7])
     run_both("ctts_axpy", [g(1000), 0.5, 1000, 1, g(1000, seed=1)])
     run_both("ctts_axpy", [g(1001), 2.0, 1001, 0, g(1001, seed=1)])
     run_both("ctts_rowscale_axpy", [g(57, 24), g(57, seed=1), -0.3, 57, 24, 1, g(57, 24, seed=2)])
