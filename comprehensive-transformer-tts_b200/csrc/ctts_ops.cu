@@ -840,6 +840,68 @@ __global__ void relshift_softmax_kernel(const float* __restrict__ content, const
     for (int j = lane; j < ldp; j += 32) out[j] = (j < T) ? expf(score(j) - mx) * inv : 0.f;
 }
 
+// Tensor-core form of the score assembly above: reads content / pos with row stride ld, writes P as bf16 planes
+// [Z, T, ldp] (zero padded) -- the A operand of the P.V GEMM -- so the fp32 probabilities never reach HBM.
+template <int NP>
+__global__ void relshift_softmax_planes_kernel(const float* __restrict__ content, const float* __restrict__ pos, int T, int ld,
+                                               int ldp, float sqrt_dim, size_t rows, const PlanePtrs out) {
+    CTTS_PDL_SYNC();
+    const size_t row = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const size_t z = row / T;
+    const int i = (int)(row - z * T);
+    const float* cz = content + row * (size_t)ld;
+    const float* pz = pos + z * (size_t)T * ld;
+    auto score = [&](int j) {
+        float p;
+        if (j <= i) p = pz[(size_t)i * ld + (T - 1 - i + j)];
+        else if (j == i + 1) p = 0.f;
+        else p = pz[(size_t)(i + 1) * ld + (j - i - 2)];
+        return (cz[j] + p) / sqrt_dim;
+    };
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, score(j));
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) sum += expf(score(j) - mx);
+    const float inv = 1.f / warp_sum(sum);
+    for (int j = lane; j < ldp; j += 32) {
+        float rem = (j < T) ? expf(score(j) - mx) * inv : 0.f;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+            out.p[p][row * (size_t)ldp + j] = h;
+            rem -= __bfloat162float(h);
+        }
+    }
+}
+
+// (x[b, t, c0 + h*DH + d] + bias[h*DH + d]) -> bf16 planes [B*T, H*DHp] with each head zero padded from DH to DHp columns:
+// a 32-wide head becomes one 64-wide (SWIZZLE_128B) k-block of the tensor-core GEMMs.
+template <int NP>
+__global__ void pad_heads_planes_kernel(const float* __restrict__ x, const float* __restrict__ bias, int ld_in, int c0, int H,
+                                        int DH, int DHp, size_t total, const PlanePtrs out) {
+    CTTS_PDL_SYNC();
+    const int Cp = H * DHp;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int cp = (int)(i % Cp);
+        const size_t r = i / Cp;
+        const int h = cp / DHp, d = cp - h * DHp;
+        float rem = 0.f;
+        if (d < DH) {
+            rem = x[r * ld_in + c0 + h * DH + d];
+            if (bias) rem += bias[h * DH + d];
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const __nv_bfloat16 hh = __float2bfloat16_rn(rem);
+            out.p[p][i] = hh;
+            rem -= __bfloat162float(hh);
+        }
+    }
+}
+
 // x [B, T, ld_in] (channel offset c0, heads of DH) -> xt [B*H, DH, ldt] (time contiguous, zero padded)
 __global__ void transpose_heads_kernel(const float* __restrict__ x, int T, int ld_in, int c0, int H, int DH, int ldt,
                                        float* __restrict__ xt) {
@@ -1335,6 +1397,38 @@ int ctts_relshift_softmax(const float* content, const float* pos, int Z, int T, 
     launch_k(relshift_softmax_kernel, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, content, pos, T, ldp, sqrt_dim, rows,
                                                                                         P);
     return check_launch("relshift_softmax");
+}
+
+int ctts_relshift_softmax_planes(const float* content, const float* pos, int Z, int T, int ld, int ldp, float sqrt_dim,
+                                 int n_planes, void* const* planes, void* stream) {
+    CTTS_REQUIRE(content && pos && planes && Z > 0 && T > 0 && ld >= T && ldp >= T && (n_planes == 2 || n_planes == 3),
+                 "relshift_softmax_planes: bad arguments");
+    PlanePtrs pp{{nullptr, nullptr, nullptr}};
+    for (int p = 0; p < n_planes; ++p) {
+        CTTS_REQUIRE(planes[p], "relshift_softmax_planes: NULL plane");
+        pp.p[p] = (__nv_bfloat16*)planes[p];
+    }
+    const size_t rows = (size_t)Z * T;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (n_planes == 3) launch_k(relshift_softmax_planes_kernel<3>, grid, 256, 0, (cudaStream_t)stream, content, pos, T, ld, ldp, sqrt_dim, rows, pp);
+    else launch_k(relshift_softmax_planes_kernel<2>, grid, 256, 0, (cudaStream_t)stream, content, pos, T, ld, ldp, sqrt_dim, rows, pp);
+    return check_launch("relshift_softmax_planes");
+}
+
+int ctts_pad_heads_planes(const float* x, const float* bias, int rows, int ld_in, int c0, int H, int DH, int DHp, int n_planes,
+                          void* const* planes, void* stream) {
+    CTTS_REQUIRE(x && planes && rows > 0 && H > 0 && DH > 0 && DHp >= DH && (n_planes == 2 || n_planes == 3),
+                 "pad_heads_planes: bad arguments");
+    PlanePtrs pp{{nullptr, nullptr, nullptr}};
+    for (int p = 0; p < n_planes; ++p) {
+        CTTS_REQUIRE(planes[p], "pad_heads_planes: NULL plane");
+        pp.p[p] = (__nv_bfloat16*)planes[p];
+    }
+    const size_t total = (size_t)rows * H * DHp;
+    const int grid = (int)((total + 255) / 256 < 8192 ? (total + 255) / 256 : 8192);
+    if (n_planes == 3) launch_k(pad_heads_planes_kernel<3>, grid, 256, 0, (cudaStream_t)stream, x, bias, ld_in, c0, H, DH, DHp, total, pp);
+    else launch_k(pad_heads_planes_kernel<2>, grid, 256, 0, (cudaStream_t)stream, x, bias, ld_in, c0, H, DH, DHp, total, pp);
+    return check_launch("pad_heads_planes");
 }
 
 int ctts_transpose_heads(const float* x, int B, int T, int ld_in, int c0, int H, int DH, int ldt, float* xt, void* stream) {

@@ -44,6 +44,8 @@ SIGNATURES = {
     "ctts_glu": [_P, _I, _I, _P, _P],
     "ctts_dwconv_bn_swish": [_P, _P, _I, _P, _P, _I, _I, _I, _P, _P],
     "ctts_relshift_softmax": [_P, _P, _I, _I, _I, _F, _P, _P],
+    "ctts_relshift_softmax_planes": [_P, _P, _I, _I, _I, _I, _F, _I, _P, _P],
+    "ctts_pad_heads_planes": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "ctts_transpose_heads": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "ctts_gemm_bf16x3": [_P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ctts_attention_bf16x3": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -161,6 +161,18 @@ def attention_tc(qkv_planes, lens, n_head):
     return out
 
 
+def gemm_batched_planes(a, a_view, w, w_view, addr, y_outer, y_inner, alpha, Z, T, K, N, y=None, y_planes=None,
+                        residual=None, lens=None):
+    """ctts_gemm_batched_planes: y[z][t, n] = alpha * sum_k A[z][t, k] W[z][n, k] on operand views of bf16 planes
+    (a_view / w_view = (d0, d1, d2, s1, s2) in elements; addr = (mod, a_div, a_c0, a_step, w_div, w_c0, w_step, lens_div, ldy))."""
+    import ctypes
+    ll = lambda v: (ctypes.c_longlong * len(v))(*[int(x) for x in v])
+    ii = (ctypes.c_int * len(addr))(*[int(x) for x in addr])
+    capi.call("ctts_gemm_batched_planes", a.n, capi.ptr_array(a.p), ll(a_view), capi.ptr_array(w.p), ll(w_view), ii,
+              int(y_outer), int(y_inner), float(alpha), residual, lens, Z, T, K, N, y,
+              capi.ptr_array(y_planes.p) if y_planes is not None else None, _stream())
+
+
 def pad_mask(lens, max_len):
     """utils/tools.py:188-196 (bool bookkeeping tensor handed back to the caller; True = padding)."""
     return torch.arange(int(max_len), device=lens.device)[None, :] >= lens[:, None]

@@ -11,7 +11,8 @@ import torch
 
 from . import capi
 from .capi import ACT_GELU, ACT_NONE, ACT_RELU
-from .engine import (_stream, attention, attention_tc, conv_gemm, gemm_tc, layernorm, layernorm_planes, split_planes)
+from .engine import (Planes, _stream, attention, attention_tc, conv_gemm, gemm_batched_planes, gemm_tc, layernorm,
+                     layernorm_planes, split_planes)
 
 
 def _interleaved_table(rows, d, device):
@@ -69,25 +70,40 @@ def prepare_transformer(prep, P, tc_decoder):
             cat = torch.cat([P[base + "w_qs.linear.weight"], P[base + "w_ks.linear.weight"],
                              P[base + "w_vs.linear.weight"]], 0).float().contiguous()
             prep.w[base + "qkv"] = cat
-            if tc_decoder and name.startswith("decoder."):
-                prep.w[base + "qkv#planes"] = split_planes(cat)
+            _cat_planes(prep, base + "qkv", cat, name, tc_decoder)
 
 
-def _stack_transformer(prep, P, pre, x, lens, n_layers, n_head, kernel, tc):
+def _cat_planes(prep, key, cat, name, tc_decoder):
+    """Operand planes of a concatenated projection: 2 planes on the decoder (bf16x3), 3 on the encoder (bf16x6)."""
+    if tc_decoder and name.startswith("decoder."):
+        prep.w[key + "#planes"] = split_planes(cat)
+    if prep.module.encoder_math == "bf16x6" and name.startswith("encoder."):
+        prep.w[key + "#planes3"] = split_planes(cat, 3)
+
+
+def _n_planes(prep, pre, tc_decoder):
+    """0 = FP32 CUDA cores, 2 = bf16x3 (decoder), 3 = bf16x6 (encoder: FP32-equivalent, upstream of the quantisers)."""
+    if pre.startswith("decoder."):
+        return 2 if tc_decoder else 0
+    return 3 if prep.module.encoder_math == "bf16x6" else 0
+
+
+def _stack_transformer(prep, P, pre, x, lens, n_layers, n_head, kernel, n):
     W = prep.w
-    xp = split_planes(x) if tc else None
+    tag = "#planes" if n == 2 else "#planes3"
+    xp = split_planes(x, n) if n else None
     for i in range(n_layers):
         a = "%slayer_stack.%d.slf_attn." % (pre, i)
         f = "%slayer_stack.%d.pos_ffn." % (pre, i)
-        if tc:
-            _, qkvp = gemm_tc(xp, W[a + "qkv#planes"], want_fp32=False, want_planes=True)
+        if n:
+            _, qkvp = gemm_tc(xp, W[a + "qkv" + tag], want_fp32=False, want_planes=True)
             ap = attention_tc(qkvp, lens, n_head)
-            o, _ = gemm_tc(ap, W[a + "fc.linear.weight#planes"], residual=x)
-            x, xp = layernorm_planes(o, P[a + "layer_norm.weight"], P[a + "layer_norm.bias"], 1e-5, lens, want_fp32=True)
-            _, hp = gemm_tc(xp, W[f + "w_1.weight#planes"], P[f + "w_1.bias"], act=ACT_RELU, taps=kernel[0],
+            o, _ = gemm_tc(ap, W[a + "fc.linear.weight" + tag], residual=x)
+            x, xp = layernorm_planes(o, P[a + "layer_norm.weight"], P[a + "layer_norm.bias"], 1e-5, lens, want_fp32=True, n=n)
+            _, hp = gemm_tc(xp, W[f + "w_1.weight" + tag], P[f + "w_1.bias"], act=ACT_RELU, taps=kernel[0],
                             want_fp32=False, want_planes=True)
-            o, _ = gemm_tc(hp, W[f + "w_2.weight#planes"], P[f + "w_2.bias"], residual=x, taps=kernel[1])
-            x, xp = layernorm_planes(o, P[f + "layer_norm.weight"], P[f + "layer_norm.bias"], 1e-5, lens, want_fp32=True)
+            o, _ = gemm_tc(hp, W[f + "w_2.weight" + tag], P[f + "w_2.bias"], residual=x, taps=kernel[1])
+            x, xp = layernorm_planes(o, P[f + "layer_norm.weight"], P[f + "layer_norm.bias"], 1e-5, lens, want_fp32=True, n=n)
         else:
             qkv = conv_gemm(x, W[a + "qkv"])
             att = attention(qkv, lens, n_head)
@@ -103,15 +119,16 @@ def encoder_transformer(prep, P, cfg, tokens, src_lens):
     c = cfg["transformer"]
     x, word = embed_abs(prep, P, cfg, c["encoder_hidden"], tokens)
     x, _ = _stack_transformer(prep, P, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"],
-                              c["conv_kernel_size"], False)
+                              c["conv_kernel_size"], _n_planes(prep, "encoder.", False))
     return x, word
 
 
 def decoder_transformer(prep, P, cfg, x, mel_lens, math_mode):
     c = cfg["transformer"]
     x = add_abs_positions(prep, P, cfg, "decoder.position_enc", x)
-    return _stack_transformer(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
-                              c["conv_kernel_size"], math_mode == "bf16x3")
+    x, xp = _stack_transformer(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
+                               c["conv_kernel_size"], _n_planes(prep, "decoder.", math_mode == "bf16x3"))
+    return x, xp
 
 
 # ---------------------------------------------------------------------------------------------
@@ -135,32 +152,33 @@ def _pool(logits, values, lens, heads, hs):
     return pooled
 
 
-def _stack_fastformer(prep, P, pre, x, lens, n_layers, heads, kernel, tc):
+def _stack_fastformer(prep, P, pre, x, lens, n_layers, heads, kernel, n):
     """FFTBlock.forward (fastformer.py:163-171) with FastAttention (:296-345); `heads` = the ctor's dim_head (128)."""
     W = prep.w
     C = x.shape[-1]
     hs = C // heads
     tied = "%slayer_stack.layers.0.0.fn." % pre   # to_{q,k}_attn_logits are shared by all layers (:157-161)
+    tag = "#planes" if n == 2 else "#planes3"
     for i in range(n_layers):
         a = "%slayer_stack.layers.%d.0." % (pre, i)
         f = "%slayer_stack.layers.%d.1." % (pre, i)
-        if tc:
-            _, hp = layernorm_planes(x, P[a + "norm.weight"], P[a + "norm.bias"], 1e-5)
-            q, qp = gemm_tc(hp, W[a + "fn.query.weight#planes"], P[a + "fn.query.bias"], want_planes=True)
-            k, _ = gemm_tc(hp, W[a + "fn.key.weight#planes"], P[a + "fn.key.bias"])
-            ql, _ = gemm_tc(qp, W[tied + "to_q_attn_logits.weight#planes"], P[tied + "to_q_attn_logits.bias"])
+        if n:
+            _, hp = layernorm_planes(x, P[a + "norm.weight"], P[a + "norm.bias"], 1e-5, n=n)
+            q, qp = gemm_tc(hp, W[a + "fn.query.weight" + tag], P[a + "fn.query.bias"], want_planes=True)
+            k, _ = gemm_tc(hp, W[a + "fn.key.weight" + tag], P[a + "fn.key.bias"])
+            ql, _ = gemm_tc(qp, W[tied + "to_q_attn_logits.weight" + tag], P[tied + "to_q_attn_logits.bias"])
             pooled_q = _pool(ql, q, lens, heads, hs)
             qk = _binary(k, pooled_q, 1, rowwise=True)
-            kl, _ = gemm_tc(split_planes(qk), W[tied + "to_k_attn_logits.weight#planes"], P[tied + "to_k_attn_logits.bias"])
+            kl, _ = gemm_tc(split_planes(qk, n), W[tied + "to_k_attn_logits.weight" + tag], P[tied + "to_k_attn_logits.bias"])
             pooled_k = _pool(kl, qk, lens, heads, hs)
             wv = _binary(q, pooled_k, 1, rowwise=True)
             r = _binary(q, x, 0)
-            gemm_tc(split_planes(wv), W[a + "fn.transform.weight#planes"], P[a + "fn.transform.bias"], residual=r,
+            gemm_tc(split_planes(wv, n), W[a + "fn.transform.weight" + tag], P[a + "fn.transform.bias"], residual=r,
                     lens=lens, out=x)
-            _, hp = layernorm_planes(x, P[f + "norm.weight"], P[f + "norm.bias"], 1e-5)
-            _, gp = gemm_tc(hp, W[f + "fn.w_1.weight#planes"], P[f + "fn.w_1.bias"], act=ACT_GELU, taps=kernel[0],
+            _, hp = layernorm_planes(x, P[f + "norm.weight"], P[f + "norm.bias"], 1e-5, n=n)
+            _, gp = gemm_tc(hp, W[f + "fn.w_1.weight" + tag], P[f + "fn.w_1.bias"], act=ACT_GELU, taps=kernel[0],
                             want_fp32=False, want_planes=True)
-            gemm_tc(gp, W[f + "fn.w_2.weight#planes"], P[f + "fn.w_2.bias"], residual=x, lens=lens, taps=kernel[1], out=x)
+            gemm_tc(gp, W[f + "fn.w_2.weight" + tag], P[f + "fn.w_2.bias"], residual=x, lens=lens, taps=kernel[1], out=x)
         else:
             h = layernorm(x, P[a + "norm.weight"], P[a + "norm.bias"], 1e-5)
             q = conv_gemm(h, P[a + "fn.query.weight"], P[a + "fn.query.bias"])
@@ -183,7 +201,8 @@ def encoder_fastformer(prep, P, cfg, tokens, src_lens):
     c = cfg["transformer"]  # sic (fastformer.py:24-34)
     x, word = embed_abs(prep, P, cfg, c["encoder_hidden"], tokens)
     heads = c["encoder_hidden"] // c["encoder_head"]
-    return _stack_fastformer(prep, P, "encoder.", x, src_lens, c["encoder_layer"], heads, c["conv_kernel_size"], False), word
+    return _stack_fastformer(prep, P, "encoder.", x, src_lens, c["encoder_layer"], heads, c["conv_kernel_size"],
+                             _n_planes(prep, "encoder.", False)), word
 
 
 def decoder_fastformer(prep, P, cfg, x, mel_lens, math_mode):
@@ -191,7 +210,7 @@ def decoder_fastformer(prep, P, cfg, x, mel_lens, math_mode):
     x = add_abs_positions(prep, P, cfg, "decoder.position_enc", x)
     heads = c["decoder_hidden"] // c["decoder_head"]
     return _stack_fastformer(prep, P, "decoder.", x, mel_lens, c["decoder_layer"], heads, c["conv_kernel_size"],
-                             math_mode == "bf16x3"), None
+                             _n_planes(prep, "decoder.", math_mode == "bf16x3")), None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -209,8 +228,7 @@ def prepare_conformer(prep, P, tc_decoder):
             cat = torch.cat([P[base + "query_proj.linear.weight"], P[base + "key_proj.linear.weight"],
                              P[base + "value_proj.linear.weight"]], 0).float().contiguous()
             prep.w[base + "qkv"] = cat
-            if tc_decoder and name.startswith("decoder."):
-                prep.w[base + "qkv#planes"] = split_planes(cat)
+            _cat_planes(prep, base + "qkv", cat, name, tc_decoder)
 
 
 def _relpos_attention(P, a, qkv, pos_proj, n_head):
@@ -248,43 +266,100 @@ def _relpos_attention(P, a, qkv, pos_proj, n_head):
     return ctx
 
 
-def _conformer_ffn(prep, P, p, x, tc):
+def _relpos_attention_tc(P, a, qkv, qkv_planes, pos_proj, n_head):
+    """The same attention on tcgen05 (bf16 planes): the 32-wide heads are zero padded to 64 columns so that one head is one
+    k-block of the GEMM engine; content and positional scores are batched plane GEMMs, the shifted sum + softmax writes the
+    probability PLANES directly (no fp32 probabilities in HBM), P.V is a third batched GEMM.  The [B*H, T, T] score tensors
+    are still materialised in fp32, like the reference does."""
+    B, T, C3 = qkv.shape
+    C = C3 // 3
+    H = n_head
+    dh = C // H
+    Z = B * H
+    n = qkv_planes.n
+    dev = qkv.device
+    st = _stream()
+    DHp = 64
+    Cp = H * DHp
+    Tp = (T + 7) // 8 * 8
+
+    def padded(src, bias, rows, ld, c0):
+        out = Planes.empty((rows, Cp), dev, n)
+        capi.call("ctts_pad_heads_planes", src, bias, rows, ld, c0, H, dh, DHp, n, capi.ptr_array(out.p), st)
+        return out
+
+    qu = padded(qkv, P[a + "attention.u_bias"], B * T, C3, 0)
+    qv = padded(qkv, P[a + "attention.v_bias"], B * T, C3, 0)
+    kp = padded(qkv, None, B * T, C3, C)
+    pp = padded(pos_proj, None, T, C, 0)
+    act_view = (Cp, T, B, Cp, T * Cp)
+    content = torch.empty(Z, T, Tp, device=dev, dtype=torch.float32)
+    pscore = torch.empty(Z, T, Tp, device=dev, dtype=torch.float32)
+    gemm_batched_planes(qu, act_view, kp, act_view, (H, H, 0, DHp, H, 0, DHp, 1, Tp), H * T * Tp, T * Tp, 1.0, Z, T, DHp, Tp,
+                        y=content)
+    gemm_batched_planes(qv, act_view, pp, (Cp, T, 1, Cp, T * Cp), (H, H, 0, DHp, 0x7fffffff, 0, DHp, 1, Tp), H * T * Tp, T * Tp,
+                        1.0, Z, T, DHp, Tp, y=pscore)
+    prob = Planes.empty((Z, T, Tp), dev, n)
+    capi.call("ctts_relshift_softmax_planes", content, pscore, Z, T, Tp, Tp, math.sqrt(C), n, capi.ptr_array(prob.p), st)
+    vt = Planes.empty((Z, dh, Tp), dev, n)
+    capi.call("ctts_transpose_v_planes", n, capi.ptr_array(qkv_planes.p), B, T, C, H, capi.ptr_array(vt.p), st)
+    ctx_planes = Planes.empty((B, T, C), dev, n)
+    gemm_batched_planes(prob, (T, T, Z, Tp, T * Tp), vt, (T, dh, Z, Tp, dh * Tp), (H, 1, 0, 0, 1, 0, 0, 1, C), T * C, dh, 1.0,
+                        Z, T, T, dh, y_planes=ctx_planes)
+    return ctx_planes
+
+
+def _conformer_ffn(prep, P, p, x, n):
     """FeedForwardModule + half-step residual: LN -> Linear -> Swish -> Linear, * 0.5 + x (conformer.py:205-213,264-295)."""
-    if tc:
-        _, hp = layernorm_planes(x, P[p + "0.weight"], P[p + "0.bias"], 1e-5)
-        _, gp = gemm_tc(hp, prep.w[p + "1.linear.weight#planes"], P[p + "1.linear.bias"], act=capi.ACT_SWISH,
+    if n:
+        tag = "#planes" if n == 2 else "#planes3"
+        _, hp = layernorm_planes(x, P[p + "0.weight"], P[p + "0.bias"], 1e-5, n=n)
+        _, gp = gemm_tc(hp, prep.w[p + "1.linear.weight" + tag], P[p + "1.linear.bias"], act=capi.ACT_SWISH,
                         want_fp32=False, want_planes=True)
-        y, _ = gemm_tc(gp, prep.w[p + "4.linear.weight#planes"], P[p + "4.linear.bias"], alpha=0.5, residual=x)
+        y, _ = gemm_tc(gp, prep.w[p + "4.linear.weight" + tag], P[p + "4.linear.bias"], alpha=0.5, residual=x)
         return y
     h = layernorm(x, P[p + "0.weight"], P[p + "0.bias"], 1e-5)
     g = conv_gemm(h, P[p + "1.linear.weight"], P[p + "1.linear.bias"], act=capi.ACT_SWISH)
     return conv_gemm(g, P[p + "4.linear.weight"], P[p + "4.linear.bias"], alpha=0.5, residual=x)
 
 
-def _stack_conformer(prep, P, cfg, pre, x, lens, n_layers, n_head, kernel, tc):
+def _stack_conformer(prep, P, cfg, pre, x, lens, n_layers, n_head, kernel, n):
     B, T, C = x.shape
     W = prep.w
     st = _stream()
+    tc = n > 0
+    tag = "#planes" if n == 2 else "#planes3"
     for i in range(n_layers):
         lp = "%slayer_stack.%d.sequential." % (pre, i)
-        x = _conformer_ffn(prep, P, lp + "0.module.sequential.", x, tc)
+        x = _conformer_ffn(prep, P, lp + "0.module.sequential.", x, n)
         a = lp + "1.module."
-        h = layernorm(x, P[a + "layer_norm.weight"], P[a + "layer_norm.bias"], 1e-5)
-        qkv = conv_gemm(h, W[a + "attention.qkv"])
         pos = abs_table(prep, P, a + "positional_encoding", T, C, cfg["max_seq_len"], x.device)[:T].contiguous()
         pos_proj = conv_gemm(pos.view(1, T, C), P[a + "attention.pos_proj.linear.weight"]).view(T, C)
-        ctx = _relpos_attention(P, a, qkv, pos_proj, n_head)
-        x = conv_gemm(ctx, P[a + "attention.out_proj.linear.weight"], residual=x)
         m = lp + "2.module.sequential."
-        h = layernorm(x, P[m + "0.weight"], P[m + "0.bias"], 1e-5)
-        pw = conv_gemm(h, W[m + "2.conv.weight"], P[m + "2.conv.bias"])
+        if tc:
+            _, hp = layernorm_planes(x, P[a + "layer_norm.weight"], P[a + "layer_norm.bias"], 1e-5, n=n)
+            qkv, qkvp = gemm_tc(hp, W[a + "attention.qkv" + tag], want_planes=True)
+            ctxp = _relpos_attention_tc(P, a, qkv, qkvp, pos_proj, n_head)
+            x, _ = gemm_tc(ctxp, W[a + "attention.out_proj.linear.weight" + tag], residual=x)
+            _, hp = layernorm_planes(x, P[m + "0.weight"], P[m + "0.bias"], 1e-5, n=n)
+            pw, _ = gemm_tc(hp, W[m + "2.conv.weight" + tag], P[m + "2.conv.bias"])
+        else:
+            h = layernorm(x, P[a + "layer_norm.weight"], P[a + "layer_norm.bias"], 1e-5)
+            qkv = conv_gemm(h, W[a + "attention.qkv"])
+            ctx = _relpos_attention(P, a, qkv, pos_proj, n_head)
+            x = conv_gemm(ctx, P[a + "attention.out_proj.linear.weight"], residual=x)
+            h = layernorm(x, P[m + "0.weight"], P[m + "0.bias"], 1e-5)
+            pw = conv_gemm(h, W[m + "2.conv.weight"], P[m + "2.conv.bias"])
         g = torch.empty(B, T, C, device=x.device, dtype=torch.float32)
         capi.call("ctts_glu", pw, B * T, C, g, st)
         d = torch.empty_like(g)
         fold = W[m + "5.fold"]
         capi.call("ctts_dwconv_bn_swish", g, P[m + "4.conv.weight"], kernel, fold[0], fold[1], B, T, C, d, st)
-        x = conv_gemm(d, W[m + "7.conv.weight"], P[m + "7.conv.bias"], residual=x)
-        x = _conformer_ffn(prep, P, lp + "3.module.sequential.", x, tc)
+        if tc:
+            x, _ = gemm_tc(split_planes(d, n), W[m + "7.conv.weight" + tag], P[m + "7.conv.bias"], residual=x)
+        else:
+            x = conv_gemm(d, W[m + "7.conv.weight"], P[m + "7.conv.bias"], residual=x)
+        x = _conformer_ffn(prep, P, lp + "3.module.sequential.", x, n)
         x = layernorm(x, P[lp + "4.weight"], P[lp + "4.bias"], 1e-5, lens)
     return x
 
@@ -293,14 +368,14 @@ def encoder_conformer(prep, P, cfg, tokens, src_lens):
     c = cfg["conformer"]
     x, word = embed_abs(prep, P, cfg, c["encoder_hidden"], tokens)
     return _stack_conformer(prep, P, cfg, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"],
-                            c["conv_kernel_size"], False), word
+                            c["conv_kernel_size"], _n_planes(prep, "encoder.", False)), word
 
 
 def decoder_conformer(prep, P, cfg, x, mel_lens, math_mode):
     c = cfg["conformer"]
     x = add_abs_positions(prep, P, cfg, "decoder.position_enc", x)
     return _stack_conformer(prep, P, cfg, "decoder.", x, mel_lens, c["decoder_layer"], c["decoder_head"],
-                            c["conv_kernel_size"], math_mode == "bf16x3"), None
+                            c["conv_kernel_size"], _n_planes(prep, "decoder.", math_mode == "bf16x3")), None
 
 
 ENCODERS = {"transformer": encoder_transformer, "fastformer": encoder_fastformer, "conformer": encoder_conformer}

@@ -227,6 +227,15 @@ int ctts_dwconv_bn_swish(const float* g, const float* w, int K, const float* sca
 int ctts_relshift_softmax(const float* content, const float* pos, int Z, int T, int ldp, float sqrt_dim, float* P,
                           void* stream);
 
+/* tensor-core form of the conformer attention (decoder): the same score assembly reading content / pos with row stride ld
+ * and writing P as bf16 planes [Z, T, ldp] (the A operand of the P.V GEMM; fp32 probabilities never reach HBM), and the
+ * head re-layout that lets the 32-wide heads of conformer.py:375-380 ride the 64-wide k-blocks of the GEMM engine:
+ *   planes[r, h*DHp + d] = d < DH ? x[r, c0 + h*DH + d] + bias[h*DH + d] : 0     (bias = u_bias / v_bias or NULL) */
+int ctts_relshift_softmax_planes(const float* content, const float* pos, int Z, int T, int ld, int ldp, float sqrt_dim,
+                                 int n_planes, void* const* planes, void* stream);
+int ctts_pad_heads_planes(const float* x, const float* bias, int rows, int ld_in, int c0, int H, int DH, int DHp, int n_planes,
+                          void* const* planes, void* stream);
+
 /* x[b, t, c0 + h*DH + d] -> xt[(b*H + h), d, t]  (row stride ldt >= T, zero padded): K-major operand for P.V */
 int ctts_transpose_heads(const float* x, int B, int T, int ld_in, int c0, int H, int DH, int ldt, float* xt, void* stream);
 

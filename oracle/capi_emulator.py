@@ -169,7 +169,13 @@ def ctts_attention(qkv, lens, B, T, C, H, scale, out, stream):
 
 
 def ctts_transpose_v_planes(n, qkvp, B, T, C, H, vtp, stream):
-    pass    # the emulated attention reads V from the qkv planes directly
+    dh = C // H
+    Tp = (T + 7) // 8 * 8
+    for src, dst in zip(_planes(qkvp, n), _planes(vtp, n)):
+        v = _v(src, B, T, 3 * C)[:, :, 2 * C:].reshape(B, T, H, dh).permute(0, 2, 3, 1)        # [B, H, dh, T]
+        out = _v(dst, B * H, dh, Tp)
+        out.zero_()
+        out[:, :, :T] = v.reshape(B * H, dh, T)
 
 
 def ctts_flash_attention_bf16x3(qh, ql, vth, vtl, lens, B, T, C, H, scale, oh, ol, stream):
@@ -348,6 +354,23 @@ def ctts_relshift_softmax(content, pos, Z, T, ldp, sqrt_dim, P, stream):
     out = _v(P, Z, T, ldp)
     out.zero_()
     out[:, :, :T] = torch.softmax((c + padded) / sqrt_dim, -1)
+
+
+def ctts_relshift_softmax_planes(content, pos, Z, T, ld, ldp, sqrt_dim, n, planes, stream):
+    c, p = _v(content, Z, T, ld)[:, :, :T], _v(pos, Z, T, ld)[:, :, :T]
+    padded = torch.cat([p.new_zeros(Z, T, 1), p], dim=-1).reshape(Z, T + 1, T)[:, 1:].reshape(Z, T, T)
+    out = torch.zeros(Z, T, ldp)
+    out[:, :, :T] = torch.softmax((c + padded) / sqrt_dim, -1)
+    _split_into(out, _planes(planes, n), Z, T, ldp)
+
+
+def ctts_pad_heads_planes(x, bias, rows, ld_in, c0, H, DH, DHp, n, planes, stream):
+    xv = _v(x, rows, ld_in)[:, c0:c0 + H * DH]
+    if bias is not None:
+        xv = xv + _v(bias, H * DH)
+    out = torch.zeros(rows, H, DHp)
+    out[:, :, :DH] = xv.reshape(rows, H, DH)
+    _split_into(out, _planes(planes, n), rows, H, DHp)
 
 
 def ctts_gru_bidir(gi_f, gi_b, whh_f, bhh_f, whh_b, bhh_b, B, T, H, out, h_final, stream):

@@ -41,3 +41,30 @@ def test_training_step_host_logic(name, math_mode, golden_dir, monkeypatch):
     assert "ctts_layernorm_bwd" in used and "ctts_act_bwd" in used
     if math_mode == "tc":
         assert "ctts_gemm_wgrad" in used and "ctts_gemm_split" in used
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_inference_engine_host_logic(name, golden_dir, monkeypatch):
+    """The INFERENCE engine (all block types; encoders on 3-plane, decoders on 2-plane tensor-core math, the conformer's
+    padded-head batched plane GEMMs and plane-writing relative-shift softmax) with emulated kernels against the reference's
+    eval-mode fixtures."""
+    emu.install(monkeypatch)
+    import ctts_b200
+    (p, m, t), sd, batch = cases.build_case(name)
+    net = ctts_b200.CompTransTTS(p, m, t).eval()
+    net.load_state_dict(sd, strict=True)
+    args, kw = cases.call_kwargs(batch)
+    out = net(*args, **kw)
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    flat = cases.flatten_outputs(out)
+    for k in ("mel", "postnet_mel"):
+        a, b = gold["ref." + k], flat[k]
+        assert a.shape == b.shape
+        bad = np.abs(a - b) > 1e-3 + 1e-2 * np.abs(a)
+        # fastformer is ill-conditioned by construction (its inverted mask rounds the logits to ulp(1e4)): flip budget, as
+        # in tests/test_gpu_configs.py
+        budget = 0.01 if "fastformer" in name else 0.0
+        assert bad.mean() <= budget, "%s: %.3f%% outside tolerance, max err %.3g" % (k, 100 * bad.mean(), np.abs(a - b).max())
+    assert np.array_equal(gold["ref.mel_lens"], flat["mel_lens"])
+    if name.startswith("conformer"):
+        assert "ctts_relshift_softmax_planes" in emu.CALLS and "ctts_gemm_batched_planes" in emu.CALLS
