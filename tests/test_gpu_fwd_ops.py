@@ -89,3 +89,15 @@ def test_phoneme_energy_sequential_in_place_semantics():
     dur = torch.tensor([[3, 0, 5, 1, 1, 7, 2, 0, 4], [1, 1, 1, 1, 1, 1, 1, 1, 1], [10, 10, 10, 0, 0, 0, 0, 0, 0]]).float()
     lens = torch.tensor([9, 9, 3])
     run_both("ctts_phoneme_energy", [dur, lens, g(B, M), B, S, M, Scratch(torch.zeros(B * M)), torch.zeros(B, S)], atol=1e-6)
+
+
+def test_conformer_tensor_core_attention_helpers():
+    from gpu_harness import PA
+    Z, T, ld, ldp = 4, 37, 40, 40
+    pl = [torch.zeros(Z, T, ldp, dtype=torch.bfloat16) for _ in range(2)]
+    run_both("ctts_relshift_softmax_planes", [g(Z, T, ld), g(Z, T, ld, seed=1), Z, T, ld, ldp, 16.0, 2, PA(pl)], atol=2e-5)
+    rows, H, DH, DHp = 50, 8, 32, 64
+    pl = [torch.zeros(rows, H * DHp, dtype=torch.bfloat16) for _ in range(3)]
+    run_both("ctts_pad_heads_planes", [g(rows, 3 * H * DH), g(H * DH, seed=1), rows, 3 * H * DH, H * DH, H, DH, DHp, 3, PA(pl)],
+             atol=1e-6)
+    run_both("ctts_pad_heads_planes", [g(rows, H * DH), None, rows, H * DH, 0, H, DH, DHp, 2, PA(pl[:2])], atol=1e-4)
