@@ -283,8 +283,9 @@ def train_record(rank, world, dev, steps=5, warmup=2, only=None):
             _train_objective(out).backward()
 
         def timed(n_steps, n_warm):
+            nonlocal_step = lambda: one_step()      # late binding: the weak-scaling variant swaps the step function
             for _ in range(n_warm):
-                one_step()
+                nonlocal_step()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -293,7 +294,7 @@ def train_record(rank, world, dev, steps=5, warmup=2, only=None):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(n_steps):
-                one_step()
+                nonlocal_step()
             e1.record()
             e1.synchronize()
             if world > 1:
@@ -310,7 +311,7 @@ def train_record(rank, world, dev, steps=5, warmup=2, only=None):
         rec["grad_arena_mb"] = arena.flat.numel() * 4 / 1e6
         if world > 1:
             net._reducer.enabled = False
-            ms_off, _ = timed(steps, 1)
+            ms_off, _ = timed(steps, 3)      # a new CUDA-graph key: eager, capture, then replays
             net._reducer.enabled = True
             # the all-reduce alone: the whole arena in one call, on an otherwise idle GPU
             torch.cuda.synchronize()
@@ -325,7 +326,7 @@ def train_record(rank, world, dev, steps=5, warmup=2, only=None):
                 ts.append(e0.elapsed_time(e1))
             ar = cdist.max_over_ranks(sorted(ts)[len(ts) // 2], dev, world)
             nbytes = arena.flat.numel() * 4
-            ms2, _ = timed(steps, 1)      # and once more with the reducer: the order of the two measurements must not matter
+            ms2, _ = timed(steps, 3)      # and once more with the reducer: the order of the two measurements must not matter
             ms = min(ms, ms2)
             rec["ms_per_step"] = ms
             rec["mel_frames_per_s"] = frames_global / (ms * 1e-3)
@@ -334,6 +335,28 @@ def train_record(rank, world, dev, steps=5, warmup=2, only=None):
                         "allreduce_standalone_ms": ar, "allreduce_bus_gbs": 2 * (world - 1) / world * nbytes / (ar * 1e-3) / 1e9,
                         "allreduce_buckets": n_buckets,
                         "nvlink_peak_gbs_per_direction": 900.0})
+        if world > 1:
+            # weak scaling: every rank keeps the WHOLE N = 1 batch (global batch = world x the quoted one)
+            bw = {k: (v.to(dev) if torch.is_tensor(v) else ({kk: vv.to(dev) for kk, vv in v.items()} if isinstance(v, dict)
+                                                              else v)) for k, v in full.items()}
+            kww = {k: bw[k] for k in ("mels", "mel_lens", "max_mel_len", "p_targets", "e_targets", "d_targets", "attn_priors",
+                                      "spker_embeds") if k in bw}
+            if mode == "unsup":
+                kww["step"] = 120000
+
+            def weak_step():
+                k2 = dict(kww)
+                k2["p_targets"] = dict(kww["p_targets"])
+                net.zero_grad(set_to_none=True)
+                out = model(bw["speakers"], bw["texts"], bw["src_lens"], bw["max_src_len"], **k2)
+                _train_objective(out).backward()
+
+            one_step_saved = one_step
+            one_step = weak_step
+            ms_w, _ = timed(steps, 3)
+            one_step = one_step_saved
+            rec["weak"] = {"per_gpu_batch": gbatch, "global_batch": gbatch * world, "ms_per_step": ms_w,
+                           "mel_frames_per_s": world * frames_global / (ms_w * 1e-3)}
         records.append(rec)
         del net, model
         torch.cuda.empty_cache()
