@@ -1451,7 +1451,8 @@ extern "C" int ctts_gemm_wgrad(int n_planes, const void* const* dzT_planes, cons
     // each, ~2 CTAs per SM in total); the partial tiles are added with fp32 atomics -- a weight gradient accumulates anyway.
     const long long tiles = (long long)((N + 127) / 128) * (long long)((KC + 127) / 128);
     const long long num_kb = (long long)B * ((T + BLOCK_K - 1) / BLOCK_K);
-    long long ksplit = (2LL * num_sms()) / tiles;
+    // (measured: splitting the 144-tile FFN conv gradient in two made it slower, 125 -> 208 us: only grids below one wave)
+    long long ksplit = (long long)num_sms() / tiles;
     if (ksplit > num_kb / 8) ksplit = num_kb / 8;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > 1) {
