@@ -17,6 +17,10 @@
 
 namespace ctts {
 
+struct TPlanes {
+    __nv_bfloat16* p[3];
+};
+
 // =====================================================================================================================
 // Generic strided FP32 GEMM:  y[z][m,n] = alpha * sum_k A[z][m,k] * B[z][n, k'] (+ y[z][m,n])
 //   z = zo * zmod + zi;  element addresses are fully strided (any operand may be "transposed").
@@ -171,6 +175,93 @@ act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ ref, int 
         }
     }
 }
+
+// The same backward step fused with the operand preparation of the two GEMMs that consume dz: one pass reads dy (+ ref),
+// writes dz (fp32, in place allowed), the row-major bf16 planes of dz (A operand of the dgrad GEMM), the TIME-MAJOR planes
+// dzT [B, N, Tp] (A operand of the wgrad GEMM) and adds the column sums to dbias.  64 x 64 tiles, one utterance per
+// blockIdx.z (rows = time steps of that utterance).
+template <int NP>
+__global__ void __launch_bounds__(256)
+act_bwd_planes_kernel(const float* __restrict__ dy, const float* __restrict__ ref, int act, float alpha,
+                      const int64_t* __restrict__ lens, int T, int N, int Tp, float* __restrict__ dz, const TPlanes zp,
+                      const TPlanes ztp, float* __restrict__ dbias) {
+    CTTS_PDL_SYNC();
+    __shared__ float tile[64][65];
+    __shared__ float colsum[16][64];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tid = threadIdx.x;
+    const int cq = (tid & 15) * 4, rr = tid >> 4;
+    const int len = lens ? (int)lens[b] : T;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rl = rr + 16 * i, t = r0 + rl, n = n0 + cq;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (t < T && n < N) {      // N % 4 == 0: a float4 never straddles the edge
+            const size_t o = ((size_t)b * T + t) * N + n;
+            if (t < len) {
+                const float4 g = *reinterpret_cast<const float4*>(dy + o);
+                v[0] = g.x * alpha; v[1] = g.y * alpha; v[2] = g.z * alpha; v[3] = g.w * alpha;
+                if (act != CTTS_ACT_NONE) {
+                    const float4 rf = *reinterpret_cast<const float4*>(ref + o);
+                    v[0] *= act_grad(rf.x, act); v[1] *= act_grad(rf.y, act);
+                    v[2] *= act_grad(rf.z, act); v[3] *= act_grad(rf.w, act);
+                }
+            }
+            if (dz) *reinterpret_cast<float4*>(dz + o) = make_float4(v[0], v[1], v[2], v[3]);
+            float rem[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(rem[0], rem[1]);
+                const __nv_bfloat162 h23 = __floats2bfloat162_rn(rem[2], rem[3]);
+                rem[0] -= __low2float(h01); rem[1] -= __high2float(h01);
+                rem[2] -= __low2float(h23); rem[3] -= __high2float(h23);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(zp.p[p] + o) = pk;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            tile[rl][cq + j] = v[j];
+            cs[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) colsum[rr][cq + j] = cs[j];
+    __syncthreads();
+    if (dbias && tid < 64 && n0 + tid < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t += colsum[i][tid];
+        atomicAdd(dbias + n0 + tid, t);
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    const int r = r0 + 2 * lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int cl = warp + 8 * i, n = n0 + cl;
+        if (n >= N || r >= Tp) continue;
+        float a = tile[2 * lane][cl], c = tile[2 * lane + 1][cl];
+        const size_t o = ((size_t)b * N + n) * Tp + r;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
+            if (r + 1 < Tp) *reinterpret_cast<__nv_bfloat162*>(ztp.p[p] + o) = h;
+            else ztp.p[p][o] = __low2bfloat16(h);
+            a -= __low2float(h);
+            c -= __high2float(h);
+        }
+    }
+}
+
+// y = (res + dropout(x)) * keep: the un-fused residual path when a dropout sits between a GEMM and its residual add
+// (transformer_fs2.py:190-192,197-199); the backward of the dropout branch is ctts_dropout on the masked gradient.
+__global__ void dropout_add_kernel(const float* __restrict__ x, const float* __restrict__ res, const int64_t* __restrict__ lens,
+                                   int T, int C, size_t n, float p, uint64_t seed, uint64_t offset,
+                                   const unsigned long long* __restrict__ offset_dev, float* __restrict__ y);
 
 // =====================================================================================================================
 // LayerNorm backward (blocks.py:137-156 / nn.LayerNorm).  forward: y = (xhat * gamma + beta) * keep.
@@ -471,10 +562,6 @@ __global__ void scale_vec_kernel(float* __restrict__ v, float a, int n) {
     if (i < n) v[i] *= a;
 }
 
-struct TPlanes {
-    __nv_bfloat16* p[3];
-};
-
 // y = act(gamma * (x - mean) * rsqrt(var + eps) + beta)  -> fp32 and / or bf16 planes
 template <int NP>
 __global__ void bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
@@ -657,6 +744,32 @@ __global__ void dropout_kernel(const float* __restrict__ x, size_t n, float p, u
         for (int e = 0; e < 4; ++e) {
             const size_t i = q * 4 + e;
             if (i < n) y[i] = (r[e] >= thresh) ? x[i] * inv : 0.f;
+        }
+    }
+}
+
+__global__ void dropout_add_kernel(const float* __restrict__ x, const float* __restrict__ res, const int64_t* __restrict__ lens,
+                                   int T, int C, size_t n, float p, uint64_t seed, uint64_t offset,
+                                   const unsigned long long* __restrict__ offset_dev, float* __restrict__ y) {
+    CTTS_PDL_SYNC();
+    if (offset_dev) offset += (uint64_t)offset_dev[0];
+    const float inv = 1.f / (1.f - p);
+    const uint32_t thresh = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+    const size_t n4 = (n + 3) >> 2;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
+        uint32_t r[4];
+        philox4x32_10(seed, (uint64_t)q, offset, r);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const size_t i = q * 4 + e;
+            if (i >= n) break;
+            bool keep = true;
+            if (lens) {
+                const size_t tok = i / C;
+                const size_t bb = tok / T;
+                keep = (int)(tok - bb * T) < (int)lens[bb];
+            }
+            y[i] = keep ? res[i] + ((r[e] >= thresh) ? x[i] * inv : 0.f) : 0.f;
         }
     }
 }
@@ -1153,6 +1266,36 @@ int ctts_act_bwd(const float* dy, const float* ref, int act, float alpha, const 
     dim3 grid((N + 31) / 32, (rows + 127) / 128, Z);
     launch_k(act_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, dy, ref, act, alpha, lens, T, rows, N, dz, dbias);
     return check_launch("act_bwd");
+}
+
+int ctts_act_bwd_planes(const float* dy, const float* ref, int act, float alpha, const int64_t* lens, int B, int T, int N, int Tp,
+                        float* dz, int n_planes, void* const* dz_planes, void* const* dzT_planes, float* dbias, void* stream) {
+    CTTS_REQUIRE(dy && dz_planes && dzT_planes && B > 0 && T > 0 && N > 0 && N % 4 == 0 && Tp >= T && Tp % 2 == 0,
+                 "act_bwd_planes: bad arguments (N=%d must be a multiple of 4)", N);
+    CTTS_REQUIRE(act == CTTS_ACT_NONE || ref != nullptr, "act_bwd_planes: activation %d needs its reference tensor", act);
+    CTTS_REQUIRE(n_planes == 2 || n_planes == 3, "act_bwd_planes: n_planes");
+    CTTS_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(ref)) & 15) == 0,
+                 "act_bwd_planes: tensors must be 16-byte aligned");
+    TPlanes zp{{nullptr, nullptr, nullptr}}, ztp{{nullptr, nullptr, nullptr}};
+    for (int p = 0; p < n_planes; ++p) {
+        CTTS_REQUIRE(dz_planes[p] && dzT_planes[p], "act_bwd_planes: NULL plane");
+        zp.p[p] = (__nv_bfloat16*)dz_planes[p];
+        ztp.p[p] = (__nv_bfloat16*)dzT_planes[p];
+    }
+    dim3 grid((N + 63) / 64, (Tp + 63) / 64, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_planes == 3) launch_k(act_bwd_planes_kernel<3>, grid, 256, 0, st, dy, ref, act, alpha, lens, T, N, Tp, dz, zp, ztp, dbias);
+    else launch_k(act_bwd_planes_kernel<2>, grid, 256, 0, st, dy, ref, act, alpha, lens, T, N, Tp, dz, zp, ztp, dbias);
+    return check_launch("act_bwd_planes");
+}
+
+int ctts_dropout_add(const float* x, const float* res, const int64_t* lens, int B, int T, int C, float p, unsigned long long seed,
+                     unsigned long long offset, const unsigned long long* offset_dev, float* y, void* stream) {
+    CTTS_REQUIRE(x && res && y && B > 0 && T > 0 && C > 0 && p >= 0.f && p < 1.f, "dropout_add: bad arguments");
+    const size_t n = (size_t)B * T * C;
+    launch_k(dropout_add_kernel, grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream, x, res, lens, T, C, n, p, (uint64_t)seed,
+             (uint64_t)offset, offset_dev, y);
+    return check_launch("dropout_add");
 }
 
 int ctts_layernorm_bwd(const float* x, const float* gamma, const float* dy, float eps, const int64_t* lens, int B, int T,

@@ -61,6 +61,8 @@ SIGNATURES = {
     # ---- training step (include/ctts_b200.h, "TRAINING STEP") ----
     "ctts_gemm_generic": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     "ctts_act_bwd": [_P, _P, _I, _F, _P, _I, _I, _I, _I, _P, _P, _P],
+    "ctts_act_bwd_planes": [_P, _P, _I, _F, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
+    "ctts_dropout_add": [_P, _P, _P, _I, _I, _I, _F, ctypes.c_ulonglong, ctypes.c_ulonglong, _P, _P, _P],
     "ctts_layernorm_bwd": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _I, _P, _P, _P],
     "ctts_mask_rows": [_P, _P, _I, _I, _I, _P],
     "ctts_axpy": [_P, _F, _Z, _I, _P, _P],

@@ -268,14 +268,19 @@ def _generic(a, b, y, Z, zmod, M, N, K, a_str, b_str, y_str, Kin=0, shift0=0, sh
               float(alpha), int(accumulate), _st())
 
 
-def _dgrad(ctx, dz, wname, taps, x):
+def _tc_dgrad_ok(ctx, N, Cin):
+    return ctx.bwd_tc and N % 8 == 0 and Cin % 4 == 0 and N >= 16
+
+
+def _dgrad(ctx, dz, wname, taps, x, dz_planes=None):
     """x.g (+)= conv(dz, w^T flipped): the data gradient of y = conv(x, w)."""
     B, T, N = dz.shape
     Cin = x.v.shape[-1]
     out, acc = grad_buffer(x)
     res = out if acc else None
-    if ctx.bwd_tc and N % 8 == 0 and Cin % 4 == 0 and N >= 16:
-        engine.gemm_tc(engine.split_planes(dz, 2), ctx.dgrad_planes(wname), residual=res, taps=taps, out=out)
+    if _tc_dgrad_ok(ctx, N, Cin):
+        dzp = dz_planes if dz_planes is not None else engine.split_planes(dz, 2)
+        engine.gemm_tc(dzp, ctx.dgrad_planes(wname), residual=res, taps=taps, out=out)
     elif N % 16 == 0:
         engine.conv_gemm(dz, ctx.dgrad_packed(wname), residual=res, taps=taps, out=out)
     else:
@@ -293,7 +298,7 @@ def transposed_planes(t, taps=1, n=2):
     return p
 
 
-def _wgrad(ctx, dz, x, wname, taps):
+def _wgrad(ctx, dz, x, wname, taps, dzT=None):
     """G[w] += dz^T (*) x : the weight gradient of y = conv(x, w)."""
     G = ctx.G.get(wname)
     if G is None:
@@ -303,7 +308,8 @@ def _wgrad(ctx, dz, x, wname, taps):
     st = _st()
     if ctx.bwd_tc and Cin % 4 == 0:
         Tp = (T + 7) // 8 * 8
-        dzT = transposed_planes(dz)
+        if dzT is None:
+            dzT = transposed_planes(dz)
         if x._tplanes is None:
             x._tplanes = {}
         xT = x._tplanes.get(taps)
@@ -374,13 +380,24 @@ def linear(ctx, x, wname, bname=None, alpha=1.0, act=ACT_NONE, residual=None, le
                 mask = None
             accumulate_copy(residual, dz)
             res_done = True
-        if mask is not None or act != ACT_NONE or alpha != 1.0 or bias is not None:
-            ref = pre if keep_pre else (y.v if act in (ACT_RELU, ACT_TANH) else None)
+        ref = pre if keep_pre else (y.v if act in (ACT_RELU, ACT_TANH) else None)
+        dzp = dzT = None
+        want_w = ctx.G.get(wname) is not None and ctx.bwd_tc and Cin % 4 == 0
+        want_d = x.needs_grad and _tc_dgrad_ok(ctx, N, Cin)
+        if want_w and want_d and N % 4 == 0:
+            # one pass: mask + activation' + alpha + bias gradient + the operand planes of both backward GEMMs
+            Tp = (T + 7) // 8 * 8
+            dzp = Planes.empty((B, T, N), dz.device, 2)
+            dzT = Planes.empty((B, 1, N, Tp), dz.device, 2)
+            capi.call("ctts_act_bwd_planes", dz, ref, int(act), float(alpha), mask, B, T, N, Tp,
+                      dz if residual is not None and not res_done else None, 2, capi.ptr_array(dzp.p), capi.ptr_array(dzT.p),
+                      ctx.G.get(bname) if bname else None, _st())
+        elif mask is not None or act != ACT_NONE or alpha != 1.0 or bias is not None:
             capi.call("ctts_act_bwd", dz, ref, int(act), float(alpha), mask, 1, T, B * T, N, dz,
                       ctx.G.get(bname) if bname else None, _st())
         if x.needs_grad:
-            _dgrad(ctx, dz, wname, taps, x)
-        _wgrad(ctx, dz, x, wname, taps)
+            _dgrad(ctx, dz, wname, taps, x, dzp)
+        _wgrad(ctx, dz, x, wname, taps, dzT)
         if residual is not None and not res_done:
             accumulate_into(residual, dz)
         y.g = None
@@ -452,11 +469,33 @@ def residual_add(ctx, res, y_in, lens):
     return y
 
 
+def dropout_residual(ctx, res, x, p, lens):
+    """(res + dropout(x)) * keep in one pass (ctts_dropout_add)."""
+    B, T, C = res.v.shape
+    off = ctx.next_offset()
+    out = torch.empty_like(res.v)
+    capi.call("ctts_dropout_add", x.v, res.v, lens, B, T, C, float(p), ctx.seed, off, ctx.offset_dev, out, _st())
+    y = Var(out)
+
+    def bwd():
+        if y.g is None:
+            return
+        if lens is not None:
+            capi.call("ctts_mask_rows", y.g, lens, B, T, C, _st())
+        accumulate_copy(res, y.g)
+        capi.call("ctts_dropout", y.g, y.g.numel(), float(p), ctx.seed, off, ctx.offset_dev, y.g, _st())
+        accumulate_into(x, y.g)
+        y.g = None
+
+    ctx.record(bwd)
+    return y
+
+
 def sublayer(ctx, x, h, wname, bname, lens, p_drop, math, alpha=1.0, taps=1):
     """x + dropout(alpha * linear(h)) masked: fused into the GEMM epilogue when there is no dropout."""
     if p_drop > 0.0 and ctx.dropout_on:
         y = linear(ctx, h, wname, bname, alpha=alpha, taps=taps, math=math)
-        return residual_add(ctx, x, dropout(ctx, y, p_drop), lens)
+        return dropout_residual(ctx, x, y, p_drop, lens)
     return linear(ctx, h, wname, bname, alpha=alpha, residual=x, lens=lens, taps=taps, math=math)
 
 

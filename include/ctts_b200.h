@@ -338,6 +338,16 @@ int ctts_gemm_generic(const float* a, const float* b, float* y, int Z, int zmod,
 int ctts_act_bwd(const float* dy, const float* ref, int act, float alpha, const int64_t* lens, int Z, int T, int rows, int N,
                  float* dz, float* dbias, void* stream);
 
+/* ctts_act_bwd fused with the operand preparation of the two GEMMs that consume dz: writes dz (fp32, nullable, may alias dy),
+ * its row-major bf16 planes [B, T, N] (dgrad operand) and its time-major planes [B, N, Tp] (wgrad operand), adds the column
+ * sums to dbias.  N % 4 == 0. */
+int ctts_act_bwd_planes(const float* dy, const float* ref, int act, float alpha, const int64_t* lens, int B, int T, int N, int Tp,
+                        float* dz, int n_planes, void* const* dz_planes, void* const* dzT_planes, float* dbias, void* stream);
+/* y = (res + dropout(x)) * keep: residual add behind a dropout (transformer_fs2.py:190-192,197-199) in one pass; the mask is
+ * the one ctts_dropout draws for (seed, offset [+ *offset_dev]) */
+int ctts_dropout_add(const float* x, const float* res, const int64_t* lens, int B, int T, int C, float p, unsigned long long seed,
+                     unsigned long long offset, const unsigned long long* offset_dev, float* y, void* stream);
+
 /* LayerNorm backward (blocks.py:137-156, nn.LayerNorm): dx (+)= ..., dgamma += , dbeta += ; statistics recomputed from x */
 int ctts_layernorm_bwd(const float* x, const float* gamma, const float* dy, float eps, const int64_t* lens, int B, int T,
                        int C, float* dx, int accumulate, float* dgamma, float* dbeta, void* stream);

@@ -441,6 +441,30 @@ def ctts_act_bwd(dy, ref, act, alpha, lens, Z, T, rows, N, dz, dbias, stream):
         db.copy_(db + g.view(Z, rows, N).sum(1))
 
 
+def ctts_act_bwd_planes(dy, ref, act, alpha, lens, B, T, N, Tp, dz, n, dzp, dztp, dbias, stream):
+    g = _v(dy, B, T, N).clone() * _keep(lens, B, T)[:, :, None] * alpha
+    if act != ACT_NONE:
+        g = g * _act_grad(_v(ref, B, T, N), act)
+    if dz is not None:
+        _v(dz, B, T, N).copy_(g)
+    _split_into(g, _planes(dzp, n), B, T, N)
+    gt = torch.zeros(B, N, Tp)
+    gt[:, :, :T] = g.transpose(1, 2)
+    _split_into(gt, _planes(dztp, n), B, N, Tp)
+    if dbias is not None:
+        _v(dbias, N).add_(g.reshape(-1, N).sum(0))
+
+
+def ctts_dropout_add(x, res, lens, B, T, C, p, seed, offset, offset_dev, y, stream):
+    n = B * T * C
+    if offset_dev is not None:
+        offset = int(offset) + int(_v(offset_dev, 1)[0])
+    keep = dropout_mask(n, p, seed, offset)
+    inv = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    out = (_v(res, n) + _v(x, n) * keep * float(inv)).view(B, T, C) * _keep(lens, B, T)[:, :, None]
+    _v(y, B, T, C).copy_(out)
+
+
 def ctts_layernorm_bwd(x, gamma, dy, eps, lens, B, T, C, dx, accumulate, dgamma, dbeta, stream):
     xv = _v(x, B, T, C).clone().requires_grad_(True)
     gm = _v(gamma, C).clone().requires_grad_(True)

@@ -291,3 +291,26 @@ def test_reference_encoder_helper_kernels():
     run_both("ctts_im2col_3x3_s12", [g(N, H, W, C), N, H, W, C, torch.zeros(N * H * Wo, 9 * C)], atol=0, rtol=0)
     run_both("ctts_col2im_3x3_s12", [g(N * H * Wo, 9 * C), N, H, W, C, torch.zeros(N, H, W, C)], atol=1e-5)
     run_both("ctts_permute_last2", [g(7, 3, 128), 7, 3, 128, torch.zeros(7, 128, 3)], atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("act,N", [(0, 256), (2, 1024), (1, 80), (3, 12)])
+def test_act_bwd_planes_fused(act, N):
+    B, T = 3, 45
+    Tp = 48
+    dy, ref = g(B, T, N), g(B, T, N, seed=1)
+    if act == 3:
+        ref = torch.tanh(ref)
+    lens = torch.tensor([45, 20, 3])
+    zp = [torch.zeros(B, T, N, dtype=torch.bfloat16) for _ in range(2)]
+    zt = [torch.zeros(B, N, Tp, dtype=torch.bfloat16) for _ in range(2)]
+    run_both("ctts_act_bwd_planes", [dy, ref if act else None, act, 0.5, lens, B, T, N, Tp, torch.zeros(B, T, N), 2, PA(zp), PA(zt),
+                                     g(N, seed=3)], atol=3e-5)
+    run_both("ctts_act_bwd_planes", [dy, ref if act else None, act, 1.0, None, B, T, N, Tp, None, 2, PA(zp), PA(zt), None], atol=3e-5)
+
+
+def test_dropout_add_fused():
+    B, T, C = 3, 20, 64
+    lens = torch.tensor([20, 11, 0])
+    run_both("ctts_dropout_add", [g(B, T, C), g(B, T, C, seed=1), lens, B, T, C, 0.1, 77, 3, torch.tensor([9]), torch.zeros(B, T, C)],
+             atol=1e-6)
+    run_both("ctts_dropout_add", [g(B, T, C), g(B, T, C, seed=1), None, B, T, C, 0.5, 77, 3, None, torch.zeros(B, T, C)], atol=1e-6)
