@@ -125,6 +125,16 @@ def attention(qkv, lens, n_head):
 
 
 FLASH = os.environ.get("CTTS_FLASH_ATTENTION", "1") != "0"
+PARALLEL_BRANCHES = os.environ.get("CTTS_PARALLEL_BRANCHES", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One extra stream per device for the independent predictor branches of a captured forward."""
+    k = str(device)
+    if k not in _SIDE_STREAMS:
+        _SIDE_STREAMS[k] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[k]
 
 
 def attention_flash(qkv_planes, lens, n_head):
@@ -585,18 +595,65 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
 
     x_sum = xe.clone()
     pitch_pred = energy_pred = None
-    if cfg["variance_embedding"]["use_pitch_embed"]:
-        pre = "variance_adaptor."
+    use_pitch = cfg["variance_embedding"]["use_pitch_embed"]
+    use_energy = cfg["variance_embedding"]["use_energy_embed"]
+    level = pcfg["preprocessing"]["energy"]["feature"]
+    pre = "variance_adaptor."
+
+    # The CWT statistics MLP (3 tiny launches on x_org[:, 0]) and the phoneme-level energy predictor (~10 launches on
+    # [B, S] rows) are independent of the frame-level CWT predictor chain: while the forward is being captured into a CUDA
+    # graph they are issued on a side stream (fork / join events become parallel graph branches), so their latency-bound
+    # kernels overlap the longer chain instead of queueing behind it.
+    side = {}
+
+    def side_work():
+        if use_pitch:
+            first = torch.empty(1, B, C, device=dev, dtype=torch.float32)
+            capi.call("ctts_copy_rows", x_org, S * C, B, C, first, C, 0, _stream())
+            s = conv_gemm(first, P[pre + "cwt_stats_layers.0.weight"], P[pre + "cwt_stats_layers.0.bias"], act=ACT_RELU)
+            s = conv_gemm(s, P[pre + "cwt_stats_layers.2.weight"], P[pre + "cwt_stats_layers.2.bias"], act=ACT_RELU)
+            side["stats"] = conv_gemm(s, P[pre + "cwt_stats_layers.4.weight"], P[pre + "cwt_stats_layers.4.bias"]).view(B, 2)
+        if use_energy and level != "frame_level":
+            et = energy_target
+            if attn_prior is not None:  # frame-level target -> phoneme level by the hard durations (modules.py:1096-1097)
+                etf = _f32(energy_target)
+                M_e = etf.shape[1]
+                work = torch.empty(B * M_e, device=dev, dtype=torch.float32)
+                et = torch.empty(B, S, device=dev, dtype=torch.float32)
+                capi.call("ctts_phoneme_energy", a["attn_out"][2], src_lens, etf, B, S, M_e, work, et, _stream())
+            pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", x_org,
+                                         alpha=1.0 if et is not None else e_control).squeeze(-1)
+            src_vals = _f32(et) if et is not None else pred
+            eidx = torch.empty(B, S, device=dev, dtype=torch.int64)
+            bins = P[pre + "energy_bins"]
+            capi.call("ctts_bucketize", src_vals, 1.0, bins, bins.shape[0], B * S, eidx, _stream())
+            side["energy"] = (et, pred, eidx)
+
+    forked = None
+    if PARALLEL_BRANCHES and dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        main = torch.cuda.current_stream()
+        branch = _side_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        with torch.cuda.stream(branch):
+            branch.wait_event(fork)
+            side_work()
+            forked = torch.cuda.Event()
+            forked.record(branch)
+    else:
+        side_work()
+
+    if use_pitch:
         if (pre + "cwt_predictor.0.weight#planes3") in prep.w:
             h, _ = gemm_tc(split_planes(xe, 3), prep.w[pre + "cwt_predictor.0.weight#planes3"],
                            P[pre + "cwt_predictor.0.bias"])
         else:
             h = conv_gemm(xe, P[pre + "cwt_predictor.0.weight"], P[pre + "cwt_predictor.0.bias"])
         cwt = pitch_style_predictor(prep, P, cfg, pre + "cwt_predictor.1.", h, alpha=p_control)
-        first = x_org[:, 0, :].contiguous().view(1, B, C)
-        s = conv_gemm(first, P[pre + "cwt_stats_layers.0.weight"], P[pre + "cwt_stats_layers.0.bias"], act=ACT_RELU)
-        s = conv_gemm(s, P[pre + "cwt_stats_layers.2.weight"], P[pre + "cwt_stats_layers.2.bias"], act=ACT_RELU)
-        stats = conv_gemm(s, P[pre + "cwt_stats_layers.4.weight"], P[pre + "cwt_stats_layers.4.bias"]).view(B, 2)
+    if forked is not None:
+        torch.cuda.current_stream().wait_event(forked)      # join
+    if use_pitch:
+        stats = side["stats"]
         f0_denorm = torch.empty(B, M, device=dev, dtype=torch.float32)
         idx = torch.empty(B, M, device=dev, dtype=torch.int64)
         use_uv = 1 if pitch_cfg["use_uv"] else 0
@@ -620,9 +677,7 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
         capi.call("ctts_gather_add", emb, idx, B * M, C, emb.shape[0], x_sum, st)
         pitch_pred = {"pitch_pred": None, "f0_denorm": f0_denorm, "cwt": cwt, "f0_mean": stats[:, 0],
                       "f0_std": stats[:, 1]}
-    if cfg["variance_embedding"]["use_energy_embed"]:
-        pre = "variance_adaptor."
-        level = pcfg["preprocessing"]["energy"]["feature"]
+    if use_energy:
         bins = P[pre + "energy_bins"]
         emb = P[pre + "energy_embedding.weight"]
         if level == "frame_level":
@@ -633,17 +688,7 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
             capi.call("ctts_bucketize", src_vals, 1.0, bins, bins.shape[0], B * M, eidx, st)
             capi.call("ctts_gather_add", emb, eidx, B * M, C, emb.shape[0], x_sum, st)
         else:
-            if attn_prior is not None:  # frame-level target -> phoneme level by the hard durations (modules.py:1096-1097)
-                et = _f32(energy_target)
-                M_e = et.shape[1]
-                work = torch.empty(B * M_e, device=dev, dtype=torch.float32)
-                energy_target = torch.empty(B, S, device=dev, dtype=torch.float32)
-                capi.call("ctts_phoneme_energy", a["attn_out"][2], src_lens, et, B, S, M_e, work, energy_target, st)
-            pred = pitch_style_predictor(prep, P, cfg, pre + "energy_predictor.", x_org,
-                                         alpha=1.0 if energy_target is not None else e_control).squeeze(-1)
-            src_vals = _f32(energy_target) if energy_target is not None else pred
-            eidx = torch.empty(B, S, device=dev, dtype=torch.int64)
-            capi.call("ctts_bucketize", src_vals, 1.0, bins, bins.shape[0], B * S, eidx, st)
+            energy_target, pred, eidx = side["energy"]
             capi.call("ctts_length_expand", None, emb, eidx, cum_lr, B, S, C, M, 1, x_sum, None, None, 0, st)
         energy_pred = pred
     return (x_sum, pitch_target, pitch_pred, energy_target, energy_pred, mel_len, mel_mask)
