@@ -648,6 +648,53 @@ __global__ void f0_to_pitch_kernel(const float* __restrict__ f0n, const float* _
     pitch_idx[i] = f0_to_coarse_dev(fd);
 }
 
+// pitch_type 'frame' (modules.py:927-938): f0 (+ voiced / unvoiced logit) per frame from the predictor or the targets
+__global__ void frame_pitch_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ f0_target,
+                                   const float* __restrict__ uv_target, const int64_t* __restrict__ mel2ph, int use_uv, int n,
+                                   float* __restrict__ f0_out, float* __restrict__ f0_denorm, int64_t* __restrict__ pitch_idx) {
+    CTTS_PDL_SYNC();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float f0 = f0_target ? f0_target[i] : pred[(size_t)i * ldp];
+    bool uv = false;
+    if (use_uv) uv = uv_target ? (uv_target[i] > 0.f) : (pred[(size_t)i * ldp + 1] > 0.f);
+    const bool pad = mel2ph[i] == 0;
+    const float fd = (uv || pad) ? 0.f : exp2f(f0);
+    f0_out[i] = pad ? 0.f : f0;          // `f0[pitch_padding] = 0`, in place on the caller's target (modules.py:934-935)
+    f0_denorm[i] = fd;
+    pitch_idx[i] = f0_to_coarse_dev(fd);
+}
+
+// pitch_type 'ph': frame index = phoneme bucket gathered through mel2ph (F.pad(pitch, [1, 0]) + torch.gather, modules.py:900-901)
+__global__ void gather_index_kernel(const int64_t* __restrict__ idx_ph, const int64_t* __restrict__ mel2ph, int S, int M, int n,
+                                    int64_t* __restrict__ out) {
+    CTTS_PDL_SYNC();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = i / M;
+    const int64_t j = mel2ph[i];
+    out[i] = (j > 0 && j <= S) ? idx_ph[(size_t)b * S + (j - 1)] : 0;
+}
+
+// get_phoneme_level_pitch (modules.py:874-880, utils/tools.py:47-53): mean of the frame-level f0 over each phoneme's frames
+__global__ void phoneme_pitch_kernel(const float* __restrict__ f0, const int64_t* __restrict__ mel2ph,
+                                     const int64_t* __restrict__ src_lens, const int64_t* __restrict__ mel_lens, int S, int M,
+                                     float* __restrict__ out) {
+    CTTS_PDL_SYNC();
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= S) return;
+    const int lane = threadIdx.x & 31;
+    const int slen = min((int)src_lens[b], S), mlen = min((int)mel_lens[b], M);
+    float sum = 0.f, cnt = 0.f;
+    if (j < slen)
+        for (int t = lane; t < mlen; t += 32)
+            if (mel2ph[(size_t)b * M + t] == j + 1) { sum += f0[(size_t)b * M + t]; cnt += 1.f; }
+    sum = warp_sum(sum);
+    cnt = warp_sum(cnt);
+    if (lane == 0) out[(size_t)b * S + j] = (j < slen) ? sum / fmaxf(cnt, 1.f) : 0.f;
+}
+
 __global__ void gather_add_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, int rows, int C,
                                   int table_rows, float* __restrict__ x) {
     CTTS_PDL_SYNC();
@@ -1313,6 +1360,30 @@ int ctts_f0_to_pitch(const float* f0_norm, const float* uv_src, int n, float* f0
     CTTS_REQUIRE(n > 0, "f0_to_pitch: empty");
     launch_k(f0_to_pitch_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, f0_norm, uv_src, n, f0_denorm, pitch_idx);
     return check_launch("f0_to_pitch");
+}
+
+int ctts_frame_pitch(const float* pred, int ldp, const float* f0_target, const float* uv_target, const int64_t* mel2ph, int use_uv,
+                     int n, float* f0_out, float* f0_denorm, int64_t* pitch_idx, void* stream) {
+    CTTS_REQUIRE((pred || f0_target) && mel2ph && f0_out && f0_denorm && pitch_idx && n > 0, "frame_pitch: bad arguments");
+    CTTS_REQUIRE(!use_uv || uv_target || (pred && ldp >= 2), "frame_pitch: use_uv needs a uv target or a 2-wide prediction");
+    launch_k(frame_pitch_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, pred, ldp, f0_target, uv_target, mel2ph, use_uv, n,
+             f0_out, f0_denorm, pitch_idx);
+    return check_launch("frame_pitch");
+}
+
+int ctts_gather_index(const int64_t* idx_ph, const int64_t* mel2ph, int B, int S, int M, int64_t* out, void* stream) {
+    CTTS_REQUIRE(idx_ph && mel2ph && out && B > 0 && S > 0 && M > 0, "gather_index: bad arguments");
+    const int n = B * M;
+    launch_k(gather_index_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, idx_ph, mel2ph, S, M, n, out);
+    return check_launch("gather_index");
+}
+
+int ctts_phoneme_pitch(const float* f0, const int64_t* mel2ph, const int64_t* src_lens, const int64_t* mel_lens, int B, int S,
+                       int M, float* out, void* stream) {
+    CTTS_REQUIRE(f0 && mel2ph && src_lens && mel_lens && out && B > 0 && S > 0 && M > 0, "phoneme_pitch: bad arguments");
+    dim3 grid((S + 7) / 8, B);
+    launch_k(phoneme_pitch_kernel, grid, 256, 0, (cudaStream_t)stream, f0, mel2ph, src_lens, mel_lens, S, M, out);
+    return check_launch("phoneme_pitch");
 }
 
 int ctts_gather_add(const float* table, const int64_t* idx, int rows, int C, int table_rows, float* x, void* stream) {

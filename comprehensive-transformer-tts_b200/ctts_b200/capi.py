@@ -30,6 +30,9 @@ SIGNATURES = {
     "ctts_length_expand": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "ctts_cwt_to_pitch": [_P, _I, _P, _P, _P, _I, _F, _F, _P, _I, _I, _I, _P, _P, _P, _P],
     "ctts_f0_to_pitch": [_P, _P, _I, _P, _P, _P],
+    "ctts_frame_pitch": [_P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "ctts_gather_index": [_P, _P, _I, _I, _I, _P, _P],
+    "ctts_phoneme_pitch": [_P, _P, _P, _P, _I, _I, _I, _P, _P],
     "ctts_gather_add": [_P, _P, _I, _I, _I, _P, _P],
     "ctts_bucketize": [_P, _F, _P, _I, _I, _P, _P],
     "ctts_add_row_broadcast": [_P, _P, _I, _I, _I, _P, _P],

@@ -79,7 +79,7 @@ def _train(dataset):
     }
 
 
-def builtin_configs(dataset="LJSpeech", block_type=None, learn_alignment=None, prosody=None):
+def builtin_configs(dataset="LJSpeech", block_type=None, learn_alignment=None, prosody=None, pitch_type=None):
     """(preprocess_config, model_config, train_config) equal, on every key this path reads, to the
     reference's config/<dataset>/*.yaml (after train.py:229-231 patched `cwt_scales` in)."""
     if dataset not in ("LJSpeech", "VCTK"):
@@ -91,4 +91,6 @@ def builtin_configs(dataset="LJSpeech", block_type=None, learn_alignment=None, p
         m["duration_modeling"]["learn_alignment"] = bool(learn_alignment)
     if prosody is not None:
         m["prosody_modeling"]["model_type"] = prosody
+    if pitch_type is not None:
+        p["preprocessing"]["pitch"]["pitch_type"] = pitch_type
     return copy.deepcopy(p), copy.deepcopy(m), copy.deepcopy(t)

@@ -606,8 +606,10 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
     # kernels overlap the longer chain instead of queueing behind it.
     side = {}
 
+    pitch_type = pitch_cfg["pitch_type"]
+
     def side_work():
-        if use_pitch:
+        if use_pitch and pitch_type == "cwt":
             first = torch.empty(1, B, C, device=dev, dtype=torch.float32)
             capi.call("ctts_copy_rows", x_org, S * C, B, C, first, C, 0, _stream())
             s = conv_gemm(first, P[pre + "cwt_stats_layers.0.weight"], P[pre + "cwt_stats_layers.0.bias"], act=ACT_RELU)
@@ -643,7 +645,13 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
     else:
         side_work()
 
-    if use_pitch:
+    if use_pitch and pitch_type != "cwt":
+        if forked is not None:
+            torch.cuda.current_stream().wait_event(forked)
+            forked = None
+        pitch_pred = _pitch_frame_or_ph(prep, P, cfg, pitch_cfg, pitch_type, xe, x_org, x_sum, pitch_target, mel2ph, src_lens,
+                                        mel_len, p_control, B, S, M, C)
+    if use_pitch and pitch_type == "cwt":
         if (pre + "cwt_predictor.0.weight#planes3") in prep.w:
             h, _ = gemm_tc(split_planes(xe, 3), prep.w[pre + "cwt_predictor.0.weight#planes3"],
                            P[pre + "cwt_predictor.0.bias"])
@@ -652,7 +660,7 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
         cwt = pitch_style_predictor(prep, P, cfg, pre + "cwt_predictor.1.", h, alpha=p_control)
     if forked is not None:
         torch.cuda.current_stream().wait_event(forked)      # join
-    if use_pitch:
+    if use_pitch and pitch_type == "cwt":
         stats = side["stats"]
         f0_denorm = torch.empty(B, M, device=dev, dtype=torch.float32)
         idx = torch.empty(B, M, device=dev, dtype=torch.int64)
@@ -692,6 +700,47 @@ def variance_stage_b(prep, P, pcfg, cfg, tcfg, a, src_lens, mel_lens, mel_mask, 
             capi.call("ctts_length_expand", None, emb, eidx, cum_lr, B, S, C, M, 1, x_sum, None, None, 0, st)
         energy_pred = pred
     return (x_sum, pitch_target, pitch_pred, energy_target, energy_pred, mel_len, mel_mask)
+
+
+def _pitch_frame_or_ph(prep, P, cfg, pitch_cfg, pitch_type, xe, x_org, x_sum, pitch_target, mel2ph, src_lens, mel_len, p_control,
+                       B, S, M, C):
+    """get_pitch_embedding for pitch_type 'frame' / 'ph' (modules.py:890-906,927-938): one PitchPredictor on the frame- or
+    phoneme-level input; adds the pitch embedding to x_sum and returns the prediction dict."""
+    pre = "variance_adaptor."
+    st = _stream()
+    dev = xe.device
+    assert pitch_cfg["pitch_norm"] == "log", "only pitch_norm 'log' (the shipped configs) is built"
+    m2p = pitch_target["mel2ph"] if pitch_target is not None else mel2ph
+    assert m2p is not None and m2p.shape[1] == M, "mel2ph / regulated length mismatch"
+    m2p = _i64(m2p)
+    emb = P[pre + "pitch_embed.weight"]
+    idx = torch.empty(B, M, device=dev, dtype=torch.int64)
+    if pitch_type == "frame":
+        pred = pitch_style_predictor(prep, P, cfg, pre + "pitch_predictor.", xe, alpha=p_control)         # [B, M, 2]
+        f0_denorm = torch.empty(B, M, device=dev, dtype=torch.float32)
+        if pitch_target is not None:
+            f0t = _f32(pitch_target["f0"])
+            capi.call("ctts_frame_pitch", None, 0, f0t, _f32(pitch_target["uv"]), m2p, 1 if pitch_cfg["use_uv"] else 0, B * M,
+                      f0t, f0_denorm, idx, st)
+            pitch_target["f0"] = f0t
+        else:
+            f0 = torch.empty(B, M, device=dev, dtype=torch.float32)
+            capi.call("ctts_frame_pitch", pred, pred.shape[-1], None, None, m2p, 1 if pitch_cfg["use_uv"] else 0, B * M, f0,
+                      f0_denorm, idx, st)
+    else:
+        pred = pitch_style_predictor(prep, P, cfg, pre + "pitch_predictor.", x_org, alpha=p_control)      # [B, S, 1]
+        if pitch_target is not None:
+            f0 = torch.empty(B, S, device=dev, dtype=torch.float32)
+            capi.call("ctts_phoneme_pitch", _f32(pitch_target["f0"]), m2p, src_lens, _i64(mel_len), B, S, M, f0, st)
+            pitch_target["f0"] = f0
+        else:
+            f0 = pred.view(B, S)
+        f0_denorm = torch.empty(B, S, device=dev, dtype=torch.float32)
+        idx_ph = torch.empty(B, S, device=dev, dtype=torch.int64)
+        capi.call("ctts_f0_to_pitch", f0, None, B * S, f0_denorm, idx_ph, st)     # pitch_padding is a scalar False (:894)
+        capi.call("ctts_gather_index", idx_ph, m2p, B, S, M, idx, st)
+    capi.call("ctts_gather_add", emb, idx, B * M, C, emb.shape[0], x_sum, st)
+    return {"pitch_pred": pred, "f0_denorm": f0_denorm, "cwt": None, "f0_mean": None, "f0_std": None}
 
 
 # ---------------------------------------------------------------------------------------------

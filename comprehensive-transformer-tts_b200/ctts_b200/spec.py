@@ -119,15 +119,21 @@ def _variance_adaptor(out, pcfg, cfg, d_model):
     _predictor(out, pre + "duration_predictor.", hid, vp["filter_size"], vp["dur_predictor_layers"],
                vp["dur_predictor_kernel"], 1, False)
     if ve["use_pitch_embed"]:
-        if pitch["pitch_type"] != "cwt":
-            raise NotImplementedError("pitch_type %r: only 'cwt' (the shipped configs) is built" % pitch["pitch_type"])
-        h = vp["cwt_hidden_size"]
-        _lin(out, pre + "cwt_predictor.0", h, hid)
-        _predictor(out, pre + "cwt_predictor.1.", h, vp["filter_size"], vp["predictor_layers"], vp["predictor_kernel"],
-                   11 if pitch["use_uv"] else 10, True)
-        _lin(out, pre + "cwt_stats_layers.0", h, hid)
-        _lin(out, pre + "cwt_stats_layers.2", h, h)
-        _lin(out, pre + "cwt_stats_layers.4", 2, h)
+        if pitch["pitch_type"] not in ("cwt", "frame", "ph"):
+            raise NotImplementedError("pitch_type %r" % pitch["pitch_type"])
+        if pitch["pitch_type"] == "cwt":
+            h = vp["cwt_hidden_size"]
+            _lin(out, pre + "cwt_predictor.0", h, hid)
+            _predictor(out, pre + "cwt_predictor.1.", h, vp["filter_size"], vp["predictor_layers"], vp["predictor_kernel"],
+                       11 if pitch["use_uv"] else 10, True)
+            _lin(out, pre + "cwt_stats_layers.0", h, hid)
+            _lin(out, pre + "cwt_stats_layers.2", h, h)
+            _lin(out, pre + "cwt_stats_layers.4", 2, h)
+        else:   # modules.py:778-785: one PitchPredictor on the frame- ('frame': f0 + uv) or phoneme-level ('ph': f0) input
+            if pitch.get("pitch_ar"):
+                raise NotImplementedError("pitch_ar (autoregressive pitch predictor, modules.py:923-926) is not built")
+            _predictor(out, pre + "pitch_predictor.", hid, vp["filter_size"], vp["predictor_layers"], vp["predictor_kernel"],
+                       2 if pitch["pitch_type"] == "frame" else 1, True)
         out.append((pre + "pitch_embed.weight", (ve["pitch_n_bins"], hid), "param", "emb:%d" % hid))
     if ve["use_energy_embed"]:
         _predictor(out, pre + "energy_predictor.", hid, vp["filter_size"], vp["predictor_layers"],

@@ -83,6 +83,10 @@ def synthetic_state_dict(spec_entries, seed=1234, pin_frames_per_phoneme=None):
     k = "variance_adaptor.cwt_stats_layers.4.bias"
     if k in out:  # put the free-running f0 near 200 Hz (log-f0 mean 5.3, std 0.4) so the pitch quantiser sees many bins
         out[k] = torch.tensor([5.3, 0.4])
+    k = "variance_adaptor.pitch_predictor.linear.bias"
+    if k in out:  # pitch_type 'frame' / 'ph': free-running log2-f0 around 7.5 (~180 Hz), voiced / unvoiced logit around 0
+        out[k] = torch.tensor([7.5, 0.0][: out[k].numel()])
+        out["variance_adaptor.pitch_predictor.linear.weight"] = out["variance_adaptor.pitch_predictor.linear.weight"] * 4.0
     if pin_frames_per_phoneme is not None:
         out["variance_adaptor.duration_predictor.linear.weight"].zero_()
         out["variance_adaptor.duration_predictor.linear.bias"].fill_(math.log(1.0 + pin_frames_per_phoneme))

@@ -972,9 +972,35 @@ def variance_adaptor(ctx, spk, text, text_embedding, src_lens, mel, mel_lens, ma
     scatter_jobs = []
     pitch_pred = energy_pred = None
     pre = "variance_adaptor."
-    if cfg["variance_embedding"]["use_pitch_embed"]:
-        pitch_cfg = pcfg["preprocessing"]["pitch"]
-        assert pitch_cfg["pitch_type"] == "cwt" and pitch_cfg["pitch_norm"] == "log"
+    pitch_cfg = pcfg["preprocessing"]["pitch"]
+    if cfg["variance_embedding"]["use_pitch_embed"] and pitch_cfg["pitch_type"] != "cwt":
+        # pitch_type 'frame' / 'ph' (modules.py:890-906,927-938): one PitchPredictor; the embedding comes from the targets
+        assert pitch_cfg["pitch_norm"] == "log" and pitch_target is not None, "training needs pitch targets"
+        m2p = _i64(pitch_target["mel2ph"])
+        assert m2p.shape[1] == M, "mel2ph length %d != regulated length %d" % (m2p.shape[1], M)
+        idx = torch.empty(B, M, device=dev, dtype=torch.int64)
+        if pitch_cfg["pitch_type"] == "frame":
+            ppred = pitch_style_predictor(ctx, pre + "pitch_predictor.", scale_grad(ctx, xe, g_pred), alpha=p_control)
+            f0t = _f32(pitch_target["f0"])
+            f0_denorm = torch.empty(B, M, device=dev, dtype=torch.float32)
+            capi.call("ctts_frame_pitch", None, 0, f0t, _f32(pitch_target["uv"]), m2p, 1 if pitch_cfg["use_uv"] else 0, B * M,
+                      f0t, f0_denorm, idx, st)
+            pitch_target["f0"] = f0t
+        else:
+            ppred = pitch_style_predictor(ctx, pre + "pitch_predictor.", scale_grad(ctx, x, g_pred), alpha=p_control)
+            f0 = torch.empty(B, S, device=dev, dtype=torch.float32)
+            capi.call("ctts_phoneme_pitch", _f32(pitch_target["f0"]), m2p, src_lens, _i64(mel_len), B, S, M, f0, st)
+            pitch_target["f0"] = f0
+            f0_denorm = torch.empty(B, S, device=dev, dtype=torch.float32)
+            idx_ph = torch.empty(B, S, device=dev, dtype=torch.int64)
+            capi.call("ctts_f0_to_pitch", f0, None, B * S, f0_denorm, idx_ph, st)
+            capi.call("ctts_gather_index", idx_ph, m2p, B, S, M, idx, st)
+        emb = P[pre + "pitch_embed.weight"]
+        capi.call("ctts_gather_add", emb, idx, B * M, C, emb.shape[0], x_sum.v, st)
+        scatter_jobs.append(("frame", pre + "pitch_embed.weight", idx))
+        pitch_pred = {"pitch_pred": ppred, "f0_denorm": f0_denorm, "cwt": None, "stats": None}
+    elif cfg["variance_embedding"]["use_pitch_embed"]:
+        assert pitch_cfg["pitch_norm"] == "log"
         h = linear(ctx, scale_grad(ctx, xe, g_pred), pre + "cwt_predictor.0.weight", pre + "cwt_predictor.0.bias",
                    math=ctx.enc_math)
         cwt = pitch_style_predictor(ctx, pre + "cwt_predictor.1.", h, alpha=p_control)
@@ -1228,7 +1254,10 @@ def run_backward(ctx, arena, out_vars, grads, world=1, reducer=None):
 def _leaves_of(va, mel, post):
     leaves = [("mel", mel), ("post", post), ("log_d", va["log_d"])]
     if va["pitch_pred"] is not None:
-        leaves += [("cwt", va["pitch_pred"]["cwt"]), ("stats", va["pitch_pred"]["stats"])]
+        if va["pitch_pred"]["cwt"] is not None:
+            leaves += [("cwt", va["pitch_pred"]["cwt"]), ("stats", va["pitch_pred"]["stats"])]
+        if va["pitch_pred"].get("pitch_pred") is not None:
+            leaves.append(("pitch_pred", va["pitch_pred"]["pitch_pred"]))
     if va["energy_pred"] is not None:
         leaves.append(("e_pred", va["energy_pred"]))
     if va["attn"] is not None:
@@ -1433,6 +1462,8 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         stats = o["stats"].view(B, 2)
         p_pred = {"pitch_pred": None, "f0_denorm": side["f0_denorm"], "cwt": o["cwt"], "f0_mean": stats[:, 0],
                   "f0_std": stats[:, 1]}
+    elif "pitch_pred" in o:
+        p_pred = {"pitch_pred": o["pitch_pred"], "f0_denorm": side["f0_denorm"], "cwt": None, "f0_mean": None, "f0_std": None}
     e_pred = o["e_pred"].squeeze(-1) if "e_pred" in o else None
     attn_outs = (None, None, None, None)
     if "attn_soft" in o:

@@ -269,6 +269,32 @@ def ctts_f0_to_pitch(f0n, uv_src, n, f0_denorm, pitch_idx, stream):
     _v(pitch_idx, n).copy_(_f0_to_coarse(fd))
 
 
+def ctts_frame_pitch(pred, ldp, f0_target, uv_target, mel2ph, use_uv, n, f0_out, f0_denorm, pitch_idx, stream):
+    pr = _v(pred, n, ldp) if pred is not None else None
+    f0 = _v(f0_target, n).clone() if f0_target is not None else pr[:, 0].clone()
+    uv = torch.zeros(n, dtype=torch.bool)
+    if use_uv:
+        uv = (_v(uv_target, n) > 0) if uv_target is not None else (pr[:, 1] > 0)
+    pad = _v(mel2ph, n) == 0
+    fd = torch.where(uv | pad, torch.zeros(n), 2 ** f0)
+    _v(f0_out, n).copy_(torch.where(pad, torch.zeros(n), f0))
+    _v(f0_denorm, n).copy_(fd)
+    _v(pitch_idx, n).copy_(_f0_to_coarse(fd))
+
+
+def ctts_gather_index(idx_ph, mel2ph, B, S, M, out, stream):
+    padded = F.pad(_v(idx_ph, B, S), [1, 0])
+    _v(out, B, M).copy_(torch.gather(padded, 1, _v(mel2ph, B, M).clamp(0, S)))
+
+
+def ctts_phoneme_pitch(f0, mel2ph, src_lens, mel_lens, B, S, M, out, stream):
+    from . import ctts_oracle as O
+    r = O.phoneme_level_pitch(None, _v(src_lens, B), _v(mel2ph, B, M), _v(mel_lens, B), _v(f0, B, M))
+    o = _v(out, B, S)
+    o.zero_()
+    o[:, : r.shape[1]] = r
+
+
 def ctts_gather_add(table, idx, rows, C, table_rows, x, stream):
     xv = _v(x, rows, C)
     xv.copy_(xv + _v(table, table_rows, C)[_v(idx, rows).clamp(0, table_rows - 1)])

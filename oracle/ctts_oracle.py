@@ -295,6 +295,53 @@ def pitch_embedding_cwt(P, cfg, pcfg, decoder_inp, f0, uv, mel2ph, control, x_or
     return pred, emb
 
 
+def phoneme_level_pitch(text, src_len, mel2ph, mel_len, pitch_frame):
+    """VarianceAdaptor.get_phoneme_level_pitch (modules.py:874-880) + utils/tools.py:47-53 + pad_1D: per utterance the
+    mean of the frame-level f0 over the frames of each phoneme (scatter-mean by mel2ph), zero for phonemes without frames."""
+    B = pitch_frame.shape[0]
+    rows = []
+    for b in range(B):
+        s, m = int(src_len[b]), int(mel_len[b])
+        idx = mel2ph[b, :m].long() - 1
+        tot = torch.zeros(s).scatter_add(0, idx, pitch_frame[b, :m].float())
+        num = torch.zeros(s).scatter_add(0, idx, torch.ones(m)).clamp_min(1)
+        rows.append(tot / num)
+    L = max(r.numel() for r in rows)
+    out = torch.zeros(B, L)
+    for b, r in enumerate(rows):
+        out[b, : r.numel()] = r
+    return out
+
+
+def pitch_embedding_frame_or_ph(P, cfg, pcfg, decoder_inp, f0, uv, mel2ph, control, x_org):
+    """get_pitch_embedding, pitch_type 'ph' and 'frame' (pitch_ar False) branches, modules.py:890-906,927-948."""
+    pitch_cfg = pcfg["preprocessing"]["pitch"]
+    pre = "variance_adaptor."
+    g = cfg["variance_predictor"]["predictor_grad"]
+    if pitch_cfg["pitch_type"] == "ph":
+        inp = x_org.detach() + g * (x_org - x_org.detach())
+        pitch_padding = x_org.sum().abs() == 0          # a SCALAR in the reference (modules.py:894): kept
+        pred = pitch_style_predictor(P, cfg, pre + "pitch_predictor.", inp) * control
+        if f0 is None:
+            f0 = pred[:, :, 0]
+        f0_denorm = denorm_f0(f0, None, pitch_cfg, pitch_padding=pitch_padding)
+        pitch = F.pad(f0_to_coarse(f0_denorm), [1, 0])
+        pitch = torch.gather(pitch, 1, mel2ph)
+    else:
+        inp = decoder_inp.detach() + g * (decoder_inp - decoder_inp.detach())
+        pitch_padding = mel2ph == 0
+        pred = pitch_style_predictor(P, cfg, pre + "pitch_predictor.", inp) * control
+        if f0 is None:
+            f0 = pred[:, :, 0]
+        if pitch_cfg["use_uv"] and uv is None:
+            uv = pred[:, :, 1] > 0
+        f0_denorm = denorm_f0(f0, uv, pitch_cfg, pitch_padding=pitch_padding)
+        f0[pitch_padding] = 0                            # in place, also on the caller's target (modules.py:934-935)
+        pitch = f0_to_coarse(f0_denorm)
+    emb = F.embedding(pitch, P[pre + "pitch_embed.weight"], padding_idx=0)
+    return {"pitch_pred": pred, "f0_denorm": f0_denorm, "cwt": None, "f0_mean": None, "f0_std": None}, emb
+
+
 def energy_embedding(P, cfg, x, target, control):
     """get_energy_embedding, modules.py:950-960."""
     pre = "variance_adaptor."
@@ -519,7 +566,8 @@ def variance_adaptor(P, pcfg, cfg, tcfg, speaker_embedding, text, text_embedding
     The predictor inputs carry the reference's gradient scaling x.detach() + predictor_grad * (x - x.detach())
     (values unchanged), so autograd through this function reproduces the reference's gradients."""
     assert cfg["prosody_modeling"]["model_type"] in ("none", "liu2021")
-    assert pcfg["preprocessing"]["pitch"]["pitch_type"] == "cwt"
+    pitch_type = pcfg["preprocessing"]["pitch"]["pitch_type"]
+    assert pitch_type in ("cwt", "frame", "ph") and not pcfg["preprocessing"]["pitch"].get("pitch_ar", False)
     learn_alignment = cfg["duration_modeling"]["learn_alignment"]
     x = text.clone()
     if speaker_embedding is not None:
@@ -572,16 +620,19 @@ def variance_adaptor(P, pcfg, cfg, tcfg, speaker_embedding, text, text_embedding
     x_sum = x.clone()
     pitch_pred = energy_pred = None
     if cfg["variance_embedding"]["use_pitch_embed"]:
+        embed = pitch_embedding_cwt if pitch_type == "cwt" else pitch_embedding_frame_or_ph
         if pitch_target is not None:
             mel2ph = pitch_target["mel2ph"]
-            pitch_target["f0"] = cwt_to_f0_norm(pitch_target["cwt_spec"], pitch_target["f0_mean"],
-                                                pitch_target["f0_std"], mel2ph.shape[1],
-                                                pcfg["preprocessing"]["pitch"])
-            pitch_target["f0_cwt"] = pitch_target["f0"]
-            pitch_pred, p_emb = pitch_embedding_cwt(P, cfg, pcfg, x, pitch_target["f0"], pitch_target["uv"],
-                                                    mel2ph, p_control, x_org)
+            if pitch_type == "cwt":
+                pitch_target["f0"] = cwt_to_f0_norm(pitch_target["cwt_spec"], pitch_target["f0_mean"],
+                                                    pitch_target["f0_std"], mel2ph.shape[1],
+                                                    pcfg["preprocessing"]["pitch"])
+                pitch_target["f0_cwt"] = pitch_target["f0"]
+            if pitch_type == "ph":
+                pitch_target["f0"] = phoneme_level_pitch(text, src_len, mel2ph, mel_len, pitch_target["f0"])
+            pitch_pred, p_emb = embed(P, cfg, pcfg, x, pitch_target["f0"], pitch_target["uv"], mel2ph, p_control, x_org)
         else:
-            pitch_pred, p_emb = pitch_embedding_cwt(P, cfg, pcfg, x, None, None, mel2ph, p_control, x_org)
+            pitch_pred, p_emb = embed(P, cfg, pcfg, x, None, None, mel2ph, p_control, x_org)
         x_sum = x_sum + p_emb
     if cfg["variance_embedding"]["use_energy_embed"]:
         level = pcfg["preprocessing"]["energy"]["feature"]

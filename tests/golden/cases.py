@@ -36,6 +36,17 @@ CASES = {
     # BASELINE configs[4] family: transformer_fs2 + liu2021 implicit prosody (eval: conv + bi-GRU predictors)
     "fs2_liu2021_infer": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="infer",
                               batch=2, s_max=40, s_step=9, pin=4, seed=9, prosody="liu2021"),
+    # the non-default pitch parametrisations (preprocess.yaml pitch_type): one PitchPredictor on the frame-level input
+    # ('frame': f0 + voiced/unvoiced logit per frame) or on the phoneme-level input ('ph': one f0 per phoneme, gathered to
+    # frames through mel2ph), modules.py:890-906,927-938
+    "fs2_pitch_frame_infer": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="infer",
+                                  batch=2, s_max=40, s_step=9, pin=4, seed=20, pitch_type="frame"),
+    "fs2_pitch_frame_teacher": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="teacher",
+                                    batch=2, s_max=30, s_step=7, pin=None, seed=21, pitch_type="frame"),
+    "fs2_pitch_ph_infer": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="infer",
+                               batch=2, s_max=40, s_step=9, pin=4, seed=22, pitch_type="ph"),
+    "fs2_pitch_ph_teacher": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="teacher",
+                                 batch=2, s_max=30, s_step=7, pin=None, seed=23, pitch_type="ph"),
 }
 
 # Training-step cases (make_golden_train.py / test_oracle_train.py): model.train() with every dropout probability 0,
@@ -63,6 +74,10 @@ TRAIN_CASES = {
     # BASELINE configs[3] family: fastformer, VCTK (DeepSpeaker embeddings -> Linear, speaker-conditioned aligner)
     "fastformer_vctk_unsup_train": dict(dataset="VCTK", block_type="fastformer", learn_alignment=True, mode="unsup",
                                         batch=2, s_max=14, s_step=4, pin=None, seed=18, step=120000),
+    "fs2_pitch_frame_train": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="teacher",
+                                  batch=2, s_max=20, s_step=6, pin=None, seed=24, pitch_type="frame"),
+    "fs2_pitch_ph_train": dict(dataset="LJSpeech", block_type="transformer_fs2", learn_alignment=False, mode="teacher",
+                               batch=2, s_max=20, s_step=6, pin=None, seed=25, pitch_type="ph"),
 }
 CASES_ALL = dict(CASES, **TRAIN_CASES)
 GRAD_SAMPLES = 512   # gradient entries stored per parameter tensor (evenly strided)
@@ -79,7 +94,7 @@ def build_case(name):
     from ctts_b200 import configs, spec, synth
     c = CASES_ALL[name]
     p, m, t = configs.builtin_configs(c["dataset"], block_type=c["block_type"], learn_alignment=c["learn_alignment"],
-                                      prosody=c.get("prosody"))
+                                      prosody=c.get("prosody"), pitch_type=c.get("pitch_type"))
     entries, _, _ = spec.parameter_spec(p, m)
     sd = synth.synthetic_state_dict(entries, pin_frames_per_phoneme=c["pin"])
     batch = synth.ljspeech_batch(batch=c["batch"], s_max=c["s_max"], s_step=c["s_step"], mode=c["mode"],

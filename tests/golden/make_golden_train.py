@@ -39,6 +39,8 @@ def run_reference(name):
     rm["duration_modeling"]["learn_alignment"] = c["learn_alignment"]
     if c.get("prosody"):
         rm["prosody_modeling"]["model_type"] = c["prosody"]
+    if c.get("pitch_type"):
+        rp["preprocessing"]["pitch"]["pitch_type"] = c["pitch_type"]
     net = ref_model.CompTransTTS(rp, rm, rt)
     net.load_state_dict(sd, strict=True)
     net.train()

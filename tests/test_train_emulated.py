@@ -16,7 +16,8 @@ from oracle import capi_emulator as emu  # noqa: E402
 import train_checks  # noqa: E402
 
 BUILT = ["fs2_train", "fs2_unsup_train_soft", "transformer_train", "fastformer_train", "conformer_train",
-         "conformer_unsup_train", "fastformer_vctk_unsup_train", "fs2_liu2021_train"]
+         "conformer_unsup_train", "fastformer_vctk_unsup_train", "fs2_liu2021_train", "fs2_pitch_frame_train",
+         "fs2_pitch_ph_train"]
 
 
 @pytest.mark.parametrize("math_mode", ["tc", "fp32"])
