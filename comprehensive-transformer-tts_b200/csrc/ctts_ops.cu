@@ -649,7 +649,7 @@ __global__ void f0_to_pitch_kernel(const float* __restrict__ f0n, const float* _
 }
 
 // pitch_type 'frame' (modules.py:927-938): f0 (+ voiced / unvoiced logit) per frame from the predictor or the targets
-__global__ void frame_pitch_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ f0_target,
+__global__ void frame_pitch_kernel(float* __restrict__ pred, int ldp, const float* __restrict__ f0_target,
                                    const float* __restrict__ uv_target, const int64_t* __restrict__ mel2ph, int use_uv, int n,
                                    float* __restrict__ f0_out, float* __restrict__ f0_denorm, int64_t* __restrict__ pitch_idx) {
     CTTS_PDL_SYNC();
@@ -661,6 +661,7 @@ __global__ void frame_pitch_kernel(const float* __restrict__ pred, int ldp, cons
     const bool pad = mel2ph[i] == 0;
     const float fd = (uv || pad) ? 0.f : exp2f(f0);
     f0_out[i] = pad ? 0.f : f0;          // `f0[pitch_padding] = 0`, in place on the caller's target (modules.py:934-935)
+    if (!f0_target && pad) pred[(size_t)i * ldp] = 0.f;   // free-running: f0 IS a view of pitch_pred[:, :, 0] there
     f0_denorm[i] = fd;
     pitch_idx[i] = f0_to_coarse_dev(fd);
 }
@@ -1362,7 +1363,7 @@ int ctts_f0_to_pitch(const float* f0_norm, const float* uv_src, int n, float* f0
     return check_launch("f0_to_pitch");
 }
 
-int ctts_frame_pitch(const float* pred, int ldp, const float* f0_target, const float* uv_target, const int64_t* mel2ph, int use_uv,
+int ctts_frame_pitch(float* pred, int ldp, const float* f0_target, const float* uv_target, const int64_t* mel2ph, int use_uv,
                      int n, float* f0_out, float* f0_denorm, int64_t* pitch_idx, void* stream) {
     CTTS_REQUIRE((pred || f0_target) && mel2ph && f0_out && f0_denorm && pitch_idx && n > 0, "frame_pitch: bad arguments");
     CTTS_REQUIRE(!use_uv || uv_target || (pred && ldp >= 2), "frame_pitch: use_uv needs a uv target or a 2-wide prediction");

@@ -154,10 +154,11 @@ int ctts_f0_to_pitch(const float* f0_norm, const float* uv_src, int n, float* f0
 /* pitch_type 'frame' / 'ph' (modules.py:890-906,927-938; preprocess.yaml pitch_type):
  * ctts_frame_pitch    per frame: f0 = f0_target ? f0_target : pred[i*ldp]; uv = uv_target > 0 or pred[i*ldp+1] > 0 (use_uv);
  *                     padding = mel2ph == 0; f0_denorm = (uv | padding) ? 0 : 2^f0; f0_out = padding ? 0 : f0 (may alias the
- *                     target: the reference zeroes it in place); idx = f0_to_coarse(f0_denorm)
+ *                     target: the reference zeroes it in place; without a target pred[i*ldp] itself is zeroed at padded
+ *                     frames, because f0 is a view of pitch_pred there); idx = f0_to_coarse(f0_denorm)
  * ctts_gather_index   out[b,t] = mel2ph[b,t] > 0 ? idx_ph[b, mel2ph[b,t]-1] : 0      (F.pad + torch.gather, :900-901)
  * ctts_phoneme_pitch  get_phoneme_level_pitch (modules.py:874-880, utils/tools.py:47-53): per-phoneme mean of frame f0 */
-int ctts_frame_pitch(const float* pred, int ldp, const float* f0_target, const float* uv_target, const int64_t* mel2ph, int use_uv,
+int ctts_frame_pitch(float* pred, int ldp, const float* f0_target, const float* uv_target, const int64_t* mel2ph, int use_uv,
                      int n, float* f0_out, float* f0_denorm, int64_t* pitch_idx, void* stream);
 int ctts_gather_index(const int64_t* idx_ph, const int64_t* mel2ph, int B, int S, int M, int64_t* out, void* stream);
 int ctts_phoneme_pitch(const float* f0, const int64_t* mel2ph, const int64_t* src_lens, const int64_t* mel_lens, int B, int S,

@@ -278,6 +278,8 @@ def ctts_frame_pitch(pred, ldp, f0_target, uv_target, mel2ph, use_uv, n, f0_out,
     pad = _v(mel2ph, n) == 0
     fd = torch.where(uv | pad, torch.zeros(n), 2 ** f0)
     _v(f0_out, n).copy_(torch.where(pad, torch.zeros(n), f0))
+    if f0_target is None:
+        pr[:, 0] = torch.where(pad, torch.zeros(n), pr[:, 0])
     _v(f0_denorm, n).copy_(fd)
     _v(pitch_idx, n).copy_(_f0_to_coarse(fd))
 

@@ -101,3 +101,22 @@ def test_conformer_tensor_core_attention_helpers():
     run_both("ctts_pad_heads_planes", [g(rows, 3 * H * DH), g(H * DH, seed=1), rows, 3 * H * DH, H * DH, H, DH, DHp, 3, PA(pl)],
              atol=1e-6)
     run_both("ctts_pad_heads_planes", [g(rows, H * DH), None, rows, H * DH, 0, H, DH, DHp, 2, PA(pl[:2])], atol=1e-4)
+
+
+def test_pitch_frame_and_phoneme_kernels():
+    B, S, M = 3, 9, 30
+    n = B * M
+    gen = torch.Generator().manual_seed(0)
+    mel2ph = torch.randint(0, S + 1, (B, M), generator=gen)
+    mel2ph, _ = torch.sort(mel2ph, dim=1)
+    pred = g(B, M, 2) * 2 + torch.tensor([7.0, 0.0])
+    run_both("ctts_frame_pitch", [pred, 2, None, None, mel2ph, 1, n, torch.zeros(n), torch.zeros(n), torch.zeros(n, dtype=torch.long)],
+             atol=1e-3, rtol=1e-5)
+    f0t = g(B, M) + 7.0
+    run_both("ctts_frame_pitch", [None, 0, f0t, (g(B, M, seed=1) > 0).float(), mel2ph, 1, n, torch.zeros(n), torch.zeros(n),
+                                  torch.zeros(n, dtype=torch.long)], atol=1e-3, rtol=1e-5)
+    idx_ph = torch.randint(1, 255, (B, S), generator=gen)
+    run_both("ctts_gather_index", [idx_ph, mel2ph, B, S, M, torch.zeros(B, M, dtype=torch.long)])
+    m2 = mel2ph.clamp(min=1)
+    run_both("ctts_phoneme_pitch", [g(B, M) + 7, m2, torch.tensor([9, 7, 9]), torch.tensor([30, 21, 30]), B, S, M, torch.zeros(B, S)],
+             atol=1e-5)
