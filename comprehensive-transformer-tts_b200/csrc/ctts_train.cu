@@ -984,14 +984,19 @@ dwconv_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__
 //   backward dcontent = dscore / sqrt_dim;  dpos = unshift(dscore) / sqrt_dim   (positions the shift never reads get 0)
 // One thread per (z, i, j) of dpos: pos[i, c] is read by score[i, j] with j = c - (T-1-i) when c >= T-1-i  (j <= i),
 // and by score[i-1, j] with j = c + (i-1) + 2 = c + i + 1 when that is < T (row i >= 1 supplies the j > i'+1 part of i' = i-1).
-__global__ void relshift_bwd_kernel(const float* __restrict__ dscore, int T, int ld, float inv_sqrt_dim, size_t total,
+__global__ void relshift_bwd_kernel(const float* __restrict__ dscore, int T, int ld, int ld_out, float inv_sqrt_dim, size_t total,
                                     float* __restrict__ dcontent, float* __restrict__ dpos) {
     CTTS_PDL_SYNC();
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(e % T);
-        const size_t zi = e / T;
+        const int c = (int)(e % ld_out);
+        const size_t zi = e / ld_out;
         const int i = (int)(zi % T);
         const size_t z = zi / T;
+        if (c >= T) {       // padding columns of the output rows
+            dcontent[e] = 0.f;
+            dpos[e] = 0.f;
+            continue;
+        }
         const float* ds = dscore + z * (size_t)T * ld;
         dcontent[e] = ds[(size_t)i * ld + c] * inv_sqrt_dim;
         float v = 0.f;
@@ -1541,10 +1546,12 @@ int ctts_dwconv_bwd(const float* dy, const float* x, const float* w, int K, int 
     return check_launch("dwconv_bwd");
 }
 
-int ctts_relshift_bwd(const float* dscore, int Z, int T, int ld, float sqrt_dim, float* dcontent, float* dpos, void* stream) {
-    CTTS_REQUIRE(dscore && dcontent && dpos && Z > 0 && T > 0 && ld >= T, "relshift_bwd: bad arguments");
-    const size_t total = (size_t)Z * T * T;
-    launch_k(relshift_bwd_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, dscore, T, ld, 1.f / sqrt_dim, total, dcontent, dpos);
+int ctts_relshift_bwd(const float* dscore, int Z, int T, int ld, int ld_out, float sqrt_dim, float* dcontent, float* dpos,
+                      void* stream) {
+    CTTS_REQUIRE(dscore && dcontent && dpos && Z > 0 && T > 0 && ld >= T && ld_out >= T, "relshift_bwd: bad arguments");
+    const size_t total = (size_t)Z * T * ld_out;
+    launch_k(relshift_bwd_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, dscore, T, ld, ld_out, 1.f / sqrt_dim, total,
+             dcontent, dpos);
     return check_launch("relshift_bwd");
 }
 

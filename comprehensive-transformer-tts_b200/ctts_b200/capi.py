@@ -89,7 +89,7 @@ SIGNATURES = {
     "ctts_glu_bwd": [_P, _P, _I, _I, _P, _P],
     "ctts_dwconv": [_P, _P, _I, _I, _I, _I, _P, _P],
     "ctts_dwconv_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
-    "ctts_relshift_bwd": [_P, _I, _I, _I, _F, _P, _P, _P],
+    "ctts_relshift_bwd": [_P, _I, _I, _I, _I, _F, _P, _P, _P],
     "ctts_fastformer_pool_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "ctts_mul_bwd": [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P],
     "ctts_act_fwd": [_P, _Z, _I, _P, _I, _P, _P],

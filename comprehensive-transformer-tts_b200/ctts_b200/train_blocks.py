@@ -259,7 +259,7 @@ def _relpos_attention(ctx, a, qkv, pos_proj, n_head, p_drop):
         capi.call("ctts_softmax_bwd", prob, dP, Z, T, T, T, 1.0, dP, st2)
         dcontent = torch.empty(Z, T, T, device=dev, dtype=torch.float32)
         dpos = torch.empty(Z, T, T, device=dev, dtype=torch.float32)
-        capi.call("ctts_relshift_bwd", dP, Z, T, T, math.sqrt(C), dcontent, dpos, st2)
+        capi.call("ctts_relshift_bwd", dP, Z, T, T, T, math.sqrt(C), dcontent, dpos, st2)
         # content = qu k^T:  dqu[t, d] = sum_s dcontent[t, s] k[s, d];  dk[s, d] = sum_t dcontent[t, s] qu[t, d]
         dqu, acc = grad_buffer(qu)
         _generic(dcontent, kk, dqu, Z, n_head, T, dh, T, (n_head * TT, TT, T, 1, 0), (T * C3, dh, 1, C3, 0), (T * C, dh, C, 1),
@@ -282,6 +282,126 @@ def _relpos_attention(ctx, a, qkv, pos_proj, n_head, p_drop):
 
     # q is a private copy of the first third of qkv: its gradient is routed back by a closure recorded BEFORE q's
     # consumers (so that it runs after them in the backward pass)
+    return y, q
+
+
+def _relpos_attention_tc(ctx, a, qkv, pos_proj, n_head, p_drop):
+    """The same attention on tcgen05 for the training step (2 bf16 planes): the 32-wide heads are zero padded to one
+    64-wide k-block (ctts_pad_heads_planes); content / positional scores, P.V and all six backward products are batched plane
+    GEMMs (ctts_gemm_batched_planes); the operands whose reduction index is time come from ctts_split_transpose.  The
+    [B*H, T, T] score tensors are materialised in fp32, as in the reference."""
+    from .engine import Planes, gemm_batched_planes, split_planes
+    B, T, C3 = qkv.v.shape
+    C = C3 // 3
+    H = n_head
+    dh = C // H
+    Z = B * H
+    DHp = 64
+    Cp = H * DHp
+    Tp = (T + 7) // 8 * 8
+    dev = qkv.v.device
+    st = _st()
+    qc = torch.empty(B, T, C, device=dev, dtype=torch.float32)
+    capi.call("ctts_copy_rows", qkv.v, C3, B * T, C, qc, C, 0, st)
+    q = Var(qc)
+    qu = _add_bias_row(ctx, q, a + "attention.u_bias")
+    qv = _add_bias_row(ctx, q, a + "attention.v_bias")
+
+    def padded(src, rows, ld, c0):
+        out = Planes.empty((rows, Cp), dev, 2)
+        capi.call("ctts_pad_heads_planes", src, None, rows, ld, c0, H, dh, DHp, 2, capi.ptr_array(out.p), _st())
+        return out
+
+    def time_major(src, Zs, ld, c0, cols):
+        """fp32 [Zs, T, ld] columns [c0, c0+cols) -> planes [Zs, cols, Tp]"""
+        out = Planes.empty((Zs, 1, cols, Tp), dev, 2)
+        capi.call("ctts_split_transpose", src, Zs, T, cols, ld, c0, Tp, 1, 2, capi.ptr_array(out.p), _st())
+        return out
+
+    act_view = (Cp, T, B, Cp, T * Cp)
+    big = (H * T * Tp, T * Tp)
+    sq_view = (T, T, Z, Tp, T * Tp)          # [Z][T rows][T valid of Tp columns]
+    hT_view = (T, dh, Z, Tp, dh * Tp)        # [Z][dh rows][time]
+    kp = padded(qkv.v, B * T, C3, C)
+    content = torch.empty(Z, T, Tp, device=dev, dtype=torch.float32)
+    pscore = torch.empty(Z, T, Tp, device=dev, dtype=torch.float32)
+    gemm_batched_planes(padded(qu.v, B * T, C, 0), act_view, kp, act_view, (H, H, 0, DHp, H, 0, DHp, 1, Tp), big[0], big[1], 1.0,
+                        Z, T, DHp, Tp, y=content)
+    gemm_batched_planes(padded(qv.v, B * T, C, 0), act_view, padded(pos_proj.v, T, C, 0), (Cp, T, 1, Cp, T * Cp),
+                        (H, H, 0, DHp, 0x7fffffff, 0, DHp, 1, Tp), big[0], big[1], 1.0, Z, T, DHp, Tp, y=pscore)
+    prob = torch.empty(Z, T, Tp, device=dev, dtype=torch.float32)
+    if Tp == T:
+        capi.call("ctts_relshift_softmax", content, pscore, Z, T, Tp, math.sqrt(C), prob, st)
+    else:
+        # the fp32 kernel reads dense [Z, T, T] score rows: re-stride first (T not a multiple of 8)
+        cd = torch.empty(Z, T, T, device=dev, dtype=torch.float32)
+        pd = torch.empty(Z, T, T, device=dev, dtype=torch.float32)
+        capi.call("ctts_copy_rows", content, Tp, Z * T, T, cd, T, 0, st)
+        capi.call("ctts_copy_rows", pscore, Tp, Z * T, T, pd, T, 0, st)
+        capi.call("ctts_relshift_softmax", cd, pd, Z, T, Tp, math.sqrt(C), prob, st)
+    del content, pscore
+    drop_off = None
+    prob_used = prob
+    if p_drop > 0.0 and ctx.dropout_on:
+        drop_off = ctx.next_offset()
+        prob_used = torch.empty_like(prob)
+        capi.call("ctts_dropout", prob, prob.numel(), float(p_drop), ctx.seed, drop_off, ctx.offset_dev, prob_used, st)
+    out = torch.empty(B, T, C, device=dev, dtype=torch.float32)
+    gemm_batched_planes(split_planes(prob_used, 2), sq_view, time_major(qkv.v, B, C3, 2 * C, C), hT_view,
+                        (H, 1, 0, 0, 1, 0, 0, 1, C), T * C, dh, 1.0, Z, T, T, dh, y=out)
+    y = Var(out)
+
+    def bwd():
+        if y.g is None:
+            return
+        st2 = _st()
+        dO = y.g
+        dqkv = torch.zeros_like(qkv.v)
+        addr_c = (H, 1, 0, 0, 1, 0, 0, 1, C)         # outputs laid out like a [B, T, C] activation
+        addr_3c = (H, 1, 0, 0, 1, 0, 0, 1, C3)        # ... like a third of qkv
+        # dP[t, s] = sum_d dO[t, d] v[s, d]   (padded heads, K = 64)
+        dP = torch.empty(Z, T, Tp, device=dev, dtype=torch.float32)
+        gemm_batched_planes(padded(dO, B * T, C, 0), act_view, padded(qkv.v, B * T, C3, 2 * C), act_view,
+                            (H, H, 0, DHp, H, 0, DHp, 1, Tp), big[0], big[1], 1.0, Z, T, DHp, Tp, y=dP)
+        # dV[s, d] = sum_t P[t, s] dO[t, d]
+        PT = Planes.empty((Z, 1, T, Tp), dev, 2)
+        capi.call("ctts_split_transpose", prob_used, Z, T, T, Tp, 0, Tp, 1, 2, capi.ptr_array(PT.p), st2)
+        gemm_batched_planes(PT, sq_view, time_major(dO, B, C, 0, C), hT_view, addr_3c, T * C3, dh, 1.0, Z, T, T, dh,
+                            y=dqkv.view(-1)[2 * C:])
+        if drop_off is not None:
+            capi.call("ctts_dropout", dP, dP.numel(), float(p_drop), ctx.seed, drop_off, ctx.offset_dev, dP, st2)
+        capi.call("ctts_softmax_bwd", prob, dP, Z, T, T, Tp, 1.0, dP, st2)
+        dcontent = torch.empty(Z, T, Tp, device=dev, dtype=torch.float32)
+        dpos = torch.empty(Z, T, Tp, device=dev, dtype=torch.float32)
+        capi.call("ctts_relshift_bwd", dP, Z, T, Tp, Tp, math.sqrt(C), dcontent, dpos, st2)
+        dcp = split_planes(dcontent, 2)
+        dcT = Planes.empty((Z, 1, T, Tp), dev, 2)
+        capi.call("ctts_split_transpose", dcontent, Z, T, T, Tp, 0, Tp, 1, 2, capi.ptr_array(dcT.p), st2)
+        # content = qu k^T:  dqu[t, d] = sum_s dcontent[t, s] k[s, d];  dk[s, d] = sum_t dcontent[t, s] qu[t, d]
+        dqu, acc = grad_buffer(qu)
+        gemm_batched_planes(dcp, sq_view, time_major(qkv.v, B, C3, C, C), hT_view, addr_c, T * C, dh, 1.0, Z, T, T, dh, y=dqu,
+                            residual=dqu if acc else None)
+        gemm_batched_planes(dcT, sq_view, time_major(qu.v, B, C, 0, C), hT_view, addr_3c, T * C3, dh, 1.0, Z, T, T, dh,
+                            y=dqkv.view(-1)[C:])
+        # pscore = qv pos^T:  dqv[t, d] = sum_j dpos[t, j] pos[j, h, d];  dpos_proj[j, h, d] = sum_{b,t} dpos[b,h][t, j] qv[b,t,h,d]
+        dpp_ = split_planes(dpos, 2)
+        pos_rep = torch.empty(B, T, C, device=dev, dtype=torch.float32)
+        capi.call("ctts_copy_rows", pos_proj.v, 0, B, T * C, pos_rep, T * C, 0, st2)     # one copy per utterance
+        dqv, acc = grad_buffer(qv)
+        gemm_batched_planes(dpp_, sq_view, time_major(pos_rep, B, C, 0, C), hT_view, addr_c, T * C, dh, 1.0, Z, T, T, dh, y=dqv,
+                            residual=dqv if acc else None)
+        dposT = Planes.empty((Z, 1, T, Tp), dev, 2)
+        capi.call("ctts_split_transpose", dpos, Z, T, T, Tp, 0, Tp, 1, 2, capi.ptr_array(dposT.p), st2)
+        part = torch.empty(B, T, C, device=dev, dtype=torch.float32)                     # per-utterance partial sums
+        gemm_batched_planes(dposT, sq_view, time_major(qv.v, B, C, 0, C), hT_view, addr_c, T * C, dh, 1.0, Z, T, T, dh, y=part)
+        if pos_proj.needs_grad:
+            if pos_proj.g is None:
+                pos_proj.g = torch.zeros_like(pos_proj.v)
+            capi.call("ctts_act_bwd", part, None, ACT_NONE, 1.0, None, 1, 1, B, T * C, None, pos_proj.g, st2)   # sum over b
+        accumulate_into(qkv, dqkv)
+        y.g = None
+
+    ctx.record(bwd)
     return y, q
 
 
@@ -361,7 +481,8 @@ def _stack_conformer(ctx, pre, x, lens, n_layers, n_head, kernel, p_drop, math):
         pos_proj = linear(ctx, pos, a + "attention.pos_proj.linear.weight")
         holder = {}
         _route_q(ctx, qkv, holder)
-        att, q = _relpos_attention(ctx, a, qkv, TE._reshape(ctx, pos_proj, (T, C)), n_head, p_drop)
+        rel = _relpos_attention_tc if (ctx.bwd_tc and C // n_head <= 64 and C % n_head == 0) else _relpos_attention
+        att, q = rel(ctx, a, qkv, TE._reshape(ctx, pos_proj, (T, C)), n_head, p_drop)
         holder["q"] = q
         x = sublayer(ctx, x, att, a + "attention.out_proj.linear.weight", None, None, p_drop, "fp32")
         m = lp + "2.module.sequential."

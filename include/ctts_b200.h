@@ -451,7 +451,8 @@ int ctts_glu_bwd(const float* h, const float* dg, int rows, int C, float* dh, vo
 int ctts_dwconv(const float* x, const float* w, int K, int B, int T, int C, float* y, void* stream);
 int ctts_dwconv_bwd(const float* dy, const float* x, const float* w, int K, int B, int T, int C, float* dx, float* dw,
                     void* stream);
-int ctts_relshift_bwd(const float* dscore, int Z, int T, int ld, float sqrt_dim, float* dcontent, float* dpos, void* stream);
+int ctts_relshift_bwd(const float* dscore, int Z, int T, int ld, int ld_out, float sqrt_dim, float* dcontent, float* dpos,
+                      void* stream);   /* dscore rows have stride ld, dcontent / dpos rows stride ld_out (zero padded) */
 int ctts_fastformer_pool_bwd(const float* logits, const float* values, const int64_t* lens, const float* dpooled, int B, int T,
                              int heads, int head_size, float* dlogits, float* dvalues, void* stream);
 int ctts_mul_bwd(const float* dy, const float* a, const float* b, int b_rowwise, const int64_t* lens, int B, int T, int C,

@@ -711,13 +711,16 @@ def ctts_dwconv_bwd(dy, x, w, K, B, T, C, dx, dw, stream):
         _v(dw, C, 1, K).add_(wv.grad)
 
 
-def ctts_relshift_bwd(dscore, Z, T, ld, sqrt_dim, dcontent, dpos, stream):
+def ctts_relshift_bwd(dscore, Z, T, ld, ld_out, sqrt_dim, dcontent, dpos, stream):
     ds = _v(dscore, Z, T, ld)[:, :, :T]
     p = torch.zeros(Z, T, T, requires_grad=True)
     padded = torch.cat([p.new_zeros(Z, T, 1), p], dim=-1).view(Z, T + 1, T)[:, 1:].reshape(Z, T, T)
     (padded / sqrt_dim).backward(ds)
-    _v(dcontent, Z, T, T).copy_(ds / sqrt_dim)
-    _v(dpos, Z, T, T).copy_(p.grad)
+    dc, dp = _v(dcontent, Z, T, ld_out), _v(dpos, Z, T, ld_out)
+    dc.zero_()
+    dp.zero_()
+    dc[:, :, :T] = ds / sqrt_dim
+    dp[:, :, :T] = p.grad
 
 
 def ctts_fastformer_pool_bwd(logits, values, lens, dpooled, B, T, heads, hs, dlogits, dvalues, stream):

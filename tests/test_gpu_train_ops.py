@@ -257,7 +257,8 @@ def test_block_specific_backward_kernels():
     run_both("ctts_dwconv", [x, w, K, B, T, C, torch.zeros(B, T, C)], atol=1e-5)
     run_both("ctts_dwconv_bwd", [g(B, T, C, seed=2), x, w, K, B, T, C, torch.zeros(B, T, C), g(C, K, seed=3)], atol=1e-4)
     Z, T = 3, 29
-    run_both("ctts_relshift_bwd", [g(Z, T, T + 3), Z, T, T + 3, 16.0, torch.zeros(Z, T, T), torch.zeros(Z, T, T)])
+    run_both("ctts_relshift_bwd", [g(Z, T, T + 3), Z, T, T + 3, T, 16.0, torch.zeros(Z, T, T), torch.zeros(Z, T, T)])
+    run_both("ctts_relshift_bwd", [g(Z, T, T + 3), Z, T, T + 3, 32, 16.0, torch.ones(Z, T, 32), torch.ones(Z, T, 32)])
     B, T, heads, hs = 2, 40, 128, 2
     lens = torch.tensor([40, 25])
     run_both("ctts_fastformer_pool_bwd", [g(B, T, heads), g(B, T, heads * hs, seed=1), lens, g(B, heads * hs, seed=2), B, T, heads,
