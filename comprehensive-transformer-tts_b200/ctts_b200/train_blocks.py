@@ -83,7 +83,7 @@ def encoder_transformer(ctx, tokens, src_lens):
     c = ctx.cfg["transformer"]
     x, word = _embed_abs(ctx, tokens, c["encoder_hidden"])
     x = _stack_transformer(ctx, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"], c["conv_kernel_size"],
-                           c["encoder_dropout"], "fp32")
+                           c["encoder_dropout"], ctx.enc_math)
     return x, word
 
 
@@ -172,7 +172,7 @@ def encoder_fastformer(ctx, tokens, src_lens):
     x, word = _embed_abs(ctx, tokens, c["encoder_hidden"])
     heads = c["encoder_hidden"] // c["encoder_head"]
     return _stack_fastformer(ctx, "encoder.", x, src_lens, c["encoder_layer"], heads, c["conv_kernel_size"],
-                             c["encoder_dropout"], "fp32"), word
+                             c["encoder_dropout"], ctx.enc_math), word
 
 
 def decoder_fastformer(ctx, x, mel_lens):
@@ -476,7 +476,7 @@ def _stack_conformer(ctx, pre, x, lens, n_layers, n_head, kernel, p_drop, math):
         h = layer_norm(ctx, x, a + "layer_norm.weight", a + "layer_norm.bias", 1e-5)
         qkv = linear_cat(ctx, h, a + "attention.qkv", [a + "attention.query_proj.linear.weight",
                                                        a + "attention.key_proj.linear.weight",
-                                                       a + "attention.value_proj.linear.weight"], "fp32")
+                                                       a + "attention.value_proj.linear.weight"], math)
         pos = Var(ctx.P[a + "positional_encoding"][0, :T].contiguous().view(1, T, C), False)
         pos_proj = linear(ctx, pos, a + "attention.pos_proj.linear.weight")
         holder = {}
@@ -484,14 +484,14 @@ def _stack_conformer(ctx, pre, x, lens, n_layers, n_head, kernel, p_drop, math):
         rel = _relpos_attention_tc if (ctx.bwd_tc and C // n_head <= 64 and C % n_head == 0) else _relpos_attention
         att, q = rel(ctx, a, qkv, TE._reshape(ctx, pos_proj, (T, C)), n_head, p_drop)
         holder["q"] = q
-        x = sublayer(ctx, x, att, a + "attention.out_proj.linear.weight", None, None, p_drop, "fp32")
+        x = sublayer(ctx, x, att, a + "attention.out_proj.linear.weight", None, None, p_drop, math)
         m = lp + "2.module.sequential."
         h = layer_norm(ctx, x, m + "0.weight", m + "0.bias", 1e-5)
-        pw = linear(ctx, h, m + "2.conv.weight", m + "2.conv.bias")
+        pw = linear(ctx, h, m + "2.conv.weight", m + "2.conv.bias", math=math)
         g = _glu(ctx, pw)
         d = _dwconv(ctx, g, m + "4.conv.weight", kernel)
         bn = batch_norm_act(ctx, d, m + "5.", ACT_SWISH)
-        x = sublayer(ctx, x, bn, m + "7.conv.weight", m + "7.conv.bias", None, p_drop, "fp32")
+        x = sublayer(ctx, x, bn, m + "7.conv.weight", m + "7.conv.bias", None, p_drop, math)
         x = _conformer_ffn(ctx, lp + "3.module.sequential.", x, p_drop, math)
         x = layer_norm(ctx, x, lp + "4.weight", lp + "4.bias", 1e-5, lens)
     return x
@@ -501,7 +501,7 @@ def encoder_conformer(ctx, tokens, src_lens):
     c = ctx.cfg["conformer"]
     x, word = _embed_abs(ctx, tokens, c["encoder_hidden"])
     return _stack_conformer(ctx, "encoder.", x, src_lens, c["encoder_layer"], c["encoder_head"], c["conv_kernel_size"],
-                            c["encoder_dropout"], "fp32"), word
+                            c["encoder_dropout"], ctx.enc_math), word
 
 
 def decoder_conformer(ctx, x, mel_lens):
