@@ -137,12 +137,25 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg
         sh = *reinterpret_cast<const float4*>(ep.col_shift + n);
     }
     const float alpha = ep.alpha;
+    // Pass 1: where every row of this lane lives, and its residual values.  The residual loads are issued back to back
+    // (y may alias the residual -- the in-place residual stream -- so the compiler cannot hoist them over the stores of
+    // pass 2 by itself; each thread only ever reads the addresses it writes, so the order below is safe).
+    bool valid[LPR], keep[LPR];
+    size_t offs[LPR];
+    float4 rs[LPR];
 #pragma unroll
     for (int i = 0; i < LPR; ++i) {
-        bool keep;
-        size_t off;
-        if (!rm.locate(row0 + RPI * i, keep, off)) break;
-        off += (size_t)n;
+        keep[i] = false;
+        offs[i] = 0;
+        valid[i] = rm.locate(row0 + RPI * i, keep[i], offs[i]);
+        offs[i] += (size_t)n;
+        rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid[i] && ep.residual) rs[i] = *reinterpret_cast<const float4*>(ep.residual + offs[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < LPR; ++i) {
+        if (!valid[i]) break;
+        const size_t off = offs[i];
         const float4 a4 = *reinterpret_cast<const float4*>(stg + (rsub + RPI * i) * LD + c4);
         float v[4] = {(a4.x + bb.x) * alpha, (a4.y + bb.y) * alpha, (a4.z + bb.z) * alpha, (a4.w + bb.w) * alpha};
         if (affine) {
@@ -151,11 +164,8 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* stg
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = act_fn<ACT>(v[j]);
-        if (ep.residual) {
-            const float4 rs = *reinterpret_cast<const float4*>(ep.residual + off);
-            v[0] += rs.x; v[1] += rs.y; v[2] += rs.z; v[3] += rs.w;
-        }
-        if (!keep) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+        v[0] += rs[i].x; v[1] += rs[i].y; v[2] += rs[i].z; v[3] += rs[i].w;
+        if (!keep[i]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
         if (ep.atomic) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) atomicAdd(ep.y + off + j, v[j]);
