@@ -168,12 +168,20 @@ def require_cuda_tensor(t):
 
 
 _arch_checked = False
+_device_seen = None
 
 
 def require_device():
-    """Fail loudly unless a CUDA device of compute capability >= 10.0 is current."""
-    global _arch_checked
+    """Fail loudly unless a CUDA device of compute capability >= 10.0 is current -- and the SAME device as before: the
+    library keeps per-process state that is really per-device (raised shared-memory limits, SM count, cluster occupancy),
+    so the model is one process per GPU (train.py:251-252 does the same with mp.spawn)."""
+    global _arch_checked, _device_seen
     if _arch_checked:
+        import torch
+        cur = torch.cuda.current_device()
+        if cur != _device_seen:
+            raise CttsError("libctts_b200 was initialised on cuda:%d and is now called on cuda:%d; use one process per GPU"
+                            % (_device_seen, cur))
         return
     lib = load()
     arch = lib.ctts_device_arch()
@@ -181,4 +189,6 @@ def require_device():
         raise CttsError("no usable CUDA device: %s" % lib.ctts_last_error().decode())
     if arch < 100:
         raise CttsError("libctts_b200 is built for sm_100a only; current device is sm_%d" % arch)
+    import torch
+    _device_seen = torch.cuda.current_device()
     _arch_checked = True
