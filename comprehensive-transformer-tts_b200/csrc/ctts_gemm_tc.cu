@@ -434,7 +434,146 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
 // tiles and the accumulator is double-buffered in TMEM (2 x BLOCK_N columns), so the epilogue of tile i (8 warps)
 // overlaps the mainloop of tile i + 1 and set-up is paid once per SM instead of once per tile; with one wave of CTAs
 // there is no wave quantisation beyond the tile granularity itself.
+#ifndef CTTS_PIPELINED_EPILOGUE
+#define CTTS_PIPELINED_EPILOGUE 1
+#endif
+constexpr bool PIPELINED_EPILOGUE = CTTS_PIPELINED_EPILOGUE != 0;
 constexpr int PSTG_LD = 20;   // floats per row of the 32 x 16 transpose tile of the persistent epilogue
+
+// Persistent-kernel epilogue for one 32 x 16 chunk with the row bookkeeping done once per tile (4 rows per lane) and,
+// optionally, the residual values already in registers (fetched while the tensor core was still working on the tile).
+template <int NP, int ACT>
+__device__ __forceinline__ void store_chunk_rows(const Epilogue& ep, const float* stg, int c4, int rsub, const bool (&valid)[4],
+                                                 const bool (&keep)[4], const size_t (&rowoff)[4], int n, const float4* pre) {
+    constexpr int LD = PSTG_LD;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bb;
+    if (ep.bias) bb = *reinterpret_cast<const float4*>(ep.bias + n);
+    const bool affine = ep.col_scale != nullptr;
+    if (affine) {
+        sc = *reinterpret_cast<const float4*>(ep.col_scale + n);
+        sh = *reinterpret_cast<const float4*>(ep.col_shift + n);
+    }
+    const float alpha = ep.alpha;
+    float4 rs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pre) rs[i] = pre[i];
+        else if (valid[i] && ep.residual) rs[i] = *reinterpret_cast<const float4*>(ep.residual + rowoff[i] + n);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!valid[i]) break;
+        const size_t off = rowoff[i] + (size_t)n;
+        const float4 a4 = *reinterpret_cast<const float4*>(stg + (rsub + 8 * i) * LD + c4);
+        float v[4] = {(a4.x + bb.x) * alpha, (a4.y + bb.y) * alpha, (a4.z + bb.z) * alpha, (a4.w + bb.w) * alpha};
+        if (affine) {
+            v[0] = v[0] * sc.x + sh.x; v[1] = v[1] * sc.y + sh.y;
+            v[2] = v[2] * sc.z + sh.z; v[3] = v[3] * sc.w + sh.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = act_fn<ACT>(v[j]);
+        v[0] += rs[i].x; v[1] += rs[i].y; v[2] += rs[i].z; v[3] += rs[i].w;
+        if (!keep[i]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+        if (ep.atomic) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(ep.y + off + j, v[j]);
+        } else if (ep.y) *reinterpret_cast<float4*>(ep.y + off) = make_float4(v[0], v[1], v[2], v[3]);
+        if (ep.yp[0]) {
+            float rem[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                __nv_bfloat162 h01 = __floats2bfloat162_rn(rem[0], rem[1]);
+                __nv_bfloat162 h23 = __floats2bfloat162_rn(rem[2], rem[3]);
+                if (p + 1 < NP) {
+                    rem[0] -= __low2float(h01); rem[1] -= __high2float(h01);
+                    rem[2] -= __low2float(h23); rem[3] -= __high2float(h23);
+                }
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(ep.yp[p] + off) = pk;
+            }
+        }
+    }
+}
+
+// One tile's epilogue of the persistent kernels (single CTA and CTA pair): software-pipelined over the 32 x 16 chunks --
+// the tcgen05.ld of chunk u+1 is in flight while chunk u goes through the shared-memory transpose and out to global
+// memory -- with the residual of a 128-wide tile fetched BEFORE the accumulator is waited for.  `arrive` hands the
+// accumulator back as soon as this warp's last TMEM read has completed.
+template <int BLOCK_N, class WaitAcc, class Arrive>
+__device__ __forceinline__ void persistent_epilogue(const Epilogue& ep, const RowMap& rm, bool tile_valid, int n0, int N, int q,
+                                                    int half, int lane, uint32_t d_tmem, float* stg, WaitAcc wait_acc,
+                                                    Arrive arrive) {
+    constexpr int NP = 2;
+    constexpr int CHUNKS = BLOCK_N / 32;       // chunks of this warp (every other 16-column chunk)
+    const int c4 = (lane & 3) * 4;
+    const int rsub = lane >> 2;
+    bool valid[4], keep[4];
+    size_t rowoff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        keep[i] = false;
+        rowoff[i] = 0;
+        valid[i] = tile_valid && rm.locate(q * 32 + rsub + 8 * i, keep[i], rowoff[i]);
+    }
+    // residual prefetch (128-wide tiles: 4 chunks x 4 rows = 16 float4 per lane), independent of the accumulator
+    constexpr bool PREFETCH = BLOCK_N <= 128;
+    float4 pre[PREFETCH ? CHUNKS : 1][4];
+    const bool use_pre = PREFETCH && ep.residual != nullptr;
+    if (use_pre) {
+#pragma unroll
+        for (int k = 0; k < (PREFETCH ? CHUNKS : 1); ++k) {
+            const int n = n0 + (half + 2 * k) * 16 + c4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                pre[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid[i] && n < N) pre[k][i] = *reinterpret_cast<const float4*>(ep.residual + rowoff[i] + n);
+            }
+        }
+    }
+    wait_acc();
+    tcgen05_fence_after();
+    uint32_t r[16];
+    const bool first_beyond = n0 + half * 16 >= N;
+    if (!first_beyond) tmem_ld_32x16_issue(d_tmem + (uint32_t)(half * 16), r);
+    constexpr int UNROLL = PREFETCH ? CHUNKS : 1;      // the prefetched residual must be indexed statically
+#pragma unroll UNROLL
+    for (int k = 0; k < CHUNKS; ++k) {
+        const int u = half + 2 * k;
+        const bool beyond = n0 + u * 16 >= N;     // warp-uniform
+        const bool last = k + 1 >= CHUNKS;
+        if (!beyond) tmem_ld_wait16(r);
+        __syncwarp();
+        if (!beyond) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(stg + lane * PSTG_LD + 4 * j) =
+                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+        }
+        const bool next_beyond = last || (n0 + (u + 2) * 16 >= N);
+        if (!next_beyond) tmem_ld_32x16_issue(d_tmem + (uint32_t)((u + 2) * 16), r);
+        if (last) {   // all TMEM reads of this warp for the tile are done: hand the accumulator back early
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive();
+        }
+        if (beyond) continue;
+        __syncwarp();
+        const int n = n0 + u * 16 + c4;
+        if (!tile_valid || n >= N) continue;
+        const float4* pp = use_pre ? pre[PREFETCH ? k : 0] : nullptr;
+        switch (ep.act) {
+            case CTTS_ACT_RELU: store_chunk_rows<NP, CTTS_ACT_RELU>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
+            case CTTS_ACT_GELU: store_chunk_rows<NP, CTTS_ACT_GELU>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
+            case CTTS_ACT_TANH: store_chunk_rows<NP, CTTS_ACT_TANH>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
+            case CTTS_ACT_SWISH: store_chunk_rows<NP, CTTS_ACT_SWISH>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
+            default: store_chunk_rows<NP, CTTS_ACT_NONE>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
+        }
+    }
+}
 
 template <int BLOCK_N, int STAGES>
 struct PSmem {
@@ -460,6 +599,8 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
     uint64_t* acc_empty = acc_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+    unsigned long long t_entry = 0;
+    if (ep.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kb_per_tap = (Cin + BLOCK_K - 1) / BLOCK_K;
     const int num_kb = taps * kb_per_tap;
@@ -485,7 +626,7 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
         mbar_init(&acc_empty[1], 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 256) ? 256u : 512u;   // allocations are powers of two (2 x 192 -> 512)
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(TMEM_COLS)
@@ -580,6 +721,10 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
             }
         }
     } else {
+        // development aid (ctts_debug_set_timing_buffer): %globaltimer stamps {CTA start, first accumulator ready, end of the
+        // CTA's last epilogue, number of tiles} at dbg[4 * blockIdx.x]
+        unsigned long long t_start = 0, t_first = 0;
+        if (ep.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         float* stg = reinterpret_cast<float*>(smem + S::STAGING_OFFSET) + (warp - 2) * (32 * PSTG_LD);
@@ -591,14 +736,25 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
             tile_coords(tile, z, t0, n0, straddle);
             const int zh = z % ad.mod;
             const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
-            mbar_wait(&acc_full[acc], aph);
-            tcgen05_fence_after();
             const bool tile_valid = z < Z;
             const int len = (ep.lens && tile_valid) ? (int)ep.lens[z / ad.lens_div] : T;
             const size_t tilebase = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner;
             const int g0 = packed ? (tile / n_tiles) * BLOCK_M : 0;
             const RowMap rm{straddle, g0, Z * T, T, len, t0, ep.lens, (size_t)ad.y_outer, tilebase, ad.ldy};
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+            if (PIPELINED_EPILOGUE) {
+                persistent_epilogue<BLOCK_N>(
+                    ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg,
+                    [&] {
+                        mbar_wait(&acc_full[acc], aph);
+                        if (ep.dbg && lt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
+                    },
+                    [&] { mbar_arrive(&acc_empty[acc]); });
+                continue;
+            }
+            mbar_wait(&acc_full[acc], aph);
+            if (ep.dbg && lt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
+            tcgen05_fence_after();
 #pragma unroll 1
             for (int u = half; u < BLOCK_N / 16; u += 2) {
                 const bool beyond = n0 + u * 16 >= N;     // warp-uniform
@@ -629,6 +785,13 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
                     default: store_chunk<NP, CTTS_ACT_NONE, 4, PSTG_LD>(ep, stg, c4, rsub, row0, rm, n); break;
                 }
             }
+        }
+        if (ep.dbg && warp == 2 && lane == 0) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            long long* d = ep.dbg + 4 * (size_t)blockIdx.x;
+            d[0] = (long long)t_entry; d[1] = (long long)t_first; d[2] = (long long)t_end;
+            d[3] = (long long)lt | ((long long)(t_start - t_entry) << 16);     // tiles | set-up ns << 16
         }
         tcgen05_fence_before();
     }
@@ -815,14 +978,20 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
             tile_coords(pt, mt, z, t0, n0, straddle);
             const int zh = z % ad.mod;
             const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
-            mbar_wait(&acc_full[acc], aph);
-            tcgen05_fence_after();
             const bool tile_valid = z < Z && mt < m_tiles;
             const int len = (ep.lens && tile_valid) ? (int)ep.lens[z / ad.lens_div] : T;
             const size_t tilebase = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner;
             const int g0 = packed ? mt * BLOCK_M : 0;
             const RowMap rm{straddle, g0, Z * T, T, len, t0, ep.lens, (size_t)ad.y_outer, tilebase, ad.ldy};
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+            if (PIPELINED_EPILOGUE) {
+                persistent_epilogue<BLOCK_N>(
+                    ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, [&] { mbar_wait(&acc_full[acc], aph); },
+                    [&] { mbar_arrive_cluster(acc_empty_leader[acc]); });
+                continue;
+            }
+            mbar_wait(&acc_full[acc], aph);
+            tcgen05_fence_after();
 #pragma unroll 1
             for (int u = half; u < BLOCK_N / 16; u += 2) {
                 const bool beyond = n0 + u * 16 >= N;     // warp-uniform
@@ -1123,13 +1292,25 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
     }
     // 128x256 or 128x128 tiles?  Whole waves cost the same whether they are full or not, so pick the shape with the
     // smaller (waves x per-tile cycles) estimate; per-tile cycles from the measured breakdown in profiles/README.md.
-    bool wide = N >= 512 && N % 256 == 0;
-    if (wide) {
+    // CTTS_WIDE_MIN_N: smallest N for which the 256-wide tile is considered (default 512; 256 lets the K = 256 / 1024
+    // projections of a block run as ONE round of 100 tiles instead of two rounds of 128-wide ones).
+    // CTTS_TILE_192=1: also consider 128x192 tiles when 192 | N (QKV: N = 768 -> 400 tiles = 2.7 rounds of 0.75-size tiles
+    // instead of 300 256-wide tiles = 2.03 -> 3 rounds).
+    static const long long wide_min_n = getenv("CTTS_WIDE_MIN_N") ? atoll(getenv("CTTS_WIDE_MIN_N")) : 512;
+    static const bool tile_192 = getenv("CTTS_TILE_192") != nullptr && atoi(getenv("CTTS_TILE_192")) != 0;
+    bool wide = N >= wide_min_n && N % 256 == 0;
+    bool mid = false;
+    {
         const long long nkb = (long long)taps * ((Cin + BLOCK_K - 1) / BLOCK_K);
         const long long sms = 148;
         const long long w256 = (m_tiles * ((N + 255) / 256) + sms - 1) / sms, w128 = (m_tiles * ((N + 127) / 128) + sms - 1) / sms;
         const long long c256 = w256 * (9000 + nkb * 1700), c128 = w128 * (6000 + nkb * 1000);
-        wide = c256 <= c128;
+        if (wide) wide = c256 <= c128;
+        if (tile_192 && np == 2 && N % 192 == 0) {
+            const long long w192 = (m_tiles * (N / 192) + sms - 1) / sms;
+            const long long c192 = w192 * (7500 + nkb * 1350);
+            mid = c192 < (wide ? c256 : c128);
+        }
     }
     static const bool use_persistent = getenv("CTTS_NO_PERSISTENT") == nullptr;
     // CTA pairs need ONE weight tile for both CTAs' rows: plain conv / linear only.  Measured with the benchmark (A/B on
@@ -1150,8 +1331,9 @@ static int launch_auto(int np, const Operand& A, const Operand& W, const Epilogu
     if (use_persistent && plain && pair_mode == 1 && pair_longk && N == 256 && num_kb >= 64 && m_tiles >= 64)
         return launch_pair<3>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
     if (use_persistent) {
-        if (plain && ((pair_mode == 1 && wide && m_tiles >= 2 && num_kb >= pair_min_kb) || pair_mode == 2))
+        if (plain && ((pair_mode == 1 && wide && N >= 512 && m_tiles >= 2 && num_kb >= pair_min_kb) || pair_mode == 2))
             return launch_pair<3>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
+        if (mid) return launch_persistent<192, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
         if (wide) return launch_persistent<256, 2>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
         return launch_persistent<128, 3>(A, W, ep, ad, Z, T, Cin, N, taps, st, seg);
     }

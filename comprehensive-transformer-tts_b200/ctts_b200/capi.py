@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libctts_b200.so")
+# CTTS_B200_LIB: load another build of the same ABI (A/B runs of a kernel change on one box)
+LIB_PATH = os.environ.get("CTTS_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libctts_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SWISH = 0, 1, 2, 3, 4
 
