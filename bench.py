@@ -439,12 +439,18 @@ def main():
     def step_device():
         return net(*dev_in)
 
+    host_out = {}
+
     def step_e2e():
         spk, txt, lens = (h.to(dev, non_blocking=True) for h in host_in)
         out = net(spk, txt, lens, batch["max_src_len"])
-        mel = out[1].to("cpu", non_blocking=False)
-        ml = out[9].to("cpu")
-        return mel, ml
+        # device -> host read of the result (post-net mel + its lengths) into pinned landing buffers, as a serving loop would
+        for k, t in (("mel", out[1]), ("mel_lens", out[9])):
+            if k not in host_out or host_out[k].shape != t.shape:
+                host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            host_out[k].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host_out["mel"], host_out["mel_lens"]
 
     def run_timed(fn, steps, warmup):
         for _ in range(warmup):

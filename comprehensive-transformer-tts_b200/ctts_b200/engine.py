@@ -204,15 +204,32 @@ class Prepared:
         self.w = {}
         self.pe = {}
         self.pe_retired = []
+        self._names = self._tensors = None
+        self._epoch = -1
+        self._host_maxes = None
 
-    def _signature(self, P):
-        return tuple((k, v.data_ptr(), v._version) for k, v in P.items())
+    def host_maxes(self, device):
+        """Pinned landing buffer of the step's single device -> host read (allocated outside any graph capture)."""
+        if self._host_maxes is None:
+            self._host_maxes = torch.zeros(2, dtype=torch.int64).pin_memory() if device.type == "cuda" \
+                else torch.zeros(2, dtype=torch.int64)
+        return self._host_maxes
+
+    def _signature(self, tensors):
+        return [(v.data_ptr(), v._version) for v in tensors]
 
     def params(self):
-        P = {k: v for k, v in self.module.named_parameters(remove_duplicate=False)}  # tied names included
-        P.update({k: v for k, v in self.module.named_buffers(remove_duplicate=False)})
-        sig = self._signature(P)
-        if sig != self.sig:
+        from .module import _Tracked
+        if self._names is None or self._epoch != _Tracked.structure_epoch:
+            # walk the module tree only when its structure changed (a tensor or sub-module attached / replaced)
+            P = {k: v for k, v in self.module.named_parameters(remove_duplicate=False)}  # tied names included
+            P.update({k: v for k, v in self.module.named_buffers(remove_duplicate=False)})
+            self._names, self._tensors = P, list(P.values())
+            self._epoch = _Tracked.structure_epoch
+            self.sig = None
+        P = self._names
+        sig = self._signature(self._tensors)
+        if self.sig is None or sig != self.sig:
             self._build(P)
             self.sig = sig
         return P
@@ -883,6 +900,8 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
                       spker_embeds=spker_embeds if module.has_speaker_emb and module.embedder_type != "none" else None),
              in_a)
 
+    host_maxes = prep.host_maxes(texts.device)
+
     def stage_a(t):
         enc, word = _encode(module, prep, P, cfg, t["texts"], t["src_lens"])
         spk = None
@@ -900,6 +919,9 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         a = variance_stage_a(prep, P, pcfg, cfg, tcfg, spk, enc, word, t["src_lens"], t.get("mels"), t.get("mel_lens"),
                              t.get("d_targets"), t.get("attn_priors"), d_control)
         a["free_running"] = free_running
+        # the two maxima the host needs (longest regulated length with / without d_control) go to pinned host memory from
+        # inside the stage: the host then only waits for the stream instead of launching a reduction and a blocking copy
+        host_maxes.copy_(a["lens2"].view(2, -1).max(dim=1).values, non_blocking=True)
         return a
 
     key_a = ("A", float(d_control), tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(in_a.items())))
@@ -911,7 +933,9 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
     # ---- the single host sync: the regulated lengths --------------------------------------------------------------
     need_m2p = attn_priors is not None or free_running
     if max_mel_len is None or need_m2p:
-        maxes = a["lens2"].view(2, B).max(dim=1).values.tolist()
+        if texts.is_cuda:
+            torch.cuda.current_stream(texts.device).synchronize()
+        maxes = host_maxes.tolist()
         M = int(max_mel_len) if max_mel_len is not None else int(maxes[0])
         M2 = int(maxes[1])
     else:
@@ -922,8 +946,6 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         raise capi.CttsError("length_regulate: every duration is zero (empty mel)")
 
     # ---- stage B: upsampling, pitch / energy embeddings, decoder, mel head ------------------------------------------
-    src_masks = pad_mask(src_lens, max_src_len)
-    mel_masks = pad_mask(_i64(mel_lens), max_mel_len) if mel_lens is not None else None
     in_b = {}
     _flatten("", dict(p_targets=p_targets, e_targets=e_targets, mel_lens=_i64(mel_lens) if mel_lens is not None else None),
              in_b)
@@ -949,6 +971,9 @@ def forward(module, speakers, texts, src_lens, max_src_len, mels=None, mel_lens=
         o, _ = graphs.run(key_b, stage_b, in_b, table=sub)
     else:
         o = stage_b(in_b)
+    # (bookkeeping masks are launched behind stage B so that their launch latency hides under it)
+    src_masks = pad_mask(src_lens, max_src_len)
+    mel_masks = pad_mask(_i64(mel_lens), max_mel_len) if mel_lens is not None else None
     if graphs is not None and sub is not None:
         # hand out private copies: the static buffers are overwritten by the next replay
         o = _tree_map(lambda v: v.clone(), o)
