@@ -52,12 +52,14 @@ struct Epilogue {
     int act;
     long long* dbg;         // optional per-CTA cycle stamps {start, setup done, accumulator ready, epilogue done}
     int atomic;             // split-K: y += v with fp32 atomics instead of a store (y only; no planes)
+    int tma_out;            // persistent kernels, planes-only output: tiles leave through TMA stores (Maps::o)
 };
 
 struct Maps {               // TMA descriptors of the operand planes (NP of each are used)
     CUtensorMap a[3];       // activation planes, box = 128 rows
     CUtensorMap w[3];
     CUtensorMap a_seg[3];   // activation planes, box = seg_rows rows (packed tiling: tiles that straddle two utterances)
+    CUtensorMap o[2];       // output planes (persistent kernels with Epilogue::tma_out), box = 32 rows x 32 columns, SWIZZLE_64B
 };
 
 // Operand / output addressing.  z = blockIdx.x / tiles_per_utt is the "utterance" index of a plain conv (z = b) or the
@@ -438,10 +440,18 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
 #define CTTS_PIPELINED_EPILOGUE 1
 #endif
 constexpr bool PIPELINED_EPILOGUE = CTTS_PIPELINED_EPILOGUE != 0;
+constexpr int PSTG_WARP_BYTES = 4096;   // per epilogue warp: 32 x 20 floats (transpose tile) or 2 planes x 32 rows x 64 B (TMA tile)
 constexpr int PSTG_LD = 20;   // floats per row of the 32 x 16 transpose tile of the persistent epilogue
 
 // Persistent-kernel epilogue for one 32 x 16 chunk with the row bookkeeping done once per tile (4 rows per lane) and,
 // optionally, the residual values already in registers (fetched while the tensor core was still working on the tile).
+// (development: -DCTTS_EPI_EXPERIMENT=1 drops the global stores of the persistent epilogue unless a value is an
+// impossible one, =2 drops everything after the TMEM read -- to see what bounds the epilogue; never in a shipped build)
+#if defined(CTTS_EPI_EXPERIMENT) && CTTS_EPI_EXPERIMENT >= 1
+#define CTTS_EPI_X1(x) &&((x) == 1.2345e38f)
+#else
+#define CTTS_EPI_X1(x)
+#endif
 template <int NP, int ACT>
 __device__ __forceinline__ void store_chunk_rows(const Epilogue& ep, const float* stg, int c4, int rsub, const bool (&valid)[4],
                                                  const bool (&keep)[4], const size_t (&rowoff)[4], int n, const float4* pre) {
@@ -454,33 +464,47 @@ __device__ __forceinline__ void store_chunk_rows(const Epilogue& ep, const float
         sh = *reinterpret_cast<const float4*>(ep.col_shift + n);
     }
     const float alpha = ep.alpha;
-    float4 rs[4];
+    // The four rows of this lane are independent: every phase (loads, arithmetic, stores) runs over all of them before the
+    // next one starts, so that the eight epilogue warps of a CTA have four rows' worth of instructions in flight each.
+    float4 rs[4], a4[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (pre) rs[i] = pre[i];
         else if (valid[i] && ep.residual) rs[i] = *reinterpret_cast<const float4*>(ep.residual + rowoff[i] + n);
+        a4[i] = *reinterpret_cast<const float4*>(stg + (rsub + 8 * i) * LD + c4);
     }
+    float v[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        if (!valid[i]) break;
-        const size_t off = rowoff[i] + (size_t)n;
-        const float4 a4 = *reinterpret_cast<const float4*>(stg + (rsub + 8 * i) * LD + c4);
-        float v[4] = {(a4.x + bb.x) * alpha, (a4.y + bb.y) * alpha, (a4.z + bb.z) * alpha, (a4.w + bb.w) * alpha};
+        v[i][0] = (a4[i].x + bb.x) * alpha; v[i][1] = (a4[i].y + bb.y) * alpha;
+        v[i][2] = (a4[i].z + bb.z) * alpha; v[i][3] = (a4[i].w + bb.w) * alpha;
         if (affine) {
-            v[0] = v[0] * sc.x + sh.x; v[1] = v[1] * sc.y + sh.y;
-            v[2] = v[2] * sc.z + sh.z; v[3] = v[3] * sc.w + sh.w;
+            v[i][0] = v[i][0] * sc.x + sh.x; v[i][1] = v[i][1] * sc.y + sh.y;
+            v[i][2] = v[i][2] * sc.z + sh.z; v[i][3] = v[i][3] * sc.w + sh.w;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = act_fn<ACT>(v[j]);
-        v[0] += rs[i].x; v[1] += rs[i].y; v[2] += rs[i].z; v[3] += rs[i].w;
-        if (!keep[i]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
-        if (ep.atomic) {
+        for (int j = 0; j < 4; ++j) v[i][j] = act_fn<ACT>(v[i][j]);
+        v[i][0] += rs[i].x; v[i][1] += rs[i].y; v[i][2] += rs[i].z; v[i][3] += rs[i].w;
+        if (!keep[i]) { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+    }
+    if (ep.atomic) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) atomicAdd(ep.y + off + j, v[j]);
-        } else if (ep.y) *reinterpret_cast<float4*>(ep.y + off) = make_float4(v[0], v[1], v[2], v[3]);
-        if (ep.yp[0]) {
-            float rem[4] = {v[0], v[1], v[2], v[3]};
+        for (int i = 0; i < 4; ++i)
+            if (valid[i]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(ep.y + rowoff[i] + n + j, v[i][j]);
+            }
+    } else if (ep.y) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (valid[i] CTTS_EPI_X1(v[i][0])) *reinterpret_cast<float4*>(ep.y + rowoff[i] + n) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+    }
+    if (ep.yp[0]) {
+        uint2 pk[NP][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float rem[4] = {v[i][0], v[i][1], v[i][2], v[i][3]};
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 __nv_bfloat162 h01 = __floats2bfloat162_rn(rem[0], rem[1]);
@@ -489,12 +513,15 @@ __device__ __forceinline__ void store_chunk_rows(const Epilogue& ep, const float
                     rem[0] -= __low2float(h01); rem[1] -= __high2float(h01);
                     rem[2] -= __low2float(h23); rem[3] -= __high2float(h23);
                 }
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&h01);
-                pk.y = *reinterpret_cast<uint32_t*>(&h23);
-                *reinterpret_cast<uint2*>(ep.yp[p] + off) = pk;
+                pk[p][i].x = *reinterpret_cast<uint32_t*>(&h01);
+                pk[p][i].y = *reinterpret_cast<uint32_t*>(&h23);
             }
         }
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (valid[i] CTTS_EPI_X1(v[i][p])) *reinterpret_cast<uint2*>(ep.yp[p] + rowoff[i] + n) = pk[p][i];
     }
 }
 
@@ -564,6 +591,9 @@ __device__ __forceinline__ void persistent_epilogue(const Epilogue& ep, const Ro
         __syncwarp();
         const int n = n0 + u * 16 + c4;
         if (!tile_valid || n >= N) continue;
+#if defined(CTTS_EPI_EXPERIMENT) && CTTS_EPI_EXPERIMENT >= 2
+        if (stg[lane] != 1.2345e38f) continue;
+#endif
         const float4* pp = use_pre ? pre[PREFETCH ? k : 0] : nullptr;
         switch (ep.act) {
             case CTTS_ACT_RELU: store_chunk_rows<NP, CTTS_ACT_RELU>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
@@ -575,17 +605,137 @@ __device__ __forceinline__ void persistent_epilogue(const Epilogue& ep, const Ro
     }
 }
 
+// Planes-only epilogue of the persistent kernels through TMA stores.  The generic epilogue above spends ~28 instructions per
+// output element (shared-memory transpose, per-row 64-bit addressing, predication) and is what bounds the short-K GEMMs:
+// 8 epilogue warps x ~3.6 k instructions per 128 x 256 tile.  Here a lane keeps its TMEM row: 16 consecutive columns ->
+// bias / scale / activation -> bf16 hi / lo -> two 16-byte shared-memory stores per plane into a [32 rows x 32 columns]
+// SWIZZLE_64B staging tile (conflict-free: the XOR spreads 8 consecutive rows over all banks), and one lane hands the
+// tile to the TMA unit, which also clips rows / columns beyond the tensor.  ~8 instructions per element.
+template <int BLOCK_N, int ACT, class WaitAcc, class Arrive>
+__device__ __forceinline__ void persistent_epilogue_tma(const Maps& tm, const Epilogue& ep, const RowMap& rm, bool tile_valid,
+                                                        int n0, int N, int q, int half, int lane, uint32_t d_tmem,
+                                                        uint8_t* stg, int row_coord, int z_coord, bool& store_pending,
+                                                        WaitAcc wait_acc, Arrive arrive) {
+    constexpr int CHUNKS = BLOCK_N / 32;       // 16-column chunks of this warp: groups (half + 2 g) of two chunks each
+    bool keep = false;
+    size_t off = 0;
+    const bool valid = tile_valid && rm.locate(q * 32 + lane, keep, off);
+    keep = keep && valid;
+    const bool affine = ep.col_scale != nullptr;
+    const float alpha = ep.alpha;
+    const int sw = (lane >> 1) & 3;
+    uint8_t* row = stg + lane * 64;
+    wait_acc();
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int k = 0; k < CHUNKS; ++k) {
+        const int u = (half + 2 * (k >> 1)) * 2 + (k & 1);
+        const bool beyond = n0 + u * 16 >= N;     // warp-uniform
+        const bool last = k + 1 >= CHUNKS;
+        uint32_t r[16];
+        if (!beyond) tmem_ld_32x16(d_tmem + (uint32_t)(u * 16), r);
+        if (last) {   // all TMEM reads of this warp for the tile are done: hand the accumulator back early
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive();
+        }
+        if ((k & 1) == 0 && store_pending) {      // a new group: the TMA unit must have read the previous one
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+            store_pending = false;
+        }
+        if (!beyond) {
+            const int n = n0 + u * 16;
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {      // 8 columns -> one 16-byte chunk of each plane
+                float v[8];
+#pragma unroll
+                for (int j4 = 0; j4 < 2; ++j4) {
+                    const int c = 8 * h8 + 4 * j4;
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ep.bias) bb = __ldg(reinterpret_cast<const float4*>(ep.bias + n + c));
+                    v[4 * j4 + 0] = (__uint_as_float(r[c + 0]) + bb.x) * alpha;
+                    v[4 * j4 + 1] = (__uint_as_float(r[c + 1]) + bb.y) * alpha;
+                    v[4 * j4 + 2] = (__uint_as_float(r[c + 2]) + bb.z) * alpha;
+                    v[4 * j4 + 3] = (__uint_as_float(r[c + 3]) + bb.w) * alpha;
+                    if (affine) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(ep.col_scale + n + c));
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(ep.col_shift + n + c));
+                        v[4 * j4 + 0] = v[4 * j4 + 0] * sc.x + sh.x; v[4 * j4 + 1] = v[4 * j4 + 1] * sc.y + sh.y;
+                        v[4 * j4 + 2] = v[4 * j4 + 2] * sc.z + sh.z; v[4 * j4 + 3] = v[4 * j4 + 3] * sc.w + sh.w;
+                    }
+                }
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = act_fn<ACT>(v[2 * j]), b = act_fn<ACT>(v[2 * j + 1]);
+                    if (!keep) { a = 0.f; b = 0.f; }
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+                    hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                }
+                const int cc = ((2 * (k & 1) + h8) ^ sw) * 16;
+                *reinterpret_cast<uint4*>(row + cc) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(row + 2048 + cc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        if (k & 1) {      // the group's 32 columns are staged (columns beyond N, if any, are clipped by the TMA unit)
+            const int ng = n0 + (half + 2 * (k >> 1)) * 32;
+            if (tile_valid && ng < N) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&tm.o[0], stg, ng, row_coord, z_coord);
+                    tma_store_3d(&tm.o[1], stg + 2048, ng, row_coord, z_coord);
+                    tma_store_commit();
+                }
+                store_pending = true;
+            }
+        }
+    }
+}
+
+template <int BLOCK_N, class WaitAcc, class Arrive>
+__device__ __forceinline__ void persistent_epilogue_tma_act(const Maps& tm, const Epilogue& ep, const RowMap& rm, bool tile_valid,
+                                                            int n0, int N, int q, int half, int lane, uint32_t d_tmem,
+                                                            uint8_t* stg, int row_coord, int z_coord, bool& store_pending,
+                                                            WaitAcc wait_acc, Arrive arrive) {
+    switch (ep.act) {
+        case CTTS_ACT_RELU:
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_RELU>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+                                                            z_coord, store_pending, wait_acc, arrive);
+            break;
+        case CTTS_ACT_GELU:
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_GELU>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+                                                            z_coord, store_pending, wait_acc, arrive);
+            break;
+        case CTTS_ACT_TANH:
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_TANH>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+                                                            z_coord, store_pending, wait_acc, arrive);
+            break;
+        case CTTS_ACT_SWISH:
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_SWISH>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+                                                             z_coord, store_pending, wait_acc, arrive);
+            break;
+        default:
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_NONE>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+                                                            z_coord, store_pending, wait_acc, arrive);
+            break;
+    }
+}
+
 template <int BLOCK_N, int STAGES>
 struct PSmem {
     static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = 2 * (A_TILE_BYTES + B_TILE_BYTES);
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int STAGING_OFFSET = BAR_OFFSET + 128;
-    static constexpr int TOTAL = STAGING_OFFSET + 8 * 32 * PSTG_LD * 4 + 1024;
+    static constexpr int STAGING_OFFSET = BAR_OFFSET + 1024;     // 8 warps x 4 KiB, 1024-byte aligned (TMA-store tiles)
+    static constexpr int TOTAL = STAGING_OFFSET + 8 * PSTG_WARP_BYTES + 1024;
     static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool TMA_OUT>
 __global__ void __launch_bounds__(320, 1)
 gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
                        int tiles_per_utt, int Z, int seg_rows, int m_tiles, int n_tiles) {
@@ -727,10 +877,11 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
         if (ep.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        float* stg = reinterpret_cast<float*>(smem + S::STAGING_OFFSET) + (warp - 2) * (32 * PSTG_LD);
+        float* stg = reinterpret_cast<float*>(smem + S::STAGING_OFFSET + (warp - 2) * PSTG_WARP_BYTES);
         const int c4 = (lane & 3) * 4;     // 4 lanes cover the 16 columns of a row
         const int rsub = lane >> 2;        // 8 rows per iteration
         uint32_t lt = 0;
+        bool store_pending = false;      // a TMA store of this warp may still be reading its staging tile
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             int z, t0, n0; bool straddle;
             tile_coords(tile, z, t0, n0, straddle);
@@ -743,13 +894,17 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
             const RowMap rm{straddle, g0, Z * T, T, len, t0, ep.lens, (size_t)ad.y_outer, tilebase, ad.ldy};
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
             if (PIPELINED_EPILOGUE) {
-                persistent_epilogue<BLOCK_N>(
-                    ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg,
-                    [&] {
-                        mbar_wait(&acc_full[acc], aph);
-                        if (ep.dbg && lt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
-                    },
-                    [&] { mbar_arrive(&acc_empty[acc]); });
+                auto wait_acc = [&] {
+                    mbar_wait(&acc_full[acc], aph);
+                    if (ep.dbg && lt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
+                };
+                auto hand_back = [&] { mbar_arrive(&acc_empty[acc]); };
+                if constexpr (TMA_OUT)
+                    persistent_epilogue_tma_act<BLOCK_N>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem,
+                                                         reinterpret_cast<uint8_t*>(stg), (packed ? g0 : t0) + q * 32,
+                                                         packed ? 0 : z, store_pending, wait_acc, hand_back);
+                else
+                    persistent_epilogue<BLOCK_N>(ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, wait_acc, hand_back);
                 continue;
             }
             mbar_wait(&acc_full[acc], aph);
@@ -786,6 +941,7 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
                 }
             }
         }
+        if (TMA_OUT && lane == 0) tma_store_wait_all();     // shared memory stays valid until the stores have read it
         if (ep.dbg && warp == 2 && lane == 0) {
             unsigned long long t_end;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -817,12 +973,12 @@ struct PairSmem {
     static constexpr int B_HALF_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;              // 16 KiB
     static constexpr int STAGE_BYTES = 2 * (A_TILE_BYTES + B_HALF_BYTES);         // per CTA: 64 KiB
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int STAGING_OFFSET = BAR_OFFSET + 128;
-    static constexpr int TOTAL = STAGING_OFFSET + 8 * 32 * PSTG_LD * 4 + 1024;
+    static constexpr int STAGING_OFFSET = BAR_OFFSET + 1024;     // 8 warps x 4 KiB, 1024-byte aligned (TMA-store tiles)
+    static constexpr int TOTAL = STAGING_OFFSET + 8 * PSTG_WARP_BYTES + 1024;
     static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <int STAGES>
+template <int STAGES, bool TMA_OUT>
 __global__ void __launch_bounds__(320, 1)
 gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
                  int tiles_per_utt, int Z, int seg_rows, int m_tiles, int n_tiles, int swap_b) {
@@ -967,12 +1123,13 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
     } else {
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
-        float* stg = reinterpret_cast<float*>(smem + S::STAGING_OFFSET) + (warp - 2) * (32 * PSTG_LD);
+        float* stg = reinterpret_cast<float*>(smem + S::STAGING_OFFSET + (warp - 2) * PSTG_WARP_BYTES);
         const int c4 = (lane & 3) * 4;     // 4 lanes cover the 16 columns of a row
         const int rsub = lane >> 2;        // 8 rows per iteration
         const uint32_t acc_empty_leader[2] = {mapa_shared(smem_u32(&acc_empty[0]), 0),
                                               mapa_shared(smem_u32(&acc_empty[1]), 0)};
         uint32_t lt = 0;
+        bool store_pending = false;
         for (int pt = pair; pt < pair_tiles; pt += n_pairs, ++lt) {
             int mt, z, t0, n0; bool straddle;
             tile_coords(pt, mt, z, t0, n0, straddle);
@@ -985,9 +1142,14 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
             const RowMap rm{straddle, g0, Z * T, T, len, t0, ep.lens, (size_t)ad.y_outer, tilebase, ad.ldy};
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
             if (PIPELINED_EPILOGUE) {
-                persistent_epilogue<BLOCK_N>(
-                    ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, [&] { mbar_wait(&acc_full[acc], aph); },
-                    [&] { mbar_arrive_cluster(acc_empty_leader[acc]); });
+                auto wait_acc = [&] { mbar_wait(&acc_full[acc], aph); };
+                auto hand_back = [&] { mbar_arrive_cluster(acc_empty_leader[acc]); };
+                if constexpr (TMA_OUT)
+                    persistent_epilogue_tma_act<BLOCK_N>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem,
+                                                         reinterpret_cast<uint8_t*>(stg), (packed ? g0 : t0) + q * 32,
+                                                         packed ? 0 : z, store_pending, wait_acc, hand_back);
+                else
+                    persistent_epilogue<BLOCK_N>(ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, wait_acc, hand_back);
                 continue;
             }
             mbar_wait(&acc_full[acc], aph);
@@ -1023,6 +1185,7 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
                 }
             }
         }
+        if (TMA_OUT && lane == 0) tma_store_wait_all();
         tcgen05_fence_before();
     }
     __syncthreads();
@@ -1143,8 +1306,34 @@ static int num_sms() {
     return n;
 }
 
+// Output maps of the TMA-store epilogue (persistent kernels, planes-only output).  Returns 0 and sets ep.tma_out when the
+// output qualifies: two planes, no fp32 copy, no residual, plain [rows, ldy] addressing with 16-byte aligned rows.
+static int make_output_maps(Maps& maps, Epilogue& ep, const Addr& ad, int Z, int T, int N, int seg_rows) {
+    static const bool enabled = getenv("CTTS_NO_TMA_STORE") == nullptr;
+    ep.tma_out = 0;
+    if (!enabled || !PIPELINED_EPILOGUE || !ep.yp[0] || !ep.yp[1] || ep.yp[2] || ep.y || ep.residual || ep.atomic) return 0;
+    if (ad.mod != 1 || ad.ldy % 8 != 0 || ad.y_outer % 8 != 0 || N % 8 != 0) return 0;
+    if (seg_rows > 0 && ad.y_outer != (long long)T * ad.ldy) return 0;      // packed tiling needs one dense [Z*T, ldy] block
+    for (int p = 0; p < 2; ++p)
+        if (reinterpret_cast<uintptr_t>(ep.yp[p]) % 16 != 0) return 0;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return 0;
+    const bool packed = seg_rows > 0;
+    cuuint64_t dims[3] = {(cuuint64_t)N, packed ? (cuuint64_t)Z * T : (cuuint64_t)T, packed ? 1 : (cuuint64_t)Z};
+    cuuint64_t str[2] = {(cuuint64_t)ad.ldy * 2, (cuuint64_t)(packed ? (long long)Z * T * ad.ldy : ad.y_outer) * 2};
+    cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+    for (int p = 0; p < 2; ++p) {
+        CUresult r = fn(&maps.o[p], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ep.yp[p], dims, str, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output plane) failed: CUresult %d", (int)r); return 4; }
+    }
+    ep.tma_out = 1;
+    return 0;
+}
+
 template <int BLOCK_N, int STAGES>
-static int launch_persistent(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin,
+static int launch_persistent(const Operand& A, const Operand& W, const Epilogue& ep_in, const Addr& ad, int Z, int T, int Cin,
                              int N, int taps, cudaStream_t st, int seg_rows) {
     using S = PSmem<BLOCK_N, STAGES>;
     constexpr int NP = 2;
@@ -1169,10 +1358,15 @@ static int launch_persistent(const Operand& A, const Operand& W, const Epilogue&
             if (int e = make_map(&maps.w[p], W.p[p], 3, dims, str, box, "weight plane")) return e;
         maps.w[2] = maps.w[0];
     }
-    auto kern = gemm_persistent_kernel<BLOCK_N, STAGES>;
+    Epilogue ep = ep_in;
+    if (int e = make_output_maps(maps, ep, ad, Z, T, N, seg_rows)) return e;
+    auto kern = ep.tma_out ? gemm_persistent_kernel<BLOCK_N, STAGES, true> : gemm_persistent_kernel<BLOCK_N, STAGES, false>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+        if (cudaFuncSetAttribute(gemm_persistent_kernel<BLOCK_N, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 S::TOTAL) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_persistent_kernel<BLOCK_N, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 S::TOTAL) != cudaSuccess) {
             set_error("gemm_persistent: cannot reserve %d bytes of shared memory", S::TOTAL);
             return 4;
         }
@@ -1188,7 +1382,7 @@ static int launch_persistent(const Operand& A, const Operand& W, const Epilogue&
 }
 
 template <int STAGES>
-static int launch_pair(const Operand& A, const Operand& W, const Epilogue& ep, const Addr& ad, int Z, int T, int Cin, int N,
+static int launch_pair(const Operand& A, const Operand& W, const Epilogue& ep_in, const Addr& ad, int Z, int T, int Cin, int N,
                        int taps, cudaStream_t st, int seg_rows) {
     using S = PairSmem<STAGES>;
     constexpr int NP = 2;
@@ -1213,10 +1407,15 @@ static int launch_pair(const Operand& A, const Operand& W, const Epilogue& ep, c
             if (int e = make_map(&maps.w[p], W.p[p], 3, dims, str, box, "weight plane")) return e;
         maps.w[2] = maps.w[0];
     }
-    auto kern = gemm_pair_kernel<STAGES>;
+    Epilogue ep = ep_in;
+    if (int e = make_output_maps(maps, ep, ad, Z, T, N, seg_rows)) return e;
+    auto kern = ep.tma_out ? gemm_pair_kernel<STAGES, true> : gemm_pair_kernel<STAGES, false>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) {
+        if (cudaFuncSetAttribute(gemm_pair_kernel<STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(gemm_pair_kernel<STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
+                cudaSuccess) {
             set_error("gemm_pair: cannot reserve %d bytes of shared memory", S::TOTAL);
             return 4;
         }
