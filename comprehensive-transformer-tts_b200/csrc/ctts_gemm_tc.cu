@@ -1654,6 +1654,234 @@ transpose_v_wide_kernel(const CPlanes3 q, int T, int Tp, int C, int H, int DH, c
     }
 }
 
+
+// ---- fused self-attention for short sequences (T <= 128 keys, head_dim 128, 3 operand planes = bf16x6) ------------------
+// The encoder's attention at S ~ 100 was four launches (scores GEMM, V transpose, softmax, P.V GEMM: ~50 us per layer for
+// 0.2 GFLOP, every one of them latency-bound).  Here one CTA owns one (batch, head): Q and K (3 planes, 96 KiB each) arrive by
+// TMA, S = Q K^T lands in TMEM, the softmax warps (TMEM lane = query row, two warps per lane quarter split the keys) write
+// the normalised probabilities as bf16 planes over the K tiles while V^T streams in over the Q tiles, and P V accumulates
+// into the same TMEM columns.  Products and accumulators as in gemm_split_kernel<NP = 3>: the hi*hi products of k-block i go
+// to accumulator i, the five small products to a third one; the three are added in FP32 on the way out.
+namespace sa {
+constexpr int TILE = 128 * 64 * 2;        // [128 rows x 64 elements] bf16, SWIZZLE_128B = 16 KiB
+constexpr int REGION = 6 * TILE;          // 3 planes x 2 k-blocks = 96 KiB
+constexpr int OFF_R0 = 0;                 // Q, later V^T
+constexpr int OFF_R1 = REGION;            // K, later P
+constexpr int OFF_BAR = 2 * REGION;
+constexpr int OFF_XCH = OFF_BAR + 128;    // [max | sum][2 halves][128 rows] floats
+constexpr int SMEM_TOTAL = OFF_XCH + 2 * 2 * 128 * 4 + 1024;
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+struct Maps {
+    CUtensorMap qkv[3];   // qkv planes [B, T, 3C], box {64, 128, 1}
+    CUtensorMap vt[3];    // V^T planes [Z, 128, Tp], box {64, 128, 1}
+};
+}  // namespace sa
+
+__global__ void __launch_bounds__(320, 1)
+small_attention_kernel(const __grid_constant__ sa::Maps tm, const int64_t* __restrict__ lens, int T, int C, int H, float scale,
+                       const Planes3 out) {
+    using namespace sa;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* qk_full = bars;
+    uint64_t* s_full = bars + 1;
+    uint64_t* v_full = bars + 2;
+    uint64_t* p_full = bars + 3;      // 8 arrivals (one per softmax warp)
+    uint64_t* o_full = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
+
+    CTTS_PDL_SYNC();   // lens[] / the operand planes come from the previous kernels
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int z = blockIdx.x, b = z / H, h = z - b * H;
+    const int len = min((int)lens[b], T);
+    const int nkb = (len + 63) >> 6;     // key blocks (64 keys) holding at least one valid key
+
+    if (warp == 0 && lane == 0) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            tma_prefetch_desc(&tm.qkv[p]);
+            tma_prefetch_desc(&tm.vt[p]);
+        }
+        mbar_init(qk_full, 1);
+        mbar_init(s_full, 1);
+        mbar_init(v_full, 1);
+        mbar_init(p_full, 8);
+        mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    constexpr uint32_t TMEM_COLS = 512;   // accumulators at columns 0 / 128 / 256 (S, then O)
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t idesc = instr_desc<128>();
+
+    // one k-block of the 6-product scheme: main accumulator `acc_main` takes hi*hi, `acc_small` the five small products
+    auto mma_block = [&](uint32_t a_region, uint32_t b_region, int kb, bool first_block) {
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t off = k * UMMA_K * 2;
+            uint64_t da[3], db[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                da[p] = umma_desc_sw128(a_region + (uint32_t)((p * 2 + kb) * TILE) + off);
+                db[p] = umma_desc_sw128(b_region + (uint32_t)((p * 2 + kb) * TILE) + off);
+            }
+            const uint32_t small_acc = tmem_base + 256;
+            umma_bf16(small_acc, da[1], db[1], idesc, (first_block && k == 0) ? 0u : 1u);
+            umma_bf16(small_acc, da[0], db[2], idesc, 1u);
+            umma_bf16(small_acc, da[2], db[0], idesc, 1u);
+            umma_bf16(small_acc, da[0], db[1], idesc, 1u);
+            umma_bf16(small_acc, da[1], db[0], idesc, 1u);
+            umma_bf16(tmem_base + (uint32_t)kb * 128, da[0], db[0], idesc, k > 0 ? 1u : 0u);
+        }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(qk_full, 2u * (uint32_t)REGION);
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_3d(&tm.qkv[p], qk_full, smem + OFF_R0 + (p * 2 + kb) * TILE, h * 128 + kb * 64, 0, b);
+                    tma_load_3d(&tm.qkv[p], qk_full, smem + OFF_R1 + (p * 2 + kb) * TILE, C + h * 128 + kb * 64, 0, b);
+                }
+            mbar_wait(s_full, 0);       // S is complete: the tensor core no longer reads Q
+            mbar_expect_tx(v_full, (uint32_t)(3 * nkb * TILE));
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                for (int kb = 0; kb < nkb; ++kb)
+                    tma_load_3d(&tm.vt[p], v_full, smem + OFF_R0 + (p * 2 + kb) * TILE, kb * 64, 0, z);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(qk_full, 0);
+            tcgen05_fence_after();
+            mma_block(smem_u32(smem + OFF_R0), smem_u32(smem + OFF_R1), 0, true);      // reduction over the head dimension
+            mma_block(smem_u32(smem + OFF_R0), smem_u32(smem + OFF_R1), 1, false);
+            umma_commit(s_full);
+            mbar_wait(p_full, 0);
+            mbar_wait(v_full, 0);
+            tcgen05_fence_after();
+            for (int kb = 0; kb < nkb; ++kb)                                            // reduction over the keys
+                mma_block(smem_u32(smem + OFF_R1), smem_u32(smem + OFF_R0), kb, kb == 0);
+            umma_commit(o_full);
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;              // query index inside the utterance
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+        mbar_wait(s_full, 0);
+        tcgen05_fence_after();
+        float sv[64];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t r0[16], r1[16], r2[16];
+            tmem_ld_32x16(taddr + c * 16, r0);
+            tmem_ld_32x16(taddr + 128 + c * 16, r1);
+            tmem_ld_32x16(taddr + 256 + c * 16, r2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float v = ((__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j])) * scale;
+                sv[c * 16 + j] = (half * 64 + c * 16 + j < len) ? v : -INFINITY;
+            }
+        }
+        tcgen05_fence_before();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) mx = fmaxf(mx, sv[j]);
+        xch[half * 128 + row] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(mx, xch[(half ^ 1) * 128 + row]);      // len >= 1: at least one half holds a finite value
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            sv[j] = expf(sv[j] - mx);                     // exp(-inf) = 0 for the masked keys
+            sum += sv[j];
+        }
+        xch[256 + half * 128 + row] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float inv = (row < len) ? 1.f / (sum + xch[256 + (half ^ 1) * 128 + row]) : 0.f;   // padded queries: P = 0
+        if (half < nkb) {
+            // probabilities of my 64 keys = one 128-byte row of the [128 x 64] K-major tile of key block `half`, per plane
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float rem[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) rem[e] = sv[c * 8 + e] * inv;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(rem[2 * e], rem[2 * e + 1]);
+                        rem[2 * e] -= __low2float(hh);
+                        rem[2 * e + 1] -= __high2float(hh);
+                        pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(smem + OFF_R1 + (p * 2 + half) * TILE + row * 128 + ((c ^ (row & 7)) * 16)) =
+                        make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+        }
+        fence_proxy_async_smem();      // the tensor core reads P through the async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        mbar_wait(o_full, 0);
+        tcgen05_fence_after();
+        {
+            // (tcgen05.ld is warp-collective: every lane loads, only rows t < T store)
+            const size_t base = ((size_t)b * T + (row < T ? row : 0)) * (size_t)C + (size_t)h * 128 + (size_t)half * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r0[16], r1[16], r2[16];
+                tmem_ld_32x16(taddr + c * 16, r0);
+                tmem_ld_32x16(taddr + 256 + c * 16, r2);
+                if (nkb > 1) tmem_ld_32x16(taddr + 128 + c * 16, r1);      // nkb is CTA-uniform
+                float rem[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float v = __uint_as_float(r0[j]);
+                    if (nkb > 1) v += __uint_as_float(r1[j]);
+                    v += __uint_as_float(r2[j]);
+                    rem[j] = (row < len) ? v : 0.f;          // rows t >= len are zeroed (as the unfused path does)
+                }
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(rem[2 * e], rem[2 * e + 1]);
+                        rem[2 * e] -= __low2float(hh);
+                        rem[2 * e + 1] -= __high2float(hh);
+                        pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    if (row < T) {
+                        uint4* dst = reinterpret_cast<uint4*>(out.p[p] + base + c * 16);
+                        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 template <int NP>
 static void launch_transpose_v(const CPlanes3& qc, int T, int Tp, int C, int H, int DH, int Z, const Planes3& vw,
                                cudaStream_t st) {
@@ -1797,6 +2025,54 @@ extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, con
     void* vt[3] = {vt_hi, vt_lo, nullptr};
     void* op[3] = {out_hi, out_lo, nullptr};
     return attention_split_impl(2, q, lens, B, T, C, H, scale, scores, pp, vt, op, out_f32, (cudaStream_t)stream);
+}
+
+// Fused self-attention for short sequences: T <= 128, head_dim 128, 3 planes (see small_attention_kernel).  vt_planes is a
+// [B*H, 128, Tp] workspace (Tp = T rounded up to 8) that receives V^T.  Replaces the four launches of ctts_attention_split
+// on the encoder (transformer_fs2.py:385-394 at S ~ 100).
+extern "C" int ctts_attention_small(const void* const* qkv_planes, const int64_t* lens, int B, int T, int C, int H, float scale,
+                                    void* const* vt_planes, void* const* out_planes, void* stream) {
+    CTTS_REQUIRE(qkv_planes && lens && vt_planes && out_planes, "attention_small: NULL argument");
+    CTTS_REQUIRE(B > 0 && T > 0 && T <= 128 && H > 0 && C == H * 128, "attention_small: needs T <= 128 and head_dim 128 (T=%d C=%d H=%d)",
+                 T, C, H);
+    const int Tp = (T + 7) & ~7, Z = B * H;
+    cudaStream_t st = (cudaStream_t)stream;
+    CPlanes3 qc{{nullptr, nullptr, nullptr}};
+    Planes3 vw{{nullptr, nullptr, nullptr}}, ow{{nullptr, nullptr, nullptr}};
+    sa::Maps maps;
+    for (int p = 0; p < 3; ++p) {
+        CTTS_REQUIRE(qkv_planes[p] && vt_planes[p] && out_planes[p], "attention_small: NULL plane %d", p);
+        CTTS_REQUIRE((((uintptr_t)qkv_planes[p] | (uintptr_t)vt_planes[p] | (uintptr_t)out_planes[p]) & 15) == 0,
+                     "attention_small: planes must be 16-byte aligned");
+        qc.p[p] = (const __nv_bfloat16*)qkv_planes[p];
+        vw.p[p] = (__nv_bfloat16*)vt_planes[p];
+        ow.p[p] = (__nv_bfloat16*)out_planes[p];
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)3 * C, (cuuint64_t)T, (cuuint64_t)B};
+            cuuint64_t str[2] = {(cuuint64_t)3 * C * 2, (cuuint64_t)T * 3 * C * 2};
+            cuuint32_t box[3] = {64, 128, 1};
+            if (int e = make_map(&maps.qkv[p], qkv_planes[p], 3, dims, str, box, "qkv plane")) return e;
+        }
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)Tp, 128, (cuuint64_t)Z};
+            cuuint64_t str[2] = {(cuuint64_t)Tp * 2, (cuuint64_t)128 * Tp * 2};
+            cuuint32_t box[3] = {64, 128, 1};
+            if (int e = make_map(&maps.vt[p], vt_planes[p], 3, dims, str, box, "V^T plane")) return e;
+        }
+    }
+    launch_transpose_v<3>(qc, T, Tp, C, H, 128, Z, vw, st);
+    if (int e = check_launch("transpose_v")) return e;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sa::SMEM_TOTAL) !=
+            cudaSuccess) {
+            set_error("attention_small: cannot reserve %d bytes of shared memory", sa::SMEM_TOTAL);
+            return 4;
+        }
+        configured = true;
+    }
+    launch_k(small_attention_kernel, dim3(Z), dim3(320), sa::SMEM_TOTAL, st, maps, lens, T, C, H, scale, ow);
+    return check_launch("attention_small");
 }
 
 extern "C" int ctts_transpose_v_planes(int n_planes, const void* const* qkv_planes, int B, int T, int C, int H,

@@ -126,6 +126,7 @@ def attention(qkv, lens, n_head):
 
 FLASH = os.environ.get("CTTS_FLASH_ATTENTION", "1") != "0"
 PARALLEL_BRANCHES = os.environ.get("CTTS_PARALLEL_BRANCHES", "1") != "0"
+SMALL_ATTENTION = os.environ.get("CTTS_SMALL_ATTENTION", "1") != "0"
 _SIDE_STREAMS = {}
 
 
@@ -162,6 +163,13 @@ def attention_tc(qkv_planes, lens, n_head):
     dev = qkv_planes.p[0].device
     Tp = (T + 7) // 8 * 8
     Z = B * n_head
+    if SMALL_ATTENTION and n == 3 and C // n_head == 128 and T <= 128:
+        # short sequences (the encoder at phoneme lengths): one fused kernel per (batch, head) behind the V transpose
+        vt = [torch.empty(B * C * Tp, device=dev, dtype=torch.bfloat16) for _ in range(3)]
+        out = Planes.empty((B, T, C), dev, 3)
+        capi.call("ctts_attention_small", capi.ptr_array(qkv_planes.p), lens, B, T, C, n_head, 1.0 / math.sqrt(C // n_head),
+                  capi.ptr_array(vt), capi.ptr_array(out.p), _stream())
+        return out
     scores = torch.empty(Z * T * Tp, device=dev, dtype=torch.float32)
     pp = [torch.empty(Z * T * Tp, device=dev, dtype=torch.bfloat16) for _ in range(n)]
     vt = [torch.empty(B * C * Tp, device=dev, dtype=torch.bfloat16) for _ in range(n)]

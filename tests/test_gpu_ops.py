@@ -362,6 +362,36 @@ def test_attention_bf16x3(B, T, C, H, n_planes):
     close(got, engine.attention(qkv.to(DEV), lens.to(DEV), H), atol=1e-4, rtol=1e-4)
 
 
+@pytest.mark.parametrize("B,T,H", [(1, 1, 2), (2, 7, 2), (3, 63, 2), (3, 64, 2), (3, 65, 2), (16, 100, 2), (4, 127, 4), (5, 128, 2)])
+def test_attention_small_fused(B, T, H, monkeypatch):
+    """ctts_attention_small (T <= 128, head_dim 128, 3 planes: one CTA per (batch, head)) against fp64 softmax attention and
+    against the four-launch path it replaces; ragged lengths down to 1, padded query rows exactly zero."""
+    C = 128 * H
+    qkv = torch.randn(B, T, 3 * C, generator=g(71)) * 1.5
+    lens = torch.tensor([max(T - 23 * b, 1) for b in range(B)])
+    dh = C // H
+    q, k, v = qkv.double().split(C, -1)
+    q = q.view(B, T, H, dh).transpose(1, 2) / math.sqrt(dh)
+    k = k.view(B, T, H, dh).transpose(1, 2)
+    v = v.view(B, T, H, dh).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    pad = torch.arange(T)[None, :] >= lens[:, None]
+    s = s.masked_fill(pad[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, T, C)
+    ref = (ref * (~pad).double()[:, :, None]).float()
+    planes = engine.split_planes(qkv.to(DEV), 3)
+    launches = capi.LAUNCHES
+    monkeypatch.setattr(engine, "SMALL_ATTENTION", True)
+    out = engine.attention_tc(planes, lens.to(DEV), H).value()
+    assert capi.LAUNCHES - launches == 1, "the fused entry point was not taken"
+    torch.cuda.synchronize()
+    close(out, ref, atol=5e-6, rtol=5e-6)
+    assert bool((out.cpu()[pad] == 0).all())
+    monkeypatch.setattr(engine, "SMALL_ATTENTION", False)
+    unfused = engine.attention_tc(planes, lens.to(DEV), H).value()
+    close(out, unfused, atol=2e-6, rtol=2e-6)
+
+
 @pytest.mark.parametrize("B,T,Cin,N,taps,act", [
     (2, 100, 256, 768, 1, "none"), (3, 100, 256, 1024, 9, "gelu"), (2, 300, 128, 256, 5, "relu"),
     (2, 261, 1024, 256, 1, "none"), (2, 100, 256, 256, 3, "relu"),
