@@ -10,7 +10,7 @@
 // The extra sweep costs 1/9 more MMA work than the minimum and saves the 3 x 82 MB round trips (scores, probability
 // planes) of the materialised version.
 //
-//   warp 0      TMA producer: Q once, K hi tiles (pass A, 4 slots), K + V^T tiles (pass B, 2-stage rings); SWIZZLE_128B
+//   warp 0      TMA producer: Q once, K hi tiles (pass A, 4 slots), K + V tiles (pass B, 2-stage rings); SWIZZLE_128B
 //   warp 1      tcgen05.mma issuer: S (M128 x N64 x K128, 3 plane products) and P V (M128 x N128 x K64)
 //   warps 2-9   softmax / epilogue: TMEM lane = query row, two warps per lane quarter split the columns
 //
@@ -32,7 +32,7 @@ constexpr int BKV = 64;      // keys per tile
 constexpr int DH = 128;      // head dim
 constexpr int Q_TILE = BQ * 64 * 2;       // [128 rows x 64 dims] bf16 = 16 KiB (one plane, one 64-dim k-block)
 constexpr int K_TILE = BKV * 64 * 2;      // [64 keys x 64 dims]  = 8 KiB
-constexpr int V_TILE = DH * BKV * 2;      // [128 dims x 64 keys] = 16 KiB (V^T: keys contiguous)
+constexpr int V_TILE = DH * BKV * 2;      // [64 keys x 128 dims] = 16 KiB: two [64 keys x 64 dims] boxes (MN-major B operand)
 constexpr int P_TILE = BQ * BKV * 2;      // [128 rows x 64 keys] = 16 KiB
 constexpr int Q_BYTES = 4 * Q_TILE;       // 2 planes x 2 k-blocks = 64 KiB
 constexpr int K_STAGE = 4 * K_TILE;       // 32 KiB
@@ -52,7 +52,6 @@ static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 struct Maps {
     CUtensorMap q[2];    // qkv planes [B, T, 3C], box {64, 128, 1}
     CUtensorMap k[2];    // qkv planes,            box {64,  64, 1}
-    CUtensorMap vt[2];   // V^T planes [Z, 128, Tp], box {64, 128, 1}
 };
 
 __host__ __device__ constexpr uint32_t idesc(int n) {
@@ -98,7 +97,6 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
         for (int p = 0; p < 2; ++p) {
             tma_prefetch_desc(&tm.q[p]);
             tma_prefetch_desc(&tm.k[p]);
-            tma_prefetch_desc(&tm.vt[p]);
         }
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) {
@@ -154,7 +152,7 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
                 const int uses = (nkv - a + KA_SLOTS - 1) / KA_SLOTS;
                 mbar_wait(&ka_empty[a], (uses - 1) & 1);
             }
-            // pass B: both planes of the key tiles and the V^T tiles, 2-stage rings
+            // pass B: both planes of the key tiles and the V tiles, 2-stage rings
             for (int j = 0; j < nkv; ++j) {
                 const int s = j & 1;
                 mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
@@ -167,14 +165,19 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
                                     C + h * DH + kb * 64, j * BKV, b);
                 mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&v_full[s], V_STAGE);
+                // V straight from the qkv planes: [64 keys x 128 dims] per plane as two boxes of 64 dims (the MN-major B
+                // operand of P V; no V^T copy in HBM)
 #pragma unroll
                 for (int p = 0; p < 2; ++p)
-                    tma_load_3d(&tm.vt[p], &v_full[s], smem + OFF_V + s * V_STAGE + p * V_TILE, j * BKV, 0, z);
+#pragma unroll
+                    for (int db = 0; db < 2; ++db)
+                        tma_load_3d(&tm.k[p], &v_full[s], smem + OFF_V + s * V_STAGE + p * V_TILE + db * (V_TILE / 2),
+                                    2 * C + h * DH + db * 64, j * BKV, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc_s = idesc(BKV), idesc_o = idesc(DH);
+            constexpr uint32_t idesc_s = idesc(BKV), idesc_o = idesc(DH) | UMMA_IDESC_B_MN_MAJOR;
             const uint32_t q_addr = smem_u32(smem + OFF_Q);
             auto issue_a = [&](int i) {   // pass A: S[i & 1] ~ Q_hi K_hi,j^T  (row maxima only)
                 const int s = i & 1, a = i & (KA_SLOTS - 1);
@@ -233,7 +236,8 @@ flash_attention_kernel(const __grid_constant__ Maps tm, const int64_t* __restric
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t off = k * 32;
                     const uint64_t ph = umma_desc_sw128(p_addr + off), pl = umma_desc_sw128(p_addr + P_TILE + off);
-                    const uint64_t vh = umma_desc_sw128(v_addr + off), vl = umma_desc_sw128(v_addr + V_TILE + off);
+                    const uint64_t vh = umma_desc_sw128_mn(v_addr + k * 2048, V_TILE / 2),
+                                   vl = umma_desc_sw128_mn(v_addr + V_TILE + k * 2048, V_TILE / 2);
                     umma_bf16(d, pl, vh, idesc_o, (j | k) ? 1u : 0u);
                     umma_bf16(d, ph, vl, idesc_o, 1u);
                     umma_bf16(d, ph, vh, idesc_o, 1u);
@@ -396,18 +400,15 @@ extern "C" int ctts_flash_attention_bf16x3(const void* qkv_hi, const void* qkv_l
                                            const int64_t* lens, int B, int T, int C, int H, float scale, void* out_hi,
                                            void* out_lo, void* stream) {
     CTTS_REQUIRE(B > 0 && T > 0 && H > 0 && C == H * fa::DH, "flash_attention: head_dim must be 128 (C=%d, H=%d)", C, H);
-    CTTS_REQUIRE(qkv_hi && qkv_lo && vt_hi && vt_lo && lens && out_hi && out_lo, "flash_attention: NULL argument");
-    const int Tp = (T + 7) & ~7;
+    CTTS_REQUIRE(qkv_hi && qkv_lo && lens && out_hi && out_lo, "flash_attention: NULL argument");
+    (void)vt_hi; (void)vt_lo;     // V is read from the qkv planes (MN-major operand); the V^T planes are no longer used
     const int Z = B * H;
     const cuuint64_t C3 = (cuuint64_t)3 * C;
     fa::Maps maps;
     const void* q[2] = {qkv_hi, qkv_lo};
-    const void* v[2] = {vt_hi, vt_lo};
     for (int p = 0; p < 2; ++p) {
         if (int e = fa::make_map3(&maps.q[p], q[p], C3, (cuuint64_t)T, (cuuint64_t)B, C3, (cuuint64_t)T * C3, 64, fa::BQ)) return e;
         if (int e = fa::make_map3(&maps.k[p], q[p], C3, (cuuint64_t)T, (cuuint64_t)B, C3, (cuuint64_t)T * C3, 64, fa::BKV)) return e;
-        if (int e = fa::make_map3(&maps.vt[p], v[p], (cuuint64_t)Tp, (cuuint64_t)fa::DH, (cuuint64_t)Z, (cuuint64_t)Tp,
-                                  (cuuint64_t)fa::DH * Tp, fa::BKV, fa::DH)) return e;
     }
     static bool configured = false;
     if (!configured) {

@@ -1659,13 +1659,13 @@ transpose_v_wide_kernel(const CPlanes3 q, int T, int Tp, int C, int H, int DH, c
 // The encoder's attention at S ~ 100 was four launches (scores GEMM, V transpose, softmax, P.V GEMM: ~50 us per layer for
 // 0.2 GFLOP, every one of them latency-bound).  Here one CTA owns one (batch, head): Q and K (3 planes, 96 KiB each) arrive by
 // TMA, S = Q K^T lands in TMEM, the softmax warps (TMEM lane = query row, two warps per lane quarter split the keys) write
-// the normalised probabilities as bf16 planes over the K tiles while V^T streams in over the Q tiles, and P V accumulates
-// into the same TMEM columns.  Products and accumulators as in gemm_split_kernel<NP = 3>: the hi*hi products of k-block i go
+// the normalised probabilities as bf16 planes over the K tiles while V streams in over the Q tiles (straight from the qkv
+// planes: [keys][dims] is the MN-major form of the B operand, no V^T copy), and P V accumulates into the same TMEM columns.  Products and accumulators as in gemm_split_kernel<NP = 3>: the hi*hi products of k-block i go
 // to accumulator i, the five small products to a third one; the three are added in FP32 on the way out.
 namespace sa {
 constexpr int TILE = 128 * 64 * 2;        // [128 rows x 64 elements] bf16, SWIZZLE_128B = 16 KiB
 constexpr int REGION = 6 * TILE;          // 3 planes x 2 k-blocks = 96 KiB
-constexpr int OFF_R0 = 0;                 // Q, later V^T
+constexpr int OFF_R0 = 0;                 // Q, later V
 constexpr int OFF_R1 = REGION;            // K, later P
 constexpr int OFF_BAR = 2 * REGION;
 constexpr int OFF_XCH = OFF_BAR + 128;    // [max | sum][2 halves][128 rows] floats
@@ -1673,7 +1673,7 @@ constexpr int SMEM_TOTAL = OFF_XCH + 2 * 2 * 128 * 4 + 1024;
 static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 struct Maps {
     CUtensorMap qkv[3];   // qkv planes [B, T, 3C], box {64, 128, 1}
-    CUtensorMap vt[3];    // V^T planes [Z, 128, Tp], box {64, 128, 1}
+    CUtensorMap v[3];     // the same planes, box {64, 64, 1}: [64 keys x 64 dims] halves of a V tile (MN-major B operand)
 };
 }  // namespace sa
 
@@ -1702,7 +1702,7 @@ small_attention_kernel(const __grid_constant__ sa::Maps tm, const int64_t* __res
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             tma_prefetch_desc(&tm.qkv[p]);
-            tma_prefetch_desc(&tm.vt[p]);
+            tma_prefetch_desc(&tm.v[p]);
         }
         mbar_init(qk_full, 1);
         mbar_init(s_full, 1);
@@ -1722,10 +1722,10 @@ small_attention_kernel(const __grid_constant__ sa::Maps tm, const int64_t* __res
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t idesc = instr_desc<128>();
-
     // one k-block of the 6-product scheme: main accumulator `acc_main` takes hi*hi, `acc_small` the five small products
-    auto mma_block = [&](uint32_t a_region, uint32_t b_region, int kb, bool first_block) {
+    // (b_mn: the B tile is [64 k-rows x 128 n] in two 8 KiB halves of 64 n -- V; otherwise [128 n-rows x 64 k] -- K)
+    auto mma_block = [&](uint32_t a_region, uint32_t b_region, int kb, bool first_block, bool b_mn) {
+        const uint32_t idesc = instr_desc<128>() | (b_mn ? UMMA_IDESC_B_MN_MAJOR : 0u);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint32_t off = k * UMMA_K * 2;
@@ -1733,7 +1733,8 @@ small_attention_kernel(const __grid_constant__ sa::Maps tm, const int64_t* __res
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
                 da[p] = umma_desc_sw128(a_region + (uint32_t)((p * 2 + kb) * TILE) + off);
-                db[p] = umma_desc_sw128(b_region + (uint32_t)((p * 2 + kb) * TILE) + off);
+                db[p] = b_mn ? umma_desc_sw128_mn(b_region + (uint32_t)((p * 2 + kb) * TILE) + k * 2048, TILE / 2)
+                             : umma_desc_sw128(b_region + (uint32_t)((p * 2 + kb) * TILE) + off);
             }
             const uint32_t small_acc = tmem_base + 256;
             umma_bf16(small_acc, da[1], db[1], idesc, (first_block && k == 0) ? 0u : 1u);
@@ -1760,20 +1761,23 @@ small_attention_kernel(const __grid_constant__ sa::Maps tm, const int64_t* __res
 #pragma unroll
             for (int p = 0; p < 3; ++p)
                 for (int kb = 0; kb < nkb; ++kb)
-                    tma_load_3d(&tm.vt[p], v_full, smem + OFF_R0 + (p * 2 + kb) * TILE, kb * 64, 0, z);
+#pragma unroll
+                    for (int db = 0; db < 2; ++db)
+                        tma_load_3d(&tm.v[p], v_full, smem + OFF_R0 + (p * 2 + kb) * TILE + db * (TILE / 2),
+                                    2 * C + h * 128 + db * 64, kb * 64, b);
         }
     } else if (warp == 1) {
         if (lane == 0) {
             mbar_wait(qk_full, 0);
             tcgen05_fence_after();
-            mma_block(smem_u32(smem + OFF_R0), smem_u32(smem + OFF_R1), 0, true);      // reduction over the head dimension
-            mma_block(smem_u32(smem + OFF_R0), smem_u32(smem + OFF_R1), 1, false);
+            mma_block(smem_u32(smem + OFF_R0), smem_u32(smem + OFF_R1), 0, true, false);      // reduction over the head dimension
+            mma_block(smem_u32(smem + OFF_R0), smem_u32(smem + OFF_R1), 1, false, false);
             umma_commit(s_full);
             mbar_wait(p_full, 0);
             mbar_wait(v_full, 0);
             tcgen05_fence_after();
             for (int kb = 0; kb < nkb; ++kb)                                            // reduction over the keys
-                mma_block(smem_u32(smem + OFF_R1), smem_u32(smem + OFF_R0), kb, kb == 0);
+                mma_block(smem_u32(smem + OFF_R1), smem_u32(smem + OFF_R0), kb, kb == 0, true);
             umma_commit(o_full);
         }
     } else {
@@ -2027,41 +2031,27 @@ extern "C" int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, con
     return attention_split_impl(2, q, lens, B, T, C, H, scale, scores, pp, vt, op, out_f32, (cudaStream_t)stream);
 }
 
-// Fused self-attention for short sequences: T <= 128, head_dim 128, 3 planes (see small_attention_kernel).  vt_planes is a
-// [B*H, 128, Tp] workspace (Tp = T rounded up to 8) that receives V^T.  Replaces the four launches of ctts_attention_split
-// on the encoder (transformer_fs2.py:385-394 at S ~ 100).
+// Fused self-attention for short sequences: T <= 128, head_dim 128, 3 planes (see small_attention_kernel): ONE launch.
+// Replaces the four launches of ctts_attention_split on the encoder (transformer_fs2.py:385-394 at S ~ 100).
 extern "C" int ctts_attention_small(const void* const* qkv_planes, const int64_t* lens, int B, int T, int C, int H, float scale,
-                                    void* const* vt_planes, void* const* out_planes, void* stream) {
-    CTTS_REQUIRE(qkv_planes && lens && vt_planes && out_planes, "attention_small: NULL argument");
+                                    void* const* out_planes, void* stream) {
+    CTTS_REQUIRE(qkv_planes && lens && out_planes, "attention_small: NULL argument");
     CTTS_REQUIRE(B > 0 && T > 0 && T <= 128 && H > 0 && C == H * 128, "attention_small: needs T <= 128 and head_dim 128 (T=%d C=%d H=%d)",
                  T, C, H);
-    const int Tp = (T + 7) & ~7, Z = B * H;
+    const int Z = B * H;
     cudaStream_t st = (cudaStream_t)stream;
-    CPlanes3 qc{{nullptr, nullptr, nullptr}};
-    Planes3 vw{{nullptr, nullptr, nullptr}}, ow{{nullptr, nullptr, nullptr}};
+    Planes3 ow{{nullptr, nullptr, nullptr}};
     sa::Maps maps;
     for (int p = 0; p < 3; ++p) {
-        CTTS_REQUIRE(qkv_planes[p] && vt_planes[p] && out_planes[p], "attention_small: NULL plane %d", p);
-        CTTS_REQUIRE((((uintptr_t)qkv_planes[p] | (uintptr_t)vt_planes[p] | (uintptr_t)out_planes[p]) & 15) == 0,
-                     "attention_small: planes must be 16-byte aligned");
-        qc.p[p] = (const __nv_bfloat16*)qkv_planes[p];
-        vw.p[p] = (__nv_bfloat16*)vt_planes[p];
+        CTTS_REQUIRE(qkv_planes[p] && out_planes[p], "attention_small: NULL plane %d", p);
+        CTTS_REQUIRE((((uintptr_t)qkv_planes[p] | (uintptr_t)out_planes[p]) & 15) == 0, "attention_small: planes must be 16-byte aligned");
         ow.p[p] = (__nv_bfloat16*)out_planes[p];
-        {
-            cuuint64_t dims[3] = {(cuuint64_t)3 * C, (cuuint64_t)T, (cuuint64_t)B};
-            cuuint64_t str[2] = {(cuuint64_t)3 * C * 2, (cuuint64_t)T * 3 * C * 2};
-            cuuint32_t box[3] = {64, 128, 1};
-            if (int e = make_map(&maps.qkv[p], qkv_planes[p], 3, dims, str, box, "qkv plane")) return e;
-        }
-        {
-            cuuint64_t dims[3] = {(cuuint64_t)Tp, 128, (cuuint64_t)Z};
-            cuuint64_t str[2] = {(cuuint64_t)Tp * 2, (cuuint64_t)128 * Tp * 2};
-            cuuint32_t box[3] = {64, 128, 1};
-            if (int e = make_map(&maps.vt[p], vt_planes[p], 3, dims, str, box, "V^T plane")) return e;
-        }
+        cuuint64_t dims[3] = {(cuuint64_t)3 * C, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t str[2] = {(cuuint64_t)3 * C * 2, (cuuint64_t)T * 3 * C * 2};
+        cuuint32_t box[3] = {64, 128, 1}, box_v[3] = {64, 64, 1};
+        if (int e = make_map(&maps.qkv[p], qkv_planes[p], 3, dims, str, box, "qkv plane")) return e;
+        if (int e = make_map(&maps.v[p], qkv_planes[p], 3, dims, str, box_v, "qkv plane (V halves)")) return e;
     }
-    launch_transpose_v<3>(qc, T, Tp, C, H, 128, Z, vw, st);
-    if (int e = check_launch("transpose_v")) return e;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sa::SMEM_TOTAL) !=

@@ -75,6 +75,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// MN-major operand (stored [K][MN], MN contiguous -- what a TMA box {64 mn, k rows} with SWIZZLE_128B leaves in shared
+// memory): 8 k-rows x 128 B per swizzle atom (SBO = 1024 B between 8-row groups), `lbo_bytes` between consecutive blocks of 64
+// MN elements; a K = 16 slice advances the start by 2048 B.  The instruction descriptor needs the matching major bit
+// (bit 15 for A, bit 16 for B).  Established with profiles/umma_mn_major_probe.cu.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+constexpr uint32_t UMMA_IDESC_B_MN_MAJOR = 1u << 16;
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t"

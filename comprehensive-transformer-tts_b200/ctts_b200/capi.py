@@ -57,7 +57,7 @@ SIGNATURES = {
     "ctts_split_planes": [_P, _Z, _I, _P, _P],
     "ctts_layernorm_planes": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _I, _P, _P],
     "ctts_attention_split": [_I, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P],
-    "ctts_attention_small": [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P],
+    "ctts_attention_small": [_P, _P, _I, _I, _I, _I, _F, _P, _P],
     "ctts_flash_attention_bf16x3": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P],
     "ctts_transpose_v_planes": [_I, _P, _I, _I, _I, _I, _P, _P],
     "ctts_debug_set_timing_buffer": [_P],

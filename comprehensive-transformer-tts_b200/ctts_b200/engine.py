@@ -143,11 +143,9 @@ def attention_flash(qkv_planes, lens, n_head):
     B, T, C3 = qkv_planes.shape
     C = C3 // 3
     dev = qkv_planes.p[0].device
-    Tp = (T + 7) // 8 * 8
-    vt = [torch.empty(B * C * Tp, device=dev, dtype=torch.bfloat16) for _ in range(2)]
-    capi.call("ctts_transpose_v_planes", 2, capi.ptr_array(qkv_planes.p), B, T, C, n_head, capi.ptr_array(vt), _stream())
     out = Planes.empty((B, T, C), dev, 2)
-    capi.call("ctts_flash_attention_bf16x3", qkv_planes.p[0], qkv_planes.p[1], vt[0], vt[1], lens, B, T, C, n_head,
+    # (the two V^T arguments are vestigial: the kernel reads V from the qkv planes as an MN-major operand)
+    capi.call("ctts_flash_attention_bf16x3", qkv_planes.p[0], qkv_planes.p[1], None, None, lens, B, T, C, n_head,
               1.0 / math.sqrt(C // n_head), out.p[0], out.p[1], _stream())
     return out
 
@@ -164,11 +162,10 @@ def attention_tc(qkv_planes, lens, n_head):
     Tp = (T + 7) // 8 * 8
     Z = B * n_head
     if SMALL_ATTENTION and n == 3 and C // n_head == 128 and T <= 128:
-        # short sequences (the encoder at phoneme lengths): one fused kernel per (batch, head) behind the V transpose
-        vt = [torch.empty(B * C * Tp, device=dev, dtype=torch.bfloat16) for _ in range(3)]
+        # short sequences (the encoder at phoneme lengths): one fused kernel, one CTA per (batch, head)
         out = Planes.empty((B, T, C), dev, 3)
         capi.call("ctts_attention_small", capi.ptr_array(qkv_planes.p), lens, B, T, C, n_head, 1.0 / math.sqrt(C // n_head),
-                  capi.ptr_array(vt), capi.ptr_array(out.p), _stream())
+                  capi.ptr_array(out.p), _stream())
         return out
     scores = torch.empty(Z * T * Tp, device=dev, dtype=torch.float32)
     pp = [torch.empty(Z * T * Tp, device=dev, dtype=torch.bfloat16) for _ in range(n)]

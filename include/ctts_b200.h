@@ -301,17 +301,17 @@ int ctts_attention_split(int n_planes, const void* const* qkv_planes, const int6
                          float* out_f32, void* stream);
 
 /* Fused self-attention for short sequences (T <= 128, head_dim 128, 3 planes = FP32-equivalent): one CTA per (batch, head)
- * keeps Q, K, the scores, the probability planes and V^T on the SM -- two launches (V transpose + attention) instead of the
- * four of ctts_attention_split.  vt_planes: [B*H, 128, Tp] workspace per plane (Tp = T rounded up to 8).  Output planes
- * [B, T, C]; rows t >= lens[b] are zero.  Replaces transformer_fs2.py:385-394 (F.multi_head_attention_forward) on the
- * encoder at LJSpeech phoneme lengths. */
+ * keeps Q, K, the scores and the probability planes on the SM and reads V straight from the qkv planes (MN-major operand)
+ * -- ONE launch instead of the four of ctts_attention_split.  Output planes [B, T, C]; rows t >= lens[b] are zero.
+ * Replaces transformer_fs2.py:385-394 (F.multi_head_attention_forward) on the encoder at LJSpeech phoneme lengths. */
 int ctts_attention_small(const void* const* qkv_planes, const int64_t* lens, int B, int T, int C, int H, float scale,
-                         void* const* vt_planes, void* const* out_planes, void* stream);
+                         void* const* out_planes, void* stream);
 
 /* ---- fused ("flash") tensor-core self-attention, head_dim 128, 2 planes ------------------------------------
  * One CTA per (batch*head, 128 queries): S = Q K^T in TMEM, softmax in registers, probability planes in shared memory,
  * O = P V in TMEM; the keys are swept twice (row statistics, then P V) so nothing is rescaled and no score ever reaches
- * HBM.  vt_* are the V^T planes [B*H, 128, Tp] from ctts_transpose_v_planes.  Output planes [B, T, C]; rows t >= lens[b]
+ * HBM.  V is read from the qkv planes ([keys][dims] = the MN-major form of the B operand); vt_hi / vt_lo are vestigial
+ * (ignored, may be NULL).  Output planes [B, T, C]; rows t >= lens[b]
  * are zero.  Same function as ctts_attention_bf16x3 (transformer_fs2.py:385-394, transformer.py:233-252).
  */
 int ctts_flash_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, const void* vt_hi, const void* vt_lo,

@@ -191,9 +191,8 @@ def ctts_attention_split(n, qkvp, lens, B, T, C, H, scale, scores, pp, vt, outp,
         _v(out_f32, B, T, C).copy_(o)
 
 
-def ctts_attention_small(qkvp, lens, B, T, C, H, scale, vt, outp, stream):
+def ctts_attention_small(qkvp, lens, B, T, C, H, scale, outp, stream):
     assert T <= 128 and C == H * 128
-    ctts_transpose_v_planes(3, qkvp, B, T, C, H, vt, stream)
     _split_into(_attention(_val(qkvp, 3, B, T, 3 * C), lens, B, T, C, H, scale), _planes(outp, 3), B, T, C)
 
 
