@@ -53,6 +53,13 @@ struct Epilogue {
     long long* dbg;         // optional per-CTA cycle stamps {start, setup done, accumulator ready, epilogue done}
     int atomic;             // split-K: y += v with fp32 atomics instead of a store (y only; no planes)
     int tma_out;            // persistent kernels, planes-only output: tiles leave through TMA stores (Maps::o)
+    // LayerNorm fused behind the GEMM (gemm_persistent_kernel<256, 2, 2>; the 256-wide tile holds complete rows): y receives
+    // the GEMM result as usual, yp (and ln_y) receive LayerNorm(y) instead of planes of y.
+    const float* ln_gamma;
+    const float* ln_beta;
+    float ln_eps;
+    int ln_masked;          // zero the LayerNorm output of rows t >= lens[b]
+    float* ln_y;            // optional fp32 copy of the LayerNorm output
 };
 
 struct Maps {               // TMA descriptors of the operand planes (NP of each are used)
@@ -75,6 +82,11 @@ struct Addr {
     // (a weight gradient: k = (utterance, time)); A tile coords (k + a_ks0 + z*a_kstep, t, kbatch), W tile coords
     // (k, n, kbatch).  z then only selects the K shift (the conv tap) and the output offset.
     int kz, a_ks0, a_kstep;
+    // Row-major K-batched mode (mn_cin > 0; ctts_gemm_wgrad_rowmajor): both operands are the ordinary [batch][time][channel]
+    // planes, used as MN-major operands (time = K runs over the rows).  A tile = dz[t-block][n0 .. n0+127], W tile =
+    // x[t-block + tap - mn_pad][c .. c+127] with (tap, c) = divmod(n0, mn_cin): the conv tap is a ROW offset of the TMA box,
+    // rows outside [0, T) are zero fill -- no transposed copies, no per-tap duplicates of x.
+    int mn_cin, mn_pad;
 };
 
 template <int BLOCK_N>
@@ -288,6 +300,21 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                 const int tap = kb / kb_per_tap;
                 const int c0 = (kb - tap * kb_per_tap) * BLOCK_K;
                 uint8_t* st = smem + s * S::STAGE_BYTES;
+                if (ad.mn_cin > 0) {   // row-major K-batched: `tap` is the operand batch, c0 the first time step of the block
+                    const int wt = n0 / ad.mn_cin, wc = n0 - wt * ad.mn_cin;
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) {
+                            tma_load_3d(&tm.a[p], &full_bar[s], st + p * A_TILE_BYTES + hb * (A_TILE_BYTES / 2), t0 + hb * 64, c0, tap);
+                            if (hb * 64 < BLOCK_N)
+                                tma_load_3d(&tm.w[p], &full_bar[s],
+                                            st + NP * A_TILE_BYTES + p * S::B_TILE_BYTES + hb * (64 * BLOCK_K * 2), wc + hb * 64,
+                                            c0 + wt - ad.mn_pad, tap);
+                        }
+                    }
+                    continue;
+                }
                 if (ad.kz > 0) {   // K-batched: `tap` is the operand batch, the K shift comes from z
                     const int ka = c0 + ad.a_ks0 + z * ad.a_kstep;
 #pragma unroll
@@ -326,7 +353,8 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc<BLOCK_N>();
+            const bool mn = ad.mn_cin > 0;       // both operands MN-major (see Addr)
+            const uint32_t idesc = instr_desc<BLOCK_N>() | (mn ? (UMMA_IDESC_A_MN_MAJOR | UMMA_IDESC_B_MN_MAJOR) : 0u);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -340,8 +368,13 @@ gemm_split_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr
                     uint64_t da[NP], db[NP];
 #pragma unroll
                     for (int p = 0; p < NP; ++p) {
-                        da[p] = umma_desc_sw128(a0 + p * A_TILE_BYTES + off);
-                        db[p] = umma_desc_sw128(b0 + p * S::B_TILE_BYTES + off);
+                        if (mn) {     // 16 k-rows of 128 bytes per slice; 64-element blocks of M / N are 8 KiB apart
+                            da[p] = umma_desc_sw128_mn(a0 + p * A_TILE_BYTES + k * 2048, A_TILE_BYTES / 2);
+                            db[p] = umma_desc_sw128_mn(b0 + p * S::B_TILE_BYTES + k * 2048, 64 * BLOCK_K * 2);
+                        } else {
+                            da[p] = umma_desc_sw128(a0 + p * A_TILE_BYTES + off);
+                            db[p] = umma_desc_sw128(b0 + p * S::B_TILE_BYTES + off);
+                        }
                     }
                     const uint32_t first = (kb | k) ? 1u : 0u;
                     if (NP == 2) {  // small terms first
@@ -452,9 +485,10 @@ constexpr int PSTG_LD = 20;   // floats per row of the 32 x 16 transpose tile of
 #else
 #define CTTS_EPI_X1(x)
 #endif
-template <int NP, int ACT>
+template <int NP, int ACT, bool STATS = false>
 __device__ __forceinline__ void store_chunk_rows(const Epilogue& ep, const float* stg, int c4, int rsub, const bool (&valid)[4],
-                                                 const bool (&keep)[4], const size_t (&rowoff)[4], int n, const float4* pre) {
+                                                 const bool (&keep)[4], const size_t (&rowoff)[4], int n,
+                                                 const float4 (&rs)[4], float* s1 = nullptr, float* s2 = nullptr) {
     constexpr int LD = PSTG_LD;
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bb;
     if (ep.bias) bb = *reinterpret_cast<const float4*>(ep.bias + n);
@@ -466,14 +500,9 @@ __device__ __forceinline__ void store_chunk_rows(const Epilogue& ep, const float
     const float alpha = ep.alpha;
     // The four rows of this lane are independent: every phase (loads, arithmetic, stores) runs over all of them before the
     // next one starts, so that the eight epilogue warps of a CTA have four rows' worth of instructions in flight each.
-    float4 rs[4], a4[4];
+    float4 a4[4];     // (rs: the residual values of the four rows, fetched ahead by the caller; zeros without a residual)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pre) rs[i] = pre[i];
-        else if (valid[i] && ep.residual) rs[i] = *reinterpret_cast<const float4*>(ep.residual + rowoff[i] + n);
-        a4[i] = *reinterpret_cast<const float4*>(stg + (rsub + 8 * i) * LD + c4);
-    }
+    for (int i = 0; i < 4; ++i) a4[i] = *reinterpret_cast<const float4*>(stg + (rsub + 8 * i) * LD + c4);
     float v[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -487,6 +516,10 @@ __device__ __forceinline__ void store_chunk_rows(const Epilogue& ep, const float
         for (int j = 0; j < 4; ++j) v[i][j] = act_fn<ACT>(v[i][j]);
         v[i][0] += rs[i].x; v[i][1] += rs[i].y; v[i][2] += rs[i].z; v[i][3] += rs[i].w;
         if (!keep[i]) { v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f; }
+        if (STATS) {      // row sums of the stored values (LayerNorm fused behind this GEMM)
+            s1[i] += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+            s2[i] += (v[i][0] * v[i][0] + v[i][1] * v[i][1]) + (v[i][2] * v[i][2] + v[i][3] * v[i][3]);
+        }
     }
     if (ep.atomic) {
 #pragma unroll
@@ -500,7 +533,7 @@ __device__ __forceinline__ void store_chunk_rows(const Epilogue& ep, const float
         for (int i = 0; i < 4; ++i)
             if (valid[i] CTTS_EPI_X1(v[i][0])) *reinterpret_cast<float4*>(ep.y + rowoff[i] + n) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
     }
-    if (ep.yp[0]) {
+    if (!STATS && ep.yp[0]) {      // (with STATS the planes belong to the LayerNorm output, written in a second pass)
         uint2 pk[NP][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -529,11 +562,12 @@ __device__ __forceinline__ void store_chunk_rows(const Epilogue& ep, const float
 // the tcgen05.ld of chunk u+1 is in flight while chunk u goes through the shared-memory transpose and out to global
 // memory -- with the residual of a 128-wide tile fetched BEFORE the accumulator is waited for.  `arrive` hands the
 // accumulator back as soon as this warp's last TMEM read has completed.
-template <int BLOCK_N, class WaitAcc, class Arrive>
+template <int BLOCK_N, bool LN = false, class WaitAcc, class Arrive>
 __device__ __forceinline__ void persistent_epilogue(const Epilogue& ep, const RowMap& rm, bool tile_valid, int n0, int N, int q,
                                                     int half, int lane, uint32_t d_tmem, float* stg, WaitAcc wait_acc,
                                                     Arrive arrive) {
     constexpr int NP = 2;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     constexpr int CHUNKS = BLOCK_N / 32;       // chunks of this warp (every other 16-column chunk)
     const int c4 = (lane & 3) * 4;
     const int rsub = lane >> 2;
@@ -560,6 +594,18 @@ __device__ __forceinline__ void persistent_epilogue(const Epilogue& ep, const Ro
             }
         }
     }
+    // wide tiles: the residual of chunk k + 1 is fetched while chunk k is processed (one chunk = 4 float4 per lane ahead)
+    const bool pipe_res = !PREFETCH && ep.residual != nullptr;
+    float4 nxt[4];
+    auto fetch_residual = [&](int k) {
+        const int n = n0 + (half + 2 * k) * 16 + c4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[i] && n < N) nxt[i] = *reinterpret_cast<const float4*>(ep.residual + rowoff[i] + n);
+        }
+    };
+    if (pipe_res) fetch_residual(0);
     wait_acc();
     tcgen05_fence_after();
     uint32_t r[16];
@@ -594,14 +640,94 @@ __device__ __forceinline__ void persistent_epilogue(const Epilogue& ep, const Ro
 #if defined(CTTS_EPI_EXPERIMENT) && CTTS_EPI_EXPERIMENT >= 2
         if (stg[lane] != 1.2345e38f) continue;
 #endif
-        const float4* pp = use_pre ? pre[PREFETCH ? k : 0] : nullptr;
-        switch (ep.act) {
-            case CTTS_ACT_RELU: store_chunk_rows<NP, CTTS_ACT_RELU>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
-            case CTTS_ACT_GELU: store_chunk_rows<NP, CTTS_ACT_GELU>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
-            case CTTS_ACT_TANH: store_chunk_rows<NP, CTTS_ACT_TANH>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
-            case CTTS_ACT_SWISH: store_chunk_rows<NP, CTTS_ACT_SWISH>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
-            default: store_chunk_rows<NP, CTTS_ACT_NONE>(ep, stg, c4, rsub, valid, keep, rowoff, n, pp); break;
+        float4 cur[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = use_pre ? pre[PREFETCH ? k : 0][i] : (pipe_res ? nxt[i] : make_float4(0.f, 0.f, 0.f, 0.f));
+        if (pipe_res && !last) fetch_residual(k + 1);       // (in place: this thread has not written those addresses yet)
+        if (LN) {     // (the projections in front of a LayerNorm have no activation)
+            store_chunk_rows<NP, CTTS_ACT_NONE, true>(ep, stg, c4, rsub, valid, keep, rowoff, n, cur, s1, s2);
+            continue;
         }
+        switch (ep.act) {
+            case CTTS_ACT_RELU: store_chunk_rows<NP, CTTS_ACT_RELU>(ep, stg, c4, rsub, valid, keep, rowoff, n, cur); break;
+            case CTTS_ACT_GELU: store_chunk_rows<NP, CTTS_ACT_GELU>(ep, stg, c4, rsub, valid, keep, rowoff, n, cur); break;
+            case CTTS_ACT_TANH: store_chunk_rows<NP, CTTS_ACT_TANH>(ep, stg, c4, rsub, valid, keep, rowoff, n, cur); break;
+            case CTTS_ACT_SWISH: store_chunk_rows<NP, CTTS_ACT_SWISH>(ep, stg, c4, rsub, valid, keep, rowoff, n, cur); break;
+            default: store_chunk_rows<NP, CTTS_ACT_NONE>(ep, stg, c4, rsub, valid, keep, rowoff, n, cur); break;
+        }
+    }
+    if (LN) {
+        // ---- LayerNorm over the rows just written (the tile is N wide: rows are complete) -------------------------------
+        // Row sums: 4 lanes share a row, the two warps of a lane quarter share its columns; the partner's partial sums come
+        // through the unused tail of its staging region ([32 rows][2] floats behind the 32 x PSTG_LD transpose tile).
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 1);
+            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], 1);
+            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 2);
+            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], 2);
+        }
+        // second pass, software-pipelined like the first: the values of chunk k + 1 (written by this very thread) are
+        // re-read while chunk k is normalised
+        float4 x4[4];
+        auto fetch_y = [&](int k) {
+            const int n = n0 + (half + 2 * k) * 16 + c4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (valid[i] && n < N) x4[i] = *reinterpret_cast<const float4*>(ep.y + rowoff[i] + n);
+        };
+        fetch_y(0);
+        float* mine = stg + 32 * PSTG_LD;
+        const float* partner = mine + (half ? -4 : 4) * (PSTG_WARP_BYTES / 4);
+        if ((lane & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                mine[(rsub + 8 * i) * 2] = s1[i];
+                mine[(rsub + 8 * i) * 2 + 1] = s2[i];
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float mean[4], rstd[4];
+        const float inv_n = 1.f / (float)N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float a = s1[i] + partner[(rsub + 8 * i) * 2], b = s2[i] + partner[(rsub + 8 * i) * 2 + 1];
+            mean[i] = a * inv_n;
+            rstd[i] = rsqrtf(fmaxf(b * inv_n - mean[i] * mean[i], 0.f) + ep.ln_eps);
+        }
+#pragma unroll 1
+        for (int k = 0; k < CHUNKS; ++k) {
+            const int n = n0 + (half + 2 * k) * 16 + c4;
+            if (!tile_valid || n >= N) continue;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n));
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + n));
+            float4 c4v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c4v[i] = x4[i];
+            if (k + 1 < CHUNKS) fetch_y(k + 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!valid[i]) continue;
+                float o[4] = {(c4v[i].x - mean[i]) * rstd[i] * g.x + bt.x, (c4v[i].y - mean[i]) * rstd[i] * g.y + bt.y,
+                              (c4v[i].z - mean[i]) * rstd[i] * g.z + bt.z, (c4v[i].w - mean[i]) * rstd[i] * g.w + bt.w};
+                if (ep.ln_masked && !keep[i]) { o[0] = o[1] = o[2] = o[3] = 0.f; }
+                if (ep.ln_y) *reinterpret_cast<float4*>(ep.ln_y + rowoff[i] + n) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(o[0], o[1]);
+                    const __nv_bfloat162 h23 = __floats2bfloat162_rn(o[2], o[3]);
+                    if (p + 1 < NP) {
+                        o[0] -= __low2float(h01); o[1] -= __high2float(h01);
+                        o[2] -= __low2float(h23); o[3] -= __high2float(h23);
+                    }
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    *reinterpret_cast<uint2*>(ep.yp[p] + rowoff[i] + n) = pk;
+                }
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the partial sums may be overwritten by the next tile
     }
 }
 
@@ -735,7 +861,7 @@ struct PSmem {
     static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <int BLOCK_N, int STAGES, bool TMA_OUT>
+template <int BLOCK_N, int STAGES, int MODE>      // MODE 0: generic epilogue, 1: TMA-store planes, 2: fused LayerNorm
 __global__ void __launch_bounds__(320, 1)
 gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
                        int tiles_per_utt, int Z, int seg_rows, int m_tiles, int n_tiles) {
@@ -899,10 +1025,12 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
                     if (ep.dbg && lt == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_first));
                 };
                 auto hand_back = [&] { mbar_arrive(&acc_empty[acc]); };
-                if constexpr (TMA_OUT)
+                if constexpr (MODE == 1)
                     persistent_epilogue_tma_act<BLOCK_N>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem,
                                                          reinterpret_cast<uint8_t*>(stg), (packed ? g0 : t0) + q * 32,
                                                          packed ? 0 : z, store_pending, wait_acc, hand_back);
+                else if constexpr (MODE == 2)
+                    persistent_epilogue<BLOCK_N, true>(ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, wait_acc, hand_back);
                 else
                     persistent_epilogue<BLOCK_N>(ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, wait_acc, hand_back);
                 continue;
@@ -941,7 +1069,7 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
                 }
             }
         }
-        if (TMA_OUT && lane == 0) tma_store_wait_all();     // shared memory stays valid until the stores have read it
+        if (MODE == 1 && lane == 0) tma_store_wait_all();     // shared memory stays valid until the stores have read it
         if (ep.dbg && warp == 2 && lane == 0) {
             unsigned long long t_end;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -1241,7 +1369,7 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
     {
         cuuint64_t dims[3] = {A.d0, A.d1, A.d2};
         cuuint64_t str[2] = {A.s1 * 2, A.s2 * 2};
-        cuuint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)(ad.mn_cin > 0 ? 64 : BLOCK_M), 1};     // MN-major: 64 x 64 boxes
         cuuint32_t box_seg[3] = {BLOCK_K, (cuuint32_t)(seg_rows > 0 ? seg_rows : BLOCK_M), 1};
         for (int p = 0; p < NP; ++p) {
             if (int e = make_map(&maps.a[p], A.p[p], 3, dims, str, box, "activation plane")) return e;
@@ -1256,7 +1384,7 @@ static int launch(const Operand& A, const Operand& W, const Epilogue& ep, const 
     {
         cuuint64_t dims[3] = {W.d0, W.d1, W.d2};
         cuuint64_t str[2] = {W.s1 * 2, W.s2 * 2};
-        cuuint32_t box[3] = {BLOCK_K, BLOCK_N / CM, 1};   // CM = 2: every CTA fetches (and multicasts) half of the tile
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)(ad.mn_cin > 0 ? 64 : BLOCK_N / CM), 1};   // CM = 2: every CTA fetches (and multicasts) half of the tile
         for (int p = 0; p < NP; ++p)
             if (int e = make_map(&maps.w[p], W.p[p], 3, dims, str, box, "weight plane")) return e;
         for (int p = NP; p < 3; ++p) maps.w[p] = maps.w[0];
@@ -1311,7 +1439,7 @@ static int num_sms() {
 static int make_output_maps(Maps& maps, Epilogue& ep, const Addr& ad, int Z, int T, int N, int seg_rows) {
     static const bool enabled = getenv("CTTS_NO_TMA_STORE") == nullptr;
     ep.tma_out = 0;
-    if (!enabled || !PIPELINED_EPILOGUE || !ep.yp[0] || !ep.yp[1] || ep.yp[2] || ep.y || ep.residual || ep.atomic) return 0;
+    if (!enabled || !PIPELINED_EPILOGUE || !ep.yp[0] || !ep.yp[1] || ep.yp[2] || ep.y || ep.residual || ep.atomic || ep.ln_gamma) return 0;
     if (ad.mod != 1 || ad.ldy % 8 != 0 || ad.y_outer % 8 != 0 || N % 8 != 0) return 0;
     if (seg_rows > 0 && ad.y_outer != (long long)T * ad.ldy) return 0;      // packed tiling needs one dense [Z*T, ldy] block
     for (int p = 0; p < 2; ++p)
@@ -1360,13 +1488,25 @@ static int launch_persistent(const Operand& A, const Operand& W, const Epilogue&
     }
     Epilogue ep = ep_in;
     if (int e = make_output_maps(maps, ep, ad, Z, T, N, seg_rows)) return e;
-    auto kern = ep.tma_out ? gemm_persistent_kernel<BLOCK_N, STAGES, true> : gemm_persistent_kernel<BLOCK_N, STAGES, false>;
+    auto kern = ep.tma_out ? gemm_persistent_kernel<BLOCK_N, STAGES, 1> : gemm_persistent_kernel<BLOCK_N, STAGES, 0>;
+    if (ep.ln_gamma) {
+        if constexpr (BLOCK_N == 256) {
+            kern = gemm_persistent_kernel<BLOCK_N, STAGES, 2>;
+        } else {
+            set_error("gemm_persistent: the fused LayerNorm needs the 256-wide tile");
+            return 2;
+        }
+    }
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_persistent_kernel<BLOCK_N, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 S::TOTAL) != cudaSuccess ||
-            cudaFuncSetAttribute(gemm_persistent_kernel<BLOCK_N, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 S::TOTAL) != cudaSuccess) {
+        bool ok = cudaFuncSetAttribute(gemm_persistent_kernel<BLOCK_N, STAGES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       S::TOTAL) == cudaSuccess &&
+                  cudaFuncSetAttribute(gemm_persistent_kernel<BLOCK_N, STAGES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       S::TOTAL) == cudaSuccess;
+        if constexpr (BLOCK_N == 256)
+            ok = ok && cudaFuncSetAttribute(gemm_persistent_kernel<BLOCK_N, STAGES, 2>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) == cudaSuccess;
+        if (!ok) {
             set_error("gemm_persistent: cannot reserve %d bytes of shared memory", S::TOTAL);
             return 4;
         }
@@ -1945,6 +2085,46 @@ extern "C" int ctts_gemm_split(int n_planes, const void* const* x_planes, const 
                            taps, y, y_planes, stream);
 }
 
+// GEMM + residual + LayerNorm in one launch: y = (conv(x) + bias) * alpha + residual (rows t >= lens[b] zeroed, y may alias
+// residual), ln_planes (and ln_y) = LayerNorm(y) * gamma + beta over the N = 256 channels, zeroed for t >= lens[b] when
+// ln_masked.  Two operand planes; the 128 x 256 tile of gemm_persistent_kernel holds complete rows, so the statistics are
+// formed in the epilogue.  Replaces the projection + LayerNorm pairs of an FFT block (transformer_fs2.py:176-200 -- out-proj ->
+// layer_norm2, ffn_2 -> the next block's layer_norm1 / the final layer_norm).
+extern "C" int ctts_gemm_split_ln(const void* const* x_planes, const void* const* w_planes, const float* bias, float alpha,
+                                  const float* residual, const int64_t* lens, int B, int T, int Cin, int N, int taps, float* y,
+                                  const float* ln_gamma, const float* ln_beta, float ln_eps, int ln_masked, float* ln_y,
+                                  void* const* ln_planes, void* stream) {
+    CTTS_REQUIRE(x_planes && w_planes && y && ln_gamma && ln_beta && ln_planes, "gemm_split_ln: NULL argument");
+    CTTS_REQUIRE(N == 256, "gemm_split_ln: N must be 256 (one tile holds a complete row), got %d", N);
+    CTTS_REQUIRE(B > 0 && T > 0 && taps >= 1 && (taps & 1) && Cin % 8 == 0, "gemm_split_ln: bad shape B=%d T=%d Cin=%d taps=%d", B, T,
+                 Cin, taps);
+    CTTS_REQUIRE(PIPELINED_EPILOGUE, "gemm_split_ln: built without the pipelined epilogue");
+    Epilogue ep{bias, nullptr, nullptr, residual, lens, y, {nullptr, nullptr, nullptr}, alpha, CTTS_ACT_NONE, nullptr};
+    ep.ln_gamma = ln_gamma;
+    ep.ln_beta = ln_beta;
+    ep.ln_eps = ln_eps;
+    ep.ln_masked = ln_masked;
+    ep.ln_y = ln_y;
+    const cuuint64_t K = (cuuint64_t)taps * Cin;
+    Operand A{{nullptr, nullptr, nullptr}, (cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)Cin, (cuuint64_t)T * Cin};
+    Operand W{{nullptr, nullptr, nullptr}, K, (cuuint64_t)N, 1, K, K * (cuuint64_t)N};
+    for (int p = 0; p < 2; ++p) {
+        CTTS_REQUIRE(x_planes[p] && w_planes[p] && ln_planes[p], "gemm_split_ln: NULL plane %d", p);
+        CTTS_REQUIRE((((uintptr_t)x_planes[p] | (uintptr_t)w_planes[p] | (uintptr_t)ln_planes[p]) & 15) == 0,
+                     "gemm_split_ln: planes must be 16-byte aligned");
+        A.p[p] = x_planes[p];
+        W.p[p] = w_planes[p];
+        ep.yp[p] = (__nv_bfloat16*)ln_planes[p];
+    }
+    ep.dbg = g_dbg_ptr;
+    Addr ad{1, 1, 0, 0, 0x7fffffff, 0, 0, 1, N, (long long)T * N, 0};
+    // packed row tiling as launch_auto does it for plain GEMMs
+    static const bool use_packed = getenv("CTTS_NO_PACKED") == nullptr;
+    int seg = 0;
+    if (use_packed && B > 1 && T % BLOCK_M != 0) seg = (T % 64 == 0) ? 64 : ((T % 32 == 0) ? 32 : 0);
+    return launch_persistent<256, 2>(A, W, ep, ad, B, T, Cin, N, taps, (cudaStream_t)stream, seg);
+}
+
 extern "C" int ctts_gemm_bf16x3(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                                 const float* bias, float alpha, const float* col_scale, const float* col_shift, int act,
                                 const float* residual, const int64_t* lens, int B, int T, int Cin, int N, int taps,
@@ -2116,6 +2296,45 @@ extern "C" int ctts_gemm_wgrad(int n_planes, const void* const* dzT_planes, cons
     const long long num_kb = (long long)B * ((T + BLOCK_K - 1) / BLOCK_K);
     // (measured: splitting the 144-tile FFN conv gradient in two made it slower, 125 -> 208 us: only grids below one wave)
     long long ksplit = (long long)num_sms() / tiles;
+    if (ksplit > num_kb / 8) ksplit = num_kb / 8;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > 1) {
+        if (!accumulate) cudaMemsetAsync(dw_packed, 0, (size_t)N * KC * sizeof(float), st);
+        ep.residual = nullptr;
+        ep.atomic = 1;
+    }
+    if (n_planes == 3) return launch<128, 2, 3, 1>(A, W, ep, ad, 1, N, T, (int)KC, 1, st, 0, (int)ksplit);
+    return launch<128, 3, 2, 1>(A, W, ep, ad, 1, N, T, (int)KC, 1, st, 0, (int)ksplit);
+}
+
+// Weight gradient straight from the ROW-MAJOR planes (no transposed copies): dz planes [B, T, N], x planes [B, T, Cin],
+//   dw[n, tap*Cin + c] (+)= alpha * sum_{b,t} dz[b, t, n] * x[b, t + tap - taps/2, c]
+// Both operands are MN-major for the tensor core (time = K runs over the rows of the TMA boxes, profiles/umma_mn_major_probe.cu)
+// and the tap is a row offset of the x box, so one set of x planes serves all taps.  Needs Cin % 128 == 0 (an output tile must
+// not straddle two taps) and N % 8 == 0.  Otherwise as ctts_gemm_wgrad.
+extern "C" int ctts_gemm_wgrad_rowmajor(int n_planes, const void* const* dz_planes, const void* const* x_planes, int B, int T,
+                                        int Cin, int N, int taps, float alpha, int accumulate, float* dw_packed, void* stream) {
+    CTTS_REQUIRE(n_planes == 2 || n_planes == 3, "gemm_wgrad_rowmajor: n_planes must be 2 or 3");
+    CTTS_REQUIRE(dz_planes && x_planes && dw_packed, "gemm_wgrad_rowmajor: NULL argument");
+    CTTS_REQUIRE(B > 0 && T > 0 && N > 0 && N % 8 == 0 && Cin > 0 && Cin % 128 == 0 && taps >= 1 && (taps & 1),
+                 "gemm_wgrad_rowmajor: bad shape B=%d T=%d Cin=%d N=%d taps=%d (Cin %% 128 and N %% 8 must be 0)", B, T, Cin, N, taps);
+    const cuuint64_t KC = (cuuint64_t)taps * Cin;
+    // operand views: innermost = channels, rows = time, batches = utterances
+    Operand A{{nullptr, nullptr, nullptr}, (cuuint64_t)N, (cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)N, (cuuint64_t)T * N};
+    Operand W{{nullptr, nullptr, nullptr}, (cuuint64_t)Cin, (cuuint64_t)T, (cuuint64_t)B, (cuuint64_t)Cin, (cuuint64_t)T * Cin};
+    for (int p = 0; p < n_planes; ++p) {
+        CTTS_REQUIRE(dz_planes[p] && x_planes[p], "gemm_wgrad_rowmajor: NULL operand plane %d", p);
+        CTTS_REQUIRE((((uintptr_t)dz_planes[p] | (uintptr_t)x_planes[p]) & 15) == 0, "gemm_wgrad_rowmajor: planes must be 16-byte aligned");
+        A.p[p] = dz_planes[p];
+        W.p[p] = x_planes[p];
+    }
+    Epilogue ep{nullptr, nullptr, nullptr, accumulate ? dw_packed : nullptr, nullptr, dw_packed, {nullptr, nullptr, nullptr},
+                alpha, CTTS_ACT_NONE, nullptr, 0};
+    Addr ad{1, 1, 0, 0, 1, 0, 0, 1, (int)KC, 0, 0, B, 0, 0, Cin, taps / 2};
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long tiles = (long long)((N + 127) / 128) * (long long)((KC + 127) / 128);
+    const long long num_kb = (long long)B * ((T + BLOCK_K - 1) / BLOCK_K);
+    long long ksplit = (long long)num_sms() / tiles;      // split-K only below one wave of tiles (as ctts_gemm_wgrad)
     if (ksplit > num_kb / 8) ksplit = num_kb / 8;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > 1) {

@@ -83,6 +83,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint3
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+constexpr uint32_t UMMA_IDESC_A_MN_MAJOR = 1u << 15;
 constexpr uint32_t UMMA_IDESC_B_MN_MAJOR = 1u << 16;
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(

@@ -238,6 +238,7 @@ act_bwd_planes_kernel(const float* __restrict__ dy, const float* __restrict__ re
         for (int i = 0; i < 16; ++i) t += colsum[i][tid];
         atomicAdd(dbias + n0 + tid, t);
     }
+    if (!ztp.p[0]) return;      // the weight gradient reads the row-major planes (ctts_gemm_wgrad_rowmajor): no transposed copy
     const int lane = tid & 31, warp = tid >> 5;
     const int r = r0 + 2 * lane;
 #pragma unroll
@@ -1275,7 +1276,7 @@ int ctts_act_bwd(const float* dy, const float* ref, int act, float alpha, const 
 
 int ctts_act_bwd_planes(const float* dy, const float* ref, int act, float alpha, const int64_t* lens, int B, int T, int N, int Tp,
                         float* dz, int n_planes, void* const* dz_planes, void* const* dzT_planes, float* dbias, void* stream) {
-    CTTS_REQUIRE(dy && dz_planes && dzT_planes && B > 0 && T > 0 && N > 0 && N % 4 == 0 && Tp >= T && Tp % 2 == 0,
+    CTTS_REQUIRE(dy && dz_planes && B > 0 && T > 0 && N > 0 && N % 4 == 0 && Tp >= T && Tp % 2 == 0,
                  "act_bwd_planes: bad arguments (N=%d must be a multiple of 4)", N);
     CTTS_REQUIRE(act == CTTS_ACT_NONE || ref != nullptr, "act_bwd_planes: activation %d needs its reference tensor", act);
     CTTS_REQUIRE(n_planes == 2 || n_planes == 3, "act_bwd_planes: n_planes");
@@ -1283,9 +1284,9 @@ int ctts_act_bwd_planes(const float* dy, const float* ref, int act, float alpha,
                  "act_bwd_planes: tensors must be 16-byte aligned");
     TPlanes zp{{nullptr, nullptr, nullptr}}, ztp{{nullptr, nullptr, nullptr}};
     for (int p = 0; p < n_planes; ++p) {
-        CTTS_REQUIRE(dz_planes[p] && dzT_planes[p], "act_bwd_planes: NULL plane");
+        CTTS_REQUIRE(dz_planes[p] && (!dzT_planes || dzT_planes[p]), "act_bwd_planes: NULL plane");
         zp.p[p] = (__nv_bfloat16*)dz_planes[p];
-        ztp.p[p] = (__nv_bfloat16*)dzT_planes[p];
+        if (dzT_planes) ztp.p[p] = (__nv_bfloat16*)dzT_planes[p];
     }
     dim3 grid((N + 63) / 64, (Tp + 63) / 64, B);
     cudaStream_t st = (cudaStream_t)stream;

@@ -56,6 +56,7 @@ SIGNATURES = {
     "ctts_gemm_split": [_I, _P, _P, _P, _F, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "ctts_split_planes": [_P, _Z, _I, _P, _P],
     "ctts_layernorm_planes": [_P, _P, _P, _F, _P, _I, _I, _I, _P, _I, _P, _P],
+    "ctts_gemm_split_ln": [_P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P],
     "ctts_attention_split": [_I, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P],
     "ctts_attention_small": [_P, _P, _I, _I, _I, _I, _F, _P, _P],
     "ctts_flash_attention_bf16x3": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P],
@@ -86,6 +87,7 @@ SIGNATURES = {
     "ctts_unpack_conv_wgrad": [_P, _I, _I, _I, _I, _P, _P],
     "ctts_split_transpose": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "ctts_gemm_wgrad": [_I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P],
+    "ctts_gemm_wgrad_rowmajor": [_I, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P, _P],
     "ctts_gemm_batched_planes": [_I, _P, _P, _P, _P, _P, _L, _L, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "ctts_aligner_attention_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
     "ctts_glu_bwd": [_P, _P, _I, _I, _P, _P],

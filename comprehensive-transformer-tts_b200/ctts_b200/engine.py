@@ -100,6 +100,23 @@ def gemm_tc(xp, wp, bias=None, alpha=1.0, bn=None, act=ACT_NONE, residual=None, 
     return y, yp
 
 
+FUSED_LN = os.environ.get("CTTS_FUSED_LN", "1") != "0"
+
+
+def gemm_tc_ln(xp, wp, bias, residual, lens, out, gamma, beta, eps, ln_lens=None, want_fp32=False, taps=1):
+    """Projection + residual + LayerNorm in one launch (ctts_gemm_split_ln; 2 planes, N = 256): `out` receives
+    conv(x) + bias + residual (rows beyond lens zeroed), returns (LayerNorm(out) fp32 or None, LayerNorm(out) planes)."""
+    B, T, Cin = xp.shape
+    N = wp.shape[0]
+    dev = xp.p[0].device
+    ln_y = torch.empty(B, T, N, device=dev, dtype=torch.float32) if want_fp32 else None
+    lp = Planes.empty((B, T, N), dev, 2)
+    assert ln_lens is None or ln_lens is lens
+    capi.call("ctts_gemm_split_ln", capi.ptr_array(xp.p), capi.ptr_array(wp.p), bias, 1.0, residual, lens, B, T, Cin, N, taps,
+              out, gamma, beta, float(eps), 1 if ln_lens is not None else 0, ln_y, capi.ptr_array(lp.p), _stream())
+    return ln_y, lp
+
+
 def layernorm_planes(x, gamma, beta, eps, lens=None, want_fp32=False, n=2):
     """LayerNorm whose result is written as bf16 planes (and optionally fp32)."""
     B, T, C = x.shape
@@ -347,6 +364,24 @@ def _fft_layers_fs2_tc(prep, P, pre, x, lens, n_layers, n_head, kernel, act, n=2
     LayerNorm, softmax and the residual stream stay FP32.  Returns (final LN fp32, final LN planes)."""
     W = prep.w
     tag = "#planes" if n == 2 else "#planes3"
+    if n == 2 and FUSED_LN and x.shape[-1] == 256:
+        # every LayerNorm but the first rides in the epilogue of the projection in front of it: 5 launches per block
+        _, hp = layernorm_planes(x, P[pre + "layers.0.op.layer_norm1.weight"], P[pre + "layers.0.op.layer_norm1.bias"], 1e-12, n=2)
+        for i in range(n_layers):
+            lp = "%slayers.%d.op." % (pre, i)
+            _, qkvp = gemm_tc(hp, W[lp + "self_attn.in_proj_weight" + tag], want_fp32=False, want_planes=True)
+            ap = attention_tc(qkvp, lens, n_head)
+            _, hp = gemm_tc_ln(ap, W[lp + "self_attn.out_proj.weight" + tag], None, x, lens, x, P[lp + "layer_norm2.weight"],
+                               P[lp + "layer_norm2.bias"], 1e-12)
+            _, fp = gemm_tc(hp, W[lp + "ffn.ffn_1.weight" + tag], P[lp + "ffn.ffn_1.bias"], alpha=kernel ** -0.5, act=act,
+                            taps=kernel, want_fp32=False, want_planes=True)
+            if i + 1 < n_layers:
+                nx = "%slayers.%d.op." % (pre, i + 1)
+                _, hp = gemm_tc_ln(fp, W[lp + "ffn.ffn_2.weight" + tag], P[lp + "ffn.ffn_2.bias"], x, lens, x,
+                                   P[nx + "layer_norm1.weight"], P[nx + "layer_norm1.bias"], 1e-12)
+            else:
+                return gemm_tc_ln(fp, W[lp + "ffn.ffn_2.weight" + tag], P[lp + "ffn.ffn_2.bias"], x, lens, x,
+                                  P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"], 1e-5, ln_lens=lens, want_fp32=True)
     for i in range(n_layers):
         lp = "%slayers.%d.op." % (pre, i)
         _, hp = layernorm_planes(x, P[lp + "layer_norm1.weight"], P[lp + "layer_norm1.bias"], 1e-12, n=n)

@@ -298,7 +298,15 @@ def transposed_planes(t, taps=1, n=2):
     return p
 
 
-def _wgrad(ctx, dz, x, wname, taps, dzT=None):
+WGRAD_ROWMAJOR = os.environ.get("CTTS_WGRAD_ROWMAJOR", "1") != "0"
+
+
+def _wgrad_rowmajor_ok(ctx, N, Cin):
+    """ctts_gemm_wgrad_rowmajor: the weight gradient straight from the row-major planes (no transposed copies)."""
+    return WGRAD_ROWMAJOR and ctx.bwd_tc and Cin % 128 == 0 and N % 8 == 0
+
+
+def _wgrad(ctx, dz, x, wname, taps, dzT=None, dzp=None):
     """G[w] += dz^T (*) x : the weight gradient of y = conv(x, w)."""
     G = ctx.G.get(wname)
     if G is None:
@@ -306,6 +314,18 @@ def _wgrad(ctx, dz, x, wname, taps, dzT=None):
     B, T, N = dz.shape
     Cin = x.v.shape[-1]
     st = _st()
+    if _wgrad_rowmajor_ok(ctx, N, Cin):
+        if dzp is None:
+            dzp = engine.split_planes(dz, 2)
+        xp = planes_of(x, 2)
+        if taps == 1:
+            capi.call("ctts_gemm_wgrad_rowmajor", 2, capi.ptr_array(dzp.p), capi.ptr_array(xp.p), B, T, Cin, N, 1, 1.0, 1, G, st)
+        else:
+            tmp = torch.empty(N, taps * Cin, device=dz.device, dtype=torch.float32)
+            capi.call("ctts_gemm_wgrad_rowmajor", 2, capi.ptr_array(dzp.p), capi.ptr_array(xp.p), B, T, Cin, N, taps, 1.0, 0, tmp,
+                      st)
+            capi.call("ctts_unpack_conv_wgrad", tmp, N, Cin, taps, 1, G, st)
+        return
     if ctx.bwd_tc and Cin % 4 == 0:
         Tp = (T + 7) // 8 * 8
         if dzT is None:
@@ -388,16 +408,17 @@ def linear(ctx, x, wname, bname=None, alpha=1.0, act=ACT_NONE, residual=None, le
             # one pass: mask + activation' + alpha + bias gradient + the operand planes of both backward GEMMs
             Tp = (T + 7) // 8 * 8
             dzp = Planes.empty((B, T, N), dz.device, 2)
-            dzT = Planes.empty((B, 1, N, Tp), dz.device, 2)
+            if not _wgrad_rowmajor_ok(ctx, N, Cin):      # (the row-major weight gradient needs no time-major copy)
+                dzT = Planes.empty((B, 1, N, Tp), dz.device, 2)
             capi.call("ctts_act_bwd_planes", dz, ref, int(act), float(alpha), mask, B, T, N, Tp,
-                      dz if residual is not None and not res_done else None, 2, capi.ptr_array(dzp.p), capi.ptr_array(dzT.p),
-                      ctx.G.get(bname) if bname else None, _st())
+                      dz if residual is not None and not res_done else None, 2, capi.ptr_array(dzp.p),
+                      capi.ptr_array(dzT.p) if dzT is not None else None, ctx.G.get(bname) if bname else None, _st())
         elif mask is not None or act != ACT_NONE or alpha != 1.0 or bias is not None:
             capi.call("ctts_act_bwd", dz, ref, int(act), float(alpha), mask, 1, T, B * T, N, dz,
                       ctx.G.get(bname) if bname else None, _st())
         if x.needs_grad:
             _dgrad(ctx, dz, wname, taps, x, dzp)
-        _wgrad(ctx, dz, x, wname, taps, dzT)
+        _wgrad(ctx, dz, x, wname, taps, dzT, dzp)
         if residual is not None and not res_done:
             accumulate_into(residual, dz)
         y.g = None

@@ -290,6 +290,15 @@ int ctts_attention_bf16x3(const void* qkv_hi, const void* qkv_lo, const int64_t*
 int ctts_gemm_split(int n_planes, const void* const* x_planes, const void* const* w_planes, const float* bias, float alpha,
                     const float* col_scale, const float* col_shift, int act, const float* residual, const int64_t* lens,
                     int B, int T, int Cin, int N, int taps, float* y, void* const* y_planes, void* stream);
+/* GEMM + residual + LayerNorm in one launch (2 operand planes, N = 256): y = (conv(x) + bias) * alpha + residual with rows
+ * t >= lens[b] zeroed (y may alias residual); ln_planes (and ln_y, nullable) = LayerNorm(y) * ln_gamma + ln_beta over the 256
+ * channels, zeroed for t >= lens[b] when ln_masked != 0.  Replaces a projection followed by nn.LayerNorm in an FFT block:
+ * transformer_fs2.py:176-200 (self_attn.out_proj -> layer_norm2, ffn.ffn_2 -> the next block's layer_norm1 or the stack's
+ * final layer_norm, :60-66). */
+int ctts_gemm_split_ln(const void* const* x_planes, const void* const* w_planes, const float* bias, float alpha,
+                       const float* residual, const int64_t* lens, int B, int T, int Cin, int N, int taps, float* y,
+                       const float* ln_gamma, const float* ln_beta, float ln_eps, int ln_masked, float* ln_y,
+                       void* const* ln_planes, void* stream);
 int ctts_split_planes(const float* x, size_t n, int n_planes, void* const* planes, void* stream);
 int ctts_layernorm_planes(const float* x, const float* gamma, const float* beta, float eps, const int64_t* lens, int B, int T,
                           int C, float* y, int n_planes, void* const* planes, void* stream);
@@ -440,6 +449,12 @@ int ctts_split_transpose(const float* x, int Z, int R, int C, int ld_in, int c0,
  * transposed planes dzT [B, N, Tp] (ctts_split_transpose, taps 1) and xT [B, taps, Cin, Tp] (ctts_split_transpose, taps) */
 int ctts_gemm_wgrad(int n_planes, const void* const* dzT_planes, const void* const* xT_planes, int B, int T, int Tp,
                     int Cin, int N, int taps, float alpha, int accumulate, float* dw_packed, void* stream);
+
+/* The same weight gradient straight from the ROW-MAJOR planes dz [B, T, N] and x [B, T, Cin] (both MN-major operands of
+ * the tensor core, the tap is a row offset of the x box): no transposed copies, one set of x planes for all taps.  Needs
+ * Cin % 128 == 0 and N % 8 == 0.  Backward of nn.Conv1d / nn.Linear weights (autograd of model/transformers/*.py). */
+int ctts_gemm_wgrad_rowmajor(int n_planes, const void* const* dz_planes, const void* const* x_planes, int B, int T, int Cin,
+                             int N, int taps, float alpha, int accumulate, float* dw_packed, void* stream);
 
 /* batched plane GEMM with explicit operand views (attention backward products); see ctts_gemm_tc.cu */
 int ctts_gemm_batched_planes(int n_planes, const void* const* a_planes, const long long* a_view,

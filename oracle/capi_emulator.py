@@ -144,6 +144,13 @@ def ctts_gemm_split(n, xp, wp, bias, alpha, cs, csh, act, residual, lens, B, T, 
         _split_into(out, _planes(yp, n), B, T, N)
 
 
+def ctts_gemm_split_ln(xp, wp, bias, alpha, residual, lens, B, T, Cin, N, taps, y, g, b, eps, ln_masked, ln_y, ln_planes, stream):
+    out = _conv_core(_val(xp, 2, B, T, Cin), _val(wp, 2, N, taps * Cin), bias, alpha, None, None, 0, residual, lens, B, T, Cin,
+                     N, taps)
+    _v(y, B, T, N).copy_(out)
+    ctts_layernorm_planes(y, g, b, eps, lens if ln_masked else None, B, T, N, ln_y, 2, ln_planes, stream)
+
+
 def ctts_split_planes(x, numel, n, planes, stream):
     _split_into(_v(x, numel), _planes(planes, n), numel)
 
@@ -481,9 +488,10 @@ def ctts_act_bwd_planes(dy, ref, act, alpha, lens, B, T, N, Tp, dz, n, dzp, dztp
     if dz is not None:
         _v(dz, B, T, N).copy_(g)
     _split_into(g, _planes(dzp, n), B, T, N)
-    gt = torch.zeros(B, N, Tp)
-    gt[:, :, :T] = g.transpose(1, 2)
-    _split_into(gt, _planes(dztp, n), B, N, Tp)
+    if dztp is not None:
+        gt = torch.zeros(B, N, Tp)
+        gt[:, :, :T] = g.transpose(1, 2)
+        _split_into(gt, _planes(dztp, n), B, N, Tp)
     if dbias is not None:
         _v(dbias, N).add_(g.reshape(-1, N).sum(0))
 
@@ -677,6 +685,15 @@ def ctts_gemm_wgrad(n, dzT, xT, B, T, Tp, Cin, N, taps, alpha, accumulate, dwp, 
     dz = _val(dzT, n, B, N, Tp)[:, :, :T]
     xs = _val(xT, n, B, taps, Cin, Tp)[:, :, :, :T]
     out = torch.einsum("bnt,bjct->njc", dz, xs)
+    d = _v(dwp, N, taps, Cin)
+    d.copy_((d if accumulate else 0) + alpha * out)
+
+
+def ctts_gemm_wgrad_rowmajor(n, dzp, xp, B, T, Cin, N, taps, alpha, accumulate, dwp, stream):
+    dz, x = _val(dzp, n, B, T, N), _val(xp, n, B, T, Cin)
+    pad = taps // 2
+    xs = torch.stack([F.pad(x, (0, 0, pad, pad))[:, j:j + T] for j in range(taps)], 1)       # [B, taps, T, Cin]
+    out = torch.einsum("btn,bjtc->njc", dz, xs)
     d = _v(dwp, N, taps, Cin)
     d.copy_((d if accumulate else 0) + alpha * out)
 

@@ -362,6 +362,43 @@ def test_attention_bf16x3(B, T, C, H, n_planes):
     close(got, engine.attention(qkv.to(DEV), lens.to(DEV), H), atol=1e-4, rtol=1e-4)
 
 
+@pytest.mark.parametrize("B,T,Cin,masked", [(16, 800, 256, False), (16, 800, 1024, True), (3, 100, 256, True), (2, 333, 1024, False),
+                                            (5, 96, 256, False), (1, 1, 256, True)])
+def test_gemm_residual_layernorm_fused(B, T, Cin, masked):
+    """ctts_gemm_split_ln (projection + residual + LayerNorm in the epilogue of the 128 x 256 tile) against the two launches it
+    replaces and against fp64; the residual stream is updated in place."""
+    N = 256
+    gen = g(81)
+    x = torch.randn(B, T, Cin, generator=gen)
+    w = torch.randn(N, Cin, generator=gen) / math.sqrt(Cin)
+    bias = torch.randn(N, generator=gen)
+    res = torch.randn(B, T, N, generator=gen)
+    gamma, beta = torch.rand(N, generator=gen) + 0.5, torch.randn(N, generator=gen)
+    lens = torch.tensor([max(T - 41 * b, 1) for b in range(B)])
+    keep = (torch.arange(T)[None, :] < lens[:, None])[:, :, None]
+    y64 = (x.double() @ w.double().t() + bias.double() + res.double()) * keep.double()
+    ln64 = F.layer_norm(y64, (N,), gamma.double(), beta.double(), 1e-5)
+    if masked:
+        ln64 = ln64 * keep.double()
+    xp, wp = engine.split_planes(x.to(DEV)), engine.split_planes(w.to(DEV))
+    stream = res.to(DEV).clone()
+    dl = lens.to(DEV)
+    ln_y, ln_p = engine.gemm_tc_ln(xp, wp, bias.to(DEV), stream, dl, stream, gamma.to(DEV), beta.to(DEV), 1e-5,
+                                   ln_lens=dl if masked else None, want_fp32=True)
+    torch.cuda.synchronize()
+    # the two launches it replaces
+    ref_stream = res.to(DEV).clone()
+    engine.gemm_tc(xp, wp, bias.to(DEV), residual=ref_stream, lens=lens.to(DEV), out=ref_stream)
+    ref_y, ref_p = engine.layernorm_planes(ref_stream, gamma.to(DEV), beta.to(DEV), 1e-5, lens.to(DEV) if masked else None,
+                                           want_fp32=True)
+    close(stream, ref_stream, atol=1e-6, rtol=1e-6)
+    close(stream, y64.float(), atol=2e-4, rtol=2e-4)
+    close(ln_y, ref_y, atol=2e-5, rtol=2e-5)
+    close(ln_y, ln64.float(), atol=5e-4, rtol=5e-4)
+    assert (ln_p.value() - ln_y).abs().max().item() < 1e-4 * max(1.0, ln_y.abs().max().item())
+    close(ln_p.value(), ref_p.value(), atol=2e-5, rtol=2e-5)
+
+
 @pytest.mark.parametrize("B,T,H", [(1, 1, 2), (2, 7, 2), (3, 63, 2), (3, 64, 2), (3, 65, 2), (16, 100, 2), (4, 127, 4), (5, 128, 2)])
 def test_attention_small_fused(B, T, H, monkeypatch):
     """ctts_attention_small (T <= 128, head_dim 128, 3 planes: one CTA per (batch, head)) against fp64 softmax attention and

@@ -203,6 +203,23 @@ def test_gemm_wgrad_tensor_core(shape):
         run_both("ctts_gemm_wgrad", [2, PA(dzT), PA(xT), B, T, Tp, Cin, N, taps, 1.0, acc, out], atol=2e-4 * scale, rtol=1e-4)
 
 
+@pytest.mark.parametrize("shape", [(2, 40, 128, 128, 1), (3, 100, 256, 1024, 9), (2, 33, 128, 160, 3), (16, 64, 256, 256, 1),
+                                   (2, 50, 512, 80, 5), (4, 50, 256, 8, 1), (16, 800, 256, 256, 1), (2, 7, 1024, 256, 1)])
+def test_gemm_wgrad_rowmajor(shape):
+    """The weight gradient straight from the row-major planes (both operands MN-major, the tap a row offset of the x box)
+    against the fp64 definition restated by the emulator; both accumulate modes."""
+    B, T, Cin, N, taps = shape
+    dz, x = g(B, T, N), g(B, T, Cin, seed=1)
+    dzp = [torch.zeros(B, T, N, dtype=torch.bfloat16) for _ in range(2)]
+    xp = [torch.zeros(B, T, Cin, dtype=torch.bfloat16) for _ in range(2)]
+    emu.ctts_split_planes(dz, dz.numel(), 2, capi.ptr_array(dzp), 0)
+    emu.ctts_split_planes(x, x.numel(), 2, capi.ptr_array(xp), 0)
+    out = g(N, taps * Cin, seed=2)
+    scale = math.sqrt(B * T)
+    for acc in (0, 1):
+        run_both("ctts_gemm_wgrad_rowmajor", [2, PA(dzp), PA(xp), B, T, Cin, N, taps, 1.0, acc, out], atol=2e-4 * scale, rtol=1e-4)
+
+
 def test_gemm_wgrad_bench_shape_accumulation_error():
     """The FFN conv of the benchmark: K = 16 x 800 rows through ONE TMEM accumulator.  Measures the error against fp64."""
     B, T, Cin, N, taps = 16, 800, 256, 1024, 9
