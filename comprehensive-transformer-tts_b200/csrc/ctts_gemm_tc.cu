@@ -737,11 +737,18 @@ __device__ __forceinline__ void persistent_epilogue(const Epilogue& ep, const Ro
 // bias / scale / activation -> bf16 hi / lo -> two 16-byte shared-memory stores per plane into a [32 rows x 32 columns]
 // SWIZZLE_64B staging tile (conflict-free: the XOR spreads 8 consecutive rows over all banks), and one lane hands the
 // tile to the TMA unit, which also clips rows / columns beyond the tensor.  ~8 instructions per element.
+// stream-K workspace: one CTA's partial accumulator [128 rows x 256 columns] fp32 in TMEM-read order -- 16-column chunk u of
+// lane quarter q: 32 lanes x 16 floats, so every warp-level access is one contiguous 2 KiB block
+__device__ __forceinline__ size_t sk_chunk_offset(int u, int q, int lane) { return ((size_t)(u * 4 + q) * 32 + lane) * 16; }
+constexpr int SK_MAX_PARTS = 3;                    // contributors per tile besides the finishing pair
+constexpr size_t SK_CTA_FLOATS = 128 * 256;        // one CTA's half of a pair tile
+
 template <int BLOCK_N, int ACT, class WaitAcc, class Arrive>
 __device__ __forceinline__ void persistent_epilogue_tma(const Maps& tm, const Epilogue& ep, const RowMap& rm, bool tile_valid,
                                                         int n0, int N, int q, int half, int lane, uint32_t d_tmem,
                                                         uint8_t* stg, int row_coord, int z_coord, bool& store_pending,
-                                                        WaitAcc wait_acc, Arrive arrive) {
+                                                        WaitAcc wait_acc, Arrive arrive, const float* sk_part = nullptr,
+                                                        int sk_parts = 0, size_t sk_stride = 0) {
     constexpr int CHUNKS = BLOCK_N / 32;       // 16-column chunks of this warp: groups (half + 2 g) of two chunks each
     bool keep = false;
     size_t off = 0;
@@ -764,6 +771,19 @@ __device__ __forceinline__ void persistent_epilogue_tma(const Maps& tm, const Ep
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) arrive();
+        }
+        if (sk_parts > 0 && !beyond) {   // stream-K: the other pairs' partial accumulators of this tile, in a fixed order
+            for (int p = 0; p < sk_parts; ++p) {
+                const float4* src = reinterpret_cast<const float4*>(sk_part + (size_t)p * sk_stride + sk_chunk_offset(u, q, lane));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t = __ldcg(src + j);
+                    r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + t.x);
+                    r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + t.y);
+                    r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + t.z);
+                    r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + t.w);
+                }
+            }
         }
         if ((k & 1) == 0 && store_pending) {      // a new group: the TMA unit must have read the previous one
             if (lane == 0) tma_store_wait_read();
@@ -826,27 +846,28 @@ template <int BLOCK_N, class WaitAcc, class Arrive>
 __device__ __forceinline__ void persistent_epilogue_tma_act(const Maps& tm, const Epilogue& ep, const RowMap& rm, bool tile_valid,
                                                             int n0, int N, int q, int half, int lane, uint32_t d_tmem,
                                                             uint8_t* stg, int row_coord, int z_coord, bool& store_pending,
-                                                            WaitAcc wait_acc, Arrive arrive) {
+                                                            WaitAcc wait_acc, Arrive arrive, const float* sk_part = nullptr,
+                                                            int sk_parts = 0, size_t sk_stride = 0) {
     switch (ep.act) {
         case CTTS_ACT_RELU:
             persistent_epilogue_tma<BLOCK_N, CTTS_ACT_RELU>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
-                                                            z_coord, store_pending, wait_acc, arrive);
+                                                            z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
         case CTTS_ACT_GELU:
             persistent_epilogue_tma<BLOCK_N, CTTS_ACT_GELU>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
-                                                            z_coord, store_pending, wait_acc, arrive);
+                                                            z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
         case CTTS_ACT_TANH:
             persistent_epilogue_tma<BLOCK_N, CTTS_ACT_TANH>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
-                                                            z_coord, store_pending, wait_acc, arrive);
+                                                            z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
         case CTTS_ACT_SWISH:
             persistent_epilogue_tma<BLOCK_N, CTTS_ACT_SWISH>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
-                                                             z_coord, store_pending, wait_acc, arrive);
+                                                             z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
         default:
             persistent_epilogue_tma<BLOCK_N, CTTS_ACT_NONE>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
-                                                            z_coord, store_pending, wait_acc, arrive);
+                                                            z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
     }
 }
@@ -1095,6 +1116,12 @@ gemm_persistent_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const
 // (64 KiB -> 3 stages).  Rank 0 (leader) issues all MMAs; both CTAs' TMA loads complete on the leader's full barrier;
 // tcgen05.commit is multicast to both CTAs' empty / accumulator-full barriers; the epilogue warps of both CTAs hand the
 // accumulator back with a (remote) arrive on the leader's accumulator-empty barrier.
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <int STAGES>
 struct PairSmem {
     static constexpr int BLOCK_N = 256;
@@ -1109,7 +1136,8 @@ struct PairSmem {
 template <int STAGES, bool TMA_OUT>
 __global__ void __launch_bounds__(320, 1)
 gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
-                 int tiles_per_utt, int Z, int seg_rows, int m_tiles, int n_tiles, int swap_b) {
+                 int tiles_per_utt, int Z, int seg_rows, int m_tiles, int n_tiles, int swap_b, float* sk_ws,
+                 unsigned int* sk_ctr) {
     using S = PairSmem<STAGES>;
     constexpr int NP = 2;
     constexpr int BLOCK_N = 256;
@@ -1179,15 +1207,68 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
         }
     };
 
+    // ---- work items of this pair ----------------------------------------------------------------------------------------
+    // Whole tiles pair, pair + n_pairs, ...  With stream-K (sk_ws != nullptr; TMA_OUT only) the LAST, partial round is not
+    // handed out tile by tile (52 tiles on 74 pairs leave 22 pairs idle for a whole tile time) but as k-blocks: the
+    // tail_tiles * num_kb blocks are cut into n_pairs equal ranges.  A range touches at most two tiles: the END of one (this
+    // pair finishes that tile: it adds the other pairs' partial accumulators, in a fixed order, and runs the epilogue) and
+    // the BEGINNING of the next (this pair contributes its partial accumulator through the workspace).  The contribution is
+    // processed FIRST, so nobody waits for work that is queued behind a wait.
+    struct Item { int pt, kb0, kb1, part, parts; };      // part >= 0: contributor slot; parts: contributors to add when finishing
+    const bool streamk = TMA_OUT && sk_ws != nullptr;
+    const int full_rounds = streamk ? pair_tiles / n_pairs : (pair_tiles + n_pairs - 1) / n_pairs;
+    const int tail_tiles = streamk ? pair_tiles - full_rounds * n_pairs : 0;
+    const long long sk_units = (long long)tail_tiles * num_kb;
+    auto pair_of_unit = [&](long long x) { return (int)(((x + 1) * n_pairs - 1) / sk_units); };
+    // this pair's share of the tail: [u0, u1) k-blocks -> a contribution (beginning of a tile) and / or a finishing piece
+    int c_tile = -1, c_kb1 = 0, c_kb0 = 0, f_tile = -1, f_kb0 = 0;
+    if (tail_tiles > 0) {
+        const long long u0 = (long long)pair * sk_units / n_pairs, u1 = (long long)(pair + 1) * sk_units / n_pairs;
+        if (u0 < u1) {
+            const int ta = (int)(u0 / num_kb), tb = (int)((u1 - 1) / num_kb);
+            const int a0 = (int)(u0 - (long long)ta * num_kb), b1 = (int)(u1 - (long long)tb * num_kb);
+            if (ta != tb) { f_tile = ta; f_kb0 = a0; c_tile = tb; c_kb0 = 0; c_kb1 = b1; }
+            else if (b1 == num_kb) { f_tile = ta; f_kb0 = a0; }
+            else { c_tile = ta; c_kb0 = a0; c_kb1 = b1; }
+        }
+    }
+    // Order: whole tiles, then the CONTRIBUTION, then the last whole tile, then the finishing piece -- a partial accumulator
+    // is in the workspace a whole tile time before the pair that finishes its tile asks for it (measured with the per-item
+    // stamps of profiles/gemm_pair_timing.py: contributing last put the 8 us workspace write and the wait on the critical path).
+    auto get_item = [&](int i, Item& it) -> bool {
+        if (!streamk) {
+            it = Item{pair + i * n_pairs, 0, num_kb, -1, 0};
+            return it.pt < pair_tiles;
+        }
+        const int has_c = c_tile >= 0 ? 1 : 0;
+        if (i < full_rounds - 1) { it = Item{pair + i * n_pairs, 0, num_kb, -1, 0}; return true; }
+        int j = i - (full_rounds - 1);
+        if (has_c) {
+            if (j == 0) {
+                it = Item{full_rounds * n_pairs + c_tile, c_kb0, c_kb1, pair - pair_of_unit((long long)c_tile * num_kb), 0};
+                return true;
+            }
+            --j;
+        }
+        if (j == 0) { it = Item{pair + (full_rounds - 1) * n_pairs, 0, num_kb, -1, 0}; return true; }
+        if (j == 1 && f_tile >= 0) {
+            it = Item{full_rounds * n_pairs + f_tile, f_kb0, num_kb, -1, pair - pair_of_unit((long long)f_tile * num_kb)};
+            return true;
+        }
+        return false;
+    };
+
     if (warp == 0) {
         if (lane == 0) {
             const int b_rows0 = (int)(swap_b ? (rank ^ 1u) : rank) * (BLOCK_N / 2);
             uint32_t it = 0;
-            for (int pt = pair; pt < pair_tiles; pt += n_pairs) {
+            Item wi;
+            for (int ii = 0; get_item(ii, wi); ++ii) {
+                const int pt = wi.pt;
                 int mt, z, t0, n0; bool straddle;
                 tile_coords(pt, mt, z, t0, n0, straddle);
                 const int zh = z % ad.mod;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -1222,12 +1303,15 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                                        ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
             uint32_t it = 0, lt = 0;
-            for (int pt = pair; pt < pair_tiles; pt += n_pairs, ++lt) {
+            Item wi;
+            for (int ii = 0; get_item(ii, wi); ++ii, ++lt) {
                 const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+                if (ep.dbg && ii < 8) ep.dbg[(size_t)blockIdx.x * 64 + 32 + ii * 3] = (long long)gtimer();
                 mbar_wait_cluster(&acc_empty[acc], aph ^ 1u);   // both CTAs' epilogues have drained this accumulator
                 tcgen05_fence_after();
+                if (ep.dbg && ii < 8) ep.dbg[(size_t)blockIdx.x * 64 + 32 + ii * 3 + 1] = (long long)gtimer();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                for (int kb = wi.kb0; kb < wi.kb1; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(&full_bar[s], ph);
@@ -1239,13 +1323,14 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
                         const uint32_t off = k * UMMA_K * 2;
                         const uint64_t dah = umma_desc_sw128(a0 + off), dal = umma_desc_sw128(a0 + A_TILE_BYTES + off);
                         const uint64_t dbh = umma_desc_sw128(b0 + off), dbl = umma_desc_sw128(b0 + S::B_HALF_BYTES + off);
-                        umma_bf16_pair(d_tmem, dal, dbh, idesc, (kb | k) ? 1u : 0u);  // small terms first
+                        umma_bf16_pair(d_tmem, dal, dbh, idesc, (kb > wi.kb0 || k) ? 1u : 0u);  // small terms first
                         umma_bf16_pair(d_tmem, dah, dbl, idesc, 1u);
                         umma_bf16_pair(d_tmem, dah, dbh, idesc, 1u);
                     }
                     umma_commit_pair(&empty_bar[s]);
                 }
                 umma_commit_pair(&acc_full[acc]);
+                if (ep.dbg && ii < 8) ep.dbg[(size_t)blockIdx.x * 64 + 32 + ii * 3 + 2] = (long long)gtimer();
             }
         }
     } else {
@@ -1258,11 +1343,56 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
                                               mapa_shared(smem_u32(&acc_empty[1]), 0)};
         uint32_t lt = 0;
         bool store_pending = false;
-        for (int pt = pair; pt < pair_tiles; pt += n_pairs, ++lt) {
+        Item wi;
+        for (int ii = 0; get_item(ii, wi); ++ii, ++lt) {
+            const int pt = wi.pt;
             int mt, z, t0, n0; bool straddle;
             tile_coords(pt, mt, z, t0, n0, straddle);
             const int zh = z % ad.mod;
             const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+            const int sk_tile = pt - full_rounds * n_pairs;      // index into the stream-K workspace (tail tiles only)
+            long long* stamp = (ep.dbg && warp == 2 && lane == 0 && ii < 8) ? ep.dbg + (size_t)blockIdx.x * 64 + ii * 4 : nullptr;
+            if (stamp) { stamp[0] = (long long)gtimer(); stamp[1] = (long long)wi.kb0 | ((long long)wi.kb1 << 16) | ((long long)(wi.part + 1) << 32) | ((long long)wi.parts << 40); }
+            if (wi.part >= 0) {
+                // ---- contributor: the raw partial accumulator goes to the workspace, then one arrival per warp ----------
+                float* dst = sk_ws + (((size_t)sk_tile * SK_MAX_PARTS + wi.part) * 2 + rank) * SK_CTA_FLOATS;
+                mbar_wait(&acc_full[acc], aph);
+                tcgen05_fence_after();
+#pragma unroll 1
+                for (int u = half; u < BLOCK_N / 16; u += 2) {
+                    uint32_t r[16];
+                    tmem_ld_32x16(tmem_base + acc * BLOCK_N + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 16), r);
+                    float4* o = reinterpret_cast<float4*>(dst + sk_chunk_offset(u, q, lane));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        __stcg(o + j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+                }
+                tcgen05_fence_before();
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_cluster(acc_empty_leader[acc]);
+                    atomicAdd(sk_ctr + 2 * sk_tile, 1u);
+                }
+                if (stamp) stamp[3] = (long long)gtimer();
+                continue;
+            }
+            if (wi.parts > 0) {
+                // ---- finishing pair: wait until every contributor warp (16 per contributing pair) has arrived ----------
+                const unsigned int want = 16u * (unsigned int)wi.parts;
+                if (lane == 0) {
+                    const volatile unsigned int* c = sk_ctr + 2 * sk_tile;
+                    unsigned long long spins = 0;
+                    while (*c < want) {
+                        __nanosleep(64);
+                        if (++spins > (1ull << 26)) __trap();      // (seconds: a protocol error must not hang the device)
+                    }
+                    __threadfence();
+                }
+                __syncwarp();
+            }
+            if (stamp) stamp[2] = (long long)gtimer();
             const bool tile_valid = z < Z && mt < m_tiles;
             const int len = (ep.lens && tile_valid) ? (int)ep.lens[z / ad.lens_div] : T;
             const size_t tilebase = (size_t)(z / ad.mod) * (size_t)ad.y_outer + (size_t)zh * (size_t)ad.y_inner;
@@ -1272,12 +1402,24 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
             if (PIPELINED_EPILOGUE) {
                 auto wait_acc = [&] { mbar_wait(&acc_full[acc], aph); };
                 auto hand_back = [&] { mbar_arrive_cluster(acc_empty_leader[acc]); };
-                if constexpr (TMA_OUT)
+                if constexpr (TMA_OUT) {
+                    const float* sk_part = wi.parts > 0
+                        ? sk_ws + (((size_t)sk_tile * SK_MAX_PARTS) * 2 + rank) * SK_CTA_FLOATS : nullptr;
                     persistent_epilogue_tma_act<BLOCK_N>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem,
                                                          reinterpret_cast<uint8_t*>(stg), (packed ? g0 : t0) + q * 32,
-                                                         packed ? 0 : z, store_pending, wait_acc, hand_back);
-                else
+                                                         packed ? 0 : z, store_pending, wait_acc, hand_back, sk_part, wi.parts,
+                                                         2 * SK_CTA_FLOATS);
+                    if (wi.parts > 0) {      // the 16th finishing warp re-arms the tile's counters for the next launch
+                        __syncwarp();
+                        if (lane == 0 && atomicAdd(sk_ctr + 2 * sk_tile + 1, 1u) == 15u) {
+                            sk_ctr[2 * sk_tile] = 0u;
+                            sk_ctr[2 * sk_tile + 1] = 0u;
+                        }
+                    }
+                } else {
                     persistent_epilogue<BLOCK_N>(ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, wait_acc, hand_back);
+                }
+                if (stamp) stamp[3] = (long long)gtimer();
                 continue;
             }
             mbar_wait(&acc_full[acc], aph);
@@ -1594,10 +1736,60 @@ static int launch_pair(const Operand& A, const Operand& W, const Epilogue& ep_in
         if (getenv("CTTS_PAIR_VERBOSE")) fprintf(stderr, "[ctts] gemm_pair: %d co-resident CTA pairs (occupancy query: %d)\n", max_pairs, n);
     }
     const int pairs = (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+    // Stream-K over the last, partial round (see the work items of gemm_pair_kernel): only for the TMA-store epilogue, only
+    // when the tail leaves a worthwhile share of the pairs idle and no tile would need more than SK_MAX_PARTS contributors.
+    // Two workspaces are used alternately so that consecutive launches never share one; launches on DIFFERENT streams that
+    // run at the same time are not supported (the library is one stream of work per device).
+    // OPT-IN (CTTS_STREAMK=1): parity-green, but measured SLOWER than three whole rounds at the decoder FFN conv (127 - 133 us
+    // against 119 - 125 us per launch; K = 1024 linear 80 against 66 us): the per-item stamps (profiles/gemm_pair_timing.py)
+    // show the median pair finishing 4 us earlier and the LAST pair 2 us later -- the finishing epilogue, which re-reads one
+    // or two 128 KiB partial accumulators per CTA chunk by chunk behind each TMEM read, is about twice as long as a plain
+    // one, and it is exposed on every pair at once.  See profiles/r02_streamk_experiment.md.
+    static const bool sk_enabled = getenv("CTTS_STREAMK") != nullptr && atoi(getenv("CTTS_STREAMK")) != 0;
+    static float* sk_ws[2] = {nullptr, nullptr};
+    static unsigned int* sk_ctr[2] = {nullptr, nullptr};
+    static bool sk_failed = false;
+    static unsigned int sk_launch = 0;
+    float* ws = nullptr;
+    unsigned int* ctr = nullptr;
+    const long long num_kb_ll = (long long)taps * ((Cin + BLOCK_K - 1) / BLOCK_K);
+    const int tail = (int)(pair_tiles % pairs);
+    if (sk_enabled && ep.tma_out && !sk_failed && pair_tiles > pairs && tail > 0 && 10 * tail <= 9 * pairs && num_kb_ll >= 8) {
+        const long long units = (long long)tail * num_kb_ll;
+        int max_parts = 0;
+        for (int t = 0; t < tail; ++t) {
+            const int first = (int)((((long long)t * num_kb_ll + 1) * pairs - 1) / units);
+            const int last = (int)((((long long)(t + 1) * num_kb_ll) * pairs - 1) / units);
+            if (last - first > max_parts) max_parts = last - first;
+        }
+        if (max_parts <= SK_MAX_PARTS) {
+            if (!sk_ws[0]) {
+                cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+                cudaStreamIsCapturing(st, &cs);
+                if (cs == cudaStreamCaptureStatusNone) {
+                    const size_t bytes = (size_t)max_pairs * SK_MAX_PARTS * 2 * SK_CTA_FLOATS * sizeof(float);
+                    for (int i = 0; i < 2 && !sk_failed; ++i) {
+                        if (cudaMalloc(&sk_ws[i], bytes) != cudaSuccess ||
+                            cudaMalloc(&sk_ctr[i], (size_t)max_pairs * 2 * sizeof(unsigned int)) != cudaSuccess ||
+                            cudaMemset(sk_ctr[i], 0, (size_t)max_pairs * 2 * sizeof(unsigned int)) != cudaSuccess) {
+                            cudaGetLastError();
+                            sk_failed = true;
+                        }
+                    }
+                    if (sk_failed) sk_ws[0] = nullptr;
+                }
+            }
+            if (sk_ws[0] && !sk_failed) {
+                ws = sk_ws[sk_launch & 1u];
+                ctr = sk_ctr[sk_launch & 1u];
+                ++sk_launch;
+            }
+        }
+    }
     cfg.gridDim = dim3(2 * pairs, 1, 1);
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t err = cudaLaunchKernelEx(&cfg, kern, maps, ep, ad, T, Cin, N, taps, tiles_per_utt, Z, seg_rows, m_tiles,
-                                         n_tiles, swap_b);
+                                         n_tiles, swap_b, ws, ctr);
     if (err != cudaSuccess) {
         set_error("gemm_pair launch: %s", cudaGetErrorString(err));
         return 1;
