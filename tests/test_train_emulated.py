@@ -69,3 +69,64 @@ def test_inference_engine_host_logic(name, golden_dir, monkeypatch):
     assert np.array_equal(gold["ref.mel_lens"], flat["mel_lens"])
     if name.startswith("conformer"):
         assert "ctts_relshift_softmax_planes" in emu.CALLS and "ctts_gemm_batched_planes" in emu.CALLS
+
+
+def test_engine_takes_the_fused_entry_points(monkeypatch):
+    """fs2 inference: the decoder's projections carry their LayerNorm (ctts_gemm_split_ln), the encoder's attention is the
+    fused short-sequence kernel, no V^T transpose is launched, and the weight gradient of the training step reads the
+    row-major planes (ctts_gemm_wgrad_rowmajor) wherever Cin % 128 == 0."""
+    emu.install(monkeypatch)
+    import ctts_b200
+    (p, m, t), sd, batch = cases.build_case("fs2_infer_c1")
+    net = ctts_b200.CompTransTTS(p, m, t).eval()
+    net.load_state_dict(sd, strict=True)
+    args, kw = cases.call_kwargs(batch)
+    del emu.CALLS[:]
+    net(*args, **kw)
+    used = list(emu.CALLS)
+    n_layers = m["transformer_fs2"]["decoder_layer"]
+    assert used.count("ctts_gemm_split_ln") == 2 * n_layers
+    assert used.count("ctts_attention_small") == m["transformer_fs2"]["encoder_layer"]
+    assert "ctts_transpose_v_planes" not in used and "ctts_attention_split" not in used
+    monkeypatch.setenv("CTTS_DROPOUT", "0")
+    del emu.CALLS[:]
+    train_checks.run_training_case("fs2_train", torch.device("cpu"))
+    used = set(emu.CALLS)
+    assert "ctts_gemm_wgrad_rowmajor" in used and "ctts_gemm_wgrad" in used      # (the 80-channel mel convs keep the transposed path)
+
+
+def test_parameter_table_follows_the_module(monkeypatch):
+    """engine.Prepared keeps the name -> tensor table between calls (the tree walk costs 0.25 ms); it must notice every way
+    the module can change under it: in-place updates (version counters), .to() / assigned state dicts (storages), and a
+    Parameter object being replaced (structure epoch)."""
+    emu.install(monkeypatch)
+    import ctts_b200
+    from ctts_b200.module import _Tracked
+    (p, m, t), sd, batch = cases.build_case("fs2_infer_c1")
+    net = ctts_b200.CompTransTTS(p, m, t).eval()
+    net.load_state_dict(sd, strict=True)
+    net.use_cuda_graphs = False          # (repeated calls: a second sighting of a shape would be captured into a CUDA graph)
+    args, kw = cases.call_kwargs(batch)
+    base = net(*args, **kw)[1].clone()
+    prep = net._prepared
+    sig = prep.sig
+    assert torch.equal(net(*args, **kw)[1], base) and prep.sig is sig, "an unchanged module must not be re-laid-out"
+    # in-place update (an optimizer step)
+    with torch.no_grad():
+        net.get_parameter("mel_linear.bias").add_(1.0)
+    out = net(*args, **kw)[1]
+    assert prep.sig is not sig and not torch.allclose(out, base)
+    # a Parameter object replaced: the cached table would still point at the old tensor
+    sig, epoch = prep.sig, _Tracked.structure_epoch
+    node = net.get_submodule("mel_linear")
+    node.bias = torch.nn.Parameter(node.bias.detach() - 1.0)
+    assert _Tracked.structure_epoch > epoch
+    out = net(*args, **kw)[1]
+    assert prep.sig is not sig
+    np.testing.assert_allclose(out.numpy(), base.numpy(), atol=1e-5, rtol=1e-5)
+    # load_state_dict(assign=True) swaps the Parameter objects as well
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["mel_linear.bias"] = sd2["mel_linear.bias"] + 2.0
+    net.load_state_dict(sd2, strict=True, assign=True)
+    out = net(*args, **kw)[1]
+    assert not torch.allclose(out, base)
