@@ -743,10 +743,29 @@ __global__ void add_row_broadcast_kernel(const float* __restrict__ x, const floa
     }
 }
 
+// 8 elements per thread: two 16-byte loads, one 16-byte store per plane (vec: every pointer 16-byte aligned; the last
+// n % 8 elements and misaligned views take the scalar loop)
 template <int NP>
-__global__ void split_bf16_kernel(const float* __restrict__ x, size_t n, const PlanePtrs out) {
+__global__ void split_bf16_kernel(const float* __restrict__ x, size_t n, const PlanePtrs out, int vec) {
     CTTS_PDL_SYNC();
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n8 = vec ? n >> 3 : 0;
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < n8; g += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = reinterpret_cast<const float4*>(x)[2 * g], b = reinterpret_cast<const float4*>(x)[2 * g + 1];
+        float rem[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(rem[2 * e], rem[2 * e + 1]);
+                rem[2 * e] -= __low2float(h);
+                rem[2 * e + 1] -= __high2float(h);
+                pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            reinterpret_cast<uint4*>(out.p[p])[g] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+    for (size_t i = (n8 << 3) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float rem = x[i];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
@@ -1409,14 +1428,18 @@ int ctts_add_row_broadcast(const float* x, const float* row, int B, int T, int C
 
 int ctts_split_planes(const float* x, size_t n, int n_planes, void* const* planes, void* stream) {
     CTTS_REQUIRE(n > 0 && (n_planes == 2 || n_planes == 3) && planes, "split_planes: bad arguments");
-    const int grid = (int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192);
     PlanePtrs pp{{nullptr, nullptr, nullptr}};
+    uintptr_t align = reinterpret_cast<uintptr_t>(x);
     for (int p = 0; p < n_planes; ++p) {
         CTTS_REQUIRE(planes[p], "split_planes: NULL plane %d", p);
         pp.p[p] = (__nv_bfloat16*)planes[p];
+        align |= reinterpret_cast<uintptr_t>(planes[p]);
     }
-    if (n_planes == 3) launch_k(split_bf16_kernel<3>, grid, 256, 0, (cudaStream_t)stream, x, n, pp);
-    else launch_k(split_bf16_kernel<2>, grid, 256, 0, (cudaStream_t)stream, x, n, pp);
+    const int vec = (align & 15) == 0 ? 1 : 0;
+    const size_t work = vec ? (n + 7) / 8 : n;
+    const int grid = (int)((work + 255) / 256 < 8192 ? (work + 255) / 256 : 8192);
+    if (n_planes == 3) launch_k(split_bf16_kernel<3>, grid, 256, 0, (cudaStream_t)stream, x, n, pp, vec);
+    else launch_k(split_bf16_kernel<2>, grid, 256, 0, (cudaStream_t)stream, x, n, pp, vec);
     return check_launch("split_planes");
 }
 

@@ -393,7 +393,18 @@ __global__ void mask_rows_scalar_kernel(float* __restrict__ x, const int64_t* __
 // y = (accumulate ? y : 0) + a * x
 __global__ void axpy_kernel(const float* __restrict__ x, float a, size_t n, int accumulate, float* __restrict__ y) {
     CTTS_PDL_SYNC();
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    size_t done = 0;
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {      // 16-byte groups, scalar tail
+        const size_t n4 = n >> 2;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 v = reinterpret_cast<const float4*>(x)[i];
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (accumulate) o = reinterpret_cast<const float4*>(y)[i];
+            reinterpret_cast<float4*>(y)[i] = make_float4(o.x + a * v.x, o.y + a * v.y, o.z + a * v.z, o.w + a * v.w);
+        }
+        done = n4 << 2;
+    }
+    for (size_t i = done + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         y[i] = (accumulate ? y[i] : 0.f) + a * x[i];
 }
 
@@ -625,6 +636,23 @@ __global__ void merge_planes_kernel(const CTPlanes in, size_t n, float* __restri
 __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_stride, size_t rows, int C, float* __restrict__ dst,
                                  long long dst_stride, int accumulate) {
     CTTS_PDL_SYNC();
+    if ((C & 3) == 0 && (src_stride & 3) == 0 && (dst_stride & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {      // 16-byte groups
+        const int c4n = C >> 2;
+        const size_t total4 = rows * (size_t)c4n;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+            const size_t r = i / c4n;
+            const int c = (int)(i - r * c4n) * 4;
+            float4* d = reinterpret_cast<float4*>(dst + r * dst_stride + c);
+            float4 v = *reinterpret_cast<const float4*>(src + r * src_stride + c);
+            if (accumulate) {
+                const float4 o = *d;
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *d = v;
+        }
+        return;
+    }
     const size_t total = rows * (size_t)C;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / C;
@@ -738,9 +766,18 @@ __global__ void dropout_kernel(const float* __restrict__ x, size_t n, float p, u
     const float inv = 1.f / (1.f - p);
     const uint32_t thresh = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
     const size_t n4 = (n + 3) >> 2;
+    // whole float4 groups move as 16-byte accesses (the tensors of the step are 16-byte aligned and a multiple of 4 long;
+    // a ragged tail or a misaligned view takes the scalar path)
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
         uint32_t r[4];
         philox4x32_10(seed, (uint64_t)q, offset, r);
+        if (vec && q * 4 + 3 < n) {
+            const float4 v = reinterpret_cast<const float4*>(x)[q];
+            reinterpret_cast<float4*>(y)[q] = make_float4((r[0] >= thresh) ? v.x * inv : 0.f, (r[1] >= thresh) ? v.y * inv : 0.f,
+                                                          (r[2] >= thresh) ? v.z * inv : 0.f, (r[3] >= thresh) ? v.w * inv : 0.f);
+            continue;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const size_t i = q * 4 + e;
@@ -757,9 +794,27 @@ __global__ void dropout_add_kernel(const float* __restrict__ x, const float* __r
     const float inv = 1.f / (1.f - p);
     const uint32_t thresh = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
     const size_t n4 = (n + 3) >> 2;
+    const bool vec4 = (C & 3) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
         uint32_t r[4];
         philox4x32_10(seed, (uint64_t)q, offset, r);
+        if (vec4 && q * 4 + 3 < n) {      // C % 4 == 0: the four elements belong to one token
+            bool keep = true;
+            if (lens) {
+                const size_t tok = (q * 4) / C;
+                const size_t bb = tok / T;
+                keep = (int)(tok - bb * T) < (int)lens[bb];
+            }
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (keep) {
+                const float4 v = reinterpret_cast<const float4*>(x)[q], rs = reinterpret_cast<const float4*>(res)[q];
+                o = make_float4(rs.x + ((r[0] >= thresh) ? v.x * inv : 0.f), rs.y + ((r[1] >= thresh) ? v.y * inv : 0.f),
+                                rs.z + ((r[2] >= thresh) ? v.z * inv : 0.f), rs.w + ((r[3] >= thresh) ? v.w * inv : 0.f));
+            }
+            reinterpret_cast<float4*>(y)[q] = o;
+            continue;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const size_t i = q * 4 + e;
