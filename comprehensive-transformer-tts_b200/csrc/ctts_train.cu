@@ -268,6 +268,9 @@ __global__ void dropout_add_kernel(const float* __restrict__ x, const float* __r
 // LayerNorm backward (blocks.py:137-156 / nn.LayerNorm).  forward: y = (xhat * gamma + beta) * keep.
 //   g = dy * keep;  dxhat = g * gamma;  dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))
 //   dgamma += sum_r g * xhat;  dbeta += sum_r g.     One warp per row (grid-stride), C <= 1024, C % 4 == 0.
+// NV = float4 groups per lane (C <= 128 * NV): the register arrays are sized for the row length at hand, so that C = 256 runs at
+// full occupancy instead of carrying the 128 registers a 1024-wide row needs.
+template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ dy, float eps,
                      const int64_t* __restrict__ lens, int rows, int T, int C, float* __restrict__ dx, int accumulate,
@@ -276,9 +279,9 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     extern __shared__ float red[];   // [8][2*C]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n4 = C >> 2;
-    float4 pg[8], pb[8];
+    float4 pg[NV], pb[NV];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pg[i] = pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV; ++i) pg[i] = pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
         bool keep = true;
         if (lens) {
@@ -293,10 +296,10 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
         }
         const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * C);
         const float4* gr = reinterpret_cast<const float4*>(dy + (size_t)row * C);
-        float4 v[8], g[8];
+        float4 v[NV], g[NV];
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int c = lane + i * 32;
             if (c < n4) {
                 v[i] = xr[c];
@@ -307,7 +310,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
         const float mean = warp_sum(s) / (float)C;
         float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int c = lane + i * 32;
             if (c < n4) {
                 v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
@@ -317,7 +320,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
         const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int c = lane + i * 32;
             if (c < n4) {
                 const float4 gm = reinterpret_cast<const float4*>(gamma)[c];
@@ -331,7 +334,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
         }
         const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < NV; ++i) {
             const int c = lane + i * 32;
             if (c < n4) {
                 float4 o;
@@ -350,7 +353,7 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     // per-CTA reduction of the parameter gradients, then one atomicAdd per column
     float* rg = red + (size_t)warp * 2 * C;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c = lane + i * 32;
         if (c < n4) {
             reinterpret_cast<float4*>(rg)[c] = pg[i];
@@ -1365,11 +1368,25 @@ int ctts_layernorm_bwd(const float* x, const float* gamma, const float* dy, floa
     CTTS_REQUIRE(x && gamma && dy && dx && B > 0 && T > 0, "layernorm_bwd: bad arguments");
     const int rows = B * T;
     int grid = (rows + 7) / 8;
-    if (grid > 592) grid = 592;
     const size_t sm = (size_t)8 * 2 * C * sizeof(float);
-    ensure_smem(layernorm_bwd_kernel, sm);
-    launch_k(layernorm_bwd_kernel, grid, 256, sm, (cudaStream_t)stream, x, gamma, dy, eps, lens, rows, T, C, dx, accumulate,
-             dgamma, dbeta);
+    // grid-stride over the rows: enough CTAs to fill the SMs at the occupancy the row width allows (every CTA ends with
+    // 2 C atomics, so not one CTA per 8 rows)
+    const int cap = C <= 256 ? 1184 : 592;
+    if (grid > cap) grid = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 128) {
+        ensure_smem(layernorm_bwd_kernel<1>, sm);
+        launch_k(layernorm_bwd_kernel<1>, grid, 256, sm, st, x, gamma, dy, eps, lens, rows, T, C, dx, accumulate, dgamma, dbeta);
+    } else if (C <= 256) {
+        ensure_smem(layernorm_bwd_kernel<2>, sm);
+        launch_k(layernorm_bwd_kernel<2>, grid, 256, sm, st, x, gamma, dy, eps, lens, rows, T, C, dx, accumulate, dgamma, dbeta);
+    } else if (C <= 512) {
+        ensure_smem(layernorm_bwd_kernel<4>, sm);
+        launch_k(layernorm_bwd_kernel<4>, grid, 256, sm, st, x, gamma, dy, eps, lens, rows, T, C, dx, accumulate, dgamma, dbeta);
+    } else {
+        ensure_smem(layernorm_bwd_kernel<8>, sm);
+        launch_k(layernorm_bwd_kernel<8>, grid, 256, sm, st, x, gamma, dy, eps, lens, rows, T, C, dx, accumulate, dgamma, dbeta);
+    }
     return check_launch("layernorm_bwd");
 }
 
