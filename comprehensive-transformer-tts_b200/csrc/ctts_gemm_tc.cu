@@ -743,7 +743,7 @@ __device__ __forceinline__ size_t sk_chunk_offset(int u, int q, int lane) { retu
 constexpr int SK_MAX_PARTS = 3;                    // contributors per tile besides the finishing pair
 constexpr size_t SK_CTA_FLOATS = 128 * 256;        // one CTA's half of a pair tile
 
-template <int BLOCK_N, int ACT, class WaitAcc, class Arrive>
+template <int BLOCK_N, int ACT, bool SK, class WaitAcc, class Arrive>
 __device__ __forceinline__ void persistent_epilogue_tma(const Maps& tm, const Epilogue& ep, const RowMap& rm, bool tile_valid,
                                                         int n0, int N, int q, int half, int lane, uint32_t d_tmem,
                                                         uint8_t* stg, int row_coord, int z_coord, bool& store_pending,
@@ -772,7 +772,7 @@ __device__ __forceinline__ void persistent_epilogue_tma(const Maps& tm, const Ep
             __syncwarp();
             if (lane == 0) arrive();
         }
-        if (sk_parts > 0 && !beyond) {   // stream-K: the other pairs' partial accumulators of this tile, in a fixed order
+        if (SK && sk_parts > 0 && !beyond) {   // stream-K: the other pairs' partial accumulators of this tile, in a fixed order
             for (int p = 0; p < sk_parts; ++p) {
                 const float4* src = reinterpret_cast<const float4*>(sk_part + (size_t)p * sk_stride + sk_chunk_offset(u, q, lane));
 #pragma unroll
@@ -842,7 +842,7 @@ __device__ __forceinline__ void persistent_epilogue_tma(const Maps& tm, const Ep
     }
 }
 
-template <int BLOCK_N, class WaitAcc, class Arrive>
+template <int BLOCK_N, bool SK = false, class WaitAcc, class Arrive>
 __device__ __forceinline__ void persistent_epilogue_tma_act(const Maps& tm, const Epilogue& ep, const RowMap& rm, bool tile_valid,
                                                             int n0, int N, int q, int half, int lane, uint32_t d_tmem,
                                                             uint8_t* stg, int row_coord, int z_coord, bool& store_pending,
@@ -850,23 +850,23 @@ __device__ __forceinline__ void persistent_epilogue_tma_act(const Maps& tm, cons
                                                             int sk_parts = 0, size_t sk_stride = 0) {
     switch (ep.act) {
         case CTTS_ACT_RELU:
-            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_RELU>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_RELU, SK>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
                                                             z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
         case CTTS_ACT_GELU:
-            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_GELU>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_GELU, SK>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
                                                             z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
         case CTTS_ACT_TANH:
-            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_TANH>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_TANH, SK>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
                                                             z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
         case CTTS_ACT_SWISH:
-            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_SWISH>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_SWISH, SK>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
                                                              z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
         default:
-            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_NONE>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
+            persistent_epilogue_tma<BLOCK_N, CTTS_ACT_NONE, SK>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem, stg, row_coord,
                                                             z_coord, store_pending, wait_acc, arrive, sk_part, sk_parts, sk_stride);
             break;
     }
@@ -1133,7 +1133,7 @@ struct PairSmem {
     static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <int STAGES, bool TMA_OUT>
+template <int STAGES, bool TMA_OUT, bool SK = false>      // SK: stream-K over the partial last round (opt-in, TMA_OUT only)
 __global__ void __launch_bounds__(320, 1)
 gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr ad, int T, int Cin, int N, int taps,
                  int tiles_per_utt, int Z, int seg_rows, int m_tiles, int n_tiles, int swap_b, float* sk_ws,
@@ -1215,7 +1215,7 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
     // the BEGINNING of the next (this pair contributes its partial accumulator through the workspace).  The contribution is
     // processed FIRST, so nobody waits for work that is queued behind a wait.
     struct Item { int pt, kb0, kb1, part, parts; };      // part >= 0: contributor slot; parts: contributors to add when finishing
-    const bool streamk = TMA_OUT && sk_ws != nullptr;
+    const bool streamk = SK && TMA_OUT && sk_ws != nullptr;
     const int full_rounds = streamk ? pair_tiles / n_pairs : (pair_tiles + n_pairs - 1) / n_pairs;
     const int tail_tiles = streamk ? pair_tiles - full_rounds * n_pairs : 0;
     const long long sk_units = (long long)tail_tiles * num_kb;
@@ -1353,7 +1353,7 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
             const int sk_tile = pt - full_rounds * n_pairs;      // index into the stream-K workspace (tail tiles only)
             long long* stamp = (ep.dbg && warp == 2 && lane == 0 && ii < 8) ? ep.dbg + (size_t)blockIdx.x * 64 + ii * 4 : nullptr;
             if (stamp) { stamp[0] = (long long)gtimer(); stamp[1] = (long long)wi.kb0 | ((long long)wi.kb1 << 16) | ((long long)(wi.part + 1) << 32) | ((long long)wi.parts << 40); }
-            if (wi.part >= 0) {
+            if (SK && wi.part >= 0) {
                 // ---- contributor: the raw partial accumulator goes to the workspace, then one arrival per warp ----------
                 float* dst = sk_ws + (((size_t)sk_tile * SK_MAX_PARTS + wi.part) * 2 + rank) * SK_CTA_FLOATS;
                 mbar_wait(&acc_full[acc], aph);
@@ -1378,7 +1378,7 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
                 if (stamp) stamp[3] = (long long)gtimer();
                 continue;
             }
-            if (wi.parts > 0) {
+            if (SK && wi.parts > 0) {
                 // ---- finishing pair: wait until every contributor warp (16 per contributing pair) has arrived ----------
                 const unsigned int want = 16u * (unsigned int)wi.parts;
                 if (lane == 0) {
@@ -1403,13 +1403,13 @@ gemm_pair_kernel(const __grid_constant__ Maps tm, const Epilogue ep, const Addr 
                 auto wait_acc = [&] { mbar_wait(&acc_full[acc], aph); };
                 auto hand_back = [&] { mbar_arrive_cluster(acc_empty_leader[acc]); };
                 if constexpr (TMA_OUT) {
-                    const float* sk_part = wi.parts > 0
+                    const float* sk_part = (SK && wi.parts > 0)
                         ? sk_ws + (((size_t)sk_tile * SK_MAX_PARTS) * 2 + rank) * SK_CTA_FLOATS : nullptr;
-                    persistent_epilogue_tma_act<BLOCK_N>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem,
+                    persistent_epilogue_tma_act<BLOCK_N, SK>(tm, ep, rm, tile_valid, n0, N, q, half, lane, d_tmem,
                                                          reinterpret_cast<uint8_t*>(stg), (packed ? g0 : t0) + q * 32,
                                                          packed ? 0 : z, store_pending, wait_acc, hand_back, sk_part, wi.parts,
                                                          2 * SK_CTA_FLOATS);
-                    if (wi.parts > 0) {      // the 16th finishing warp re-arms the tile's counters for the next launch
+                    if (SK && wi.parts > 0) {      // the 16th finishing warp re-arms the tile's counters for the next launch
                         __syncwarp();
                         if (lane == 0 && atomicAdd(sk_ctr + 2 * sk_tile + 1, 1u) == 15u) {
                             sk_ctr[2 * sk_tile] = 0u;
@@ -1691,12 +1691,14 @@ static int launch_pair(const Operand& A, const Operand& W, const Epilogue& ep_in
     }
     Epilogue ep = ep_in;
     if (int e = make_output_maps(maps, ep, ad, Z, T, N, seg_rows)) return e;
-    auto kern = ep.tma_out ? gemm_pair_kernel<STAGES, true> : gemm_pair_kernel<STAGES, false>;
+    auto kern = ep.tma_out ? gemm_pair_kernel<STAGES, true, false> : gemm_pair_kernel<STAGES, false, false>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_pair_kernel<STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
+        if (cudaFuncSetAttribute(gemm_pair_kernel<STAGES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
                 cudaSuccess ||
-            cudaFuncSetAttribute(gemm_pair_kernel<STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
+            cudaFuncSetAttribute(gemm_pair_kernel<STAGES, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(gemm_pair_kernel<STAGES, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) !=
                 cudaSuccess) {
             set_error("gemm_pair: cannot reserve %d bytes of shared memory", S::TOTAL);
             return 4;
@@ -1783,6 +1785,7 @@ static int launch_pair(const Operand& A, const Operand& W, const Epilogue& ep_in
                 ws = sk_ws[sk_launch & 1u];
                 ctr = sk_ctr[sk_launch & 1u];
                 ++sk_launch;
+                kern = gemm_pair_kernel<STAGES, true, true>;      // the default instantiation carries no stream-K code
             }
         }
     }
