@@ -203,6 +203,32 @@ def ctts_attention_small(qkvp, lens, B, T, C, H, scale, outp, stream):
     _split_into(_attention(_val(qkvp, 3, B, T, 3 * C), lens, B, T, C, H, scale), _planes(outp, 3), B, T, C)
 
 
+class _PA:
+    """Stand-in of capi.ptr_array for the legacy two-plane entry points (hi / lo passed as separate pointers)."""
+
+    def __init__(self, *tensors):
+        self._keepalive = list(tensors)
+
+
+def ctts_gemm_bf16x3(x_hi, x_lo, w_hi, w_lo, bias, alpha, cs, csh, act, residual, lens, B, T, Cin, N, taps, y, y_hi, y_lo, stream):
+    ctts_gemm_split(2, _PA(x_hi, x_lo), _PA(w_hi, w_lo), bias, alpha, cs, csh, act, residual, lens, B, T, Cin, N, taps, y,
+                    _PA(y_hi, y_lo) if y_hi is not None else None, stream)
+
+
+def ctts_attention_bf16x3(qkv_hi, qkv_lo, lens, B, T, C, H, scale, scores, p_hi, p_lo, vt_hi, vt_lo, out_hi, out_lo, out_f32,
+                          stream):
+    ctts_attention_split(2, _PA(qkv_hi, qkv_lo), lens, B, T, C, H, scale, scores, _PA(p_hi, p_lo), _PA(vt_hi, vt_lo),
+                         _PA(out_hi, out_lo) if out_hi is not None else None, out_f32, stream)
+
+
+def ctts_split_bf16(x, n, hi, lo, stream):
+    ctts_split_planes(x, n, 2, _PA(hi, lo), stream)
+
+
+def ctts_layernorm_split(x, gamma, beta, eps, lens, B, T, C, y, y_hi, y_lo, stream):
+    ctts_layernorm_planes(x, gamma, beta, eps, lens, B, T, C, y, 2, _PA(y_hi, y_lo), stream)
+
+
 def ctts_decode_durations(log_d, d_control, n, dur, stream):
     _v(dur, n).copy_(torch.clamp(torch.round(torch.exp(_v(log_d, n)) - 1) * d_control, min=0))
 

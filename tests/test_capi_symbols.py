@@ -94,3 +94,24 @@ def test_ctypes_signatures_match_the_header():
                 assert re.match(r"(const )?int\b", p), "%s: unexpected parameter type %r" % (name, p)
                 want = ctypes.c_int
             assert c is want, "%s parameter %d (%s): binding uses %s" % (name, i, p, c.__name__)
+
+
+def test_emulator_restates_every_kernel_entry_point():
+    """oracle/capi_emulator.py is the per-kernel oracle of the GPU tests and the stand-in of the CPU host-logic tests: every
+    kernel-launching entry point of the ABI has a torch restatement there with the same number of arguments."""
+    import inspect
+    from ctts_b200 import capi
+    from oracle import capi_emulator as emu
+    not_kernels = {"ctts_abi_version", "ctts_last_error", "ctts_device_arch", "ctts_debug_set_timing_buffer"}
+    # entry points that only exist as thin aliases / legacy forms of a restated one
+    missing = []
+    for name, argtypes in capi.SIGNATURES.items():
+        if name in not_kernels:
+            continue
+        fn = getattr(emu, name, None)
+        if fn is None:
+            missing.append(name)
+            continue
+        n_args = len(inspect.signature(fn).parameters)
+        assert n_args == len(argtypes), "%s: emulator takes %d arguments, the ABI %d" % (name, n_args, len(argtypes))
+    assert not missing, "no restatement in oracle/capi_emulator.py for: %s" % ", ".join(sorted(missing))
